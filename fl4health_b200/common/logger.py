@@ -1,0 +1,51 @@
+"""Process-wide logger (replaces ``flwr.common.logger``)."""
+
+from __future__ import annotations
+
+import logging
+import os
+import sys
+
+LOGGER_NAME = "fl4health_b200"
+FLOWER_LOGGER = logging.getLogger(LOGGER_NAME)
+FLOWER_LOGGER.setLevel(logging.DEBUG)
+FLOWER_LOGGER.propagate = False
+
+DEFAULT_FORMAT = "%(levelname)s %(name)s %(asctime)s | %(filename)s:%(lineno)d | %(message)s"
+
+
+class _RankFilter(logging.Filter):
+    """Prefix records with the SPMD rank when one is set so interleaved logs stay readable."""
+
+    def filter(self, record: logging.LogRecord) -> bool:
+        rank = os.environ.get("RANK")
+        if rank is not None and not str(record.msg).startswith("[r"):
+            record.msg = f"[r{rank}] {record.msg}"
+        return True
+
+
+console_handler = logging.StreamHandler(sys.stderr)
+console_handler.setLevel(getattr(logging, os.environ.get("FL4H_LOG_LEVEL", "INFO").upper(), logging.INFO))
+console_handler.setFormatter(logging.Formatter(DEFAULT_FORMAT))
+console_handler.addFilter(_RankFilter())
+FLOWER_LOGGER.addHandler(console_handler)
+
+
+def update_console_handler(level: int | None = None, fmt: str | None = None) -> None:
+    if level is not None:
+        console_handler.setLevel(level)
+    if fmt is not None:
+        console_handler.setFormatter(logging.Formatter(fmt))
+
+
+def configure(identifier: str, filename: str | None = None) -> None:
+    """Optionally mirror the log into a file, tagged with an identifier."""
+    if filename:
+        fh = logging.FileHandler(filename)
+        fh.setLevel(logging.DEBUG)
+        fh.setFormatter(logging.Formatter(f"{identifier} | {DEFAULT_FORMAT}"))
+        FLOWER_LOGGER.addHandler(fh)
+
+
+def log(level: int, msg: object, *args: object, **kwargs: object) -> None:
+    FLOWER_LOGGER.log(level, msg, *args, stacklevel=2, **kwargs)  # type: ignore[arg-type]

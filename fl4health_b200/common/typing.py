@@ -1,0 +1,157 @@
+"""Wire types of the engine.
+
+These play the role of ``flwr.common`` dataclasses but are *zero-copy*: a ``Parameters``
+object carries references to live ``torch.Tensor``s (usually views into a rank's flat device arena) or numpy
+arrays, never serialized bytes.  The np.save/protobuf/gRPC path of the reference
+(``fl4health/parameter_exchange/full_exchanger.py:30``) simply does not exist here.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Callable
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Any, Union
+
+import numpy as np
+import torch
+
+Scalar = Union[bool, bytes, float, int, str]
+Config = dict[str, Scalar]
+Metrics = dict[str, Scalar]
+Properties = dict[str, Scalar]
+NDArray = Union[np.ndarray, torch.Tensor]
+MetricsAggregationFn = Callable[[list[tuple[int, Metrics]]], Metrics]
+
+
+class NDArrays(list):
+    """A list of arrays with optional arena metadata.
+
+    When every entry is a view into one contiguous flat buffer, ``flat`` holds that buffer and ``layout`` the
+    (offset, numel, shape) triples; strategies and exchangers use it to replace per-layer loops with one fused
+    kernel over the flat storage.  It behaves as a plain ``list`` otherwise.
+    """
+
+    flat: torch.Tensor | None
+    layout: Any
+
+    def __init__(self, iterable: Any = (), flat: torch.Tensor | None = None, layout: Any = None) -> None:
+        super().__init__(iterable)
+        self.flat = flat
+        self.layout = layout
+
+
+class Code(Enum):
+    OK = 0
+    GET_PROPERTIES_NOT_IMPLEMENTED = 1
+    GET_PARAMETERS_NOT_IMPLEMENTED = 2
+    FIT_NOT_IMPLEMENTED = 3
+    EVALUATE_NOT_IMPLEMENTED = 4
+
+
+@dataclass
+class Status:
+    code: Code = Code.OK
+    message: str = "Success"
+
+
+@dataclass
+class Parameters:
+    tensors: list[Any]
+    tensor_type: str = "torch"
+    # arena metadata (optional): one contiguous buffer backing every entry of ``tensors``.
+    flat: Any = None
+    layout: Any = None
+
+
+def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
+    return Parameters(
+        tensors=list(ndarrays),
+        tensor_type="torch",
+        flat=getattr(ndarrays, "flat", None),
+        layout=getattr(ndarrays, "layout", None),
+    )
+
+
+def parameters_to_ndarrays(parameters: Parameters) -> NDArrays:
+    tensors = parameters.tensors
+    materialize = getattr(parameters, "materialize", None)
+    if materialize is not None:  # lazily-fetched remote payloads (SPMD transport)
+        tensors = materialize()
+    return NDArrays(tensors, flat=parameters.flat, layout=parameters.layout)
+
+
+def to_numpy(array: NDArray) -> np.ndarray:
+    if isinstance(array, torch.Tensor):
+        return array.detach().cpu().numpy()
+    return np.asarray(array)
+
+
+def to_tensor(array: NDArray, device: torch.device | str | None = None) -> torch.Tensor:
+    if isinstance(array, torch.Tensor):
+        return array if device is None else array.to(device, non_blocking=True)
+    arr = np.asarray(array)
+    if arr.dtype.kind in ("U", "S", "O"):
+        raise TypeError("string arrays cannot be converted to tensors")
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t if device is None else t.to(device, non_blocking=True)
+
+
+@dataclass
+class FitIns:
+    parameters: Parameters
+    config: Config = field(default_factory=dict)
+
+
+@dataclass
+class FitRes:
+    status: Status
+    parameters: Parameters
+    num_examples: int
+    metrics: Metrics = field(default_factory=dict)
+
+
+@dataclass
+class EvaluateIns:
+    parameters: Parameters
+    config: Config = field(default_factory=dict)
+
+
+@dataclass
+class EvaluateRes:
+    status: Status
+    loss: float
+    num_examples: int
+    metrics: Metrics = field(default_factory=dict)
+
+
+@dataclass
+class GetPropertiesIns:
+    config: Config = field(default_factory=dict)
+
+
+@dataclass
+class GetPropertiesRes:
+    status: Status
+    properties: Properties = field(default_factory=dict)
+
+
+@dataclass
+class GetParametersIns:
+    config: Config = field(default_factory=dict)
+
+
+@dataclass
+class GetParametersRes:
+    status: Status
+    parameters: Parameters
+
+
+@dataclass
+class ReconnectIns:
+    seconds: int | None = None
+
+
+@dataclass
+class DisconnectRes:
+    reason: str = ""

@@ -1,0 +1,70 @@
+"""ResNet-18 for 32x32 inputs (the CIFAR variant: 3x3 stem, no max-pool) — 11.17 M parameters.
+
+The reference only ever uses ``torchvision.models.resnet18`` (``research/rxrx1/utils.py:91``); ``BASELINE.json``'s
+headline config is "CIFAR-10 ResNet-18", so the framework ships its own.  State-dict key names follow torchvision
+(``conv1/bn1/layer{1-4}.{0,1}.{conv,bn}{1,2}/downsample.{0,1}/fc``) so torchvision weights load with
+``strict=True`` when ``imagenet_stem=True``.
+"""
+
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample: nn.Module | None = None
+        if stride != 1 or in_planes != planes:
+            self.downsample = nn.Sequential(
+                nn.Conv2d(in_planes, planes, 1, stride=stride, bias=False), nn.BatchNorm2d(planes)
+            )
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + identity)
+
+
+class ResNet18(nn.Module):
+    def __init__(self, num_classes: int = 10, in_channels: int = 3, imagenet_stem: bool = False) -> None:
+        super().__init__()
+        if imagenet_stem:
+            self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
+            self.maxpool: nn.Module = nn.MaxPool2d(3, stride=2, padding=1)
+        else:
+            self.conv1 = nn.Conv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)
+            self.maxpool = nn.Identity()
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        widths, strides = (64, 128, 256, 512), (1, 2, 2, 2)
+        in_planes = 64
+        for idx, (planes, stride) in enumerate(zip(widths, strides), start=1):
+            setattr(self, f"layer{idx}", nn.Sequential(BasicBlock(in_planes, planes, stride), BasicBlock(planes, planes)))
+            in_planes = planes
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(512, num_classes)
+        for module in self.modules():
+            if isinstance(module, nn.Conv2d):
+                nn.init.kaiming_normal_(module.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return torch.flatten(self.avgpool(x), 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.fc(self.forward_features(x))
+
+
+def resnet18_cifar(num_classes: int = 10) -> ResNet18:
+    return ResNet18(num_classes=num_classes)

@@ -1,0 +1,273 @@
+"""Flat parameter arena: the memory layout everything else in the engine is built around.
+
+A model's exchangeable floating-point state (parameters *and* float buffers such as BatchNorm running statistics) is
+re-homed into ONE contiguous fp32 buffer per rank; ``nn.Parameter.data`` / buffers become views into it.  Consequences:
+
+* parameter exchange is a single contiguous buffer operation (one fused kernel / one collective) instead of the
+  reference's per-layer ``val.cpu().numpy()`` / ``torch.tensor(v)`` loops (``full_exchanger.py:30,45-47``);
+* the local optimizer is one multi-tensor kernel over ``flat[:trainable]`` + ``grad[:trainable]`` with the FedProx
+  drift term and SCAFFOLD correction folded in;
+* companion regions (gradient, momentum, FedProx anchor ``w_t``, SCAFFOLD ``c``/``c_i``/``c-c_i``, server moments,
+  bf16 compute shadow) share the same offsets, so "slices" (FedPer base module, FedBN exclusions, ...) are just
+  offset ranges;
+* on multi-GPU runs the arena is allocated from peer-mapped symmetric memory so other ranks' kernels can read/write it
+  over NVLink directly.
+
+Layout: ``[trainable params | frozen params | float buffers]``, every entry aligned to ``ALIGN`` elements; the list
+order handed to strategies still follows ``state_dict()`` order (views may point anywhere in the flat buffer).
+Integer buffers (``num_batches_tracked``) are not in the arena; they travel as separate tiny tensors.
+"""
+
+from __future__ import annotations
+
+from collections import OrderedDict
+from collections.abc import Callable, Iterable
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+from fl4health_b200.common.typing import NDArrays
+
+import weakref
+
+_ARENAS: "weakref.WeakKeyDictionary[nn.Module, ParameterArena]" = weakref.WeakKeyDictionary()
+
+ALIGN = 32  # elements (128 B of fp32): keeps every entry 16B-vectorizable in fp32 *and* bf16
+
+
+@dataclass(frozen=True)
+class ArenaEntry:
+    name: str
+    offset: int
+    numel: int
+    shape: tuple[int, ...]
+    kind: str  # "trainable" | "frozen" | "buffer"
+    dtype: torch.dtype  # original dtype of the tensor (restored on export)
+    nhwc: bool = False  # 4-D tensor stored channels-last inside the flat buffer
+
+    @property
+    def end(self) -> int:
+        return self.offset + self.numel
+
+
+def _round_up(n: int, multiple: int) -> int:
+    return (n + multiple - 1) // multiple * multiple
+
+
+Allocator = Callable[[int, torch.dtype, torch.device], torch.Tensor]
+
+
+def _default_allocator(numel: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    return torch.zeros(numel, dtype=dtype, device=device)
+
+
+class ParameterArena:
+    """Flat fp32 home for a module's float state, plus named companion regions with identical offsets."""
+
+    def __init__(
+        self,
+        module: nn.Module,
+        device: torch.device | str | None = None,
+        allocator: Allocator | None = None,
+        with_grad: bool = True,
+        channels_last: bool = False,
+    ) -> None:
+        self.module = module
+        self.channels_last = channels_last
+        first = next(iter(module.state_dict().values()), None)
+        self.device = torch.device(device) if device is not None else (first.device if first is not None else torch.device("cpu"))
+        self._alloc: Allocator = allocator or _default_allocator
+        self.entries: list[ArenaEntry] = []
+        self.by_name: dict[str, ArenaEntry] = {}
+        self.int_state: OrderedDict[str, torch.Tensor] = OrderedDict()
+        self.state_keys: list[str] = []
+        self.regions: dict[str, torch.Tensor] = {}
+        self._build_layout()
+        self.flat = self._alloc(self.total, torch.float32, self.device)
+        self._rehome()
+        self.grad: torch.Tensor | None = None
+        if with_grad and self.trainable_numel > 0:
+            self.grad = self._alloc(self.trainable_padded, torch.float32, self.device)
+            self._attach_grads()
+        _ARENAS[module] = self
+
+    # ------------------------------------------------------------------------------------------------------
+    def _build_layout(self) -> None:
+        params = dict(self.module.named_parameters(remove_duplicate=False))
+        state = self.module.state_dict(keep_vars=True)
+        self.state_keys = list(state.keys())
+        groups: dict[str, list[tuple[str, torch.Tensor]]] = {"trainable": [], "frozen": [], "buffer": []}
+        seen: dict[int, str] = {}
+        self.aliases: dict[str, str] = {}
+        for name, tensor in state.items():
+            if id(tensor) in seen:  # tied weights: one home, several names
+                self.aliases[name] = seen[id(tensor)]
+                continue
+            seen[id(tensor)] = name
+            if not tensor.is_floating_point():
+                self.int_state[name] = tensor
+                continue
+            if name in params:
+                groups["trainable" if params[name].requires_grad else "frozen"].append((name, tensor))
+            else:
+                groups["buffer"].append((name, tensor))
+        offset = 0
+        for kind in ("trainable", "frozen", "buffer"):
+            for name, tensor in groups[kind]:
+                nhwc = self.channels_last and tensor.dim() == 4
+                entry = ArenaEntry(name, offset, tensor.numel(), tuple(tensor.shape), kind, tensor.dtype, nhwc)
+                self.entries.append(entry)
+                self.by_name[name] = entry
+                offset = _round_up(offset + tensor.numel(), ALIGN)
+            if kind == "trainable":
+                self.trainable_padded = offset
+        self.total = max(offset, ALIGN)
+        self.trainable_numel = sum(e.numel for e in self.entries if e.kind == "trainable")
+        self.numel = sum(e.numel for e in self.entries)
+
+    @staticmethod
+    def _shaped(base: torch.Tensor, entry: ArenaEntry) -> torch.Tensor:
+        chunk = base[entry.offset : entry.end]
+        if entry.nhwc:
+            n, c, h, w = entry.shape
+            return chunk.view(n, h, w, c).permute(0, 3, 1, 2)  # logical NCHW, physical NHWC
+        return chunk.view(entry.shape)
+
+    def _find_owner(self, dotted: str) -> tuple[nn.Module, str]:
+        owner: nn.Module = self.module
+        parts = dotted.split(".")
+        for part in parts[:-1]:
+            owner = getattr(owner, part)
+        return owner, parts[-1]
+
+    def _rehome(self) -> None:
+        state = self.module.state_dict(keep_vars=True)
+        with torch.no_grad():
+            for entry in self.entries:
+                src = state[entry.name]
+                view = self._shaped(self.flat, entry)
+                view.copy_(src.detach().to(device=self.device, dtype=torch.float32))
+                if isinstance(src, nn.Parameter):
+                    src.data = view
+                else:
+                    owner, leaf = self._find_owner(entry.name)
+                    owner._buffers[leaf] = view
+            for name, tensor in list(self.int_state.items()):
+                if tensor.device != self.device:
+                    owner, leaf = self._find_owner(name)
+                    moved = tensor.to(self.device)
+                    if leaf in owner._buffers:
+                        owner._buffers[leaf] = moved
+                    self.int_state[name] = moved
+
+    def _attach_grads(self) -> None:
+        assert self.grad is not None
+        params = dict(self.module.named_parameters(remove_duplicate=False))
+        for entry in self.entries:
+            if entry.kind == "trainable":
+                params[entry.name].grad = self._shaped(self.grad, entry)
+
+    # ------------------------------------------------------------------------------------------------------
+    def view(self, name: str, region: torch.Tensor | None = None) -> torch.Tensor:
+        entry = self.by_name[self.aliases.get(name, name)]
+        base = self.flat if region is None else region
+        return self._shaped(base, entry)
+
+    def companion(self, name: str, trainable_only: bool = False, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """Get-or-create a zero-initialised region with the arena's offsets (anchor, momentum, variates, ...)."""
+        if name not in self.regions:
+            numel = self.trainable_padded if trainable_only else self.total
+            self.regions[name] = self._alloc(max(numel, ALIGN), dtype, self.device)
+        return self.regions[name]
+
+    def zero_grad(self) -> None:
+        if self.grad is not None:
+            self.grad.zero_()
+
+    def trainable(self, region: torch.Tensor | None = None) -> torch.Tensor:
+        base = self.flat if region is None else region
+        return base[: self.trainable_padded]
+
+    # ------------------------------------------------------------------------------------------------------
+    def ndarrays(self, names: Iterable[str] | None = None, region: torch.Tensor | None = None) -> NDArrays:
+        """state_dict-ordered list of views (``FullParameterExchanger`` order, ``full_exchanger.py:30``)."""
+        keys = list(names) if names is not None else self.state_keys
+        out = NDArrays()
+        for key in keys:
+            key = self.aliases.get(key, key)
+            if key in self.by_name:
+                out.append(self.view(key, region))
+            else:
+                out.append(self.int_state[key])
+        if names is None:
+            out.flat = self.flat if region is None else region
+            out.layout = self
+        return out
+
+    def load_ndarrays(self, arrays: list, names: Iterable[str] | None = None) -> None:
+        """Copy a list of arrays into the arena.  A single flat copy when the source is arena-shaped."""
+        keys = list(names) if names is not None else self.state_keys
+        src_flat = getattr(arrays, "flat", None)
+        src_layout = getattr(arrays, "layout", None)
+        with torch.no_grad():
+            if names is None and src_flat is not None and isinstance(src_layout, ParameterArena) and src_layout.same_layout(self):
+                if src_flat.data_ptr() != self.flat.data_ptr():
+                    self.flat.copy_(src_flat, non_blocking=True)
+                for key, arr in zip(keys, arrays):
+                    if key in self.int_state:
+                        self.int_state[key].copy_(_as_tensor(arr, self.device))
+                return
+            assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
+            for key, arr in zip(keys, arrays):
+                key = self.aliases.get(key, key)
+                t = _as_tensor(arr, self.device)
+                if key in self.by_name:
+                    dst = self.view(key)
+                    assert dst.shape == t.shape, f"shape mismatch for {key}: {tuple(dst.shape)} vs {tuple(t.shape)}"
+                    dst.copy_(t, non_blocking=True)
+                else:
+                    self.int_state[key].copy_(t.to(self.int_state[key].dtype))
+
+    def same_layout(self, other: ParameterArena) -> bool:
+        return self.total == other.total and [(e.name, e.offset, e.numel, e.nhwc) for e in self.entries] == [
+            (e.name, e.offset, e.numel, e.nhwc) for e in other.entries
+        ]
+
+    def range_of(self, names: Iterable[str]) -> list[tuple[int, int]]:
+        """Merged (start, end) element ranges covering the given entries — the arena form of a layer subset."""
+        spans = sorted((self.by_name[n].offset, _round_up(self.by_name[n].end, ALIGN)) for n in names if n in self.by_name)
+        merged: list[tuple[int, int]] = []
+        for start, end in spans:
+            if merged and start <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(end, merged[-1][1]))
+            else:
+                merged.append((start, end))
+        return merged
+
+
+def _as_tensor(arr: object, device: torch.device) -> torch.Tensor:
+    if isinstance(arr, torch.Tensor):
+        return arr.to(device, non_blocking=True) if arr.device != device else arr
+    import numpy as np
+
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+
+
+def arena_of(module: nn.Module) -> ParameterArena | None:
+    """The arena a module's state lives in, if any.  Kept in a weak side-table (not on the module) so that
+    ``copy.deepcopy(model)`` / ``torch.save(model)`` see a plain module with ordinary tensors."""
+    return _ARENAS.get(module)
+
+
+def attach_arena(
+    module: nn.Module,
+    device: torch.device | str | None = None,
+    allocator: Allocator | None = None,
+    with_grad: bool = True,
+    channels_last: bool = False,
+) -> ParameterArena:
+    existing = arena_of(module)
+    if existing is not None and existing.module is module:
+        return existing
+    return ParameterArena(module, device=device, allocator=allocator, with_grad=with_grad, channels_last=channels_last)

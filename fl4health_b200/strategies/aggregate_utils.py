@@ -1,0 +1,104 @@
+"""Aggregation primitives.
+
+Parity: ``fl4health/strategies/aggregate_utils.py:8-55`` (and Flower's ``aggregate`` / ``weighted_loss_avg``).  The
+reference reduces per layer with ``functools.reduce(np.add, ...)`` over NumPy arrays on the server CPU.  Here:
+
+* if every client's list is arena-backed (one flat buffer each, identical layout) the whole model is reduced by ONE
+  launch of the K-way ``weighted_sum`` kernel over the flat buffers (fixed client order ⇒ bit-deterministic);
+* otherwise each layer is reduced with device-side tensor ops (still no host round trip);
+* string/object side arrays (layer names) are passed through untouched.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+from fl4health_b200.common.typing import NDArray, NDArrays, to_tensor
+from fl4health_b200.ops import flat as flat_ops
+
+
+def _common_flat(arrays: Sequence[NDArrays]) -> list[torch.Tensor] | None:
+    """The clients' flat buffers if all lists are whole-arena views with one shared layout."""
+    flats = []
+    layout0 = None
+    for nds in arrays:
+        flat, layout = getattr(nds, "flat", None), getattr(nds, "layout", None)
+        if flat is None or layout is None or len(nds) != len(layout.state_keys):
+            return None
+        if layout0 is None:
+            layout0 = layout
+        elif not layout.same_layout(layout0):
+            return None
+        flats.append(flat)
+    if len({(f.device, f.dtype, f.numel()) for f in flats}) != 1:
+        return None
+    return flats
+
+
+def _is_meta_array(arr: NDArray) -> bool:
+    return isinstance(arr, np.ndarray) and arr.dtype.kind in ("U", "S", "O")
+
+
+def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) -> NDArrays:
+    """``sum_k coefficients[k] * arrays[k]`` layer-wise (or in one fused pass when arena-backed)."""
+    assert len(arrays) == len(coefficients) and len(arrays) > 0
+    flats = _common_flat(arrays)
+    if flats is not None:
+        layout = arrays[0].layout
+        out_flat = torch.empty_like(flats[0])
+        flat_ops.weighted_sum(out_flat, flats, coefficients)
+        out = layout.ndarrays(region=out_flat)
+        # integer state (e.g. num_batches_tracked) is not in the flat buffer: average it like the reference does
+        for idx, key in enumerate(layout.state_keys):
+            if key in layout.int_state:
+                out[idx] = _combine_layer([nds[idx] for nds in arrays], coefficients)
+        return out
+    n_layers = len(arrays[0])
+    assert all(len(nds) == n_layers for nds in arrays), "clients sent different numbers of arrays"
+    return NDArrays([_combine_layer([nds[i] for nds in arrays], coefficients) for i in range(n_layers)])
+
+
+def _combine_layer(layers: Sequence[NDArray], coefficients: Sequence[float]) -> NDArray:
+    first = layers[0]
+    if _is_meta_array(first):
+        return first
+    if all(isinstance(layer, np.ndarray) for layer in layers):
+        acc = np.asarray(layers[0]) * coefficients[0]
+        for layer, coef in zip(layers[1:], coefficients[1:]):
+            acc = acc + np.asarray(layer) * coef
+        return acc
+    device = next((layer.device for layer in layers if isinstance(layer, torch.Tensor)), None)
+    tensors = [to_tensor(layer, device) for layer in layers]
+    work_dtype = tensors[0].dtype if tensors[0].is_floating_point() else torch.float64
+    acc = tensors[0].to(work_dtype) * coefficients[0]
+    for tensor, coef in zip(tensors[1:], coefficients[1:]):
+        acc = acc + tensor.to(work_dtype) * coef
+    return acc if tensors[0].is_floating_point() else acc.to(tensors[0].dtype)
+
+
+def aggregate_results(results: list[tuple[NDArrays, int]], weighted: bool = True) -> NDArrays:
+    """Weighted (by sample count) or uniform average of client array lists."""
+    arrays = [nds for nds, _ in results]
+    if weighted:
+        total = sum(n for _, n in results)
+        coefficients = [n / total for _, n in results]
+    else:
+        coefficients = [1.0 / len(results)] * len(results)
+    return weighted_combine(arrays, coefficients)
+
+
+def aggregate_losses(results: list[tuple[int, float]], weighted: bool = True) -> float:
+    """Average client losses; sorted first so the float sum is order-independent."""
+    ordered = sorted(results, key=lambda item: item[1])
+    if weighted:
+        total = sum(n for n, _ in ordered)
+        return sum(n * loss for n, loss in ordered) / total
+    return sum(loss for _, loss in ordered) / len(ordered)
+
+
+def weighted_loss_avg(results: list[tuple[int, float]]) -> float:
+    total = sum(n for n, _ in results)
+    return sum(n * loss for n, loss in results) / total

@@ -1,0 +1,155 @@
+"""Loss containers and meters.
+
+Parity: ``fl4health/utils/losses.py:10-234`` (``TrainingLosses``, ``EvaluationLosses``, ``LossMeter``), with a
+B200-first change of mechanics: the reference keeps a Python list of per-step loss objects and aggregates through
+``torch.FloatTensor([...])`` (a device→host sync per element, SURVEY hot-op L16).  Here a meter owns *device-side
+running sums*; ``update`` is a handful of in-place adds that are CUDA-graph capturable and the host only reads the
+result once, in ``compute().as_dict()``.
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from enum import Enum
+from typing import Generic, TypeVar
+
+import torch
+
+
+class Losses(ABC):
+    def __init__(self, additional_losses: dict[str, torch.Tensor] | None = None) -> None:
+        self.additional_losses: dict[str, torch.Tensor] = additional_losses if additional_losses else {}
+
+    def as_dict(self) -> dict[str, float]:
+        return {key: float(val.item()) for key, val in self.additional_losses.items()}
+
+    def _flat_items(self) -> dict[str, torch.Tensor]:
+        """All scalar tensors of this container under unique keys (used by the meter)."""
+        return {f"additional::{k}": v for k, v in self.additional_losses.items()}
+
+    @staticmethod
+    @abstractmethod
+    def aggregate(loss_meter: LossMeter) -> Losses:
+        raise NotImplementedError
+
+
+class EvaluationLosses(Losses):
+    def __init__(self, checkpoint: torch.Tensor, additional_losses: dict[str, torch.Tensor] | None = None) -> None:
+        super().__init__(additional_losses)
+        self.checkpoint = checkpoint
+
+    def as_dict(self) -> dict[str, float]:
+        out = super().as_dict()
+        out["checkpoint"] = float(self.checkpoint.item())
+        return out
+
+    def _flat_items(self) -> dict[str, torch.Tensor]:
+        items = super()._flat_items()
+        items["checkpoint"] = self.checkpoint
+        return items
+
+    @staticmethod
+    def aggregate(loss_meter: LossMeter[EvaluationLosses]) -> EvaluationLosses:
+        sums = loss_meter._reduced()
+        additional = {k.split("::", 1)[1]: v for k, v in sums.items() if k.startswith("additional::")}
+        return EvaluationLosses(checkpoint=sums["checkpoint"], additional_losses=additional)
+
+
+class TrainingLosses(Losses):
+    def __init__(
+        self,
+        backward: torch.Tensor | dict[str, torch.Tensor],
+        additional_losses: dict[str, torch.Tensor] | None = None,
+    ) -> None:
+        super().__init__(additional_losses)
+        self.backward: dict[str, torch.Tensor] = backward if isinstance(backward, dict) else {"backward": backward}
+
+    def as_dict(self) -> dict[str, float]:
+        out = super().as_dict()
+        out.update({key: float(loss.item()) for key, loss in self.backward.items()})
+        return out
+
+    def _flat_items(self) -> dict[str, torch.Tensor]:
+        items = super()._flat_items()
+        items.update({f"backward::{k}": v for k, v in self.backward.items()})
+        return items
+
+    @staticmethod
+    def aggregate(loss_meter: LossMeter[TrainingLosses]) -> TrainingLosses:
+        sums = loss_meter._reduced()
+        additional = {k.split("::", 1)[1]: v for k, v in sums.items() if k.startswith("additional::")}
+        backward = {k.split("::", 1)[1]: v for k, v in sums.items() if k.startswith("backward::")}
+        if set(backward.keys()) == {"backward"}:
+            return TrainingLosses(backward=backward["backward"], additional_losses=additional)
+        return TrainingLosses(backward=backward, additional_losses=additional)
+
+
+class LossMeterType(Enum):
+    AVERAGE = "AVERAGE"
+    ACCUMULATION = "ACCUMULATION"
+
+
+LossesType = TypeVar("LossesType", bound=Losses)
+
+
+class LossMeter(Generic[LossesType]):
+    def __init__(self, loss_meter_type: LossMeterType, losses_type: type[LossesType]) -> None:
+        self.loss_meter_type = loss_meter_type
+        self.losses_type = losses_type
+        self._sums: dict[str, torch.Tensor] = {}
+        self.count = 0
+
+    def update(self, losses: LossesType) -> None:
+        self.accumulate(losses)
+        self.count += 1
+
+    def accumulate(self, losses: LossesType) -> None:
+        """Device-side part of ``update`` (safe inside CUDA-graph capture once every key has been seen)."""
+        for key, value in losses._flat_items().items():
+            value = value.detach()
+            acc = self._sums.get(key)
+            if acc is None:
+                self._sums[key] = value.to(torch.float32).clone().reshape(())
+            else:
+                acc.add_(value.reshape(()))
+
+    def mark_step(self, n: int = 1) -> None:
+        """Count steps whose accumulation was replayed by a captured graph."""
+        self.count += n
+
+    def clear(self) -> None:
+        # zero in place: accumulators referenced by captured graphs must keep their addresses.
+        for acc in self._sums.values():
+            acc.zero_()
+        self.count = 0
+
+    def reset(self) -> None:
+        self._sums = {}
+        self.count = 0
+
+    def _reduced(self) -> dict[str, torch.Tensor]:
+        assert self.count > 0, "Cannot compute the aggregate of an empty loss meter"
+        if self.loss_meter_type == LossMeterType.AVERAGE:
+            return {k: v / self.count for k, v in self._sums.items()}
+        return {k: v.clone() for k, v in self._sums.items()}
+
+    def compute(self) -> LossesType:
+        return self.losses_type.aggregate(self)  # type: ignore[return-value]
+
+    @staticmethod
+    def aggregate_losses_dict(
+        loss_list: list[dict[str, torch.Tensor]], loss_meter_type: LossMeterType
+    ) -> dict[str, torch.Tensor]:
+        totals: dict[str, torch.Tensor] = {}
+        for loss_dict in loss_list:
+            for key, loss in loss_dict.items():
+                totals[key] = totals[key] + loss if key in totals else loss.clone()
+        if loss_meter_type == LossMeterType.AVERAGE:
+            return {key: total / len(loss_list) for key, total in totals.items()}
+        return totals
+
+    # --- state (pickled by the client state checkpointer) -------------------------------------------------
+    def __getstate__(self) -> dict:
+        state = self.__dict__.copy()
+        state["_sums"] = {k: v.detach().cpu() for k, v in self._sums.items()}
+        return state
