@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: FL rounds/sec, CIFAR-10-shaped ResNet-18 FedAvg, one client per GPU (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 20 --warmup 3
+
+One "step" = one full federated round driven through the public API (``FlServer.fit``): server->client parameter
+exchange, ``local_steps`` SGD(momentum) steps of batch 32 on each client GPU, client->server weighted FedAvg
+aggregation, then a federated evaluation pass (``val_batches`` batches per client) with metric aggregation.
+Synthetic CIFAR-10-shaped data, random-init ResNet-18 (there is no network for datasets).  Timed with CUDA events
+on every rank (barrier + synchronize on both sides), max over ranks.  Two timed regions:
+
+* ``value``  — datasets resident in HBM (no host traffic except the per-round scalar read-back);
+* ``e2e``    — every batch is staged from pinned host memory (H2D inside the timed region) and every round's loss /
+  metrics are read back (D2H), through the same public API.
+
+``--impl reference`` would run the unmodified reference; it cannot be installed offline (its build backend
+``hatchling`` and its core dependency ``flwr`` are absent from the image and the wheelhouse), so that arm reports
+``unavailable``.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+os.environ.setdefault("FL4H_LOG_LEVEL", "WARNING")
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+
+def parse_args() -> argparse.Namespace:
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20, help="timed FL rounds")
+    p.add_argument("--warmup", type=int, default=3, help="untimed warm-up FL rounds")
+    p.add_argument("--impl", default="native", choices=["native", "reference", "eager"])
+    p.add_argument("--local-steps", type=int, default=8)
+    p.add_argument("--batch-size", type=int, default=32)
+    p.add_argument("--val-batches", type=int, default=4)
+    p.add_argument("--train-samples", type=int, default=4096)
+    p.add_argument("--collectives", default="auto", choices=["auto", "nccl", "fused"])
+    p.add_argument("--no-graphs", action="store_true")
+    p.add_argument("--fp32", action="store_true")
+    p.add_argument("--skip-e2e", action="store_true")
+    return p.parse_args()
+
+
+def reference_arm() -> None:
+    print(json.dumps({
+        "impl": "reference",
+        "unavailable": "reference cannot be installed offline: build backend hatchling and core dependency flwr "
+                       "(plus opacus, torchmetrics, dp-accounting) are not in the image or /opt/wheelhouse",
+    }))
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, sm_max, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(sm_max) if sm_max else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm()
+        return
+
+    import torch
+    from torch import nn
+
+    from fl4health_b200 import ops
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.engine.data import BatchedTensorLoader
+    from fl4health_b200.engine.options import EngineOptions
+    from fl4health_b200.metrics import Accuracy
+    from fl4health_b200.metrics.metric_aggregation import evaluate_metrics_aggregation_fn, fit_metrics_aggregation_fn
+    from fl4health_b200.models import resnet18_cifar
+    from fl4health_b200.parallel.spmd import SpmdContext, build_spmd_federation
+    from fl4health_b200.servers.base_server import FlServer
+    from fl4health_b200.servers.client_manager import SimpleClientManager
+    from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
+    from fl4health_b200.utils.dataset import TensorDataset
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    os.environ["FL4H_COLLECTIVES"] = args.collectives
+    ctx = SpmdContext()
+    world = ctx.world_size
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    device = ctx.device
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(1234 + ctx.rank)
+
+    eager_impl = args.impl == "eager"
+    engine = EngineOptions(
+        arena=not eager_impl, fused_optimizer=not eager_impl, cuda_graphs=not (args.no_graphs or eager_impl),
+        amp_dtype=None if args.fp32 else torch.bfloat16, channels_last=not eager_impl,
+    )
+
+    def synthetic(n: int, seed: int) -> TensorDataset:
+        gen = torch.Generator().manual_seed(seed)
+        targets = torch.randint(0, 10, (n,), generator=gen)
+        data = torch.randn(n, 3, 32, 32, generator=gen) * 0.5 + (targets.float().view(-1, 1, 1, 1) - 4.5) * 0.1
+        return TensorDataset(data, targets)
+
+    class CifarResNetClient(BasicClient):
+        placement = "device"
+
+        def get_model(self, config):  # noqa: ANN001, ANN202
+            torch.manual_seed(1234)
+            return resnet18_cifar()
+
+        def get_data_loaders(self, config):  # noqa: ANN001, ANN202
+            bs = int(config["batch_size"])
+            train = BatchedTensorLoader(synthetic(args.train_samples, 100 + ctx.rank), bs, shuffle=True, drop_last=True,
+                                        placement=self.placement, device=self.device)
+            val = BatchedTensorLoader(synthetic(args.val_batches * bs, 900 + ctx.rank), bs, placement=self.placement,
+                                      device=self.device)
+            return train, val
+
+        def get_criterion(self, config):  # noqa: ANN001, ANN202
+            return nn.CrossEntropyLoss()
+
+        def get_optimizer(self, config):  # noqa: ANN001, ANN202
+            return torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9)
+
+    def config_fn(server_round: int) -> dict:
+        return {"current_server_round": server_round, "local_steps": args.local_steps, "batch_size": args.batch_size}
+
+    client = CifarResNetClient(Path("."), [Accuracy()], device, client_name=f"rank{ctx.rank}", engine_options=engine)
+    strategy = BasicFedAvg(
+        min_fit_clients=world, min_evaluate_clients=world, min_available_clients=world,
+        on_fit_config_fn=config_fn, on_evaluate_config_fn=config_fn,
+        fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
+        evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
+    )
+    server = FlServer(SimpleClientManager(), {"n_server_rounds": args.steps + args.warmup, "local_steps": args.local_steps},
+                      strategy, on_init_parameters_config_fn=config_fn, accept_failures=False)
+    build_spmd_federation(ctx, server, client)
+    if world > 1 and args.collectives != "nccl":
+        ctx.enable_fused_collectives()
+
+    l2_flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
+
+    def timed_fit(label: str) -> dict:
+        """Run warmup+steps rounds through FlServer.fit; time the last `steps` rounds on the device."""
+        marks: dict[str, object] = {}
+        sampler = ClockSampler(device.index) if ctx.rank == 0 else None
+
+        def on_round_end(server_round: int) -> None:
+            l2_flush.fill_(1.0)  # evict L2 between rounds (inside the timed region; ~40 us)
+            if server_round == args.warmup:
+                ctx.barrier()
+                torch.cuda.synchronize()
+                if sampler is not None:
+                    sampler.start()
+                ops.reset_launch_count()
+                marks["start"] = torch.cuda.Event(enable_timing=True)
+                marks["start"].record()
+                marks["wall0"] = time.perf_counter()
+            elif server_round == args.warmup + args.steps:
+                marks["end"] = torch.cuda.Event(enable_timing=True)
+                marks["end"].record()
+                torch.cuda.synchronize()
+                ctx.barrier()
+                marks["wall1"] = time.perf_counter()
+                marks["launches"] = ops.launch_count()
+                if sampler is not None:
+                    marks["clocks"] = sampler.stop()
+
+        server.round_end_hooks = [on_round_end]
+        if args.warmup == 0:
+            on_round_end(0)
+        history, _ = server.fit(num_rounds=args.warmup + args.steps)
+        ms = marks["start"].elapsed_time(marks["end"])  # type: ignore[union-attr]
+        ms = ctx.all_reduce_max(ms)
+        final_loss = history.losses_distributed[-1][1]
+        return {"label": label, "ms_total": ms, "ms_per_round": ms / args.steps, "launches": marks["launches"],
+                "clocks": marks.get("clocks"), "final_loss": final_loss,
+                "wall_s": marks["wall1"] - marks["wall0"]}  # type: ignore[operator]
+
+    # ---- e2e first (pinned host datasets -> H2D every batch), then device-resident ----------------------------
+    e2e = None
+    if not args.skip_e2e:
+        CifarResNetClient.placement = "pinned"
+        e2e = timed_fit("e2e")
+        # re-create loaders for the device-resident run (graphs and model state are reused)
+        CifarResNetClient.placement = "device"
+        client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
+        client.train_iterator = None
+    main_run = timed_fit("device")
+
+    rounds_per_s = 1000.0 / main_run["ms_per_round"]
+    bytes_in = args.local_steps * args.batch_size * (3 * 32 * 32 * 4 + 8) + args.val_batches * args.batch_size * (3 * 32 * 32 * 4 + 8)
+    result = {
+        "metric": "fl_rounds_per_sec_cifar10_resnet18_fedavg",
+        "value": rounds_per_s,
+        "unit": "rounds/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": main_run["ms_per_round"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "fp32" if args.fp32 else "bf16",
+        "data": "synthetic CIFAR-10-shaped (3x32x32, 10 classes), random-init ResNet-18",
+        "impl": args.impl,
+        "config": {
+            "model": "resnet18_cifar (11.17M params)", "clients": world, "parallelism": f"fl_dp{world} (one client per GPU)",
+            "global_batch": args.batch_size * world, "batch_per_client": args.batch_size,
+            "local_steps": args.local_steps, "val_batches_per_client": args.val_batches, "strategy": "BasicFedAvg (weighted)",
+            "optimizer": "SGD lr=0.01 momentum=0.9", "seq_len": None,
+            "l2": "explicit 256 MiB write between rounds (inside the timed region)",
+            "collectives": "fused-p2p" if ctx.fused is not None else ("nccl" if world > 1 else "local"),
+            "cuda_graphs": engine.cuda_graphs, "channels_last": engine.channels_last,
+        },
+        "gpu_launches": main_run["launches"],
+        "clocks": main_run["clocks"],
+        "final_val_loss": main_run["final_loss"],
+        "wall_s": main_run["wall_s"],
+    }
+    if e2e is not None:
+        result["e2e"] = {
+            "value": 1000.0 / e2e["ms_per_round"], "unit": "rounds/s", "ms_per_step": e2e["ms_per_round"],
+            "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 6 * 4,
+            "note": "per round: every train/val batch copied from pinned host memory; loss+accuracy scalars read back",
+        }
+    if ctx.rank == 0:
+        print(json.dumps(result))
+    ctx.shutdown()
+
+
+if __name__ == "__main__":
+    main()

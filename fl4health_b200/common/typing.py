@@ -74,11 +74,10 @@ def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
 
 
 def parameters_to_ndarrays(parameters: Parameters) -> NDArrays:
-    tensors = parameters.tensors
-    materialize = getattr(parameters, "materialize", None)
-    if materialize is not None:  # lazily-fetched remote payloads (SPMD transport)
-        tensors = materialize()
-    return NDArrays(tensors, flat=parameters.flat, layout=parameters.layout)
+    tagged = getattr(parameters, "_arrays", None)
+    if tagged is not None:  # SPMD transport: keep ownership tags / remote placeholders intact
+        return tagged
+    return NDArrays(parameters.tensors, flat=parameters.flat, layout=parameters.layout)
 
 
 def to_numpy(array: NDArray) -> np.ndarray:

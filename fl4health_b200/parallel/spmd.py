@@ -1,0 +1,426 @@
+"""SPMD federation runtime: one process per GPU, one client per process, the server logic replicated on every rank.
+
+The reference's deployment is a star of OS processes around a CPU server talking gRPC.  Here the K
+clients of a round are the K ranks of a single NVSwitch box:
+
+* every rank builds the same ``FlServer`` + strategy and runs the same round loop in lock-step ("who is the server?":
+  everyone, redundantly, on identical aggregated data — SURVEY Appendix F.2).  Artifacts (model checkpoints, server
+  reports) are written by rank 0 only;
+* ``SpmdTransport.fit_clients`` runs the local client, then exchanges only *metadata* (sample counts, metrics, status,
+  payload shapes) between ranks.  Model payloads stay where they are: remote clients appear as ``RemoteNDArrays``
+  placeholders;
+* aggregation-aware strategies reduce those payloads with ONE collective over the flat arenas —
+  ``backend="nccl"``: pre-scale + ``all_reduce`` (the measured baseline), ``backend="fused"``: the hand-written
+  peer-memory reduce-scatter→epilogue→all-gather kernel (``ops.p2p``).  Any other strategy can still call
+  ``materialize()`` to fetch full client payloads (K broadcasts) and run unchanged;
+* client sampling is a *mask over ranks*: non-selected ranks skip training and contribute weight 0, so collective
+  shapes stay static.
+
+CPU multi-process tests use the same code with the ``gloo`` backend.
+"""
+
+from __future__ import annotations
+
+import os
+import pickle
+from dataclasses import dataclass
+from logging import INFO, WARNING
+from typing import Any
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from fl4health_b200.common.logger import log
+from fl4health_b200.common.typing import (
+    Code,
+    EvaluateIns,
+    EvaluateRes,
+    FitIns,
+    FitRes,
+    GetParametersIns,
+    GetParametersRes,
+    GetPropertiesIns,
+    GetPropertiesRes,
+    NDArrays,
+    Parameters,
+    Status,
+    ndarrays_to_parameters,
+)
+from fl4health_b200.servers.client_proxy import ClientProxy, InProcessClientProxy
+
+_CONTEXT: SpmdContext | None = None
+
+
+def current_context() -> SpmdContext | None:
+    return _CONTEXT
+
+
+@dataclass
+class PayloadSpec:
+    """Shapes/dtypes of one client's array list; tiny or non-numeric arrays ride along by value."""
+
+    entries: list[tuple[tuple[int, ...], str, Any]]  # (shape, dtype-string, inline value or None)
+    flat_numel: int | None = None  # set when the list is a whole-arena view
+
+    @staticmethod
+    def of(arrays: NDArrays) -> PayloadSpec:
+        entries: list[tuple[tuple[int, ...], str, Any]] = []
+        for arr in arrays:
+            if isinstance(arr, torch.Tensor):
+                inline = arr.detach().cpu().numpy() if arr.numel() <= 8 and arr.dim() == 0 else None
+                entries.append((tuple(arr.shape), str(arr.dtype), inline))
+            else:
+                np_arr = np.asarray(arr)
+                small = np_arr.dtype.kind in ("U", "S", "O") or np_arr.size <= 64
+                entries.append((tuple(np_arr.shape), f"numpy.{np_arr.dtype}", np_arr if small else None))
+        flat = getattr(arrays, "flat", None)
+        layout = getattr(arrays, "layout", None)
+        whole = flat is not None and layout is not None and len(arrays) == len(layout.state_keys)
+        return PayloadSpec(entries, int(flat.numel()) if whole else None)
+
+
+class RemoteNDArrays(NDArrays):
+    """Placeholder for another rank's payload.  Entries known by value (packed scalars, names) are filled in;
+    tensor entries are ``None`` until ``materialize()`` (a broadcast from the owning rank) is called."""
+
+    def __init__(self, ctx: SpmdContext, rank: int, spec: PayloadSpec) -> None:
+        super().__init__([entry[2] for entry in spec.entries])
+        self.ctx, self.rank, self.spec = ctx, rank, spec
+        self.remote = True
+        self.materialized = False
+
+
+def is_remote(arrays: Any) -> bool:
+    return bool(getattr(arrays, "remote", False)) and not getattr(arrays, "materialized", True)
+
+
+_TORCH_DTYPES = {str(d): d for d in (torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int64,
+                                      torch.int32, torch.int16, torch.int8, torch.uint8, torch.bool)}
+
+
+class SpmdContext:
+    def __init__(self, backend: str | None = None, collective_backend: str | None = None) -> None:
+        global _CONTEXT
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", str(self.rank)))
+        use_cuda = torch.cuda.is_available()
+        if use_cuda:
+            torch.cuda.set_device(self.local_rank % torch.cuda.device_count())
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device("cpu")
+        self.backend = backend or ("nccl" if use_cuda else "gloo")
+        if self.world_size > 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            kwargs: dict[str, Any] = {}
+            if self.backend == "nccl":
+                kwargs["device_id"] = self.device
+            dist.init_process_group(self.backend, rank=self.rank, world_size=self.world_size, **kwargs)
+        # which implementation reduces / broadcasts model payloads
+        self.collective_backend = collective_backend or os.environ.get("FL4H_COLLECTIVES", "auto")
+        self.fused: Any = None  # ops.p2p.FusedCollectives when peer memory is available
+        self.timings: dict[str, float] = {}
+        _CONTEXT = self
+
+    # -- lifecycle ---------------------------------------------------------------------------------------------
+    def enable_fused_collectives(self) -> bool:
+        """Try to set up peer-mapped symmetric memory + the fused kernels; fall back to NCCL when unavailable."""
+        if self.fused is not None:
+            return True
+        if self.world_size == 1 or self.device.type != "cuda" or self.collective_backend == "nccl":
+            return False
+        try:
+            from fl4health_b200.ops.p2p import FusedCollectives
+
+            self.fused = FusedCollectives(self)
+            log(INFO, f"fused peer-memory collectives enabled (multicast={self.fused.has_multicast})")
+            return True
+        except Exception as exc:  # noqa: BLE001
+            if self.collective_backend == "fused":
+                raise
+            log(WARNING, f"fused collectives unavailable ({type(exc).__name__}: {exc}); using {self.backend}")
+            return False
+
+    def shutdown(self) -> None:
+        global _CONTEXT
+        if self.fused is not None:
+            self.fused.close()
+            self.fused = None
+        if self.world_size > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+        _CONTEXT = None
+
+    # -- small helpers -----------------------------------------------------------------------------------------
+    def barrier(self) -> None:
+        if self.world_size > 1:
+            if self.backend == "nccl":
+                dist.barrier(device_ids=[self.device.index])
+            else:
+                dist.barrier()
+
+    def all_gather_object(self, obj: Any) -> list[Any]:
+        if self.world_size == 1:
+            return [obj]
+        out: list[Any] = [None] * self.world_size
+        dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast_object(self, obj: Any, src: int = 0) -> Any:
+        if self.world_size == 1:
+            return obj
+        box = [obj if self.rank == src else None]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def all_reduce_max(self, value: float) -> float:
+        if self.world_size == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -- payload collectives -----------------------------------------------------------------------------------
+    def weighted_sum_flat(
+        self, local: torch.Tensor | None, coef_by_rank: list[float], numel: int, out: torch.Tensor | None = None,
+        epilogue: dict[str, Any] | None = None,
+    ) -> torch.Tensor:
+        """``out = epilogue(sum_r coef[r] * flat_r)`` on every rank.  ``local`` is this rank's flat buffer (or None
+        when the rank was not sampled: it then contributes zeros)."""
+        if self.fused is not None and local is not None and self.fused.owns(local) and all(c >= 0 for c in coef_by_rank):
+            return self.fused.aggregate(local, coef_by_rank, out=out, epilogue=epilogue)
+        from fl4health_b200.ops import flat as flat_ops
+
+        target = out if (out is not None and not epilogue) else torch.empty(numel, dtype=torch.float32, device=self.device)
+        if local is None:
+            target.zero_()
+        else:  # pre-scale by this client's FedAvg weight (one streaming kernel), then sum across ranks
+            flat_ops.weighted_sum(target, [local[:numel]], [coef_by_rank[self.rank]])
+        if self.world_size > 1:
+            dist.all_reduce(target, op=dist.ReduceOp.SUM)
+        if epilogue:
+            result = out if out is not None else torch.empty_like(target)
+            flat_ops.weighted_sum(result, [target], [1.0], **epilogue)
+            return result
+        return target
+
+    def broadcast_flat(self, tensor: torch.Tensor, src: int) -> torch.Tensor:
+        if self.world_size > 1:
+            dist.broadcast(tensor, src=src)
+        return tensor
+
+    def materialize(self, arrays: NDArrays, owner_rank: int, spec: PayloadSpec) -> NDArrays:
+        """Full copy of ``owner_rank``'s payload on every rank (generic fallback: one broadcast per tensor entry,
+        or a single one when the payload is a whole arena)."""
+        local_owner = owner_rank == self.rank
+        out = NDArrays()
+        for idx, (shape, dtype, inline) in enumerate(spec.entries):
+            if inline is not None:
+                out.append(inline)
+                continue
+            if dtype.startswith("numpy."):
+                np_dtype = np.dtype(dtype[len("numpy."):])
+                buf = torch.from_numpy(np.ascontiguousarray(arrays[idx])).to(self.device) if local_owner else torch.empty(
+                    shape, dtype=torch.from_numpy(np.zeros(1, np_dtype)).dtype, device=self.device)
+                self.broadcast_flat(buf, owner_rank)
+                out.append(buf.cpu().numpy())
+                continue
+            if local_owner:
+                src = arrays[idx]
+                buf = src.detach().to(self.device).contiguous()
+                if self.world_size > 1:
+                    buf = buf.clone()
+            else:
+                buf = torch.empty(shape, dtype=_TORCH_DTYPES[dtype], device=self.device)
+            self.broadcast_flat(buf, owner_rank)
+            out.append(buf)
+        return out
+
+
+def materialize(arrays: NDArrays) -> NDArrays:
+    """Resolve a (possibly remote) payload into local tensors.  Collective: every rank must call it in the same
+    order — which replicated strategy code naturally does."""
+    remote_rank = getattr(arrays, "rank", None)
+    ctx = getattr(arrays, "ctx", None)
+    if ctx is None or remote_rank is None:
+        return arrays
+    full = ctx.materialize(arrays, remote_rank, arrays.spec)
+    if isinstance(arrays, RemoteNDArrays):
+        arrays[:] = full
+        arrays.materialized = True
+        return arrays
+    return full
+
+
+class _LocalPayload(NDArrays):
+    """This rank's own payload, tagged so collectives know who owns it."""
+
+
+def _tag_local(arrays: NDArrays, ctx: SpmdContext) -> NDArrays:
+    tagged = _LocalPayload(arrays, flat=getattr(arrays, "flat", None), layout=getattr(arrays, "layout", None))
+    tagged.ctx, tagged.rank, tagged.spec = ctx, ctx.rank, PayloadSpec.of(arrays)  # type: ignore[attr-defined]
+    return tagged
+
+
+class _TaggedParameters(Parameters):
+    """``Parameters`` whose conversion back to arrays preserves SPMD ownership tags."""
+
+    def __init__(self, arrays: NDArrays) -> None:
+        super().__init__(tensors=list(arrays), tensor_type="torch", flat=getattr(arrays, "flat", None),
+                         layout=getattr(arrays, "layout", None))
+        self._arrays = arrays
+
+    def materialize(self) -> NDArrays:  # picked up by common.typing.parameters_to_ndarrays
+        return self._arrays
+
+
+def parameters_to_tagged(parameters: Parameters) -> NDArrays:
+    return parameters._arrays if isinstance(parameters, _TaggedParameters) else NDArrays(parameters.tensors)
+
+
+class SpmdClientProxy(ClientProxy):
+    def __init__(self, ctx: SpmdContext, rank: int, client: Any | None) -> None:
+        super().__init__(cid=f"rank{rank:03d}")
+        self.ctx, self.rank = ctx, rank
+        self.local = InProcessClientProxy(self.cid, client) if client is not None else None
+
+    @property
+    def is_local(self) -> bool:
+        return self.local is not None
+
+    def _require_local(self) -> InProcessClientProxy:
+        assert self.local is not None, f"proxy for rank {self.rank} has no local client on rank {self.ctx.rank}"
+        return self.local
+
+    def get_properties(self, ins: GetPropertiesIns, timeout: float | None = None, group_id: int | None = None) -> GetPropertiesRes:
+        return self._require_local().get_properties(ins, timeout, group_id)
+
+    def get_parameters(self, ins: GetParametersIns, timeout: float | None = None, group_id: int | None = None) -> GetParametersRes:
+        return self._require_local().get_parameters(ins, timeout, group_id)
+
+    def fit(self, ins: FitIns, timeout: float | None = None, group_id: int | None = None) -> FitRes:
+        return self._require_local().fit(ins, timeout, group_id)
+
+    def evaluate(self, ins: EvaluateIns, timeout: float | None = None, group_id: int | None = None) -> EvaluateRes:
+        return self._require_local().evaluate(ins, timeout, group_id)
+
+    def reconnect(self, ins: Any, timeout: float | None = None, group_id: int | None = None) -> Any:
+        if self.local is not None:
+            return self.local.reconnect(ins, timeout, group_id)
+        return super().reconnect(ins, timeout, group_id)
+
+
+class SpmdTransport:
+    """``fit_clients`` / ``evaluate_clients`` / ``poll_clients`` across ranks."""
+
+    def __init__(self, ctx: SpmdContext) -> None:
+        self.ctx = ctx
+
+    def is_coordinator(self) -> bool:
+        return self.ctx.rank == 0
+
+    def _run_local(self, pairs: list[tuple[ClientProxy, Any]], method: str, timeout: float | None, group_id: int | None) -> tuple[Any, Any]:
+        """(result, error-string) of this rank's own client if it was selected."""
+        for proxy, ins in pairs:
+            if isinstance(proxy, SpmdClientProxy) and proxy.rank == self.ctx.rank:
+                try:
+                    return getattr(proxy, method)(ins, timeout=timeout, group_id=group_id), None
+                except Exception as exc:  # noqa: BLE001
+                    log(WARNING, f"local client failed in {method}: {exc!r}")
+                    return None, repr(exc)
+        return None, None
+
+    def fit_clients(self, client_instructions: list[tuple[ClientProxy, FitIns]], max_workers: int | None,
+                    timeout: float | None, group_id: int | None = None) -> tuple[list, list]:
+        res, err = self._run_local(client_instructions, "fit", timeout, group_id)
+        local_arrays: NDArrays | None = None
+        meta: dict[str, Any] | None = None
+        if res is not None:
+            local_arrays = _tag_local(NDArrays(res.parameters.tensors, flat=res.parameters.flat, layout=res.parameters.layout), self.ctx)
+            meta = {"n": res.num_examples, "metrics": res.metrics, "spec": local_arrays.spec, "code": res.status.code}  # type: ignore[attr-defined]
+        elif err is not None:
+            meta = {"error": err}
+        all_meta = self.ctx.all_gather_object(meta)
+        results: list = []
+        failures: list = []
+        for proxy, _ in client_instructions:
+            assert isinstance(proxy, SpmdClientProxy)
+            m = all_meta[proxy.rank]
+            if m is None or "error" in m:
+                failures.append(RuntimeError(f"client {proxy.cid} failed: {m['error'] if m else 'no result'}"))
+                continue
+            if proxy.rank == self.ctx.rank:
+                assert local_arrays is not None
+                arrays: NDArrays = local_arrays
+            else:
+                arrays = RemoteNDArrays(self.ctx, proxy.rank, m["spec"])
+            fit_res = FitRes(Status(m["code"]), _TaggedParameters(arrays), m["n"], m["metrics"])
+            (results if m["code"] == Code.OK else failures).append((proxy, fit_res))
+        return results, failures
+
+    def evaluate_clients(self, client_instructions: list[tuple[ClientProxy, EvaluateIns]], max_workers: int | None,
+                         timeout: float | None, group_id: int | None = None) -> tuple[list, list]:
+        res, err = self._run_local(client_instructions, "evaluate", timeout, group_id)
+        meta = None
+        if res is not None:
+            meta = {"loss": res.loss, "n": res.num_examples, "metrics": res.metrics, "code": res.status.code}
+        elif err is not None:
+            meta = {"error": err}
+        all_meta = self.ctx.all_gather_object(meta)
+        results: list = []
+        failures: list = []
+        for proxy, _ in client_instructions:
+            assert isinstance(proxy, SpmdClientProxy)
+            m = all_meta[proxy.rank]
+            if m is None or "error" in m:
+                failures.append(RuntimeError(f"client {proxy.cid} failed: {m['error'] if m else 'no result'}"))
+                continue
+            eval_res = EvaluateRes(Status(m["code"]), m["loss"], m["n"], m["metrics"])
+            (results if m["code"] == Code.OK else failures).append((proxy, eval_res))
+        return results, failures
+
+    def poll_clients(self, client_instructions: list[tuple[ClientProxy, GetPropertiesIns]], max_workers: int | None,
+                     timeout: float | None) -> tuple[list, list]:
+        res, err = self._run_local(client_instructions, "get_properties", timeout, None)
+        meta = {"properties": res.properties, "code": res.status.code} if res is not None else ({"error": err} if err else None)
+        all_meta = self.ctx.all_gather_object(meta)
+        results: list = []
+        failures: list = []
+        for proxy, _ in client_instructions:
+            assert isinstance(proxy, SpmdClientProxy)
+            m = all_meta[proxy.rank]
+            if m is None or "error" in m:
+                failures.append(RuntimeError(f"client {proxy.cid} failed to report properties"))
+            else:
+                results.append((proxy, GetPropertiesRes(Status(m["code"]), m["properties"])))
+        return results, failures
+
+    def get_parameters(self, proxy: ClientProxy, ins: GetParametersIns, timeout: float | None, server_round: int) -> GetParametersRes:
+        """Initial-parameter request: the chosen rank's client answers, everyone receives a copy."""
+        assert isinstance(proxy, SpmdClientProxy)
+        arrays: NDArrays = NDArrays()
+        spec = None
+        if proxy.rank == self.ctx.rank:
+            res = proxy.get_parameters(ins, timeout, server_round)
+            arrays = NDArrays(res.parameters.tensors)
+            spec = PayloadSpec.of(arrays)
+        spec = self.ctx.broadcast_object(spec, src=proxy.rank)
+        full = self.ctx.materialize(arrays, proxy.rank, spec)
+        return GetParametersRes(Status(Code.OK), ndarrays_to_parameters(full))
+
+
+def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any) -> list[SpmdClientProxy]:
+    """Register one proxy per rank with the server's client manager; only this rank's proxy holds a client."""
+    proxies = []
+    for rank in range(ctx.world_size):
+        proxy = SpmdClientProxy(ctx, rank, local_client if rank == ctx.rank else None)
+        server.client_manager().register(proxy)
+        proxies.append(proxy)
+    server.transport = SpmdTransport(ctx)
+    return proxies
+
+
+def pickle_size(obj: Any) -> int:
+    return len(pickle.dumps(obj))

@@ -61,6 +61,8 @@ class FlServer(Server):
         self.history: History
         self.reports_manager = ReportsManager(reporters)
         self.reports_manager.initialize(id=self.server_name)
+        # observability: callables invoked with the round number after each completed round (fit + evaluate)
+        self.round_end_hooks: list[Callable[[int], None]] = []
         self._log_fl_config()
 
     # ------------------------------------------------------------------------------------------------------
@@ -124,6 +126,8 @@ class FlServer(Server):
                     self.history.add_loss_distributed(server_round=self.current_round, loss=loss_fed)
                     self.history.add_metrics_distributed(server_round=self.current_round, metrics=evaluate_metrics_fed)
 
+            for hook in self.round_end_hooks:
+                hook(self.current_round)
             self.current_round += 1
             if resumable:
                 self._save_server_state()

@@ -45,6 +45,8 @@ def _is_meta_array(arr: NDArray) -> bool:
 def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) -> NDArrays:
     """``sum_k coefficients[k] * arrays[k]`` layer-wise (or in one fused pass when arena-backed)."""
     assert len(arrays) == len(coefficients) and len(arrays) > 0
+    if any(getattr(nds, "ctx", None) is not None for nds in arrays):
+        return _spmd_weighted_combine(arrays, coefficients)
     flats = _common_flat(arrays)
     if flats is not None:
         layout = arrays[0].layout
@@ -59,6 +61,59 @@ def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) 
     n_layers = len(arrays[0])
     assert all(len(nds) == n_layers for nds in arrays), "clients sent different numbers of arrays"
     return NDArrays([_combine_layer([nds[i] for nds in arrays], coefficients) for i in range(n_layers)])
+
+
+def _spmd_weighted_combine(
+    arrays: Sequence[NDArrays], coefficients: Sequence[float], epilogue: dict | None = None,
+    out_flat: torch.Tensor | None = None,
+) -> NDArrays:
+    """SPMD form of ``weighted_combine``: each rank owns at most one entry of ``arrays`` (its own client's payload);
+    the others are ``RemoteNDArrays`` placeholders.  One collective over the flat payload reduces them all."""
+    from fl4health_b200.parallel.spmd import PayloadSpec
+
+    ctx = next(nds.ctx for nds in arrays if getattr(nds, "ctx", None) is not None)
+    coef_by_rank = [0.0] * ctx.world_size
+    local: NDArrays | None = None
+    spec: PayloadSpec | None = None
+    for nds, coef in zip(arrays, coefficients):
+        coef_by_rank[nds.rank] = float(coef)
+        spec = nds.spec
+        if nds.rank == ctx.rank:
+            local = nds
+    assert spec is not None
+    if spec.flat_numel is not None:
+        layout = local.layout if local is not None else None
+        local_flat = local.flat if local is not None else None
+        result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.flat_numel, out=out_flat, epilogue=epilogue)
+        if layout is None:
+            raise RuntimeError("rank without a local payload cannot rebuild arena views; sample all ranks or use weight 0")
+        out = layout.ndarrays(region=result_flat)
+        int_idx = [i for i, key in enumerate(layout.state_keys) if key in layout.int_state]
+        if int_idx:
+            ints = torch.stack([out[i].to(torch.float64) * coef_by_rank[ctx.rank] for i in int_idx])
+            if ctx.world_size > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(ints)
+            for j, i in enumerate(int_idx):
+                out[i] = ints[j].to(out[i].dtype)
+        return out
+    # non-arena payloads: pack the tensor entries into one temporary flat buffer, reduce, unpack
+    assert epilogue is None, "server-optimizer epilogues need arena-backed payloads in SPMD mode"
+    tensor_idx = [i for i, (_, _, inline) in enumerate(spec.entries) if inline is None]
+    shapes = [spec.entries[i][0] for i in tensor_idx]
+    sizes = [int(np.prod(s)) if len(s) else 1 for s in shapes]
+    total = sum(sizes)
+    packed = None
+    if local is not None:
+        packed = torch.cat([to_tensor(local[i], ctx.device).reshape(-1).to(torch.float32) for i in tensor_idx]) if tensor_idx else torch.zeros(0, device=ctx.device)
+    reduced = ctx.weighted_sum_flat(packed, coef_by_rank, total)
+    out = NDArrays([entry[2] for entry in spec.entries])
+    cursor = 0
+    for i, shape, size in zip(tensor_idx, shapes, sizes):
+        out[i] = reduced[cursor : cursor + size].view(shape)
+        cursor += size
+    return out
 
 
 def _combine_layer(layers: Sequence[NDArray], coefficients: Sequence[float]) -> NDArray:

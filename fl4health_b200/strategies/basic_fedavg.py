@@ -109,7 +109,7 @@ class BasicFedAvg(FedAvg, StrategyWithPolling):
     ) -> tuple[Parameters | None, dict[str, Scalar]]:
         if not results or (not self.accept_failures and failures):
             return None, {}
-        decoded = decode_and_pseudo_sort_results(results)
+        decoded = decode_and_pseudo_sort_results(results, materialize=False)
         aggregated = aggregate_results([(arrays, n) for _, arrays, n in decoded], self.weighted_aggregation)
         return ndarrays_to_parameters(aggregated), self._aggregate_fit_metrics(server_round, results)
 

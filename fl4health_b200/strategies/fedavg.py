@@ -125,7 +125,7 @@ class FedAvg(Strategy):
             return None, {}
         if not self.accept_failures and failures:
             return None, {}
-        decoded = decode_and_pseudo_sort_results(results)
+        decoded = decode_and_pseudo_sort_results(results, materialize=False)
         aggregated = aggregate_results([(arrays, n) for _, arrays, n in decoded], weighted=True)
         return ndarrays_to_parameters(aggregated), self._aggregate_fit_metrics(server_round, results)
 

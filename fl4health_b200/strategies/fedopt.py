@@ -24,7 +24,7 @@ from fl4health_b200.common.typing import (
 )
 from fl4health_b200.ops import flat as flat_ops
 from fl4health_b200.servers.client_proxy import ClientProxy
-from fl4health_b200.strategies.aggregate_utils import _common_flat, aggregate_results
+from fl4health_b200.strategies.aggregate_utils import _common_flat, _spmd_weighted_combine, aggregate_results
 from fl4health_b200.strategies.fedavg import FedAvg
 from fl4health_b200.utils.functions import decode_and_pseudo_sort_results
 
@@ -60,13 +60,26 @@ class FedOpt(FedAvg):
     ) -> tuple[Parameters | None, dict[str, Scalar]]:
         if not results or (not self.accept_failures and failures):
             return None, {}
-        decoded = decode_and_pseudo_sort_results(results)
+        decoded = decode_and_pseudo_sort_results(results, materialize=False)
         client_arrays = [arrays for _, arrays, _ in decoded]
         counts = [n for _, _, n in decoded]
         metrics = self._aggregate_fit_metrics(server_round, results)
 
-        flats = _common_flat(client_arrays)
         current_flat = getattr(self.current_weights, "flat", None)
+        spmd = any(getattr(a, "ctx", None) is not None for a in client_arrays)
+        if spmd and current_flat is not None and self._mode != flat_ops.EPI_NONE and all(
+            a.spec.flat_numel == current_flat.numel() for a in client_arrays
+        ):
+            if self._flat_m is None:
+                self._flat_m = torch.zeros_like(current_flat)
+                self._flat_v = torch.zeros_like(current_flat)
+            total = float(sum(counts))
+            epilogue = dict(mode=self._mode, current=current_flat, m=self._flat_m, v=self._flat_v, eta=self.eta,
+                            beta1=self.beta_1, beta2=self.beta_2, tau=self.tau)
+            new_weights = _spmd_weighted_combine(client_arrays, [n / total for n in counts], epilogue=epilogue)
+            self.current_weights = new_weights
+            return ndarrays_to_parameters(new_weights), metrics
+        flats = _common_flat(client_arrays) if not spmd else None
         if flats is not None and current_flat is not None and current_flat.numel() == flats[0].numel() and self._mode != flat_ops.EPI_NONE:
             layout = client_arrays[0].layout
             if self._flat_m is None:

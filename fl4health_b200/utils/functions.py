@@ -49,12 +49,23 @@ def pseudo_sort_scoring_function(client_result: tuple[Any, NDArrays, int]) -> fl
     return total + sample_count
 
 
-def decode_and_pseudo_sort_results(results: list[tuple[Any, FitRes]]) -> list[tuple[Any, NDArrays, int]]:
+def decode_and_pseudo_sort_results(
+    results: list[tuple[Any, FitRes]], materialize: bool = True
+) -> list[tuple[Any, NDArrays, int]]:
     """(proxy, arrays, n) triples in a canonical order.
 
     The reference sorts by a numeric pseudo-score because Flower client ids are random UUIDs
     (``fl4health/utils/functions.py:84-108``).  Here client ids are stable (rank / client name), so ordering by
     ``cid`` gives bit-deterministic fixed-order summation without touching (or syncing on) the payload.
     """
-    decoded = [(proxy, parameters_to_ndarrays(res.parameters), res.num_examples) for proxy, res in results]
-    return sorted(decoded, key=lambda item: str(getattr(item[0], "cid", "")))
+    ordered = sorted(results, key=lambda item: str(getattr(item[0], "cid", "")))
+    decoded = []
+    for proxy, res in ordered:
+        arrays = parameters_to_ndarrays(res.parameters)
+        if materialize and getattr(arrays, "remote", False):
+            # SPMD fallback for strategies that need every client's full payload: broadcast from the owner.
+            from fl4health_b200.parallel.spmd import materialize as _materialize
+
+            arrays = _materialize(arrays)
+        decoded.append((proxy, arrays, res.num_examples))
+    return decoded

@@ -1,0 +1,168 @@
+"""Numerics of the sm_100a flat-arena kernels against plain PyTorch fp32 references (run on a B200)."""
+
+import pytest
+import torch
+
+from fl4health_b200.ops import flat as F
+
+pytestmark = pytest.mark.gpu
+N = 1 << 20
+
+
+def _rand(n=N, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(n, generator=g, device="cuda") * scale
+
+
+def _hp(**kw):
+    hp = F.make_hyper_params("cuda")
+    for k, v in kw.items():
+        hp[getattr(F, k)] = v
+    return hp
+
+
+def test_library_loaded():
+    from fl4health_b200 import ops
+
+    assert ops.available()
+
+
+@pytest.mark.parametrize("anchor,cv,shadow,nesterov", [(False, False, False, False), (True, False, True, False),
+                                                        (False, True, False, True), (True, True, True, False)])
+def test_sgd_step_matches_reference(anchor, cv, shadow, nesterov):
+    w, g = _rand(seed=1), _rand(seed=2, scale=0.1)
+    a = _rand(seed=3) if anchor else None
+    c = _rand(seed=4, scale=0.01) if cv else None
+    results = []
+    for use_kernel in (True, False):
+        wk, mk = w.clone(), torch.zeros_like(w)
+        sk = torch.zeros(N, dtype=torch.bfloat16, device="cuda") if shadow else None
+        hp = _hp(HP_LR=0.05, HP_MOM=0.9, HP_WD=1e-4, HP_MU=0.1, HP_NESTEROV=float(nesterov), HP_FIRST=1.0)
+        for _ in range(3):
+            if use_kernel:
+                F.sgd_step(wk, g, mk, hp, a, c, sk)
+            else:
+                F.sgd_step_reference(wk, g, mk, hp, a, c, sk)
+        results.append((wk, mk, sk))
+    torch.cuda.synchronize()
+    assert torch.allclose(results[0][0], results[1][0], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(results[0][1], results[1][1], atol=1e-6, rtol=1e-5)
+    if shadow:
+        assert torch.equal(results[0][2], results[1][2])
+
+
+def test_sgd_matches_torch_optim():
+    w = _rand(seed=5)
+    p = torch.nn.Parameter(w.clone())
+    opt = torch.optim.SGD([p], lr=0.1, momentum=0.9, weight_decay=1e-3)
+    wk, mk = w.clone(), torch.zeros_like(w)
+    hp = _hp(HP_LR=0.1, HP_MOM=0.9, HP_WD=1e-3, HP_FIRST=1.0)
+    for step in range(4):
+        g = _rand(seed=10 + step, scale=0.1)
+        p.grad = g.clone()
+        opt.step()
+        F.sgd_step(wk, g, mk, hp)
+    assert torch.allclose(wk, p.data, atol=1e-6, rtol=1e-5)
+
+
+def test_bf16_grad_path():
+    w, g = _rand(seed=1), _rand(seed=2, scale=0.1).to(torch.bfloat16)
+    wk, mk = w.clone(), torch.zeros_like(w)
+    wr, mr = w.clone(), torch.zeros_like(w)
+    F.sgd_step(wk, g, mk, _hp(HP_LR=0.05, HP_MOM=0.9, HP_FIRST=1.0))
+    F.sgd_step_reference(wr, g, mr, _hp(HP_LR=0.05, HP_MOM=0.9, HP_FIRST=1.0))
+    assert torch.allclose(wk, wr, atol=1e-6)
+
+
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_adamw_matches_torch_optim(decoupled):
+    w = _rand(seed=6)
+    p = torch.nn.Parameter(w.clone())
+    cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+    opt = cls([p], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    wk, m, v = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    hp = _hp(HP_LR=1e-2, HP_B1=0.9, HP_B2=0.99, HP_EPS=1e-8, HP_WD=1e-2)
+    for step in range(5):
+        g = _rand(seed=20 + step, scale=0.1)
+        p.grad = g.clone()
+        opt.step()
+        F.adamw_step(wk, g, m, v, hp, decoupled=decoupled)
+    assert torch.allclose(wk, p.data, atol=2e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("k", [1, 2, 8, 16])
+def test_weighted_sum(k):
+    srcs = [_rand(seed=30 + i) for i in range(k)]
+    coefs = [(i + 1) / sum(range(1, k + 1)) for i in range(k)]
+    out = torch.empty(N, device="cuda")
+    F.weighted_sum(out, srcs, coefs)
+    ref = torch.zeros(N, device="cuda", dtype=torch.float64)
+    for s, c in zip(srcs, coefs):
+        ref += s.double() * c
+    assert torch.allclose(out.double(), ref, atol=1e-5)
+    # determinism: same inputs, same bits
+    out2 = torch.empty(N, device="cuda")
+    F.weighted_sum(out2, srcs, coefs)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("mode", [F.EPI_FEDADAM, F.EPI_FEDADAGRAD, F.EPI_FEDYOGI, F.EPI_SERVER_LR, F.EPI_MOMENTUM])
+def test_weighted_sum_epilogues(mode):
+    srcs = [_rand(seed=40 + i) for i in range(4)]
+    coefs = [0.25] * 4
+    cur = _rand(seed=50)
+    kw = dict(mode=mode, eta=0.1, beta1=0.9, beta2=0.99, tau=1e-3, server_lr=0.7, momentum=0.9)
+    outs = []
+    for fn in (F.weighted_sum, F.weighted_sum_reference):
+        m, v = _rand(seed=51, scale=0.1), _rand(seed=52, scale=0.1).abs()
+        out = torch.empty(N, device="cuda")
+        fn(out, srcs, coefs, current=cur.clone(), m=m, v=v, **kw)
+        outs.append((out, m, v))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-4)
+
+
+def test_bcast_unpack_and_scaffold():
+    g, cs, cl = _rand(seed=60), _rand(seed=61), _rand(seed=62)
+    w, a, cv = torch.empty(N, device="cuda"), torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    sh = torch.empty(N, device="cuda", dtype=torch.bfloat16)
+    F.bcast_unpack(g, w, a, sh, cs, cl, cv)
+    assert torch.equal(w, g) and torch.equal(a, g) and torch.equal(sh, g.to(torch.bfloat16))
+    assert torch.allclose(cv, cs - cl)
+    x, y = _rand(seed=63), _rand(seed=64)
+    ci, dc = cl.clone(), torch.empty(N, device="cuda")
+    F.scaffold_variate_update(x, y, cs, ci, dc, local_steps=5, lr=0.1)
+    expect = cl - cs + (x - y) / 0.5
+    assert torch.allclose(ci, expect, atol=1e-5) and torch.allclose(dc, expect - cl, atol=1e-5)
+
+
+def test_reductions_and_clip():
+    a, b = _rand(seed=70), _rand(seed=71)
+    assert abs(F.sq_diff_sum(a, b).item() - ((a - b).double() ** 2).sum().item()) < 1e-2 * N ** 0.5
+    assert abs(F.dot(a, b).item() - torch.dot(a.double(), b.double()).item()) < 1.0
+    ga, gb = _rand(seed=72), _rand(seed=73)
+    ref = torch.dot((a - b).double(), (0.3 * ga + 0.7 * gb).double()).item()
+    assert abs(F.apfl_alpha_grad(a, b, ga, gb, 0.3).item() - ref) < 1.0
+    x = a.clone()
+    sq = F.sq_diff_sum(x)
+    bit = torch.zeros(1, device="cuda")
+    F.clip_scale_(x, sq, 10.0, bit)
+    assert abs(x.norm().item() - 10.0) < 1e-2 and bit.item() == 0.0
+
+
+def test_gaussian_noise_statistics():
+    y = torch.zeros(N, device="cuda")
+    F.add_gaussian_(y, 2.0, seed=123)
+    assert abs(y.mean().item()) < 0.02 and abs(y.std().item() - 2.0) < 0.02
+    y2 = torch.zeros(N, device="cuda")
+    F.add_gaussian_(y2, 2.0, seed=123)
+    assert torch.equal(y, y2)
+
+
+def test_fedpm_vote():
+    masks = [(torch.rand(4096, device="cuda") > 0.5).to(torch.uint8) for _ in range(3)]
+    alpha, beta = torch.ones(4096, device="cuda"), torch.ones(4096, device="cuda")
+    theta = F.fedpm_vote(masks, alpha, beta, bayesian=True)
+    s = sum(m.float() for m in masks)
+    assert torch.allclose(alpha, 1 + s) and torch.allclose(beta, 1 + 3 - s)
+    assert torch.allclose(theta, (alpha - 1) / (alpha + beta - 2))
