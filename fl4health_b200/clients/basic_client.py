@@ -349,7 +349,7 @@ class BasicClient:
         losses, preds = self.train_step(input, target)
         self.train_loss_meter.accumulate(losses)
         self.update_metric_manager(preds, target, self.train_metric_manager)
-        return losses, preds
+        return losses.detach(), {key: value.detach() for key, value in preds.items()}  # type: ignore[return-value]
 
     def _sync_optimizer_hyperparams(self) -> None:
         for optimizer in self.optimizers.values():

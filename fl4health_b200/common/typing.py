@@ -92,7 +92,7 @@ def to_tensor(array: NDArray, device: torch.device | str | None = None) -> torch
     arr = np.asarray(array)
     if arr.dtype.kind in ("U", "S", "O"):
         raise TypeError("string arrays cannot be converted to tensors")
-    t = torch.from_numpy(np.ascontiguousarray(arr))
+    t = torch.from_numpy(np.asarray(arr, order="C").copy())
     return t if device is None else t.to(device, non_blocking=True)
 
 

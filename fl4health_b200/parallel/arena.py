@@ -216,7 +216,8 @@ class ParameterArena:
                     self.flat.copy_(src_flat, non_blocking=True)
                 for key, arr in zip(keys, arrays):
                     if key in self.int_state:
-                        self.int_state[key].copy_(_as_tensor(arr, self.device))
+                        dst_int = self.int_state[key]
+                        dst_int.copy_(_as_tensor(arr, self.device).to(dst_int.dtype).reshape(dst_int.shape))
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
             for key, arr in zip(keys, arrays):
@@ -227,7 +228,8 @@ class ParameterArena:
                     assert dst.shape == t.shape, f"shape mismatch for {key}: {tuple(dst.shape)} vs {tuple(t.shape)}"
                     dst.copy_(t, non_blocking=True)
                 else:
-                    self.int_state[key].copy_(t.to(self.int_state[key].dtype))
+                    dst_int = self.int_state[key]
+                    dst_int.copy_(t.to(dst_int.dtype).reshape(dst_int.shape))
 
     def same_layout(self, other: ParameterArena) -> bool:
         return self.total == other.total and [(e.name, e.offset, e.numel, e.nhwc) for e in self.entries] == [
@@ -251,7 +253,7 @@ def _as_tensor(arr: object, device: torch.device) -> torch.Tensor:
         return arr.to(device, non_blocking=True) if arr.device != device else arr
     import numpy as np
 
-    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+    return torch.from_numpy(np.asarray(arr, order="C").copy()).to(device, non_blocking=True)
 
 
 def arena_of(module: nn.Module) -> ParameterArena | None:

@@ -222,7 +222,7 @@ class SpmdContext:
                 continue
             if dtype.startswith("numpy."):
                 np_dtype = np.dtype(dtype[len("numpy."):])
-                buf = torch.from_numpy(np.ascontiguousarray(arrays[idx])).to(self.device) if local_owner else torch.empty(
+                buf = torch.from_numpy(np.asarray(arrays[idx], order="C").copy()).to(self.device) if local_owner else torch.empty(
                     shape, dtype=torch.from_numpy(np.zeros(1, np_dtype)).dtype, device=self.device)
                 self.broadcast_flat(buf, owner_rank)
                 out.append(buf.cpu().numpy())
@@ -328,7 +328,9 @@ class SpmdTransport:
                 try:
                     return getattr(proxy, method)(ins, timeout=timeout, group_id=group_id), None
                 except Exception as exc:  # noqa: BLE001
-                    log(WARNING, f"local client failed in {method}: {exc!r}")
+                    import traceback
+
+                    log(WARNING, f"local client failed in {method}: {exc!r}\n{traceback.format_exc()}")
                     return None, repr(exc)
         return None, None
 

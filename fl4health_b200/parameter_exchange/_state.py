@@ -40,7 +40,7 @@ def inject_state(model: nn.Module, names: list[str], arrays: list, full: bool = 
             if name not in state:
                 raise KeyError(f"Unexpected key {name} in exchanged parameters")
             dst = state[name]
-            src = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
+            src = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.asarray(arr, order="C").copy())
             if tuple(src.shape) != tuple(dst.shape):
                 raise RuntimeError(f"size mismatch for {name}: {tuple(src.shape)} vs {tuple(dst.shape)}")
             dst.data.copy_(src.to(device=dst.device, dtype=dst.dtype), non_blocking=True)

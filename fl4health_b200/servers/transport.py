@@ -25,6 +25,12 @@ class LocalTransport:
             try:
                 res = getattr(proxy, method)(ins, timeout=timeout, group_id=group_id)
             except Exception as exc:  # noqa: BLE001 - a failing client is a *failure*, the policy decides what next
+                import traceback
+                from logging import WARNING
+
+                from fl4health_b200.common.logger import log
+
+                log(WARNING, f"client {proxy.cid} raised in {method}: {exc!r}\n{traceback.format_exc()}")
                 failures.append(exc)
                 continue
             if res.status.code == Code.OK:

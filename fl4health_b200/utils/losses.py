@@ -27,6 +27,20 @@ class Losses(ABC):
         """All scalar tensors of this container under unique keys (used by the meter)."""
         return {f"additional::{k}": v for k, v in self.additional_losses.items()}
 
+    def detach(self) -> Losses:
+        """Same values without autograd history.  The engine hands *detached* losses back to the training loop so no
+        autograd graph (and none of its AccumulateGrad nodes) outlives the step — a requirement for CUDA-graph
+        capture of the next step and a memory saving otherwise."""
+        import copy
+
+        clone = copy.copy(self)
+        for name, value in list(vars(clone).items()):
+            if isinstance(value, torch.Tensor):
+                setattr(clone, name, value.detach())
+            elif isinstance(value, dict):
+                setattr(clone, name, {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in value.items()})
+        return clone
+
     @staticmethod
     @abstractmethod
     def aggregate(loss_meter: LossMeter) -> Losses:

