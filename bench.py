@@ -189,9 +189,7 @@ def main() -> None:
     )
     server = FlServer(SimpleClientManager(), {"n_server_rounds": args.steps + args.warmup, "local_steps": args.local_steps},
                       strategy, on_init_parameters_config_fn=config_fn, accept_failures=False)
-    build_spmd_federation(ctx, server, client)
-    if world > 1 and args.collectives != "nccl":
-        ctx.enable_fused_collectives()
+    build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
 
     l2_flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
 

@@ -1,0 +1,330 @@
+// Fused collective kernels over peer-mapped (NVLink 5 / NVSwitch) symmetric memory for sm_100a.
+//
+// The two communication hot paths of an FL round as ONE kernel each, issuing the peer loads/stores
+// from inside the kernel and fusing the adjacent compute:
+//
+//   agg_fused   : reduce-scatter (weighted FedAvg sum, fixed rank order => bit-deterministic)
+//                 -> strategy epilogue (FedAvg | FedAdam/FedAdagrad/FedYogi server step | SCAFFOLD server-lr | FedAvgM)
+//                 -> all-gather (result slice stored into every rank's global buffer)
+//   bcast_fused : scatter from the root + all-gather between peers (every NVLink carries 1/K of the payload),
+//                 cross-GPU barrier, then the receiver-side unpack in the same kernel:
+//                 w <- g, FedProx anchor w_t <- g, bf16 compute shadow <- g, SCAFFOLD d <- c - c_i.
+//
+// Synchronisation is done with flags in peer-mapped memory (release/acquire at system scope) + a grid barrier, so no
+// host round trip and no NCCL call sits between the local training kernels and the aggregate.  Kernels are launched
+// cooperatively (all CTAs co-resident: the grid barrier cannot deadlock).
+//
+// What the reference does for the same step: K gRPC messages of np.save bytes into a CPU server, reduce(np.add) per
+// layer, K gRPC messages back (fl4health/strategies/aggregate_utils.py:23-32, parameter_exchange/full_exchanger.py).
+
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace cg = cooperative_groups;
+
+#define FL4H_MAX_RANKS 16
+
+namespace {
+
+constexpr int kThreads = 512;
+
+struct PeerTable {
+    float* contrib[FL4H_MAX_RANKS];     // each rank's contribution buffer (its client arena flat)
+    float* result[FL4H_MAX_RANKS];      // each rank's global/result buffer
+    uint32_t* flags[FL4H_MAX_RANKS];    // each rank's signal pad: [phase][FL4H_MAX_RANKS] epochs
+    float coef[FL4H_MAX_RANKS];
+    int rank;
+    int world;
+};
+
+struct EpiArgs {
+    float eta, beta1, beta2, tau, server_lr, momentum;
+    int mode;  // same codes as flat_ops.cu
+};
+enum { EPI_NONE = 0, EPI_FEDADAM = 1, EPI_FEDADAGRAD = 2, EPI_FEDYOGI = 3, EPI_SERVER_LR = 4, EPI_MOMENTUM = 5 };
+
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+    // volatile => relaxed.sys semantics: never served from a stale L1 line, goes to the owner over NVLink
+    float4 r;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_peer4(float* p, float4 v) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-GPU barrier executed by CTA 0 (threads 0..world-1), bracketed by grid barriers by the caller.
+// flags layout on every rank: flags[phase * FL4H_MAX_RANKS + src_rank] = epoch written by src_rank.
+__device__ __forceinline__ void peer_barrier(const PeerTable& t, int phase, uint32_t epoch) {
+    if (blockIdx.x == 0 && threadIdx.x < t.world) {
+        const int peer = threadIdx.x;
+        __threadfence_system();
+        st_release_sys(t.flags[peer] + phase * FL4H_MAX_RANKS + t.rank, epoch);
+        const uint32_t* mine = t.flags[t.rank] + phase * FL4H_MAX_RANKS + peer;
+        while (ld_acquire_sys(mine) < epoch) { __nanosleep(64); }
+    }
+}
+
+__device__ __forceinline__ float epi_apply(int mode, const EpiArgs& ea, float avg, float wcur, float& m, float& v) {
+    switch (mode) {
+        case EPI_FEDADAM: {
+            float d = avg - wcur;
+            m = ea.beta1 * m + (1.f - ea.beta1) * d;
+            v = ea.beta2 * v + (1.f - ea.beta2) * d * d;
+            return wcur + ea.eta * m / (sqrtf(v) + ea.tau);
+        }
+        case EPI_FEDADAGRAD: {
+            float d = avg - wcur;
+            m = ea.beta1 * m + (1.f - ea.beta1) * d;
+            v = v + d * d;
+            return wcur + ea.eta * m / (sqrtf(v) + ea.tau);
+        }
+        case EPI_FEDYOGI: {
+            float d = avg - wcur;
+            m = ea.beta1 * m + (1.f - ea.beta1) * d;
+            float d2 = d * d;
+            float sgn = (v - d2) > 0.f ? 1.f : ((v - d2) < 0.f ? -1.f : 0.f);
+            v = v - (1.f - ea.beta2) * d2 * sgn;
+            return wcur + ea.eta * m / (sqrtf(v) + ea.tau);
+        }
+        case EPI_SERVER_LR:
+            return wcur + ea.server_lr * (avg - wcur);
+        case EPI_MOMENTUM:
+            m = ea.momentum * m + avg;
+            return wcur + ea.server_lr * m;
+        default:
+            return avg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// agg_fused: every rank owns slice [rank*slice, (rank+1)*slice) of the flat payload.
+//   wcur/m/v are LOCAL full-length buffers (only the owned slice is touched): server optimizer state is sharded by
+//   slice ownership, the updated weights are what gets all-gathered.
+// ---------------------------------------------------------------------------------------------------------------
+template <int kWorld>
+__global__ void __launch_bounds__(kThreads, 1)
+agg_fused_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__ m, float* __restrict__ v,
+                 EpiArgs ea, int64_t numel, int64_t slice, uint32_t epoch) {
+    cg::grid_group grid = cg::this_grid();
+    // (0) all ranks finished local training and are inside the kernel: contributions may be read.
+    peer_barrier(t, 0, epoch);
+    grid.sync();
+
+    const int64_t begin = (int64_t)t.rank * slice;
+    int64_t end = begin + slice;
+    if (end > numel) end = numel;
+    const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t e = begin + (i << 2);
+        float4 vals[kWorld];
+#pragma unroll
+        for (int k = 0; k < kWorld; ++k) vals[k] = ld_peer4(t.contrib[k] + e);   // K loads in flight (NVLink MLP)
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kWorld; ++k) {                                        // fixed order => deterministic
+            const float c = t.coef[k];
+            acc.x = fmaf(c, vals[k].x, acc.x); acc.y = fmaf(c, vals[k].y, acc.y);
+            acc.z = fmaf(c, vals[k].z, acc.z); acc.w = fmaf(c, vals[k].w, acc.w);
+        }
+        if (ea.mode != EPI_NONE) {
+            float4 wv = *reinterpret_cast<const float4*>(wcur + e);
+            float4 mv = m ? *reinterpret_cast<const float4*>(m + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 vv = v ? *reinterpret_cast<const float4*>(v + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc.x = epi_apply(ea.mode, ea, acc.x, wv.x, mv.x, vv.x);
+            acc.y = epi_apply(ea.mode, ea, acc.y, wv.y, mv.y, vv.y);
+            acc.z = epi_apply(ea.mode, ea, acc.z, wv.z, mv.z, vv.z);
+            acc.w = epi_apply(ea.mode, ea, acc.w, wv.w, mv.w, vv.w);
+            if (m) *reinterpret_cast<float4*>(m + e) = mv;
+            if (v) *reinterpret_cast<float4*>(v + e) = vv;
+        }
+#pragma unroll
+        for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, acc);          // all-gather: push to every rank
+    }
+    // (1) my slice is stored everywhere; wait until every peer's slice landed here before the kernel may complete.
+    __threadfence_system();
+    grid.sync();
+    peer_barrier(t, 1, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bcast_fused: root's `contrib[root]` buffer -> every rank's `result` buffer, then receiver-side unpack.
+// ---------------------------------------------------------------------------------------------------------------
+template <int kWorld>
+__global__ void __launch_bounds__(kThreads, 1)
+bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restrict__ anchor,
+                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ c_server,
+                   const float* __restrict__ c_local, float* __restrict__ cv_out, int64_t numel, int64_t slice,
+                   uint32_t epoch) {
+    cg::grid_group grid = cg::this_grid();
+    peer_barrier(t, 0, epoch);  // root's buffer is final; everyone's result buffer may be overwritten
+    grid.sync();
+
+    const int64_t begin = (int64_t)t.rank * slice;
+    int64_t end = begin + slice;
+    if (end > numel) end = numel;
+    const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float* src = t.contrib[root];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t e = begin + (i << 2);
+        const float4 val = ld_peer4(src + e);                                     // scatter: my 1/K from the root
+#pragma unroll
+        for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, val);          // all-gather to every peer
+    }
+    __threadfence_system();
+    grid.sync();
+    peer_barrier(t, 1, epoch);
+    grid.sync();
+
+    // receiver-side tail: one read of the landed global buffer, up to four writes
+    const float* g = t.result[t.rank];
+    const int64_t total4 = numel >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int64_t e = i << 2;
+        const float4 gv = ld_peer4(g + e);
+        if (w) *reinterpret_cast<float4*>(w + e) = gv;
+        if (anchor) *reinterpret_cast<float4*>(anchor + e) = gv;
+        if (shadow) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(shadow + e) = packed;
+        }
+        if (cv_out) {
+            const float4 cs = *reinterpret_cast<const float4*>(c_server + e);
+            const float4 cl = *reinterpret_cast<const float4*>(c_local + e);
+            *reinterpret_cast<float4*>(cv_out + e) = make_float4(cs.x - cl.x, cs.y - cl.y, cs.z - cl.z, cs.w - cl.w);
+        }
+    }
+}
+
+template <typename Kernel>
+int coop_grid(Kernel kernel) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sms;  // one CTA per SM: plenty of bytes in flight for NVLink, leaves room for the grid barrier
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- symmetric memory plumbing (CUDA IPC) -----------------------------------------------------------------------
+int fl4h_ipc_alloc(size_t bytes, void** ptr) {
+    cudaError_t err = cudaMalloc(ptr, bytes);
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaMemset(*ptr, 0, bytes);
+}
+int fl4h_ipc_free(void* ptr) { return (int)cudaFree(ptr); }
+int fl4h_ipc_get_handle(void* ptr, void* handle_out /* 64 bytes */) {
+    cudaIpcMemHandle_t handle;
+    cudaError_t err = cudaIpcGetMemHandle(&handle, ptr);
+    if (err != cudaSuccess) return (int)err;
+    memcpy(handle_out, &handle, sizeof(handle));
+    return 0;
+}
+int fl4h_ipc_open_handle(const void* handle_in, void** ptr) {
+    cudaIpcMemHandle_t handle;
+    memcpy(&handle, handle_in, sizeof(handle));
+    return (int)cudaIpcOpenMemHandle(ptr, handle, cudaIpcMemLazyEnablePeerAccess);
+}
+int fl4h_ipc_close_handle(void* ptr) { return (int)cudaIpcCloseMemHandle(ptr); }
+int fl4h_can_access_peer(int dev, int peer) {
+    int ok = 0;
+    cudaDeviceCanAccessPeer(&ok, dev, peer);
+    return ok;
+}
+
+struct Fl4hPeerArgs {
+    void* contrib[FL4H_MAX_RANKS];
+    void* result[FL4H_MAX_RANKS];
+    void* flags[FL4H_MAX_RANKS];
+    float coef[FL4H_MAX_RANKS];
+    int rank;
+    int world;
+};
+
+static PeerTable make_table(const Fl4hPeerArgs* a) {
+    PeerTable t;
+    for (int i = 0; i < FL4H_MAX_RANKS; ++i) {
+        t.contrib[i] = reinterpret_cast<float*>(a->contrib[i]);
+        t.result[i] = reinterpret_cast<float*>(a->result[i]);
+        t.flags[i] = reinterpret_cast<uint32_t*>(a->flags[i]);
+        t.coef[i] = a->coef[i];
+    }
+    t.rank = a->rank;
+    t.world = a->world;
+    return t;
+}
+
+#define DISPATCH_WORLD(W, CALL)        \
+    switch (W) {                       \
+        case 1: { constexpr int KW = 1; CALL; } break;   \
+        case 2: { constexpr int KW = 2; CALL; } break;   \
+        case 3: { constexpr int KW = 3; CALL; } break;   \
+        case 4: { constexpr int KW = 4; CALL; } break;   \
+        case 5: { constexpr int KW = 5; CALL; } break;   \
+        case 6: { constexpr int KW = 6; CALL; } break;   \
+        case 7: { constexpr int KW = 7; CALL; } break;   \
+        case 8: { constexpr int KW = 8; CALL; } break;   \
+        default: return (int)cudaErrorInvalidValue;      \
+    }
+
+int fl4h_agg_fused(const Fl4hPeerArgs* args, const float* wcur, float* m, float* v, int mode, float eta, float beta1,
+                   float beta2, float tau, float server_lr, float momentum, int64_t numel, uint32_t epoch,
+                   cudaStream_t stream) {
+    if (numel & 3) return (int)cudaErrorInvalidValue;
+    PeerTable t = make_table(args);
+    EpiArgs ea{eta, beta1, beta2, tau, server_lr, momentum, mode};
+    // slice = ceil(numel / world) rounded up to 4 elements
+    int64_t slice = (numel + t.world - 1) / t.world;
+    slice = (slice + 3) & ~int64_t(3);
+    cudaError_t err = cudaSuccess;
+    DISPATCH_WORLD(t.world, {
+        auto kernel = agg_fused_kernel<KW>;
+        const int grid = coop_grid(kernel);
+        void* kargs[] = {&t, &wcur, &m, &v, &ea, &numel, &slice, &epoch};
+        err = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+    });
+    return (int)err;
+}
+
+int fl4h_bcast_fused(const Fl4hPeerArgs* args, int root, float* w, float* anchor, void* shadow,
+                     const float* c_server, const float* c_local, float* cv_out, int64_t numel, uint32_t epoch,
+                     cudaStream_t stream) {
+    if (numel & 3) return (int)cudaErrorInvalidValue;
+    PeerTable t = make_table(args);
+    int64_t slice = (numel + t.world - 1) / t.world;
+    slice = (slice + 3) & ~int64_t(3);
+    __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
+    cudaError_t err = cudaSuccess;
+    DISPATCH_WORLD(t.world, {
+        auto kernel = bcast_fused_kernel<KW>;
+        const int grid = coop_grid(kernel);
+        void* kargs[] = {&t, &root, &w, &anchor, &sh, &c_server, &c_local, &cv_out, &numel, &slice, &epoch};
+        err = cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+    });
+    return (int)err;
+}
+
+}  // extern "C"

@@ -413,8 +413,15 @@ class SpmdTransport:
         return GetParametersRes(Status(Code.OK), ndarrays_to_parameters(full))
 
 
-def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any) -> list[SpmdClientProxy]:
-    """Register one proxy per rank with the server's client manager; only this rank's proxy holds a client."""
+def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any, fused: bool | None = None) -> list[SpmdClientProxy]:
+    """Register one proxy per rank with the server's client manager; only this rank's proxy holds a client.
+
+    ``fused`` (default: try) sets up peer-mapped symmetric memory and makes the client allocate its parameter arena
+    from it, so the aggregate/broadcast kernels read and write the arenas in place over NVLink."""
+    if fused is not False and ctx.enable_fused_collectives():
+        local_client.arena_allocator = ctx.fused.allocator
+    elif fused is True:
+        raise RuntimeError("fused collectives requested but unavailable")
     proxies = []
     for rank in range(ctx.world_size):
         proxy = SpmdClientProxy(ctx, rank, local_client if rank == ctx.rank else None)

@@ -44,7 +44,8 @@ def main() -> None:
         strategy = BasicFedAvg(**common)
     server = FlServer(SimpleClientManager(), {"n_server_rounds": 2}, strategy,
                       on_init_parameters_config_fn=fit_config_fn())
-    build_spmd_federation(ctx, server, client)
+    fused_mode = os.environ.get("FL4H_COLLECTIVES", "auto")
+    build_spmd_federation(ctx, server, client, fused=True if fused_mode == "fused" else (False if fused_mode == "nccl" or ctx.device.type != "cuda" else None))
     history, _ = server.fit(num_rounds=2)
     state = {k: v.detach().cpu().double().sum().item() for k, v in client.model.state_dict().items()}
     if ctx.rank == 0:
