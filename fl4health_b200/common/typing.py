@@ -34,11 +34,28 @@ class NDArrays(list):
 
     flat: torch.Tensor | None
     layout: Any
+    # second flat region for packed side payloads that are themselves arena-shaped (SCAFFOLD variates)
+    aux_flat: torch.Tensor | None = None
+    aux_layout: Any = None
 
     def __init__(self, iterable: Any = (), flat: torch.Tensor | None = None, layout: Any = None) -> None:
         super().__init__(iterable)
         self.flat = flat
         self.layout = layout
+
+    def sliced(self, start: int | None, stop: int | None) -> NDArrays:
+        """``self[start:stop]`` that keeps arena / ownership metadata (packers use it to split side information
+        from weights without losing the fused-aggregation fast path)."""
+        part = NDArrays(list.__getitem__(self, slice(start, stop)))
+        layout = self.layout
+        if self.flat is not None and layout is not None and len(part) == len(layout.state_keys) and (start in (None, 0)):
+            part.flat, part.layout = self.flat, layout
+        elif (
+            self.aux_flat is not None and self.aux_layout is not None and layout is not None
+            and start == len(layout.state_keys) and len(part) == len(self.aux_layout.state_keys)
+        ):
+            part.flat, part.layout = self.aux_flat, self.aux_layout
+        return part
 
 
 class Code(Enum):

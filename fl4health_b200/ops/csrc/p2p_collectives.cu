@@ -130,31 +130,47 @@ agg_fused_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict_
     if (end > numel) end = numel;
     const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int64_t e = begin + (i << 2);
-        float4 vals[kWorld];
+    // kUnroll x kWorld 16-byte peer loads are issued before any is consumed: the NVLink round trip (~2 us) is
+    // amortised over kUnroll*kWorld*16 B per thread (volatile accesses are never reordered by the compiler, so the
+    // memory-level parallelism has to be explicit).
+    constexpr int kUnroll = (kWorld <= 2) ? 8 : (kWorld <= 4 ? 4 : 2);
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * kUnroll) {
+        float4 vals[kUnroll][kWorld];
 #pragma unroll
-        for (int k = 0; k < kWorld; ++k) vals[k] = ld_peer4(t.contrib[k] + e);   // K loads in flight (NVLink MLP)
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i < n4) {
+                const int64_t e = begin + (i << 2);
 #pragma unroll
-        for (int k = 0; k < kWorld; ++k) {                                        // fixed order => deterministic
-            const float c = t.coef[k];
-            acc.x = fmaf(c, vals[k].x, acc.x); acc.y = fmaf(c, vals[k].y, acc.y);
-            acc.z = fmaf(c, vals[k].z, acc.z); acc.w = fmaf(c, vals[k].w, acc.w);
-        }
-        if (ea.mode != EPI_NONE) {
-            float4 wv = *reinterpret_cast<const float4*>(wcur + e);
-            float4 mv = m ? *reinterpret_cast<const float4*>(m + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 vv = v ? *reinterpret_cast<const float4*>(v + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc.x = epi_apply(ea.mode, ea, acc.x, wv.x, mv.x, vv.x);
-            acc.y = epi_apply(ea.mode, ea, acc.y, wv.y, mv.y, vv.y);
-            acc.z = epi_apply(ea.mode, ea, acc.z, wv.z, mv.z, vv.z);
-            acc.w = epi_apply(ea.mode, ea, acc.w, wv.w, mv.w, vv.w);
-            if (m) *reinterpret_cast<float4*>(m + e) = mv;
-            if (v) *reinterpret_cast<float4*>(v + e) = vv;
+                for (int k = 0; k < kWorld; ++k) vals[u][k] = ld_peer4(t.contrib[k] + e);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, acc);          // all-gather: push to every rank
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i >= n4) continue;
+            const int64_t e = begin + (i << 2);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < kWorld; ++k) {                                    // fixed order => deterministic
+                const float c = t.coef[k];
+                acc.x = fmaf(c, vals[u][k].x, acc.x); acc.y = fmaf(c, vals[u][k].y, acc.y);
+                acc.z = fmaf(c, vals[u][k].z, acc.z); acc.w = fmaf(c, vals[u][k].w, acc.w);
+            }
+            if (ea.mode != EPI_NONE) {
+                float4 wv = *reinterpret_cast<const float4*>(wcur + e);
+                float4 mv = m ? *reinterpret_cast<const float4*>(m + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 vv = v ? *reinterpret_cast<const float4*>(v + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x = epi_apply(ea.mode, ea, acc.x, wv.x, mv.x, vv.x);
+                acc.y = epi_apply(ea.mode, ea, acc.y, wv.y, mv.y, vv.y);
+                acc.z = epi_apply(ea.mode, ea, acc.z, wv.z, mv.z, vv.z);
+                acc.w = epi_apply(ea.mode, ea, acc.w, wv.w, mv.w, vv.w);
+                if (m) *reinterpret_cast<float4*>(m + e) = mv;
+                if (v) *reinterpret_cast<float4*>(v + e) = vv;
+            }
+#pragma unroll
+            for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, acc);      // all-gather: push to every rank
+        }
     }
     // (1) my slice is stored everywhere; wait until every peer's slice landed here before the kernel may complete.
     __threadfence_system();
@@ -181,11 +197,22 @@ bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restri
     const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float* src = t.contrib[root];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int64_t e = begin + (i << 2);
-        const float4 val = ld_peer4(src + e);                                     // scatter: my 1/K from the root
+    constexpr int kUnroll = 8;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * kUnroll) {
+        float4 vals[kUnroll];
 #pragma unroll
-        for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, val);          // all-gather to every peer
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i < n4) vals[u] = ld_peer4(src + begin + (i << 2));               // scatter: my 1/K from the root
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i >= n4) continue;
+            const int64_t e = begin + (i << 2);
+#pragma unroll
+            for (int k = 0; k < kWorld; ++k) st_peer4(t.result[k] + e, vals[u]);  // all-gather to every peer
+        }
     }
     __threadfence_system();
     grid.sync();
@@ -197,7 +224,7 @@ bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restri
     const int64_t total4 = numel >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
         const int64_t e = i << 2;
-        const float4 gv = ld_peer4(g + e);
+        const float4 gv = ld_peer4(g + e);  // volatile: written by peers during this kernel, never in L1
         if (w) *reinterpret_cast<float4*>(w + e) = gv;
         if (anchor) *reinterpret_cast<float4*>(anchor + e) = gv;
         if (shadow) {
@@ -277,16 +304,16 @@ static PeerTable make_table(const Fl4hPeerArgs* a) {
     return t;
 }
 
-#define DISPATCH_WORLD(W, CALL)        \
+#define DISPATCH_WORLD(W, ...)         \
     switch (W) {                       \
-        case 1: { constexpr int KW = 1; CALL; } break;   \
-        case 2: { constexpr int KW = 2; CALL; } break;   \
-        case 3: { constexpr int KW = 3; CALL; } break;   \
-        case 4: { constexpr int KW = 4; CALL; } break;   \
-        case 5: { constexpr int KW = 5; CALL; } break;   \
-        case 6: { constexpr int KW = 6; CALL; } break;   \
-        case 7: { constexpr int KW = 7; CALL; } break;   \
-        case 8: { constexpr int KW = 8; CALL; } break;   \
+        case 1: { constexpr int KW = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int KW = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int KW = 3; __VA_ARGS__; } break;   \
+        case 4: { constexpr int KW = 4; __VA_ARGS__; } break;   \
+        case 5: { constexpr int KW = 5; __VA_ARGS__; } break;   \
+        case 6: { constexpr int KW = 6; __VA_ARGS__; } break;   \
+        case 7: { constexpr int KW = 7; __VA_ARGS__; } break;   \
+        case 8: { constexpr int KW = 8; __VA_ARGS__; } break;   \
         default: return (int)cudaErrorInvalidValue;      \
     }
 

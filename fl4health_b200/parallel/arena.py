@@ -248,6 +248,29 @@ class ParameterArena:
         return merged
 
 
+class TrainableRegionLayout:
+    """Layout of a companion region restricted to the trainable parameters (in ``parameters()`` order): the shape
+    SCAFFOLD control variates travel in.  Quacks like a ``ParameterArena`` for the aggregation fast path."""
+
+    def __init__(self, arena: ParameterArena) -> None:
+        self.arena = arena
+        self.state_keys = [
+            name for name, p in arena.module.named_parameters() if p.requires_grad and name in arena.by_name
+        ]
+        self.int_state: dict[str, torch.Tensor] = {}
+        self.total = arena.trainable_padded
+
+    def ndarrays(self, names: Iterable[str] | None = None, region: torch.Tensor | None = None) -> NDArrays:
+        assert region is not None
+        out = NDArrays([self.arena.view(name, region) for name in (names or self.state_keys)])
+        if names is None:
+            out.flat, out.layout = region[: self.total], self
+        return out
+
+    def same_layout(self, other: object) -> bool:
+        return isinstance(other, TrainableRegionLayout) and self.arena.same_layout(other.arena)
+
+
 def _as_tensor(arr: object, device: torch.device) -> torch.Tensor:
     if isinstance(arr, torch.Tensor):
         return arr.to(device, non_blocking=True) if arr.device != device else arr

@@ -90,6 +90,30 @@ class RemoteNDArrays(NDArrays):
         self.remote = True
         self.materialized = False
 
+    def sliced(self, start: int | None, stop: int | None) -> NDArrays:
+        return _sliced_with_tags(self, start, stop)
+
+
+def _slice_spec(spec: PayloadSpec, start: int | None, stop: int | None, total: int) -> PayloadSpec:
+    entries = spec.entries[slice(start, stop)]
+    keeps_arena = spec.flat_numel is not None and start in (None, 0) and len(entries) >= 1 and all(
+        e[2] is not None for e in spec.entries[len(entries):]
+    )
+    return PayloadSpec(entries, spec.flat_numel if keeps_arena else None)
+
+
+def _sliced_with_tags(source: Any, start: int | None, stop: int | None) -> NDArrays:
+    base = NDArrays.sliced(source, start, stop)
+    spec = _slice_spec(source.spec, start, stop, len(source))
+    if isinstance(source, RemoteNDArrays):
+        part: NDArrays = RemoteNDArrays(source.ctx, source.rank, spec)
+        part[:] = list(base)
+        part.materialized = source.materialized  # type: ignore[attr-defined]
+    else:
+        part = _LocalPayload(base, flat=base.flat, layout=base.layout)
+        part.ctx, part.rank, part.spec = source.ctx, source.rank, spec  # type: ignore[attr-defined]
+    return part
+
 
 def is_remote(arrays: Any) -> bool:
     return bool(getattr(arrays, "remote", False)) and not getattr(arrays, "materialized", True)
@@ -257,6 +281,9 @@ def materialize(arrays: NDArrays) -> NDArrays:
 class _LocalPayload(NDArrays):
     """This rank's own payload, tagged so collectives know who owns it."""
 
+    def sliced(self, start: int | None, stop: int | None) -> NDArrays:
+        return _sliced_with_tags(self, start, stop)
+
 
 def _tag_local(arrays: NDArrays, ctx: SpmdContext) -> NDArrays:
     tagged = _LocalPayload(arrays, flat=getattr(arrays, "flat", None), layout=getattr(arrays, "layout", None))
@@ -422,6 +449,12 @@ def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any, fuse
         local_client.arena_allocator = ctx.fused.allocator
     elif fused is True:
         raise RuntimeError("fused collectives requested but unavailable")
+    # replicated server logic must draw identical client samples on every rank: align the sampling RNGs
+    import random
+
+    seed = ctx.broadcast_object(random.getrandbits(31), src=0)
+    random.seed(seed)
+    np.random.seed(seed)
     proxies = []
     for rank in range(ctx.world_size):
         proxy = SpmdClientProxy(ctx, rank, local_client if rank == ctx.rank else None)

@@ -18,6 +18,12 @@ from fl4health_b200.common.typing import NDArray, NDArrays
 T = TypeVar("T")
 
 
+def _slice(arrays: list, start: int | None, stop: int | None) -> NDArrays:
+    if isinstance(arrays, NDArrays):
+        return arrays.sliced(start, stop)
+    return NDArrays(arrays[slice(start, stop)])
+
+
 def _scalar(value: object) -> float:
     if isinstance(value, torch.Tensor):
         return float(value.item())
@@ -39,11 +45,15 @@ class ParameterPackerWithControlVariates(ParameterPacker[NDArrays]):
         self.size_of_model_params = size_of_model_params
 
     def pack_parameters(self, model_weights: NDArrays, additional_parameters: NDArrays) -> NDArrays:
-        return NDArrays(list(model_weights) + list(additional_parameters))
+        packed = NDArrays(list(model_weights) + list(additional_parameters))
+        packed.flat, packed.layout = getattr(model_weights, "flat", None), getattr(model_weights, "layout", None)
+        packed.aux_flat = getattr(additional_parameters, "flat", None)
+        packed.aux_layout = getattr(additional_parameters, "layout", None)
+        return packed
 
     def unpack_parameters(self, packed_parameters: NDArrays) -> tuple[NDArrays, NDArrays]:
         split = self.size_of_model_params
-        return NDArrays(packed_parameters[:split]), NDArrays(packed_parameters[split:])
+        return _slice(packed_parameters, None, split), _slice(packed_parameters, split, None)
 
 
 class _TrailingScalarPacker(ParameterPacker[float]):
@@ -55,12 +65,7 @@ class _TrailingScalarPacker(ParameterPacker[float]):
 
     def unpack_parameters(self, packed_parameters: NDArrays) -> tuple[NDArrays, float]:
         assert len(packed_parameters) >= 1
-        weights = NDArrays(
-            packed_parameters[:-1],
-            flat=getattr(packed_parameters, "flat", None),
-            layout=getattr(packed_parameters, "layout", None),
-        )
-        return weights, _scalar(packed_parameters[-1])
+        return _slice(packed_parameters, None, -1), _scalar(packed_parameters[-1])
 
 
 class ParameterPackerWithClippingBit(_TrailingScalarPacker):
@@ -78,7 +83,7 @@ class ParameterPackerWithLayerNames(ParameterPacker[list[str]]):
     def unpack_parameters(self, packed_parameters: NDArrays) -> tuple[NDArrays, list[str]]:
         names = packed_parameters[-1]
         names_list = names.tolist() if isinstance(names, np.ndarray) else list(names)
-        return NDArrays(packed_parameters[:-1]), [str(n) for n in names_list]
+        return _slice(packed_parameters, None, -1), [str(n) for n in names_list]
 
 
 class SparseCooParameterPacker(ParameterPacker[tuple[NDArrays, NDArrays, list[str]]]):

@@ -36,14 +36,17 @@ class TinyNet(nn.Module):
         return self.fc(torch.flatten(x, 1))
 
 
-class SyntheticCifarClient(BasicClient):
-    """BasicClient on synthetic CIFAR-shaped data; model/optimizer selectable for tests."""
+class SyntheticCifarMixin:
+    """User hooks on synthetic CIFAR-shaped data; combine with any client class: ``class C(SyntheticCifarMixin, X)``.
+    Knobs are plain attributes so the mixin never touches ``__init__`` signatures."""
 
-    def __init__(self, *args, seed: int = 0, n_train: int = 256, n_val: int = 64, model_fn=Net, lr: float = 0.05,  # noqa: ANN001, ANN002
-                 momentum: float = 0.9, optimizer: str = "sgd", **kwargs) -> None:  # noqa: ANN003
-        super().__init__(*args, **kwargs)
-        self.seed, self.n_train, self.n_val, self.model_fn = seed, n_train, n_val, model_fn
-        self.lr, self.momentum, self.optimizer_name = lr, momentum, optimizer
+    seed: int = 0
+    n_train: int = 256
+    n_val: int = 64
+    model_fn = staticmethod(Net)
+    lr: float = 0.05
+    momentum: float = 0.9
+    optimizer_name: str = "sgd"
 
     def get_model(self, config: Config) -> nn.Module:
         torch.manual_seed(1234)  # same init everywhere (the server overrides it anyway)
@@ -63,6 +66,27 @@ class SyntheticCifarClient(BasicClient):
         if self.optimizer_name == "adamw":
             return torch.optim.AdamW(self.model.parameters(), lr=self.lr)
         return torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum)
+
+
+class SyntheticCifarClient(SyntheticCifarMixin, BasicClient):
+    def __init__(self, *args, seed: int = 0, n_train: int = 256, n_val: int = 64, model_fn=Net, lr: float = 0.05,  # noqa: ANN001, ANN002
+                 momentum: float = 0.9, optimizer: str = "sgd", **kwargs) -> None:  # noqa: ANN003
+        super().__init__(*args, **kwargs)
+        self.seed, self.n_train, self.n_val, self.model_fn = seed, n_train, n_val, model_fn
+        self.lr, self.momentum, self.optimizer_name = lr, momentum, optimizer
+
+
+def make_mixed_clients(client_cls, k: int, device: str = "cpu", engine: EngineOptions | None = None, **attrs):  # noqa: ANN001, ANN003, ANN201
+    """K clients of ``class _(SyntheticCifarMixin, client_cls)`` with per-client data seeds."""
+    mixed = type(f"Synthetic{client_cls.__name__}", (SyntheticCifarMixin, client_cls), {})
+    clients = []
+    for idx in range(k):
+        client = mixed(Path("."), [Accuracy()], torch.device(device), client_name=f"c{idx}", engine_options=engine)
+        client.seed = idx
+        for key, value in attrs.items():
+            setattr(client, key, value)
+        clients.append(client)
+    return clients
 
 
 def make_clients(k: int, device: str = "cpu", engine: EngineOptions | None = None, **kwargs) -> list[SyntheticCifarClient]:  # noqa: ANN003
