@@ -59,6 +59,8 @@ class AdaptiveDriftConstraintClient(BasicClient):
         self.drift_penalty_weight: float | None = None
         self.loss_for_adaptation: float = 0.0
         self.penalty_loss_function = WeightDriftLoss(self.device)
+        # which optimizer steps the drift-constrained model (Ditto: the personal model's "local" optimizer)
+        self.penalty_optimizer_key = "global"
 
     # ---------------------------------------------------------------------------------------- wire format
     def get_parameters(self, config: Config) -> NDArrays:
@@ -97,7 +99,7 @@ class AdaptiveDriftConstraintClient(BasicClient):
         """The flat optimizer that can absorb the penalty gradient, if the fast path applies."""
         if type(self).compute_penalty_loss is not AdaptiveDriftConstraintClient.compute_penalty_loss:
             return None
-        optimizer = self.optimizers.get("global") if hasattr(self, "optimizers") else None
+        optimizer = self.optimizers.get(self.penalty_optimizer_key) if hasattr(self, "optimizers") else None
         arena = arena_of(self.model)
         if not isinstance(optimizer, _FlatOptimizer) or arena is None or optimizer.arena is not arena:
             return None

@@ -120,6 +120,7 @@ class BasicClient:
 
         # engine state
         self._train_runner: GraphStepRunner | None = None
+        self._train_runners: dict[Any, GraphStepRunner] = {}
         self._val_runners: dict[int, GraphStepRunner] = {}
 
     # ==================================================================================================================
@@ -358,12 +359,16 @@ class BasicClient:
 
     def _run_train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
         if self.engine.cuda_graphs and self.device.type == "cuda":
-            if self._train_runner is None:
-                self._train_runner = GraphStepRunner(
+            variant = self._graph_variant()
+            runner = self._train_runners.get(variant)
+            if runner is None:
+                runner = GraphStepRunner(
                     self._train_unit, self.device, warmup=self.engine.graph_warmup_steps,
-                    name=f"{self.client_name}/train", before_replay=self._sync_optimizer_hyperparams,
+                    name=f"{self.client_name}/train[{variant}]", before_replay=self._sync_optimizer_hyperparams,
                 )
-            losses, preds = self._train_runner(input, target)
+                self._train_runners[variant] = runner
+                self._train_runner = runner
+            losses, preds = runner(input, target)
         else:
             losses, preds = self._train_unit(input, target)
         self.train_loss_meter.mark_step()
@@ -391,9 +396,15 @@ class BasicClient:
         loss_meter.mark_step()
         return losses, preds
 
+    def _graph_variant(self) -> Any:
+        """Hashable tag of everything *besides input shapes* that changes what ``train_step`` launches (e.g. FedRep's
+        head/representation phase).  One captured graph is kept per (variant, input signature)."""
+        return "default"
+
     def _invalidate_graphs(self) -> None:
         """Drop captured graphs (call after anything that re-binds tensors the step reads: new model, new optimizer)."""
         self._train_runner = None
+        self._train_runners = {}
         self._val_runners = {}
 
     def _prepare_batch(self, input: TorchInputType, target: TorchTargetType) -> tuple[TorchInputType, TorchTargetType]:

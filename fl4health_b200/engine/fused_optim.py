@@ -91,7 +91,15 @@ class _FlatOptimizer(Optimizer):
                 self._hp_cache[idx] = key
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002 - grads are arena views, never dropped
-        self.arena.zero_grad()
+        grad = self.arena.grad
+        assert grad is not None
+        covered = sum(end - start for ranges in self._ranges for start, end in ranges)
+        if covered >= self.arena.trainable_padded:
+            grad.zero_()
+            return
+        for ranges in self._ranges:  # an optimizer over a sub-module only clears its own gradients
+            for start, end in ranges:
+                grad[start:end].zero_()
 
     def _ensure_grad_views(self) -> None:
         """If something (e.g. ``zero_grad(set_to_none=True)`` on another handle) detached the gradient views, copy
