@@ -121,7 +121,7 @@ class BasicClient:
         # engine state
         self._train_runner: GraphStepRunner | None = None
         self._train_runners: dict[Any, GraphStepRunner] = {}
-        self._val_runners: dict[int, GraphStepRunner] = {}
+        self._val_runners: dict[Any, GraphStepRunner] = {}
 
     # ==================================================================================================================
     # protocol: parameters in / out
@@ -362,6 +362,7 @@ class BasicClient:
             variant = self._graph_variant()
             runner = self._train_runners.get(variant)
             if runner is None:
+                self._evict_stale_runners(self._train_runners)
                 runner = GraphStepRunner(
                     self._train_unit, self.device, warmup=self.engine.graph_warmup_steps,
                     name=f"{self.client_name}/train[{variant}]", before_replay=self._sync_optimizer_hyperparams,
@@ -384,9 +385,10 @@ class BasicClient:
             return losses, preds
 
         if self.engine.cuda_graphs and self.device.type == "cuda":
-            key = id(loss_meter)
+            key = (id(loss_meter), self._graph_variant())
             runner = self._val_runners.get(key)
             if runner is None:
+                self._evict_stale_runners(self._val_runners)
                 runner = GraphStepRunner(unit, self.device, warmup=self.engine.graph_warmup_steps,
                                          name=f"{self.client_name}/eval")
                 self._val_runners[key] = runner
@@ -395,6 +397,13 @@ class BasicClient:
             losses, preds = unit(input, target)
         loss_meter.mark_step()
         return losses, preds
+
+    @staticmethod
+    def _evict_stale_runners(runners: dict, keep: int = 6) -> None:
+        """Captured graphs pin device memory; variants that re-bind tensors every round (MOON's frozen models) would
+        otherwise accumulate.  Oldest-first eviction keeps alternating variants (FedRep phases) resident."""
+        while len(runners) >= keep:
+            runners.pop(next(iter(runners)))
 
     def _graph_variant(self) -> Any:
         """Hashable tag of everything *besides input shapes* that changes what ``train_step`` launches (e.g. FedRep's
