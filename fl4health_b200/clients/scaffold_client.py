@@ -183,3 +183,45 @@ class ScaffoldClient(BasicClient):
         super().setup_client(config)
         self._check_optimizer()
         self.learning_rate = float(self.optimizers["global"].defaults["lr"])
+
+
+class DPScaffoldClient(ScaffoldClient):
+    """SCAFFOLD + instance-level DP-SGD (parity: ``scaffold_client.py:297-355``).  The reference uses diamond
+    inheritance with ``InstanceLevelDpClient``; here the DP wrapping is composed in ``setup_client``."""
+
+    def __init__(self, *args, **kwargs) -> None:  # noqa: ANN002, ANN003
+        super().__init__(*args, **kwargs)
+        self.clipping_bound: float
+        self.noise_multiplier: float
+        self.engine.cuda_graphs = False
+
+    def _place_model(self, model, with_grad: bool = True):  # noqa: ANN001, ANN201
+        from fl4health_b200.utils.privacy_utilities import privacy_validate_and_fix_modules
+
+        model, _ = privacy_validate_and_fix_modules(model)
+        return super()._place_model(model, with_grad)
+
+    def _check_optimizer(self) -> None:
+        from fl4health_b200.privacy.dp_engine import DPOptimizer
+
+        assert isinstance(self.optimizers["global"], DPOptimizer)
+
+    def setup_client(self, config: Config) -> None:
+        from fl4health_b200.privacy.dp_engine import PrivacyEngine
+        from fl4health_b200.utils.config import narrow_dict_type
+
+        self.clipping_bound = narrow_dict_type(config, "clipping_bound", float)
+        self.noise_multiplier = narrow_dict_type(config, "noise_multiplier", float)
+        BasicClient.setup_client(self, config)
+        inner_lr = float(self.optimizers["global"].defaults["lr"])
+        self.model, optimizer, self.train_loader = PrivacyEngine().make_private(
+            module=self.model, optimizer=self.optimizers["global"], data_loader=self.train_loader,
+            noise_multiplier=self.noise_multiplier, max_grad_norm=self.clipping_bound, clipping="flat",
+        )
+        self.optimizers = {"global": optimizer}
+        self.train_iterator = None
+        self._check_optimizer()
+        self.learning_rate = inner_lr
+
+    def _arena_regions(self):  # noqa: ANN202 - wrapped model: variates are kept as plain per-tensor lists
+        return None
