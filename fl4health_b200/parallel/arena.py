@@ -85,6 +85,8 @@ class ParameterArena:
         self.regions: dict[str, torch.Tensor] = {}
         self._build_layout()
         self.flat = self._alloc(self.total, torch.float32, self.device)
+        self.int_flat: torch.Tensor | None = None
+        self._views_cache: dict[tuple[int, int], NDArrays] = {}
         self._rehome()
         self.grad: torch.Tensor | None = None
         if with_grad and self.trainable_numel > 0:
@@ -153,6 +155,20 @@ class ParameterArena:
                 else:
                     owner, leaf = self._find_owner(entry.name)
                     owner._buffers[leaf] = view
+            # integer buffers (num_batches_tracked ...) live in ONE int64 buffer so they aggregate with one op
+            int_sizes = [(name, t.numel()) for name, t in self.int_state.items() if t.dtype == torch.int64]
+            if int_sizes:
+                self.int_flat = torch.zeros(sum(n for _, n in int_sizes), dtype=torch.int64, device=self.device)
+                cursor = 0
+                for name, numel in int_sizes:
+                    old = self.int_state[name]
+                    view = self.int_flat[cursor : cursor + numel].view(old.shape)
+                    view.copy_(old.to(self.device))
+                    owner, leaf = self._find_owner(name)
+                    if leaf in owner._buffers:
+                        owner._buffers[leaf] = view
+                    self.int_state[name] = view
+                    cursor += numel
             for name, tensor in list(self.int_state.items()):
                 if tensor.device != self.device:
                     owner, leaf = self._find_owner(name)
@@ -192,6 +208,13 @@ class ParameterArena:
     # ------------------------------------------------------------------------------------------------------
     def ndarrays(self, names: Iterable[str] | None = None, region: torch.Tensor | None = None) -> NDArrays:
         """state_dict-ordered list of views (``FullParameterExchanger`` order, ``full_exchanger.py:30``)."""
+        base = self.flat if region is None else region
+        if names is None:
+            cache_key = (base.data_ptr(), base.numel())
+            cached = self._views_cache.get(cache_key)
+            if cached is not None and cached.flat is base:
+                fresh = NDArrays(cached, flat=base, layout=self)  # shallow copy: callers may mutate the list
+                return fresh
         keys = list(names) if names is not None else self.state_keys
         out = NDArrays()
         for key in keys:
@@ -201,8 +224,11 @@ class ParameterArena:
             else:
                 out.append(self.int_state[key])
         if names is None:
-            out.flat = self.flat if region is None else region
+            out.flat = base
             out.layout = self
+            if len(self._views_cache) > 8:
+                self._views_cache.pop(next(iter(self._views_cache)))
+            self._views_cache[(base.data_ptr(), base.numel())] = NDArrays(out, flat=base, layout=self)
         return out
 
     def load_ndarrays(self, arrays: list, names: Iterable[str] | None = None) -> None:

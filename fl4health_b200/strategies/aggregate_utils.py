@@ -38,6 +38,22 @@ def _common_flat(arrays: Sequence[NDArrays]) -> list[torch.Tensor] | None:
     return flats
 
 
+_RESULT_BUFFERS: dict[tuple, list[torch.Tensor]] = {}
+
+
+def _result_buffer(layout: object, like: torch.Tensor) -> torch.Tensor:
+    """Aggregation output buffers are recycled (two per layout, alternating) so that the per-layer view lists built
+    over them stay cached and the allocator is not hit with a model-sized request every round.  Two buffers: the
+    previous round's aggregate (= the server's current parameters) must stay intact while the next one is written."""
+    key = (id(layout), like.numel(), like.device, like.dtype)
+    ring = _RESULT_BUFFERS.setdefault(key, [])
+    if len(ring) < 2:
+        ring.append(torch.empty_like(like))
+        return ring[-1]
+    ring.append(ring.pop(0))
+    return ring[-1]
+
+
 def _is_meta_array(arr: NDArray) -> bool:
     return isinstance(arr, np.ndarray) and arr.dtype.kind in ("U", "S", "O")
 
@@ -50,13 +66,25 @@ def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) 
     flats = _common_flat(arrays)
     if flats is not None:
         layout = arrays[0].layout
-        out_flat = torch.empty_like(flats[0])
+        out_flat = _result_buffer(layout, flats[0])
         flat_ops.weighted_sum(out_flat, flats, coefficients)
         out = layout.ndarrays(region=out_flat)
         # integer state (e.g. num_batches_tracked) is not in the flat buffer: average it like the reference does
-        for idx, key in enumerate(layout.state_keys):
-            if key in layout.int_state:
-                out[idx] = _combine_layer([nds[idx] for nds in arrays], coefficients)
+        int_flats = [getattr(nds.layout, "int_flat", None) for nds in arrays]
+        if layout.int_state and all(f is not None for f in int_flats):
+            stacked = torch.stack([f.to(torch.float64) for f in int_flats])  # [K, n_int]
+            weights = torch.tensor(list(coefficients), dtype=torch.float64, device=stacked.device).unsqueeze(1)
+            merged = (stacked * weights).sum(dim=0).to(torch.int64)
+            cursor = 0
+            for idx, key in enumerate(layout.state_keys):
+                if key in layout.int_state:
+                    numel = layout.int_state[key].numel()
+                    out[idx] = merged[cursor : cursor + numel].view(layout.int_state[key].shape)
+                    cursor += numel
+        else:
+            for idx, key in enumerate(layout.state_keys):
+                if key in layout.int_state:
+                    out[idx] = _combine_layer([nds[idx] for nds in arrays], coefficients)
         return out
     n_layers = len(arrays[0])
     assert all(len(nds) == n_layers for nds in arrays), "clients sent different numbers of arrays"
@@ -84,19 +112,29 @@ def _spmd_weighted_combine(
     if spec.flat_numel is not None:
         layout = local.layout if local is not None else None
         local_flat = local.flat if local is not None else None
+        if out_flat is None and local_flat is not None and layout is not None and ctx.fused is None:
+            out_flat = _result_buffer(layout, local_flat)
         result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.flat_numel, out=out_flat, epilogue=epilogue)
         if layout is None:
             raise RuntimeError("rank without a local payload cannot rebuild arena views; sample all ranks or use weight 0")
         out = layout.ndarrays(region=result_flat)
         int_idx = [i for i, key in enumerate(layout.state_keys) if key in layout.int_state]
         if int_idx:
-            ints = torch.stack([out[i].to(torch.float64) * coef_by_rank[ctx.rank] for i in int_idx])
+            int_flat = getattr(layout, "int_flat", None)
+            if int_flat is not None and int_flat.numel() == sum(out[i].numel() for i in int_idx):
+                ints = int_flat.to(torch.float64) * coef_by_rank[ctx.rank]  # one tensor for all integer buffers
+            else:
+                ints = torch.cat([out[i].reshape(-1).to(torch.float64) * coef_by_rank[ctx.rank] for i in int_idx])
             if ctx.world_size > 1:
                 import torch.distributed as dist
 
                 dist.all_reduce(ints)
-            for j, i in enumerate(int_idx):
-                out[i] = ints[j].to(out[i].dtype)
+            ints = ints.to(torch.int64)
+            cursor = 0
+            for i in int_idx:
+                numel = out[i].numel()
+                out[i] = ints[cursor : cursor + numel].view(out[i].shape).to(out[i].dtype)
+                cursor += numel
         return out
     # non-arena payloads: pack the tensor entries into one temporary flat buffer, reduce, unpack
     assert epilogue is None, "server-optimizer epilogues need arena-backed payloads in SPMD mode"

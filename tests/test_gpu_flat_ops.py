@@ -166,3 +166,37 @@ def test_fedpm_vote():
     s = sum(m.float() for m in masks)
     assert torch.allclose(alpha, 1 + s) and torch.allclose(beta, 1 + 3 - s)
     assert torch.allclose(theta, (alpha - 1) / (alpha + beta - 2))
+
+
+def test_fused_moon_contrastive_matches_reference():
+    from fl4health_b200.ops.contrastive import moon_contrastive, moon_contrastive_reference
+
+    torch.manual_seed(0)
+    z = torch.randn(32, 512, device="cuda", requires_grad=True)
+    pos = torch.randn(32, 512, device="cuda", requires_grad=True)
+    neg = torch.randn(3, 32, 512, device="cuda", requires_grad=True)
+    ref = moon_contrastive_reference(z, pos, neg, 0.5)
+    ref.backward()
+    z2, p2, n2 = (t.detach().clone().requires_grad_() for t in (z, pos, neg))
+    out = moon_contrastive(z2, p2, n2, 0.5)
+    assert out.grad_fn is not None and "FusedMoon" in type(out.grad_fn).__name__
+    out.backward()
+    assert abs(out.item() - ref.item()) < 1e-5
+    for a, b in ((z, z2), (pos, p2), (neg, n2)):
+        assert torch.allclose(a.grad, b.grad, atol=1e-6, rtol=1e-4)
+
+
+def test_fused_masked_parameter_statistics_and_gradient():
+    from fl4health_b200.ops.masked import masked_parameter
+
+    scores = torch.full((1 << 18,), 0.8, device="cuda", requires_grad=True)
+    frozen = torch.full((1 << 18,), 2.0, device="cuda")
+    out = masked_parameter(scores, frozen)
+    keep = (out != 0).float().mean().item()
+    p = torch.sigmoid(torch.tensor(0.8)).item()
+    assert abs(keep - p) < 0.01 and set(out.unique().tolist()) <= {0.0, 2.0}
+    out2 = masked_parameter(scores, frozen)
+    assert not torch.equal(out, out2)  # fresh mask every call (device seed counter ticks)
+    out.sum().backward()
+    expected = 2.0 * p * p * (1 - p)
+    assert torch.allclose(scores.grad, torch.full_like(scores, expected), atol=1e-5)
