@@ -48,6 +48,7 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--collectives", default="auto", choices=["auto", "nccl", "fused"])
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--fp32", action="store_true")
+    p.add_argument("--no-master-weights", action="store_true", help="bf16 autocast over fp32 params instead of bf16 shadow params")
     p.add_argument("--skip-e2e", action="store_true")
     return p.parse_args()
 
@@ -148,6 +149,7 @@ def main() -> None:
     engine = EngineOptions(
         arena=not eager_impl, fused_optimizer=not eager_impl, cuda_graphs=not (args.no_graphs or eager_impl),
         amp_dtype=None if args.fp32 else torch.bfloat16, channels_last=not eager_impl,
+        master_weights=not (eager_impl or args.fp32 or args.no_master_weights),
     )
 
     def synthetic(n: int, seed: int) -> TensorDataset:

@@ -61,7 +61,8 @@ def main() -> None:
     device = torch.device("cuda:0")
     torch.backends.cudnn.benchmark = True
     graphs = os.environ.get("GRAPHS", "1") == "1"
-    engine = EngineOptions(cuda_graphs=graphs, amp_dtype=torch.bfloat16, channels_last=True)
+    engine = EngineOptions(cuda_graphs=graphs, amp_dtype=torch.bfloat16, channels_last=True,
+                           master_weights=os.environ.get("MASTER", "1") == "1")
     client = Client(Path("."), [Accuracy()], device, client_name="prof", engine_options=engine)
     cfg = {"current_server_round": 1, "local_steps": 8, "batch_size": BS}
     client.setup_client(cfg)

@@ -26,7 +26,7 @@ class C(BasicClient):
                 BatchedTensorLoader(vs, 32, placement="device", device=self.device))
     def get_criterion(self, config): return nn.CrossEntropyLoss()
     def get_optimizer(self, config): return torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9)
-c = C(Path("."), [Accuracy()], dev, client_name="p", engine_options=EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16, channels_last=True))
+c = C(Path("."), [Accuracy()], dev, client_name="p", engine_options=EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16, channels_last=True, master_weights=True))
 def cfg(r): return {"current_server_round": r, "local_steps": 8, "batch_size": 32}
 params = c.get_parameters(cfg(0))
 params = NDArrays([p.clone() for p in params])

@@ -31,9 +31,16 @@ CheckpointScoreFunctionType = Callable[[float, dict[str, Scalar]], float]
 def materialize_module(model: nn.Module) -> nn.Module:
     """Deep copy whose tensors own their (CPU) storage — safe to pickle regardless of how ``model`` is stored."""
     clone = copy.deepcopy(model)
+    from fl4health_b200.parallel.arena import arena_of
+
+    arena = arena_of(model)
+    masters = arena.shadow_names if arena is not None else set()
     with torch.no_grad():
-        for param in clone.parameters():
-            param.data = param.data.detach().cpu().clone()
+        for name, param in clone.named_parameters():
+            if name in masters:  # low-precision compute view: checkpoint the fp32 master instead
+                param.data = arena.view(name).detach().cpu().clone().contiguous()
+            else:
+                param.data = param.data.detach().cpu().clone()
             param.grad = None
         for module in clone.modules():
             for name, buf in list(module._buffers.items()):

@@ -323,8 +323,8 @@ class BasicClient:
     # the per-batch step
     # ==================================================================================================================
     def _amp(self) -> contextlib.AbstractContextManager:
-        if self.engine.amp_dtype is not None and self.device.type == "cuda":
-            return torch.autocast(device_type="cuda", dtype=self.engine.amp_dtype)
+        if self.engine.amp_dtype is not None and (self.device.type == "cuda" or self.engine.master_weights):
+            return torch.autocast(device_type=self.device.type, dtype=self.engine.amp_dtype)
         return contextlib.nullcontext()
 
     def train_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
@@ -596,8 +596,10 @@ class BasicClient:
         """Move a model to the device and (engine option) re-home its state into a flat arena."""
         model = model.to(self.device)
         if self.engine.arena:
-            attach_arena(model, self.device, with_grad=with_grad, channels_last=self.engine.channels_last,
-                         allocator=self._arena_allocator())
+            arena = attach_arena(model, self.device, with_grad=with_grad, channels_last=self.engine.channels_last,
+                                 allocator=self._arena_allocator())
+            if self.engine.master_weights and self.engine.amp_dtype is not None and self.engine.fused_optimizer and with_grad:
+                arena.enable_compute_shadow(self.engine.amp_dtype)
         elif self.engine.channels_last:
             model = model.to(memory_format=torch.channels_last)
         return model

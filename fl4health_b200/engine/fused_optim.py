@@ -23,6 +23,7 @@ from torch import nn
 from torch.optim import Optimizer
 
 from fl4health_b200.ops import flat as F
+from fl4health_b200.ops import multi_tensor as MT
 from fl4health_b200.parallel.arena import ALIGN, ParameterArena, _round_up
 
 
@@ -56,14 +57,30 @@ class _FlatOptimizer(Optimizer):
     def __init__(self, arena: ParameterArena, params: Any, defaults: dict[str, Any]) -> None:
         self.arena = arena
         super().__init__(params, defaults)
-        assert arena.grad is not None, "arena was built without a gradient region"
+        # table mode (``arena.enable_compute_shadow``): no flat gradient region, per-tensor (bf16/fp32) gradients are
+        # consumed through a pointer table by ONE multi-tensor launch per group (ops/csrc/mt_optim.cu)
+        self.table_mode = arena.grad is None
+        self._table_params: list[list[tuple[nn.Parameter, Any]]] = []
+        if self.table_mode:
+            by_id = {id(p): name for name, p in arena.module.named_parameters(remove_duplicate=False)}
+            for group in self.param_groups:
+                seen: set[str] = set()
+                pairs = []
+                for p in group["params"]:
+                    if id(p) not in by_id:
+                        raise ValueError("optimizer parameter does not belong to the arena's module")
+                    name = arena.aliases.get(by_id[id(p)], by_id[id(p)])
+                    if arena.by_name[name].kind == "trainable" and name not in seen:
+                        seen.add(name)
+                        pairs.append((p, arena.by_name[name]))
+                self._table_params.append(pairs)
         self._ranges: list[list[tuple[int, int]]] = [_group_ranges(arena, g["params"]) for g in self.param_groups]
         self._hp: list[torch.Tensor] = [F.make_hyper_params(arena.device) for _ in self.param_groups]
         self._hp_cache: list[tuple | None] = [None for _ in self.param_groups]
         self.anchor: torch.Tensor | None = None  # FedProx / Ditto / MR-MTL w_t (arena offsets)
         self.mu: float = 0.0
         self.cv: torch.Tensor | None = None  # SCAFFOLD c - c_i (arena offsets)
-        self.shadow: torch.Tensor | None = None  # bf16 compute copy refreshed in the same pass
+        self.shadow: torch.Tensor | None = arena.shadow  # bf16 compute copy refreshed in the same pass
         self._grad_checked = 0
 
     # -- FL-specific fused terms ------------------------------------------------------------------------
@@ -91,6 +108,11 @@ class _FlatOptimizer(Optimizer):
                 self._hp_cache[idx] = key
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002 - grads are arena views, never dropped
+        if self.table_mode:  # autograd then *assigns* fresh gradients: no zero-fill, no accumulate kernels
+            for pairs in self._table_params:
+                for p, _ in pairs:
+                    p.grad = None
+            return
         grad = self.arena.grad
         assert grad is not None
         covered = sum(end - start for ranges in self._ranges for start, end in ranges)
@@ -104,7 +126,7 @@ class _FlatOptimizer(Optimizer):
     def _ensure_grad_views(self) -> None:
         """If something (e.g. ``zero_grad(set_to_none=True)`` on another handle) detached the gradient views, copy
         the stray grads into the arena and re-attach.  Checked on the first steps only."""
-        if self._grad_checked >= 2 or _capturing():
+        if self.table_mode or self._grad_checked >= 2 or _capturing():
             return
         self._grad_checked += 1
         grad = self.arena.grad
@@ -121,6 +143,21 @@ class _FlatOptimizer(Optimizer):
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
+
+    def _table_entries(self, idx: int) -> list[MT.TableEntry]:
+        entries = []
+        for p, entry in self._table_params[idx]:
+            g = p.grad
+            if g is None:
+                continue
+            if g.stride() != p.stride():  # physical order must match the arena's (e.g. channels-last weights)
+                g = torch.empty_like(p, dtype=g.dtype).copy_(g)
+            entries.append(MT.TableEntry(g, entry.offset, entry.numel))
+        return entries
+
+    def _table_regions(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        anchor = self.anchor if (self.anchor is not None and self.mu != 0.0) else None
+        return anchor, self.cv
 
     def _slices(self, start: int, end: int) -> dict[str, torch.Tensor | None]:
         arena = self.arena
@@ -165,6 +202,12 @@ class FlatSGD(_FlatOptimizer):
         if not _capturing():
             self.sync_hyperparams()
             self._ensure_grad_views()
+        if self.table_mode:
+            anchor, cv = self._table_regions()
+            for idx in range(len(self.param_groups)):
+                MT.mt_step(self._table_entries(idx), False, self.arena.flat, self.momentum_buffer, None, self._hp[idx],
+                           anchor, cv, self.shadow)
+            return loss
         for idx, ranges in enumerate(self._ranges):
             for start, end in ranges:
                 s = self._slices(start, end)
@@ -223,6 +266,12 @@ class FlatAdamW(_FlatOptimizer):
         if not _capturing():
             self.sync_hyperparams()
             self._ensure_grad_views()
+        if self.table_mode:
+            anchor, _ = self._table_regions()
+            for idx in range(len(self.param_groups)):
+                MT.mt_step(self._table_entries(idx), True, self.arena.flat, self.exp_avg, self.exp_avg_sq, self._hp[idx],
+                           anchor, None, self.shadow, self.decoupled)
+            return loss
         for idx, ranges in enumerate(self._ranges):
             for r, (start, end) in enumerate(ranges):
                 s = self._slices(start, end)
@@ -259,7 +308,7 @@ def translate_optimizer(optimizer: Optimizer, arena: ParameterArena) -> Optimize
     if isinstance(optimizer, _FlatOptimizer):
         return optimizer
     kind = type(optimizer)
-    if kind not in (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW) or arena.grad is None:
+    if kind not in (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW) or (arena.grad is None and arena.shadow is None):
         return optimizer
     module_params = {id(p) for p in arena.module.parameters()}
     groups = []

@@ -25,6 +25,9 @@ class EngineOptions:
     * ``cuda_graphs``      capture ``train_step`` (+ loss/metric accumulation) into a CUDA graph after warm-up
     * ``amp_dtype``        autocast dtype for forward + loss (``None`` = fp32)
     * ``channels_last``    store 4-D parameters NHWC inside the arena and feed NHWC activations
+    * ``master_weights``   with ``amp_dtype``: conv/linear parameters become ``amp_dtype`` views of an arena shadow
+                           region (fp32 masters stay in the arena and are what is exchanged); the optimizer becomes one
+                           multi-tensor launch that reads per-tensor low-precision gradients and writes master+shadow
     """
 
     arena: bool = True
@@ -32,6 +35,7 @@ class EngineOptions:
     cuda_graphs: bool = False
     amp_dtype: torch.dtype | None = None
     channels_last: bool = False
+    master_weights: bool = False
     graph_warmup_steps: int = 3
     step_reports: bool | None = None  # None = only when a reporter asks for per-step data
 
@@ -45,4 +49,5 @@ class EngineOptions:
             cuda_graphs=_env_flag("FL4H_CUDA_GRAPHS", False),
             amp_dtype=amp_dtype,
             channels_last=_env_flag("FL4H_CHANNELS_LAST", False),
+            master_weights=_env_flag("FL4H_MASTER_WEIGHTS", False),
         )

@@ -89,6 +89,8 @@ class ParameterArena:
         self._views_cache: dict[tuple[int, int], NDArrays] = {}
         self._rehome()
         self.grad: torch.Tensor | None = None
+        self.shadow: torch.Tensor | None = None  # bf16 compute copy (see enable_compute_shadow)
+        self.shadow_names: set[str] = set()
         if with_grad and self.trainable_numel > 0:
             self.grad = self._alloc(self.trainable_padded, torch.float32, self.device)
             self._attach_grads()
@@ -185,6 +187,57 @@ class ParameterArena:
                 params[entry.name].grad = self._shaped(self.grad, entry)
 
     # ------------------------------------------------------------------------------------------------------
+    def enable_compute_shadow(
+        self, dtype: torch.dtype = torch.bfloat16, module_types: tuple[type, ...] | None = None
+    ) -> torch.Tensor:
+        """Master-weight mode: the parameters of GEMM-shaped layers (conv / linear by default) become ``dtype`` views
+        of a *shadow* region with the arena's offsets; ``flat`` keeps the fp32 masters that are exchanged, aggregated
+        and checkpointed.  The forward then needs no per-step weight casts, autograd produces ``dtype`` gradients
+        (no cast-back kernels), and gradients are no longer accumulated into a flat fp32 region: ``.grad`` is None
+        before each backward, so autograd assigns instead of adding, and the multi-tensor optimizer kernel
+        (``ops/csrc/mt_optim.cu``) consumes the per-tensor gradients through a pointer table while writing both the
+        master and the shadow.  Normalisation parameters stay fp32 views of the master.
+
+        Whoever writes ``flat`` outside the optimizer (parameter pull, aggregation broadcast) must call
+        ``refresh_shadow``; ``load_ndarrays`` does so itself."""
+        if self.shadow is not None:
+            return self.shadow
+        if module_types is None:
+            module_types = (nn.modules.conv._ConvNd, nn.Linear)
+        self.shadow = self._alloc(self.total, dtype, self.device)
+        params = dict(self.module.named_parameters(remove_duplicate=False))
+        selected: set[int] = set()
+        for mod in self.module.modules():
+            if isinstance(mod, module_types):
+                selected.update(id(p) for p in mod.parameters(recurse=False))
+        for entry in self.entries:
+            if entry.kind == "buffer":
+                continue
+            param = params[entry.name]
+            if id(param) in selected:
+                param.data = self._shaped(self.shadow, entry)
+                self.shadow_names.add(entry.name)
+            param.grad = None
+        self.grad = None  # table mode: gradients live wherever autograd allocates them
+        self.refresh_shadow()
+        return self.shadow
+
+    @property
+    def params_end(self) -> int:
+        ends = [_round_up(e.end, ALIGN) for e in self.entries if e.kind != "buffer"]
+        return max(ends) if ends else 0
+
+    def refresh_shadow(self) -> None:
+        if self.shadow is None:
+            return
+        from fl4health_b200.ops import flat as flat_ops
+
+        end = self.params_end
+        with torch.no_grad():
+            flat_ops.cast_bf16(self.flat[:end], self.shadow[:end]) if self.shadow.dtype == torch.bfloat16 else self.shadow[
+                :end
+            ].copy_(self.flat[:end])
+
     def view(self, name: str, region: torch.Tensor | None = None) -> torch.Tensor:
         entry = self.by_name[self.aliases.get(name, name)]
         base = self.flat if region is None else region
@@ -244,6 +297,7 @@ class ParameterArena:
                     if key in self.int_state:
                         dst_int = self.int_state[key]
                         dst_int.copy_(_as_tensor(arr, self.device).to(dst_int.dtype).reshape(dst_int.shape))
+                self.refresh_shadow()
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
             for key, arr in zip(keys, arrays):
@@ -256,6 +310,7 @@ class ParameterArena:
                 else:
                     dst_int = self.int_state[key]
                     dst_int.copy_(t.to(dst_int.dtype).reshape(dst_int.shape))
+            self.refresh_shadow()
 
     def same_layout(self, other: ParameterArena) -> bool:
         return self.total == other.total and [(e.name, e.offset, e.numel, e.nhwc) for e in self.entries] == [

@@ -94,19 +94,25 @@ def test_adaptive_mu_rule() -> None:
     assert strategy.loss_weight == pytest.approx(0.0)  # floored at zero
 
 
-def test_fedprox_end_to_end() -> None:
+def _run_fedprox(client_cls=FedProxClient, engine=None, rounds: int = 3):  # noqa: ANN001, ANN202
     set_all_random_seeds(5)
-
-    clients = make_mixed_clients(FedProxClient, 2)
+    clients = make_mixed_clients(client_cls, 2, engine=engine)
     strategy = FedAvgWithAdaptiveConstraint(
         min_fit_clients=2, min_evaluate_clients=2, min_available_clients=2, on_fit_config_fn=fit_config_fn(),
         on_evaluate_config_fn=fit_config_fn(), fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
         evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn, initial_parameters=None,
         initial_loss_weight=0.1, adapt_loss_weight=True, loss_weight_delta=0.05, loss_weight_patience=1,
     )
-    server = FedProxServer(SimpleClientManager(), {"n_server_rounds": 3}, strategy,
+    server = FedProxServer(SimpleClientManager(), {"n_server_rounds": rounds}, strategy,
                            on_init_parameters_config_fn=fit_config_fn())
-    history = run_simulation(server, clients, 3)
+    history = run_simulation(server, clients, rounds)
+    history.strategy = strategy
+    return history, clients
+
+
+def test_fedprox_end_to_end() -> None:
+    history, clients = _run_fedprox()
+    strategy = history.strategy
     losses = [l for _, l in history.losses_distributed]
     assert losses[-1] < losses[0]
     assert isinstance(clients[0].optimizers["global"], _FlatOptimizer)

@@ -73,3 +73,22 @@ def test_bf16_channels_last_graph_trains():
     losses = [l for _, l in history.losses_distributed]
     assert losses[-1] < losses[0], losses
     assert clients[0]._train_runner.replays > 0
+
+
+def test_master_weights_graph_trains_like_autocast():
+    """bf16 master-weight mode (table optimizer, bf16 parameter views) tracks plain bf16 autocast training."""
+    auto = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16, channels_last=True)
+    master = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16, channels_last=True, master_weights=True)
+    h0, s0, _ = _run(auto, rounds=3, local_steps=12)
+    h1, s1, c1 = _run(master, rounds=3, local_steps=12)
+    opt = c1[0].optimizers["global"]
+    assert opt.table_mode and c1[0]._train_runner.replays > 0
+    losses = [l for _, l in h1.losses_distributed]
+    assert losses[-1] < losses[0], losses
+    for (_, a), (_, b) in zip(h0.losses_distributed, h1.losses_distributed):
+        assert abs(a - b) < 0.15 * max(abs(a), 1.0), (h0.losses_distributed, h1.losses_distributed)
+    # exchanged state is the fp32 master, and the compute shadow is its bf16 rounding
+    arena = opt.arena
+    name = next(iter(sorted(arena.shadow_names)))
+    assert arena.view(name).dtype == torch.float32
+    assert torch.allclose(arena.view(name, arena.shadow).float(), arena.view(name), atol=1e-2, rtol=1e-2)

@@ -200,3 +200,45 @@ def test_fused_masked_parameter_statistics_and_gradient():
     out.sum().backward()
     expected = 2.0 * p * p * (1 - p)
     assert torch.allclose(scores.grad, torch.full_like(scores, expected), atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("adam", [False, True])
+def test_multi_tensor_step_matches_reference(adam: bool) -> None:
+    """mt_optim.cu vs the per-slice PyTorch reference: mixed bf16/fp32 gradients, odd sizes, misaligned pointers."""
+    from fl4health_b200.ops import multi_tensor as MT
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    sizes = [5, 4096, 4097, 33, 70001, 8, 12289]
+    offsets, total = [], 0
+    for n in sizes:
+        offsets.append(total)
+        total = (total + n + 31) // 32 * 32
+    w = torch.randn(total, device=dev)
+    m1, m2 = torch.randn(total, device=dev) * 0.1, torch.rand(total, device=dev) * 0.01
+    anchor, cv = torch.randn(total, device=dev), torch.randn(total, device=dev) * 0.1
+    shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16)
+    grads = []
+    for i, n in enumerate(sizes):
+        dtype = torch.bfloat16 if i % 2 == 0 else torch.float32
+        store = torch.randn(n + 3, device=dev).to(dtype)
+        grads.append(store[1:1 + n] if i in (2, 3) else store[:n])  # entries 2,3: misaligned base pointers
+    hp = F.make_hyper_params(dev)
+    for slot, value in ((F.HP_LR, 0.05), (F.HP_MOM, 0.9), (F.HP_WD, 1e-2), (F.HP_MU, 0.3), (F.HP_B1, 0.9), (F.HP_B2, 0.99),
+                        (F.HP_EPS, 1e-8), (F.HP_STEP, 2.0), (F.HP_FIRST, 0.0), (F.HP_NESTEROV, 1.0)):
+        hp[slot] = value
+    ref = [t.detach().cpu().clone() for t in (w, m1, m2, anchor, cv, shadow, hp)]
+    entries = [MT.TableEntry(g, o, n) for g, o, n in zip(grads, offsets, sizes)]
+    MT.mt_step(entries, adam, w, m1, m2, hp, anchor, None if adam else cv, shadow)
+    torch.cuda.synchronize()
+    cpu_entries = [MT.TableEntry(g.detach().cpu(), o, n) for g, o, n in zip(grads, offsets, sizes)]
+    rw, rm1, rm2, ranchor, rcv, rshadow, rhp = ref
+    MT.mt_step_reference(cpu_entries, adam, rw, rm1, rm2, rhp, ranchor, None if adam else rcv, rshadow)
+    for o, n in zip(offsets, sizes):
+        assert torch.allclose(w[o:o + n].cpu(), rw[o:o + n], rtol=2e-5, atol=2e-6)
+        assert torch.allclose(m1[o:o + n].cpu(), rm1[o:o + n], rtol=2e-5, atol=2e-6)
+        assert torch.allclose(shadow[o:o + n].float().cpu(), rshadow[o:o + n].float(), rtol=1e-2, atol=1e-3)
+        if adam:
+            assert torch.allclose(m2[o:o + n].cpu(), rm2[o:o + n], rtol=2e-5, atol=1e-7)
+    assert float(hp[F.HP_STEP]) == (3.0 if adam else 2.0) and float(hp[F.HP_FIRST]) == 0.0
