@@ -37,6 +37,8 @@ class NDArrays(list):
     # second flat region for packed side payloads that are themselves arena-shaped (SCAFFOLD variates)
     aux_flat: torch.Tensor | None = None
     aux_layout: Any = None
+    # all integer entries (``num_batches_tracked`` ...) as one int64 tensor, in list order, when available
+    int_flat: torch.Tensor | None = None
 
     def __init__(self, iterable: Any = (), flat: torch.Tensor | None = None, layout: Any = None) -> None:
         super().__init__(iterable)
@@ -49,7 +51,7 @@ class NDArrays(list):
         part = NDArrays(list.__getitem__(self, slice(start, stop)))
         layout = self.layout
         if self.flat is not None and layout is not None and len(part) == len(layout.state_keys) and (start in (None, 0)):
-            part.flat, part.layout = self.flat, layout
+            part.flat, part.layout, part.int_flat = self.flat, layout, self.int_flat
         elif (
             self.aux_flat is not None and self.aux_layout is not None and layout is not None
             and start == len(layout.state_keys) and len(part) == len(self.aux_layout.state_keys)

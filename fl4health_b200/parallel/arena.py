@@ -267,6 +267,7 @@ class ParameterArena:
             cached = self._views_cache.get(cache_key)
             if cached is not None and cached.flat is base:
                 fresh = NDArrays(cached, flat=base, layout=self)  # shallow copy: callers may mutate the list
+                fresh.int_flat = self.int_flat if region is None else None
                 return fresh
         keys = list(names) if names is not None else self.state_keys
         out = NDArrays()
@@ -279,6 +280,7 @@ class ParameterArena:
         if names is None:
             out.flat = base
             out.layout = self
+            out.int_flat = self.int_flat if region is None else None
             if len(self._views_cache) > 8:
                 self._views_cache.pop(next(iter(self._views_cache)))
             self._views_cache[(base.data_ptr(), base.numel())] = NDArrays(out, flat=base, layout=self)
@@ -293,10 +295,15 @@ class ParameterArena:
             if names is None and src_flat is not None and isinstance(src_layout, ParameterArena) and src_layout.same_layout(self):
                 if src_flat.data_ptr() != self.flat.data_ptr():
                     self.flat.copy_(src_flat, non_blocking=True)
-                for key, arr in zip(keys, arrays):
-                    if key in self.int_state:
-                        dst_int = self.int_state[key]
-                        dst_int.copy_(_as_tensor(arr, self.device).to(dst_int.dtype).reshape(dst_int.shape))
+                src_int = getattr(arrays, "int_flat", None)
+                all_flat = self.int_flat is not None and all(t.dtype == torch.int64 for t in self.int_state.values())
+                if all_flat and src_int is not None and src_int.numel() == self.int_flat.numel():
+                    if src_int.data_ptr() != self.int_flat.data_ptr():
+                        self.int_flat.copy_(src_int, non_blocking=True)
+                else:
+                    for idx in self._int_positions():
+                        dst_int = self.int_state[self.aliases.get(keys[idx], keys[idx])]
+                        dst_int.copy_(_as_tensor(arrays[idx], self.device).to(dst_int.dtype).reshape(dst_int.shape))
                 self.refresh_shadow()
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
@@ -312,10 +319,22 @@ class ParameterArena:
                     dst_int.copy_(t.to(dst_int.dtype).reshape(dst_int.shape))
             self.refresh_shadow()
 
+    def _int_positions(self) -> list[int]:
+        cached = getattr(self, "_int_pos_cache", None)
+        if cached is None:
+            cached = [i for i, key in enumerate(self.state_keys) if self.aliases.get(key, key) in self.int_state]
+            self._int_pos_cache = cached
+        return cached
+
+    def _signature(self) -> tuple:
+        sig = getattr(self, "_sig_cache", None)
+        if sig is None:
+            sig = (self.total, tuple((e.name, e.offset, e.numel, e.nhwc) for e in self.entries))
+            self._sig_cache = sig
+        return sig
+
     def same_layout(self, other: ParameterArena) -> bool:
-        return self.total == other.total and [(e.name, e.offset, e.numel, e.nhwc) for e in self.entries] == [
-            (e.name, e.offset, e.numel, e.nhwc) for e in other.entries
-        ]
+        return other is self or self._signature() == other._signature()
 
     def range_of(self, names: Iterable[str]) -> list[tuple[int, int]]:
         """Merged (start, end) element ranges covering the given entries — the arena form of a layer subset."""

@@ -75,6 +75,7 @@ def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) 
             stacked = torch.stack([f.to(torch.float64) for f in int_flats])  # [K, n_int]
             weights = torch.tensor(list(coefficients), dtype=torch.float64, device=stacked.device).unsqueeze(1)
             merged = (stacked * weights).sum(dim=0).to(torch.int64)
+            out.int_flat = merged
             cursor = 0
             for idx, key in enumerate(layout.state_keys):
                 if key in layout.int_state:
@@ -82,6 +83,7 @@ def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) 
                     out[idx] = merged[cursor : cursor + numel].view(layout.int_state[key].shape)
                     cursor += numel
         else:
+            out.int_flat = None
             for idx, key in enumerate(layout.state_keys):
                 if key in layout.int_state:
                     out[idx] = _combine_layer([nds[idx] for nds in arrays], coefficients)
@@ -130,6 +132,7 @@ def _spmd_weighted_combine(
 
                 dist.all_reduce(ints)
             ints = ints.to(torch.int64)
+            out.int_flat = ints
             cursor = 0
             for i in int_idx:
                 numel = out[i].numel()
