@@ -11,6 +11,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from fl4health_b200.models.fused_layers import BatchNormAct2d, bn_act
+
 
 class BasicBlock(nn.Module):
     expansion = 1
@@ -18,21 +20,19 @@ class BasicBlock(nn.Module):
     def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
         super().__init__()
         self.conv1 = nn.Conv2d(in_planes, planes, 3, stride=stride, padding=1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = BatchNormAct2d(planes, relu=True)  # bn + relu fused
         self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BatchNormAct2d(planes, relu=True)  # bn + residual add + relu fused
         self.downsample: nn.Module | None = None
         if stride != 1 or in_planes != planes:
             self.downsample = nn.Sequential(
-                nn.Conv2d(in_planes, planes, 1, stride=stride, bias=False), nn.BatchNorm2d(planes)
+                nn.Conv2d(in_planes, planes, 1, stride=stride, bias=False), BatchNormAct2d(planes, relu=False)
             )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return self.relu(out + identity)
+        out = bn_act(self.bn1, self.conv1(x))
+        return bn_act(self.bn2, self.conv2(out), residual=identity)
 
 
 class ResNet18(nn.Module):
@@ -44,8 +44,7 @@ class ResNet18(nn.Module):
         else:
             self.conv1 = nn.Conv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)
             self.maxpool = nn.Identity()
-        self.bn1 = nn.BatchNorm2d(64)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = BatchNormAct2d(64, relu=True)
         widths, strides = (64, 128, 256, 512), (1, 2, 2, 2)
         in_planes = 64
         for idx, (planes, stride) in enumerate(zip(widths, strides), start=1):
@@ -58,7 +57,7 @@ class ResNet18(nn.Module):
                 nn.init.kaiming_normal_(module.weight, mode="fan_out", nonlinearity="relu")
 
     def forward_features(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.bn1, self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return torch.flatten(self.avgpool(x), 1)
 

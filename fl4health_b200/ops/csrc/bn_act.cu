@@ -1,0 +1,357 @@
+// Fused BatchNorm(+residual add)(+ReLU) for channels-last activations on sm_100a.
+//
+// ResNet-style FL clients at CIFAR scale are launch-latency bound: ATen runs ~10 kernels per BN layer and step
+// (collect stats, update running stats, transform, add, relu, num_batches_tracked += 1, and their backward twins).
+// Here a training forward is 2 kernels and a backward is 2 kernels, whatever the tail ops:
+//
+//   fwd  K1  per-channel shifted sums (shift = running_mean, kills the E[x^2]-E[x]^2 cancellation) reduced through
+//            smem -> fp32 RED atomics in L2; the last CTA to finish turns them into mean / invstd / scale / shift,
+//            updates running_mean / running_var / num_batches_tracked and re-zeroes the workspace
+//        K2  y = relu(x * scale + shift + residual)               (16-byte vectors of 8 channels)
+//   bwd  K3  g = dy * (y > 0);  sum(g), sum(g * xhat) -> last CTA writes dgamma, dbeta and dx coefficients
+//        K4  dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat));  dresidual = g
+//
+// Layout: x is [M, C] with C contiguous (NHWC storage), C % 8 == 0.  T is bf16 or fp32; statistics are fp32.
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T> struct Vec8;
+
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+            v[2 * k] = f.x;
+            v[2 * k + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
+
+// Shared tail of both reduction kernels: fold the per-thread pairs (a, b) over the CTA's rows, RED them into
+// acc[0..C) / acc[C..2C), and elect the last CTA.  Returns true in every thread of the last CTA.
+__device__ __forceinline__ bool reduce_and_elect(const float (&a)[8], const float (&b)[8], int C, int LP, int RP, int lane,
+                                                 int ty, float* acc, unsigned* counter, float* smem) {
+    if (ty < RP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            smem[(ty * 2 + 0) * C + lane * 8 + k] = a[k];
+            smem[(ty * 2 + 1) * C + lane * 8 + k] = b[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sa = 0.f, sb = 0.f;
+        for (int t = 0; t < RP; ++t) {
+            sa += smem[(t * 2 + 0) * C + c];
+            sb += smem[(t * 2 + 1) * C + c];
+        }
+        atomicAdd(acc + c, sa);
+        atomicAdd(acc + C + c, sb);
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_fwd_stats_kernel(const T* __restrict__ x, int64_t M, int C, int rows_per_cta, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* running_mean, float* running_var, int64_t* nbt,
+                    float momentum, float eps, float* mean_out, float* invstd_out, float* scale_shift, float* acc,
+                    unsigned* counter) {
+    extern __shared__ float smem[];
+    const int LP = C >> 3, RP = blockDim.x / LP;
+    const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
+    float shift[8], s[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; shift[k] = 0.f; }
+    if (running_mean != nullptr && ty < RP) load8f(running_mean + lane * 8, shift);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+    if (ty < RP) {
+        for (int64_t r = r0 + ty; r < r1; r += RP) {
+            float v[8];
+            Vec8<T>::load(x + r * C + lane * 8, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float d = v[k] - shift[k];
+                s[k] += d;
+                q[k] = fmaf(d, d, q[k]);
+            }
+        }
+    }
+    if (!reduce_and_elect(s, q, C, LP, RP, lane, ty, acc, counter, smem)) return;
+    const float inv_m = 1.f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sd = __ldcg(acc + c), sq = __ldcg(acc + C + c);
+        acc[c] = 0.f;
+        acc[C + c] = 0.f;
+        const float k0 = running_mean != nullptr ? running_mean[c] : 0.f;
+        const float md = sd * inv_m;
+        const float mean = k0 + md;
+        float var = fmaf(-md, md, sq * inv_m);
+        var = var > 0.f ? var : 0.f;
+        const float invstd = rsqrtf(var + eps);
+        mean_out[c] = mean;
+        invstd_out[c] = invstd;
+        const float sc = (gamma != nullptr ? gamma[c] : 1.f) * invstd;
+        scale_shift[c] = sc;
+        scale_shift[C + c] = (beta != nullptr ? beta[c] : 0.f) - mean * sc;
+        if (running_mean != nullptr) {
+            const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+            running_mean[c] = (1.f - momentum) * k0 + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    }
+    if (threadIdx.x == 0) {
+        *counter = 0u;
+        if (nbt != nullptr) *nbt += 1;
+    }
+}
+
+// mode 0: scale/shift precomputed in scale_shift[2][C];  mode 1 (eval): derive them from the running statistics.
+template <typename T, bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t nvec, int C,
+                const float* __restrict__ scale_shift, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int mode) {
+    const int LP = C >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % LP) * 8;
+        float sc[8], sh[8], v[8], r[8];
+        if (mode == 0) {
+            load8f(scale_shift + c0, sc);
+            load8f(scale_shift + C + c0, sh);
+        } else {
+            float g[8], b[8], m[8], var[8];
+            load8f(rmean + c0, m);
+            load8f(rvar + c0, var);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { g[k] = 1.f; b[k] = 0.f; }
+            if (gamma != nullptr) load8f(gamma + c0, g);
+            if (beta != nullptr) load8f(beta + c0, b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sc[k] = g[k] * rsqrtf(var[k] + eps);
+                sh[k] = b[k] - m[k] * sc[k];
+            }
+        }
+        Vec8<T>::load(x + i * 8, v);
+        if (kRes) Vec8<T>::load(res + i * 8, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float o = fmaf(v[k], sc[k], sh[k]);
+            if (kRes) o += r[k];
+            if (kRelu) o = o > 0.f ? o : 0.f;
+            v[k] = o;
+        }
+        Vec8<T>::store(y + i * 8, v);
+    }
+}
+
+template <typename T, bool kRelu>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, int64_t M, int C,
+                     int rows_per_cta, const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef, float* acc,
+                     unsigned* counter) {
+    extern __shared__ float smem[];
+    const int LP = C >> 3, RP = blockDim.x / LP;
+    const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
+    float sg[8], sgx[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; mu[k] = 0.f; is[k] = 0.f; }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+    if (ty < RP) {
+        load8f(mean + lane * 8, mu);
+        load8f(invstd + lane * 8, is);
+        for (int64_t r = r0 + ty; r < r1; r += RP) {
+            float g[8], xv[8], yv[8];
+            const int64_t off = r * C + lane * 8;
+            Vec8<T>::load(dy + off, g);
+            Vec8<T>::load(x + off, xv);
+            if (kRelu) Vec8<T>::load(y + off, yv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+                sg[k] += gi;
+                sgx[k] = fmaf(gi, (xv[k] - mu[k]) * is[k], sgx[k]);
+            }
+        }
+    }
+    if (!reduce_and_elect(sg, sgx, C, LP, RP, lane, ty, acc, counter, smem)) return;
+    const float inv_m = 1.f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float a = __ldcg(acc + c), b = __ldcg(acc + C + c);
+        acc[c] = 0.f;
+        acc[C + c] = 0.f;
+        if (dbeta != nullptr) dbeta[c] = a;
+        if (dgamma != nullptr) dgamma[c] = b;
+        coef[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd[c];  // a
+        coef[C + c] = a * inv_m;                                     // mean(g)
+        coef[2 * C + c] = b * inv_m;                                 // mean(g * xhat)
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+template <typename T, bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, T* __restrict__ dx,
+                    T* __restrict__ dres, int64_t nvec, int C, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ coef) {
+    const int LP = C >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % LP) * 8;
+        float mu[8], is[8], a[8], mg[8], mgx[8], g[8], xv[8], yv[8];
+        load8f(mean + c0, mu);
+        load8f(invstd + c0, is);
+        load8f(coef + c0, a);
+        load8f(coef + C + c0, mg);
+        load8f(coef + 2 * C + c0, mgx);
+        Vec8<T>::load(dy + i * 8, g);
+        Vec8<T>::load(x + i * 8, xv);
+        if (kRelu) Vec8<T>::load(y + i * 8, yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+            g[k] = gi;
+            xv[k] = a[k] * (gi - mg[k] - (xv[k] - mu[k]) * is[k] * mgx[k]);
+        }
+        Vec8<T>::store(dx + i * 8, xv);
+        if (kRes) Vec8<T>::store(dres + i * 8, g);
+    }
+}
+
+inline int reduce_grid(int64_t M, int C, int* rows_per_cta) {
+    const int LP = C / 8, RP = kThreads / LP;
+    int64_t rows = (int64_t)RP * 8;              // at least 8 rows per thread
+    const int64_t even = (M + 147) / 148;          // ... and no more than one CTA per SM
+    if (rows < even) rows = even;
+    rows = (rows + RP - 1) / RP * RP;
+    *rows_per_cta = (int)rows;
+    return (int)((M + rows - 1) / rows);
+}
+
+inline int apply_grid(int64_t nvec) {
+    int64_t g = (nvec + kThreads - 1) / kThreads;
+    const int64_t cap = 148 * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+#define FL4H_BN_DISPATCH(T, relu, res, ...)                                       \
+    do {                                                                           \
+        if (relu) { if (res) { __VA_ARGS__(T, true, true); } else { __VA_ARGS__(T, true, false); } } \
+        else      { if (res) { __VA_ARGS__(T, false, true); } else { __VA_ARGS__(T, false, false); } } \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int fl4h_bn_supported(int64_t M, int C) { return (C % 8 == 0 && C / 8 <= kThreads && M >= 1) ? 1 : 0; }
+
+// workspace (persistent, zero-initialised by the caller once): acc [2*C] fp32, counter [1] u32; scratch scale_shift [2*C].
+int fl4h_bn_fwd_train(const void* x, const void* res, void* y, int64_t M, int C, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, float* mean_out,
+                      float* invstd_out, float* scale_shift, float* acc, unsigned* counter, int is_bf16, int relu,
+                      cudaStream_t stream) {
+    int rows = 0;
+    const int grid = reduce_grid(M, C, &rows);
+    const size_t smem = (size_t)kThreads * 16 * sizeof(float);
+    const int64_t nvec = M * C / 8;
+    const bool has_res = res != nullptr;
+#define LAUNCH_FWD(T, R, S)                                                                                          \
+    bn_apply_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)x, (const T*)res, (T*)y, nvec, C, \
+        scale_shift, nullptr, nullptr, nullptr, nullptr, eps, 0)
+    if (is_bf16) {
+        bn_fwd_stats_kernel<__nv_bfloat16><<<grid, kThreads, smem, stream>>>((const __nv_bfloat16*)x, M, C, rows, gamma,
+            beta, running_mean, running_var, nbt, momentum, eps, mean_out, invstd_out, scale_shift, acc, counter);
+        FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, LAUNCH_FWD);
+    } else {
+        bn_fwd_stats_kernel<float><<<grid, kThreads, smem, stream>>>((const float*)x, M, C, rows, gamma, beta,
+            running_mean, running_var, nbt, momentum, eps, mean_out, invstd_out, scale_shift, acc, counter);
+        FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_FWD);
+    }
+#undef LAUNCH_FWD
+    return (int)cudaGetLastError();
+}
+
+int fl4h_bn_fwd_eval(const void* x, const void* res, void* y, int64_t M, int C, const float* gamma, const float* beta,
+                     const float* running_mean, const float* running_var, float eps, int is_bf16, int relu,
+                     cudaStream_t stream) {
+    const int64_t nvec = M * C / 8;
+    const bool has_res = res != nullptr;
+#define LAUNCH_EVAL(T, R, S)                                                                                         \
+    bn_apply_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)x, (const T*)res, (T*)y, nvec, C, \
+        nullptr, gamma, beta, running_mean, running_var, eps, 1)
+    if (is_bf16) FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, LAUNCH_EVAL);
+    else FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_EVAL);
+#undef LAUNCH_EVAL
+    return (int)cudaGetLastError();
+}
+
+int fl4h_bn_bwd(const void* dy, const void* y, const void* x, int64_t M, int C, const float* gamma, const float* mean,
+                const float* invstd, void* dx, void* dres, float* dgamma, float* dbeta, float* coef, float* acc,
+                unsigned* counter, int is_bf16, int relu, cudaStream_t stream) {
+    int rows = 0;
+    const int grid = reduce_grid(M, C, &rows);
+    const size_t smem = (size_t)kThreads * 16 * sizeof(float);
+    const int64_t nvec = M * C / 8;
+    const bool has_res = dres != nullptr;
+#define LAUNCH_BWD(T, R, S)                                                                                     \
+    bn_bwd_apply_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)dy, (const T*)y, (const T*)x, \
+        (T*)dx, (T*)dres, nvec, C, mean, invstd, coef)
+    if (is_bf16) {
+        if (relu) bn_bwd_reduce_kernel<__nv_bfloat16, true><<<grid, kThreads, smem, stream>>>((const __nv_bfloat16*)dy,
+            (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, M, C, rows, gamma, mean, invstd, dgamma, dbeta, coef, acc, counter);
+        else bn_bwd_reduce_kernel<__nv_bfloat16, false><<<grid, kThreads, smem, stream>>>((const __nv_bfloat16*)dy,
+            (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, M, C, rows, gamma, mean, invstd, dgamma, dbeta, coef, acc, counter);
+        FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, LAUNCH_BWD);
+    } else {
+        if (relu) bn_bwd_reduce_kernel<float, true><<<grid, kThreads, smem, stream>>>((const float*)dy, (const float*)y,
+            (const float*)x, M, C, rows, gamma, mean, invstd, dgamma, dbeta, coef, acc, counter);
+        else bn_bwd_reduce_kernel<float, false><<<grid, kThreads, smem, stream>>>((const float*)dy, (const float*)y,
+            (const float*)x, M, C, rows, gamma, mean, invstd, dgamma, dbeta, coef, acc, counter);
+        FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_BWD);
+    }
+#undef LAUNCH_BWD
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -242,3 +242,95 @@ def test_multi_tensor_step_matches_reference(adam: bool) -> None:
         if adam:
             assert torch.allclose(m2[o:o + n].cpu(), rm2[o:o + n], rtol=2e-5, atol=1e-7)
     assert float(hp[F.HP_STEP]) == (3.0 if adam else 2.0) and float(hp[F.HP_FIRST]) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False), (False, True)])
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (8, 512, 4, 4), (5, 24, 7, 3)])
+def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape) -> None:
+    """bn_act.cu (training fwd/bwd + eval fwd) vs F.batch_norm + add + relu in fp32."""
+    from fl4health_b200.ops.bn_act import batch_norm_act, batch_norm_act_reference, kernel_eligible
+
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    n, c, h, w = shape
+    x32 = (torch.randn(shape, device=dev) * 1.7 + 0.8).contiguous(memory_format=torch.channels_last)
+    r32 = torch.randn(shape, device=dev).contiguous(memory_format=torch.channels_last) if with_res else None
+    g32 = torch.randn(shape, device=dev).contiguous(memory_format=torch.channels_last)
+    x = x32.to(dtype).requires_grad_(True)
+    res = r32.to(dtype).requires_grad_(True) if with_res else None
+    weight = (torch.rand(c, device=dev) + 0.5).requires_grad_(True)
+    bias = torch.randn(c, device=dev).requires_grad_(True)
+    rm, rv, nbt = torch.randn(c, device=dev) * 0.1, torch.rand(c, device=dev) + 0.5, torch.tensor(3, device=dev)
+    assert kernel_eligible(x, res, 0.1, True, rm)
+    # reference in fp32 on the (rounded) inputs
+    xr = x.detach().float().requires_grad_(True)
+    rr = res.detach().float().requires_grad_(True) if with_res else None
+    wr, br = weight.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = batch_norm_act_reference(xr, wr, br, rm_ref, rv_ref, True, 0.1, 1e-5, rr, relu)
+    y_ref.backward(g32.to(dtype).float())
+    from fl4health_b200 import ops
+
+    before = ops.launch_count()
+    y = batch_norm_act(x, weight, bias, rm, rv, nbt, True, 0.1, 1e-5, residual=res, relu=relu)
+    y.backward(g32.to(dtype))
+    torch.cuda.synchronize()
+    assert ops.launch_count() - before == 4
+    tol = dict(rtol=2e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
+    assert torch.allclose(y.float(), y_ref, **tol)
+    assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    assert int(nbt) == 4
+    m = n * h * w
+    gtol = dict(rtol=3e-2, atol=3e-2 * (m ** 0.5) / 8) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=2e-3)
+    assert torch.allclose(x.grad.float(), xr.grad, **tol)
+    assert torch.allclose(weight.grad, wr.grad, **gtol), (weight.grad - wr.grad).abs().max()
+    assert torch.allclose(bias.grad, br.grad, **gtol)
+    if with_res:
+        assert torch.allclose(res.grad.float(), rr.grad, **tol)
+    # eval mode
+    y_eval = batch_norm_act(x.detach(), weight.detach(), bias.detach(), rm, rv, nbt, False, 0.1, 1e-5,
+                            residual=res.detach() if with_res else None, relu=relu)
+    y_eval_ref = batch_norm_act_reference(xr.detach(), wr.detach(), br.detach(), rm_ref, rv_ref, False, 0.1, 1e-5,
+                                          rr.detach() if with_res else None, relu)
+    assert torch.allclose(y_eval.float(), y_eval_ref, **tol)
+    assert int(nbt) == 4
+
+
+@pytest.mark.gpu
+def test_resnet_fused_bn_matches_stock_bn() -> None:
+    """Whole-model check: ResNet-18 with the fused BN path vs the same weights through the stock-op fallback."""
+    import fl4health_b200.ops.bn_act as bn_mod
+    from fl4health_b200.models import resnet18_cifar
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    model = resnet18_cifar().to(dev).to(memory_format=torch.channels_last)
+    x = torch.randn(16, 3, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
+    target = torch.randint(0, 10, (16,), device=dev)
+
+    def run(fused: bool):
+        model.zero_grad()
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        original = bn_mod.kernel_eligible
+        if not fused:
+            bn_mod.kernel_eligible = lambda *a, **k: False
+        try:
+            loss = torch.nn.functional.cross_entropy(model(x), target)
+            loss.backward()
+        finally:
+            bn_mod.kernel_eligible = original
+        grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        stats = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "tracked" in k}
+        model.load_state_dict(state)
+        return loss.item(), grads, stats
+
+    l0, g0, s0 = run(False)
+    l1, g1, s1 = run(True)
+    assert abs(l0 - l1) < 1e-4
+    for name in g0:
+        denom = g0[name].abs().max().clamp_min(1e-6)
+        assert ((g0[name] - g1[name]).abs().max() / denom) < 5e-3, name
+    for name in s0:
+        assert torch.allclose(s0[name].float(), s1[name].float(), rtol=1e-4, atol=1e-5), name
