@@ -1,7 +1,7 @@
 """Fused BatchNorm2d (+ residual add) (+ ReLU) for channels-last activations (kernels: ``csrc/bn_act.cu``).
 
-``batch_norm_act(x, bn_module_state..., residual, relu)`` is an autograd function whose training forward is two
-launches and whose backward is two launches; the stock composition (``F.batch_norm`` + ``add`` + ``relu`` and their
+``batch_norm_act(x, bn_module_state..., residual, relu)`` is an autograd function whose training forward is ONE
+cooperative launch (reduce -> grid barrier -> apply) and whose backward is one; the stock composition (``F.batch_norm`` + ``add`` + ``relu`` and their
 backward, plus the running-stat and ``num_batches_tracked`` updates) is ~10 launches per layer and step, which is what a
 CIFAR-scale ResNet client is bound by.  ``batch_norm_act_reference`` is that stock composition: the CPU path, the
 fallback for unsupported layouts, and the numerics oracle for the GPU tests.
@@ -10,6 +10,7 @@ fallback for unsupported layouts, and the numerics oracle for the GPU tests.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F_nn
@@ -17,15 +18,24 @@ import torch.nn.functional as F_nn
 from fl4health_b200.ops import _lib
 
 _WORKSPACES: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
+_ACC_STRIDE = 4096  # floats; must match kAccStride in bn_act.cu (supports C <= 2048)
+
+
+def _allow_fused() -> int:
+    """One cooperative kernel per direction (default) vs the two-kernel chain (``FL4H_BN_FUSED=0``, for A/B runs)."""
+    return 0 if os.environ.get("FL4H_BN_FUSED", "1") == "0" else 1
 
 
 def _workspace(device: torch.device, channels: int) -> tuple[torch.Tensor, torch.Tensor]:
     """Persistent zero-initialised accumulators + election counter (self-resetting: every kernel leaves them zero)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    assert 2 * channels <= _ACC_STRIDE
+    # one workspace per (device, stream): kernels of one stream serialise, so they can share accumulators
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACES.get(key)
-    if ws is None or ws[0].numel() < 2 * channels:
-        size = max(2 * channels, 4096)
-        ws = (torch.zeros(size, dtype=torch.float32, device=device), torch.zeros(4, dtype=torch.int32, device=device))
+    if ws is None:
+        # [2 x stride] double-buffered accumulators of the fused kernels + [stride] for the two-kernel fallback;
+        # counter[0] = last-CTA election, counter[1] = accumulator parity
+        ws = (torch.zeros(3 * _ACC_STRIDE, dtype=torch.float32, device=device), torch.zeros(4, dtype=torch.int32, device=device))
         _WORKSPACES[key] = ws
     return ws
 
@@ -80,10 +90,10 @@ class _BatchNormAct(torch.autograd.Function):
                 _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(nbt),
                 ctypes.c_float(momentum if momentum is not None else 0.0), ctypes.c_float(eps), _lib.ptr(stats[0]),
                 _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(acc), _lib.ptr(counter), ctypes.c_int(is_bf16),
-                ctypes.c_int(1 if relu else 0), stream,
+                ctypes.c_int(1 if relu else 0), ctypes.c_int(_allow_fused()), stream,
             )
             _lib.check(err, "fl4h_bn_fwd_train")
-            _lib.count_launches(2)
+            _lib.count_launches(1 if _allow_fused() else 2)
             ctx.save_for_backward(x, y, weight, stats)
             ctx.relu, ctx.has_res, ctx.has_bias = relu, residual is not None, bias is not None
         else:
@@ -127,10 +137,10 @@ class _BatchNormAct(torch.autograd.Function):
             _lib.ptr(dy), _lib.ptr(y), _lib.ptr(x), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(weight),
             _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(grads[0]), _lib.ptr(grads[1]),
             _lib.ptr(coef), _lib.ptr(acc), _lib.ptr(counter), ctypes.c_int(1 if x.dtype == torch.bfloat16 else 0),
-            ctypes.c_int(1 if ctx.relu else 0), _lib.stream_ptr(x.device),
+            ctypes.c_int(1 if ctx.relu else 0), ctypes.c_int(_allow_fused()), _lib.stream_ptr(x.device),
         )
         _lib.check(err, "fl4h_bn_bwd")
-        _lib.count_launches(2)
+        _lib.count_launches(1 if _allow_fused() else 2)
         dweight = grads[0] if weight is not None else None
         dbias = grads[1] if ctx.has_bias else None
         return dx, dres, dweight, dbias, None, None, None, None, None, None, None

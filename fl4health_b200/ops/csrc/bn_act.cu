@@ -11,11 +11,20 @@
 //   bwd  K3  g = dy * (y > 0);  sum(g), sum(g * xhat) -> last CTA writes dgamma, dbeta and dx coefficients
 //        K4  dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat));  dresidual = g
 //
+// On top of that, the default training path fuses each pair into ONE cooperative kernel (reduce -> grid barrier ->
+// apply): measured on B200 the two-kernel chain costs ~15 us per layer and direction regardless of tensor size (it is
+// a pure latency chain: load, smem reduce, RED + fence, election atomic, last-CTA epilogue, second launch), the fused
+// kernel replaces the fence/election/second launch by one grid barrier and keeps the forward tile in registers.
+// The two-kernel kernels remain as the fallback when a cooperative launch is not possible.
+//
 // Layout: x is [M, C] with C contiguous (NHWC storage), C % 8 == 0.  T is bf16 or fp32; statistics are fp32.
 
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -258,6 +267,241 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused cooperative kernels: reduce -> grid.sync() -> apply
+// workspace: acc2 = two accumulator buffers of kAccStride floats used alternately (the buffer of the previous launch is
+// re-zeroed by CTA 0 of the current one, so no extra barrier is needed for the reset); *parity selects the buffer.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAccStride = 4096;
+constexpr int kCacheRows = 8;
+
+__device__ __forceinline__ void red_partials(const float (&a)[8], const float (&b)[8], int C, int LP, int RP, int lane, int ty,
+                                             float* acc, float* smem) {
+    if (ty < RP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            smem[(ty * 2 + 0) * C + lane * 8 + k] = a[k];
+            smem[(ty * 2 + 1) * C + lane * 8 + k] = b[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sa = 0.f, sb = 0.f;
+        for (int t = 0; t < RP; ++t) {
+            sa += smem[(t * 2 + 0) * C + c];
+            sb += smem[(t * 2 + 1) * C + c];
+        }
+        atomicAdd(acc + c, sa);
+        atomicAdd(acc + C + c, sb);
+    }
+}
+
+template <typename T, bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t M, int C, int rows_per_cta,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                    float* running_var, int64_t* nbt, float momentum, float eps, float* mean_out, float* invstd_out,
+                    float* acc2, unsigned* parity) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float smem[];            // [4096] reduce scratch (later scale|shift) + [C] shift values
+    float* kshift = smem + 4096;
+    const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
+    float* acc = acc2 + par * kAccStride;
+    if (blockIdx.x == 0) {
+        float* other = acc2 + (par ^ 1u) * kAccStride;
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+    }
+    const int LP = C >> 3, RP = blockDim.x / LP;
+    const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) kshift[c] = running_mean != nullptr ? running_mean[c] : 0.f;
+    __syncthreads();
+    float shift[8], s[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; shift[k] = 0.f; }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+    const bool cached = rows_per_cta <= kCacheRows * RP;   // uniform: the whole tile stays in registers
+    float tile[kCacheRows][8];
+    if (ty < RP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) shift[k] = kshift[lane * 8 + k];
+        if (cached) {
+#pragma unroll
+            for (int it = 0; it < kCacheRows; ++it) {
+                const int64_t r = r0 + ty + (int64_t)it * RP;
+                if (r < r1) {
+                    Vec8<T>::load(x + r * C + lane * 8, tile[it]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float d = tile[it][k] - shift[k];
+                        s[k] += d;
+                        q[k] = fmaf(d, d, q[k]);
+                    }
+                }
+            }
+        } else {
+            for (int64_t r = r0 + ty; r < r1; r += RP) {
+                float v[8];
+                Vec8<T>::load(x + r * C + lane * 8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float d = v[k] - shift[k];
+                    s[k] += d;
+                    q[k] = fmaf(d, d, q[k]);
+                }
+            }
+        }
+    }
+    red_partials(s, q, C, LP, RP, lane, ty, acc, smem);
+    grid.sync();
+    const float inv_m = 1.f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sd = __ldcg(acc + c), sq = __ldcg(acc + C + c);
+        const float k0 = kshift[c];
+        const float md = sd * inv_m;
+        const float mean = k0 + md;
+        float var = fmaf(-md, md, sq * inv_m);
+        var = var > 0.f ? var : 0.f;
+        const float invstd = rsqrtf(var + eps);
+        const float sc = (gamma != nullptr ? gamma[c] : 1.f) * invstd;
+        smem[c] = sc;
+        smem[C + c] = (beta != nullptr ? beta[c] : 0.f) - mean * sc;
+        if (blockIdx.x == 0) {
+            mean_out[c] = mean;
+            invstd_out[c] = invstd;
+            if (running_mean != nullptr) {
+                const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+                running_mean[c] = (1.f - momentum) * k0 + momentum * mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+            }
+        }
+    }
+    __syncthreads();
+    if (ty < RP) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = smem[lane * 8 + k]; sh[k] = smem[C + lane * 8 + k]; }
+        if (cached) {
+#pragma unroll
+            for (int it = 0; it < kCacheRows; ++it) {
+                const int64_t r = r0 + ty + (int64_t)it * RP;
+                if (r < r1) {
+                    const int64_t off = r * C + lane * 8;
+                    float rr[8];
+                    if (kRes) Vec8<T>::load(res + off, rr);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float o = fmaf(tile[it][k], sc[k], sh[k]);
+                        if (kRes) o += rr[k];
+                        if (kRelu) o = o > 0.f ? o : 0.f;
+                        tile[it][k] = o;
+                    }
+                    Vec8<T>::store(y + off, tile[it]);
+                }
+            }
+        } else {
+            for (int64_t r = r0 + ty; r < r1; r += RP) {
+                const int64_t off = r * C + lane * 8;
+                float v[8], rr[8];
+                Vec8<T>::load(x + off, v);
+                if (kRes) Vec8<T>::load(res + off, rr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float o = fmaf(v[k], sc[k], sh[k]);
+                    if (kRes) o += rr[k];
+                    if (kRelu) o = o > 0.f ? o : 0.f;
+                    v[k] = o;
+                }
+                Vec8<T>::store(y + off, v);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *parity = par ^ 1u;
+        if (nbt != nullptr) *nbt += 1;
+    }
+}
+
+template <typename T, bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, T* __restrict__ dx,
+                    T* __restrict__ dres, int64_t M, int C, int rows_per_cta, const float* __restrict__ gamma,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                    float* acc2, unsigned* parity) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float smem[];            // max(4096, 3C) floats: reduce scratch, later a | mean(g) | mean(g xhat)
+    const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
+    float* acc = acc2 + par * kAccStride;
+    if (blockIdx.x == 0) {
+        float* other = acc2 + (par ^ 1u) * kAccStride;
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+    }
+    const int LP = C >> 3, RP = blockDim.x / LP;
+    const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
+    float sg[8], sgx[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; mu[k] = 0.f; is[k] = 0.f; }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+    if (ty < RP) {
+        load8f(mean + lane * 8, mu);
+        load8f(invstd + lane * 8, is);
+        for (int64_t r = r0 + ty; r < r1; r += RP) {
+            float g[8], xv[8], yv[8];
+            const int64_t off = r * C + lane * 8;
+            Vec8<T>::load(dy + off, g);
+            Vec8<T>::load(x + off, xv);
+            if (kRelu) Vec8<T>::load(y + off, yv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+                sg[k] += gi;
+                sgx[k] = fmaf(gi, (xv[k] - mu[k]) * is[k], sgx[k]);
+            }
+        }
+    }
+    red_partials(sg, sgx, C, LP, RP, lane, ty, acc, smem);
+    grid.sync();
+    const float inv_m = 1.f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float a = __ldcg(acc + c), b = __ldcg(acc + C + c);
+        smem[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd[c];
+        smem[C + c] = a * inv_m;
+        smem[2 * C + c] = b * inv_m;
+        if (blockIdx.x == 0) {
+            if (dbeta != nullptr) dbeta[c] = a;
+            if (dgamma != nullptr) dgamma[c] = b;
+        }
+    }
+    __syncthreads();
+    if (ty < RP) {
+        float a[8], mg[8], mgx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a[k] = smem[lane * 8 + k];
+            mg[k] = smem[C + lane * 8 + k];
+            mgx[k] = smem[2 * C + lane * 8 + k];
+        }
+        for (int64_t r = r0 + ty; r < r1; r += RP) {   // second read of the tile comes from L2
+            float g[8], xv[8], yv[8];
+            const int64_t off = r * C + lane * 8;
+            Vec8<T>::load(dy + off, g);
+            Vec8<T>::load(x + off, xv);
+            if (kRelu) Vec8<T>::load(y + off, yv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+                g[k] = gi;
+                xv[k] = a[k] * (gi - mg[k] - (xv[k] - mu[k]) * is[k] * mgx[k]);
+            }
+            Vec8<T>::store(dx + off, xv);
+            if (kRes) Vec8<T>::store(dres + off, g);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *parity = par ^ 1u;
+}
+
 inline int reduce_grid(int64_t M, int C, int* rows_per_cta) {
     const int LP = C / 8, RP = kThreads / LP;
     int64_t rows = (int64_t)RP * 8;              // at least 8 rows per thread
@@ -287,15 +531,33 @@ extern "C" {
 int fl4h_bn_supported(int64_t M, int C) { return (C % 8 == 0 && C / 8 <= kThreads && M >= 1) ? 1 : 0; }
 
 // workspace (persistent, zero-initialised by the caller once): acc [2*C] fp32, counter [1] u32; scratch scale_shift [2*C].
+// `acc` layout: [0, 2*kAccStride) double-buffered accumulators of the fused kernels, [2*kAccStride, 3*kAccStride) the
+// accumulator of the two-kernel fallback.  counter[0] = election counter (fallback), counter[1] = buffer parity (fused).
 int fl4h_bn_fwd_train(const void* x, const void* res, void* y, int64_t M, int C, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, float* mean_out,
                       float* invstd_out, float* scale_shift, float* acc, unsigned* counter, int is_bf16, int relu,
-                      cudaStream_t stream) {
+                      int allow_fused, cudaStream_t stream) {
     int rows = 0;
     const int grid = reduce_grid(M, C, &rows);
     const size_t smem = (size_t)kThreads * 16 * sizeof(float);
     const int64_t nvec = M * C / 8;
     const bool has_res = res != nullptr;
+    if (allow_fused) {
+        unsigned* parity = counter + 1;
+        void* kargs[] = {(void*)&x, (void*)&res, (void*)&y, (void*)&M, (void*)&C, (void*)&rows, (void*)&gamma, (void*)&beta,
+                         (void*)&running_mean, (void*)&running_var, (void*)&nbt, (void*)&momentum, (void*)&eps,
+                         (void*)&mean_out, (void*)&invstd_out, (void*)&acc, (void*)&parity};
+        const size_t fsmem = (size_t)(4096 + C) * sizeof(float);
+        const void* fn = nullptr;
+#define PICK_FWD(T, R, S) fn = (const void*)bn_fwd_fused_kernel<T, R, S>
+        if (is_bf16) FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, PICK_FWD);
+        else FL4H_BN_DISPATCH(float, relu, has_res, PICK_FWD);
+#undef PICK_FWD
+        cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), kargs, fsmem, stream);
+        if (err == cudaSuccess) return 0;
+        (void)cudaGetLastError();  // not launchable cooperatively right now: use the two-kernel path below
+    }
+    acc += 2 * kAccStride;
 #define LAUNCH_FWD(T, R, S)                                                                                          \
     bn_apply_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)x, (const T*)res, (T*)y, nvec, C, \
         scale_shift, nullptr, nullptr, nullptr, nullptr, eps, 0)
@@ -328,12 +590,27 @@ int fl4h_bn_fwd_eval(const void* x, const void* res, void* y, int64_t M, int C, 
 
 int fl4h_bn_bwd(const void* dy, const void* y, const void* x, int64_t M, int C, const float* gamma, const float* mean,
                 const float* invstd, void* dx, void* dres, float* dgamma, float* dbeta, float* coef, float* acc,
-                unsigned* counter, int is_bf16, int relu, cudaStream_t stream) {
+                unsigned* counter, int is_bf16, int relu, int allow_fused, cudaStream_t stream) {
     int rows = 0;
     const int grid = reduce_grid(M, C, &rows);
     const size_t smem = (size_t)kThreads * 16 * sizeof(float);
     const int64_t nvec = M * C / 8;
     const bool has_res = dres != nullptr;
+    if (allow_fused) {
+        unsigned* parity = counter + 1;
+        void* kargs[] = {(void*)&dy, (void*)&y, (void*)&x, (void*)&dx, (void*)&dres, (void*)&M, (void*)&C, (void*)&rows,
+                         (void*)&gamma, (void*)&mean, (void*)&invstd, (void*)&dgamma, (void*)&dbeta, (void*)&acc, (void*)&parity};
+        const size_t fsmem = (size_t)(3 * C > 4096 ? 3 * C : 4096) * sizeof(float);
+        const void* fn = nullptr;
+#define PICK_BWD(T, R, S) fn = (const void*)bn_bwd_fused_kernel<T, R, S>
+        if (is_bf16) FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, PICK_BWD);
+        else FL4H_BN_DISPATCH(float, relu, has_res, PICK_BWD);
+#undef PICK_BWD
+        cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), kargs, fsmem, stream);
+        if (err == cudaSuccess) return 0;
+        (void)cudaGetLastError();
+    }
+    acc += 2 * kAccStride;
 #define LAUNCH_BWD(T, R, S)                                                                                     \
     bn_bwd_apply_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)dy, (const T*)y, (const T*)x, \
         (T*)dx, (T*)dres, nvec, C, mean, invstd, coef)

@@ -247,10 +247,14 @@ def test_multi_tensor_step_matches_reference(adam: bool) -> None:
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False), (False, True)])
-@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (8, 512, 4, 4), (5, 24, 7, 3)])
-def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape) -> None:
-    """bn_act.cu (training fwd/bwd + eval fwd) vs F.batch_norm + add + relu in fp32."""
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (8, 512, 4, 4), (5, 24, 7, 3), (64, 64, 32, 32)])
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape, fused, monkeypatch) -> None:
+    """bn_act.cu (training fwd/bwd + eval fwd) vs F.batch_norm + add + relu in fp32; ``fused`` selects the one-kernel
+    cooperative path or the two-kernel chain; the last shape exceeds the register-cached tile size."""
     from fl4health_b200.ops.bn_act import batch_norm_act, batch_norm_act_reference, kernel_eligible
+
+    monkeypatch.setenv("FL4H_BN_FUSED", fused)
 
     torch.manual_seed(1)
     dev = torch.device("cuda")
@@ -277,7 +281,7 @@ def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape) -> 
     y = batch_norm_act(x, weight, bias, rm, rv, nbt, True, 0.1, 1e-5, residual=res, relu=relu)
     y.backward(g32.to(dtype))
     torch.cuda.synchronize()
-    assert ops.launch_count() - before == 4
+    assert ops.launch_count() - before == (2 if fused == "1" else 4)  # launches per fwd+bwd
     tol = dict(rtol=2e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
     assert torch.allclose(y.float(), y_ref, **tol)
     assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
@@ -306,6 +310,10 @@ def test_resnet_fused_bn_matches_stock_bn() -> None:
 
     torch.manual_seed(0)
     dev = torch.device("cuda")
+    # TF32 convolutions round their inputs to 10 mantissa bits: 1e-7 differences between the two BN paths would be
+    # amplified to 1e-3 per layer and drown the comparison
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = False, False
     model = resnet18_cifar().to(dev).to(memory_format=torch.channels_last)
     x = torch.randn(16, 3, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
     target = torch.randint(0, 10, (16,), device=dev)
@@ -326,11 +334,14 @@ def test_resnet_fused_bn_matches_stock_bn() -> None:
         model.load_state_dict(state)
         return loss.item(), grads, stats
 
-    l0, g0, s0 = run(False)
-    l1, g1, s1 = run(True)
+    try:
+        l0, g0, s0 = run(False)
+        l1, g1, s1 = run(True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     assert abs(l0 - l1) < 1e-4
-    for name in g0:
-        denom = g0[name].abs().max().clamp_min(1e-6)
-        assert ((g0[name] - g1[name]).abs().max() / denom) < 5e-3, name
+    errors = {name: float((g0[name] - g1[name]).abs().max() / g0[name].abs().max().clamp_min(1e-6)) for name in g0}
+    worst = sorted(errors.items(), key=lambda kv: -kv[1])[:5]
+    assert worst[0][1] < 5e-3, worst
     for name in s0:
         assert torch.allclose(s0[name].float(), s1[name].float(), rtol=1e-4, atol=1e-5), name
