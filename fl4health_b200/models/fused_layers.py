@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from fl4health_b200.engine import streams
 from fl4health_b200.ops.bn_act import batch_norm_act
 
 
@@ -41,3 +42,50 @@ def bn_act(bn: nn.Module, x: torch.Tensor, residual: torch.Tensor | None = None,
     if residual is not None:
         out = out + residual
     return torch.relu(out) if relu else out
+
+
+class _ConvOverlappedWgrad(torch.autograd.Function):
+    """``conv2d`` whose backward issues the data gradient on the current stream (critical path) and the weight
+    gradient on a side stream (only the optimizer needs it); see ``engine/streams.py``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):  # noqa: ANN001, ANN205
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (stride, padding, dilation, groups, None if bias is None else list(bias.shape))
+        return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, grad_out):  # noqa: ANN001, ANN205
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, bias_sizes = ctx.conf
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], bias_sizes is not None and ctx.needs_input_grad[2]
+        zeros = [0] * len(stride)
+        grad_w = grad_b = grad_x = None
+        if need_w or need_b:
+            main = torch.cuda.current_stream(x.device)
+            side = streams.fork(x.device)
+            with torch.cuda.stream(side):
+                _, grad_w, grad_b = torch.ops.aten.convolution_backward(
+                    grad_out, x, weight, bias_sizes, stride, padding, dilation, False, zeros, groups, [False, need_w, need_b])
+            for g in (grad_w, grad_b):
+                if g is not None:
+                    g.record_stream(main)  # produced on the side stream, consumed (and freed) on the main stream
+            streams.defer_join(x.device, grad_out, x, weight)
+        if need_x:
+            grad_x, _, _ = torch.ops.aten.convolution_backward(
+                grad_out, x, weight, bias_sizes, stride, padding, dilation, False, zeros, groups, [True, False, False])
+        return grad_x, grad_w, grad_b, None, None, None, None
+
+
+class Conv2dOverlapWgrad(nn.Conv2d):
+    """``nn.Conv2d`` (same parameters / state-dict) whose weight-gradient kernel overlaps the rest of the backward
+    pass on CUDA.  Falls back to the stock op whenever the fast path's assumptions do not hold."""
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002
+        if (
+            input.is_cuda and torch.is_grad_enabled() and self.padding_mode == "zeros" and streams.overlap_enabled()
+            and not isinstance(self.padding, str) and input.dtype == self.weight.dtype
+            and (self.weight.requires_grad or input.requires_grad)
+        ):
+            return _ConvOverlappedWgrad.apply(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return super().forward(input)

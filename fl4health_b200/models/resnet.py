@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from fl4health_b200.models.fused_layers import BatchNormAct2d, bn_act
+from fl4health_b200.models.fused_layers import BatchNormAct2d, Conv2dOverlapWgrad, bn_act
 
 
 class BasicBlock(nn.Module):
@@ -19,14 +19,14 @@ class BasicBlock(nn.Module):
 
     def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
         super().__init__()
-        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv1 = Conv2dOverlapWgrad(in_planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn1 = BatchNormAct2d(planes, relu=True)  # bn + relu fused
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=1, bias=False)
+        self.conv2 = Conv2dOverlapWgrad(planes, planes, 3, stride=1, padding=1, bias=False)
         self.bn2 = BatchNormAct2d(planes, relu=True)  # bn + residual add + relu fused
         self.downsample: nn.Module | None = None
         if stride != 1 or in_planes != planes:
             self.downsample = nn.Sequential(
-                nn.Conv2d(in_planes, planes, 1, stride=stride, bias=False), BatchNormAct2d(planes, relu=False)
+                Conv2dOverlapWgrad(in_planes, planes, 1, stride=stride, bias=False), BatchNormAct2d(planes, relu=False)
             )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -39,10 +39,10 @@ class ResNet18(nn.Module):
     def __init__(self, num_classes: int = 10, in_channels: int = 3, imagenet_stem: bool = False) -> None:
         super().__init__()
         if imagenet_stem:
-            self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
+            self.conv1 = Conv2dOverlapWgrad(in_channels, 64, 7, stride=2, padding=3, bias=False)
             self.maxpool: nn.Module = nn.MaxPool2d(3, stride=2, padding=1)
         else:
-            self.conv1 = nn.Conv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)
+            self.conv1 = Conv2dOverlapWgrad(in_channels, 64, 3, stride=1, padding=1, bias=False)
             self.maxpool = nn.Identity()
         self.bn1 = BatchNormAct2d(64, relu=True)
         widths, strides = (64, 128, 256, 512), (1, 2, 2, 2)
