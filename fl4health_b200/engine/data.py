@@ -6,8 +6,11 @@ The reference feeds clients with ``DataLoader(num_workers=0, pin_memory=False)``
 ``BatchedTensorLoader`` therefore:
 
 * gathers a whole batch with one ``index_select`` (no per-sample Python);
-* ``placement="pinned"``: keeps the dataset in page-locked host memory and stages each batch into a ring of pinned
-  buffers so the engine's H2D copy is asynchronous and overlaps the previous step;
+* ``placement="pinned"``: keeps the dataset in page-locked host memory.  Shuffled epochs are materialised ONCE per
+  epoch (one permuted gather into a second pinned buffer, prepared by a background thread while the previous epoch is
+  being consumed) and batches are contiguous *views* of that buffer: no per-batch gather, no staging copy, and the
+  engine's H2D copy is asynchronous.  (Measured on the B200 box: a per-batch ``index_select`` of 32 CIFAR rows from
+  pinned memory costs ~1 ms of host time -- more than the whole GPU training step.)
 * ``placement="device"``: keeps the whole dataset resident in HBM — batches never touch the host;
 * exposes ``dataset`` / ``batch_size`` / ``__len__`` like a ``DataLoader`` so ``BasicClient`` code is unchanged.
 """
@@ -15,6 +18,7 @@ The reference feeds clients with ``DataLoader(num_workers=0, pin_memory=False)``
 from __future__ import annotations
 
 from collections.abc import Iterator
+from concurrent.futures import Future, ThreadPoolExecutor
 
 import torch
 
@@ -44,6 +48,12 @@ class BatchedTensorLoader:
         self._ring_size = ring
         self._ring: list[tuple[torch.Tensor, torch.Tensor]] = []
         self._ring_pos = 0
+        # epoch-level shuffling (host / pinned placements): two epoch buffers, the next one filled in the background
+        self._epoch_bufs: list[tuple[torch.Tensor, torch.Tensor] | None] = [None, None]
+        self._epoch_next: tuple[int, Future] | None = None
+        self._epoch_pool: ThreadPoolExecutor | None = None
+        self._epoch_done: dict[int, torch.cuda.Event] = {}  # H2D copies out of an epoch buffer have been enqueued
+        self.max_epoch_buffer_bytes = 8 << 30
         if placement == "device":
             assert self.device is not None, "device placement needs a device"
             dataset.data = dataset.data.to(self.device)
@@ -76,7 +86,77 @@ class BatchedTensorLoader:
         slot_t.copy_(target)
         return slot_d, slot_t
 
+    # ------------------------------------------------------------------------------------------------------
+    def _plain(self) -> bool:
+        """True when batches are exactly ``apply_transforms(data[idx], targets[idx])`` (no dataset-level override)."""
+        ds = self.dataset
+        return (
+            type(ds).get_batch is TensorDataset.get_batch and getattr(ds, "targets", None) is not None
+            and isinstance(ds.data, torch.Tensor) and isinstance(ds.targets, torch.Tensor)
+        )
+
+    def _epoch_mode(self) -> bool:
+        if not (self.shuffle and self.placement in ("host", "pinned") and self._plain()):
+            return False
+        ds = self.dataset
+        nbytes = ds.data.numel() * ds.data.element_size()
+        return len(self) >= 8 and nbytes <= self.max_epoch_buffer_bytes
+
+    def _fill_epoch(self, slot: int, perm: torch.Tensor) -> int:
+        ds = self.dataset
+        bufs = self._epoch_bufs[slot]
+        if bufs is None or bufs[0].shape != ds.data.shape or bufs[0].dtype != ds.data.dtype:
+            pin = self.placement == "pinned" and torch.cuda.is_available()
+            data_buf, target_buf = torch.empty_like(ds.data), torch.empty_like(ds.targets)
+            bufs = (data_buf.pin_memory(), target_buf.pin_memory()) if pin else (data_buf, target_buf)
+            self._epoch_bufs[slot] = bufs
+        done = self._epoch_done.pop(slot, None)
+        if done is not None:
+            done.synchronize()  # asynchronous H2D copies may still be reading this buffer's previous contents
+        torch.index_select(ds.data, 0, perm, out=bufs[0])
+        torch.index_select(ds.targets, 0, perm, out=bufs[1])
+        return slot
+
+    def _iter_epoch_buffered(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
+        n = len(self.dataset)
+        if self._epoch_pool is None:
+            self._epoch_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fl4h-epoch")
+        if self._epoch_next is not None:
+            slot = self._epoch_next[1].result()
+        else:
+            slot = self._fill_epoch(0, torch.randperm(n, generator=self.generator))
+        # permutations are drawn on the caller's thread (deterministic RNG consumption); only the gather is offloaded
+        upcoming = torch.randperm(n, generator=self.generator)
+        self._epoch_next = (1 - slot, self._epoch_pool.submit(self._fill_epoch, 1 - slot, upcoming))
+        data, targets = self._epoch_bufs[slot]  # type: ignore[misc]
+        try:
+            for start in range(0, n, self.batch_size):
+                stop = min(start + self.batch_size, n)
+                if stop - start < self.batch_size and self.drop_last:
+                    return
+                yield self.dataset.apply_transforms(data[start:stop], targets[start:stop])
+        finally:
+            if self.placement == "pinned" and torch.cuda.is_available():
+                event = torch.cuda.Event()
+                event.record()
+                self._epoch_done[slot] = event
+
+    def _iter_sequential(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
+        ds, n = self.dataset, len(self.dataset)
+        for start in range(0, n, self.batch_size):
+            stop = min(start + self.batch_size, n)
+            if stop - start < self.batch_size and self.drop_last:
+                return
+            yield ds.apply_transforms(ds.data[start:stop], ds.targets[start:stop])
+
     def __iter__(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
+        if not self.shuffle and self._plain():
+            return self._iter_sequential()  # contiguous views: zero-copy for every placement
+        if self._epoch_mode():
+            return self._iter_epoch_buffered()
+        return self._iter_gathered()
+
+    def _iter_gathered(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
         n = len(self.dataset)
         index_device = self.dataset.data.device if self.placement == "device" else torch.device("cpu")
         if self.shuffle:

@@ -22,6 +22,7 @@ import torch
 from torch import nn
 from torch.optim import Optimizer
 
+from fl4health_b200.engine import streams
 from fl4health_b200.ops import flat as F
 from fl4health_b200.ops import multi_tensor as MT
 from fl4health_b200.parallel.arena import ALIGN, ParameterArena, _round_up
@@ -199,6 +200,8 @@ class FlatSGD(_FlatOptimizer):
     @torch.no_grad()
     def step(self, closure: Any = None) -> Any:  # type: ignore[override]
         loss = closure() if closure is not None else None
+        if streams.pending_count():  # gradients produced on the side stream (normally joined at the end of backward)
+            streams.join()
         if not _capturing():
             self.sync_hyperparams()
             self._ensure_grad_views()
@@ -263,6 +266,8 @@ class FlatAdamW(_FlatOptimizer):
     @torch.no_grad()
     def step(self, closure: Any = None) -> Any:  # type: ignore[override]
         loss = closure() if closure is not None else None
+        if streams.pending_count():
+            streams.join()
         if not _capturing():
             self.sync_hyperparams()
             self._ensure_grad_views()

@@ -20,27 +20,37 @@ from typing import Any
 
 import torch
 
-_STATE = threading.local()
+_LOCK = threading.Lock()
+
+
+class _State:
+    """Process-wide (NOT thread-local): backward nodes run on the autograd engine's device thread while the engine's
+    final callback -- and the optimizer -- run on the thread that called ``backward()``."""
+
+    def __init__(self) -> None:
+        self.side: dict[int, torch.cuda.Stream] = {}
+        self.pending: list[tuple[torch.device, torch.cuda.Event, tuple[Any, ...]]] = []
+        self.callback_queued = False
+
+
+_STATE = _State()
 
 
 def overlap_enabled() -> bool:
     return os.environ.get("FL4H_OVERLAP_WGRAD", "1") != "0"
 
 
-def _state() -> Any:
-    if not hasattr(_STATE, "side"):
-        _STATE.side = {}
-        _STATE.pending = []
-        _STATE.callback_queued = False
+def _state() -> _State:
     return _STATE
 
 
 def side_stream(device: torch.device) -> torch.cuda.Stream:
     st = _state()
     index = device.index if device.index is not None else torch.cuda.current_device()
-    if index not in st.side:
-        st.side[index] = torch.cuda.Stream(device=device)
-    return st.side[index]
+    with _LOCK:
+        if index not in st.side:
+            st.side[index] = torch.cuda.Stream(device=device)
+        return st.side[index]
 
 
 def fork(device: torch.device) -> torch.cuda.Stream:
@@ -55,18 +65,26 @@ def defer_join(device: torch.device, *keepalive: Any) -> None:
     st = _state()
     event = torch.cuda.Event()
     event.record(side_stream(device))
-    st.pending.append((device, event, keepalive))
-    if not st.callback_queued:
+    with _LOCK:
+        st.pending.append((device, event, keepalive))
+        need_callback = not st.callback_queued
+        st.callback_queued = True
+    if need_callback:
         try:
             torch.autograd.Variable._execution_engine.queue_callback(join)  # runs when this backward pass finishes
-            st.callback_queued = True
         except RuntimeError:  # not inside a backward pass: the caller joins explicitly
-            pass
+            with _LOCK:
+                st.callback_queued = False
 
 
 def join() -> None:
     st = _state()
-    st.callback_queued = False
-    pending, st.pending = st.pending, []
+    with _LOCK:
+        st.callback_queued = False
+        pending, st.pending = st.pending, []
     for device, event, _ in pending:
         torch.cuda.current_stream(device).wait_event(event)
+
+
+def pending_count() -> int:
+    return len(_state().pending)

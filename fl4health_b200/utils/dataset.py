@@ -63,7 +63,10 @@ class TensorDataset(BaseDataset):
 
     def get_batch(self, indices: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         assert self.targets is not None
-        data, target = self.data.index_select(0, indices), self.targets.index_select(0, indices)
+        return self.apply_transforms(self.data.index_select(0, indices), self.targets.index_select(0, indices))
+
+    def apply_transforms(self, data: torch.Tensor, target: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Transforms of an already gathered ``[B, ...]`` batch (the loader gathers whole epochs at once)."""
         if self.batch_transform is not None:
             data = self.batch_transform(data)
         elif self.transform is not None:
