@@ -8,6 +8,7 @@ from torch import nn
 
 from fl4health_b200.engine import streams
 from fl4health_b200.ops.bn_act import batch_norm_act
+from fl4health_b200.ops.tc_gemm import linear_bias_act
 
 
 class BatchNormAct2d(nn.BatchNorm2d):
@@ -89,3 +90,20 @@ class Conv2dOverlapWgrad(nn.Conv2d):
         ):
             return _ConvOverlappedWgrad.apply(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
         return super().forward(input)
+
+
+class LinearAct(nn.Linear):
+    """``nn.Linear`` (+ optional fused ReLU) whose bf16 CUDA forward is the hand-written tcgen05 / TMEM / TMA GEMM with
+    the bias + activation epilogue (``ops/csrc/tc_gemm.cu``); identical parameters and state-dict keys."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, relu: bool = False, device=None, dtype=None) -> None:  # noqa: ANN001
+        super().__init__(in_features, out_features, bias, device=device, dtype=dtype)
+        self.relu = relu
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002
+        if torch.is_autocast_enabled() and input.is_cuda and input.dtype != self.weight.dtype == torch.bfloat16:
+            input = input.to(torch.bfloat16)  # master-weight mode: weights already bf16, activations follow autocast
+        return linear_bias_act(input, self.weight, self.bias, self.relu)
+
+    def extra_repr(self) -> str:
+        return super().extra_repr() + f", relu={self.relu}"

@@ -1,0 +1,256 @@
+// Fused Linear forward on the 5th-generation tensor cores:  C[M,N] = act(A[M,K] . W[N,K]^T + bias)   (bf16 in, fp32
+// accumulate, bf16 out) -- hand-written tcgen05 / TMEM / TMA kernel for sm_100a.
+//
+//   * operands: A (activations) and W (nn.Linear weight) are both K-major, so one TMA tensor map each with a
+//     [128 rows x 64 bf16] box and the 128-byte swizzle lands tiles in shared memory in exactly the canonical
+//     K-major SWIZZLE_128B layout tcgen05.mma consumes (no smem re-layout, no register staging);
+//   * pipeline: kStages-deep ring of (A, W) tiles guarded by full/empty mbarriers; warp 0 (one lane) is the TMA
+//     producer, warp 1 (one lane) issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128x128x16, 4 per 64-wide K block)
+//     and releases ring slots with tcgen05.commit; the fp32 accumulator tile (128 lanes x 128 columns) lives in
+//     TMEM (allocated by warp 2);
+//   * epilogue: warps 4-7 wait on the accumulator-full mbarrier, pull their 32-lane quarter out of TMEM with
+//     tcgen05.ld.32x32b.x32 (one output row per thread, 32 columns per instruction), add the bias, apply the optional
+//     ReLU, convert to bf16 and store 64-byte row segments.
+//
+// One CTA per 128x128 output tile; ragged M / N / K edges are handled by TMA zero fill on loads and guards on stores.
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB per operand tile
+constexpr int kTmemCols = BN;                           // fp32 accumulator: one column per output column
+constexpr int kSmemBytes = 2 * kStages * kTileBytes + 256 + 1024;  // tiles + barriers + 1024 B alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1 (sm_100) |
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    desc |= static_cast<uint64_t>(1) << 16;
+    desc |= static_cast<uint64_t>(1024 >> 4) << 32;
+    desc |= static_cast<uint64_t>(1) << 46;
+    desc |= static_cast<uint64_t>(2) << 61;
+    return desc;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both operands K-major.
+__host__ __device__ constexpr uint32_t make_instr_desc() {
+    return (1u << 4)                    // c_format  = F32
+           | (1u << 7)                  // a_format  = BF16
+           | (1u << 10)                 // b_format  = BF16
+           | (0u << 15) | (0u << 16)    // a_major = b_major = K
+           | (uint32_t(BN >> 3) << 17)  // n_dim
+           | (uint32_t(BM >> 4) << 24); // m_dim
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 __nv_bfloat16* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * kTileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+    const int num_k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // whole warp: allocate the accumulator columns, publish the base address through smem
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int stage = kb % kStages;
+                const uint32_t phase = (kb / kStages) & 1;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_expect_tx(full_bar + stage, 2 * kTileBytes);
+                tma_load_2d(smem_a + stage * kTileBytes, &tma_a, kb * BK, m_blk * BM, full_bar + stage);
+                tma_load_2d(smem_b + stage * kTileBytes, &tma_b, kb * BK, n_blk * BN, full_bar + stage);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer (single thread) =====
+            constexpr uint32_t idesc = make_instr_desc();
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int stage = kb % kStages;
+                const uint32_t phase = (kb / kStages) & 1;
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem_a + stage * kTileBytes);
+                const uint32_t b_addr = smem_u32(smem_b + stage * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advancing K inside the 128-byte swizzle atom = advancing the start address by 32 bytes
+                    const uint64_t desc_a = make_smem_desc(a_addr + k * UMMA_K * 2);
+                    const uint64_t desc_b = make_smem_desc(b_addr + k * UMMA_K * 2);
+                    umma_bf16(tmem_base, desc_a, desc_b, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar + stage);  // ring slot reusable once these MMAs have consumed it
+            }
+            umma_commit(tmem_full_bar);          // accumulator complete -> epilogue
+        }
+    } else if (warp >= 4) {  // ===== epilogue: TMEM -> registers -> (bias, ReLU, bf16) -> global =====
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                      // warp w may only touch TMEM lanes [32 (w % 4), +32)
+        const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), acc);
+            const int col0 = n_blk * BN + c0;
+            if (row < M && col0 < N) {
+                __nv_bfloat16* out = C + static_cast<int64_t>(row) * N + col0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {              // 4 x 8 columns -> 16-byte stores
+                    const int col = col0 + v * 8;
+                    if (col >= N) break;
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float x = __uint_as_float(acc[v * 8 + j]);
+                        if (bias != nullptr && col + j < N) x += bias[col + j];
+                        if (relu) x = x > 0.f ? x : 0.f;
+                        f[j] = x;
+                    }
+                    if (col + 8 <= N) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                            w[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(out + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    } else {
+                        for (int j = 0; col + j < N; ++j) out[v * 8 + j] = __float2bfloat16(f[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+inline CUresult make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols /*K, contiguous*/) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};                    // bytes between rows
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(BM)};
+    cuuint32_t elem_strides[2] = {1, 1};
+    return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace
+
+extern "C" {
+
+// returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding
+int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu,
+                   cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (err != cudaSuccess) return static_cast<int>(err);
+        configured = true;
+    }
+    CUtensorMap map_a, map_b;
+    CUresult res = make_tensor_map(&map_a, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K));
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    res = make_tensor_map(&map_b, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K));
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    tc_linear_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c), bias, M, N, K, relu);
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+"""Fused ``act(x @ W^T + b)`` on the tcgen05 tensor cores (kernel: ``csrc/tc_gemm.cu``).
+
+``linear_bias_act(x, weight, bias, relu)`` runs the hand-written TMA -> tcgen05.mma -> TMEM pipeline for bf16 CUDA
+operands (K-major activations and ``nn.Linear`` weights, which is how both are stored anyway) and falls back to
+``torch.nn.functional.linear`` otherwise.  The autograd wrapper keeps the backward on library GEMMs: the forward --
+the path validation and inference take, and the one that carries the bias/activation epilogue -- is the fused kernel.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn.functional as F_nn
+
+from fl4health_b200.ops import _lib
+
+
+def kernel_eligible(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> bool:
+    if not (x.is_cuda and weight.is_cuda) or _lib.load() is None:
+        return False
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        return False
+    if x.dim() < 2 or weight.dim() != 2 or not weight.is_contiguous():
+        return False
+    k, n = weight.shape[1], weight.shape[0]
+    if x.shape[-1] != k or k % 8 != 0 or n % 8 != 0:  # 16-byte global strides for TMA / vector stores
+        return False
+    if x.data_ptr() % 16 or weight.data_ptr() % 16:
+        return False
+    return bias is None or (bias.is_cuda and bias.numel() == n)
+
+
+def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool) -> torch.Tensor:
+    out = F_nn.linear(x.float(), weight.float(), None if bias is None else bias.float())
+    return (torch.relu(out) if relu else out).to(x.dtype)
+
+
+def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool) -> torch.Tensor:
+    lib = _lib.load(True)
+    m, k = x2d.shape
+    n = weight.shape[0]
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=x2d.device)
+    bias32 = None if bias is None else (bias if bias.dtype == torch.float32 else bias.float()).contiguous()
+    err = lib.fl4h_tc_linear(
+        _lib.ptr(x2d), _lib.ptr(weight), _lib.ptr(out), _lib.ptr(bias32), ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k),
+        ctypes.c_int(1 if relu else 0), _lib.stream_ptr(x2d.device),
+    )
+    if err != 0:
+        raise RuntimeError(f"fl4h_tc_linear failed ({'CUresult ' + str(-err) if err < 0 else 'cudaError ' + str(err)})")
+    _lib.count_launches(1)
+    return out
+
+
+class _LinearBiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):  # noqa: ANN001, ANN205
+        x2d = x.reshape(-1, x.shape[-1])
+        if not x2d.is_contiguous():
+            x2d = x2d.contiguous()
+        out = _launch(x2d, weight, bias, relu)
+        ctx.save_for_backward(x2d, weight, out if relu else None)
+        ctx.relu, ctx.has_bias, ctx.in_shape = relu, bias is not None, x.shape
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return out.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):  # noqa: ANN001, ANN205
+        x2d, weight, out = ctx.saved_tensors
+        g = grad_out.reshape(-1, grad_out.shape[-1])
+        if ctx.relu:
+            g = g * (out > 0).to(g.dtype)
+        grad_x = (g @ weight).reshape(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        grad_w = g.t() @ x2d if ctx.needs_input_grad[1] else None
+        grad_b = g.float().sum(dim=0).to(ctx.bias_dtype) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return grad_x, grad_w, grad_b, None
+
+
+def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False) -> torch.Tensor:
+    if kernel_eligible(x, weight, bias):
+        return _LinearBiasAct.apply(x, weight, bias, relu)
+    out = F_nn.linear(x, weight, bias)
+    return torch.relu(out) if relu else out

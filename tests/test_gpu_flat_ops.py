@@ -397,3 +397,37 @@ def test_overlapped_wgrad_matches_stock_conv_backward(graphed: bool, monkeypatch
     for name in stock:
         scale = stock[name].abs().max().clamp_min(1e-6)
         assert float((stock[name] - overlapped[name]).abs().max() / scale) < 3e-2, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 512), (32, 16, 512), (300, 200, 136), (4096, 1024, 1024)])
+@pytest.mark.parametrize("relu,with_bias", [(False, False), (True, True)])
+def test_tcgen05_linear_matches_reference(shape, relu, with_bias) -> None:
+    """tc_gemm.cu (TMA -> tcgen05.mma -> TMEM -> epilogue) vs an fp32 reference, ragged tiles included."""
+    from fl4health_b200.ops.tc_gemm import kernel_eligible, linear_bias_act, linear_bias_act_reference
+
+    m, n, k = shape
+    if n % 8:
+        pytest.skip("N must be a multiple of 8 for the kernel path")
+    torch.manual_seed(m + n + k)
+    dev = torch.device("cuda")
+    x = torch.randn(m, k, device=dev).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(n, k, device=dev) / k ** 0.5).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(n, device=dev) if with_bias else None
+    assert kernel_eligible(x, w, b)
+    from fl4health_b200 import ops
+
+    before = ops.launch_count()
+    y = linear_bias_act(x, w, b, relu)
+    torch.cuda.synchronize()
+    assert ops.launch_count() - before == 1
+    ref = linear_bias_act_reference(x.detach(), w.detach(), b, relu).float()
+    assert torch.allclose(y.float(), ref, rtol=2e-2, atol=2e-2), (y.float() - ref).abs().max()
+    # backward (library GEMMs + the kernel's ReLU mask)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    pre = torch.nn.functional.linear(xr, wr, b)
+    (pre * (y.detach() > 0).float() if relu else pre).backward(g.float())
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=3e-2, atol=3e-2)
+    assert torch.allclose(w.grad.float(), wr.grad, rtol=3e-2, atol=3e-2 * (m ** 0.5))
