@@ -168,7 +168,7 @@ def test_nnunet_utils() -> None:
     local = LocalPolyLRScheduler(opt, 0.1, 10)
     local.step()
     local.step()
-    assert opt.param_groups[0]["lr"] == pytest.approx(0.1 * (1 - 1 / 10) ** 0.9)
+    assert opt.param_groups[0]["lr"] == pytest.approx(0.1 * (1 - 2 / 10) ** 0.9)  # the base class steps once at construction
     wrapper = NnUNetDataLoaderWrapper(ToyAugmenter(0, True), "2d", set_len=3)
     batches = list(wrapper)
     assert len(batches) == 3 and set(batches[0][1]) == {"0-16x16", "1-8x8"} and len(list(wrapper)) == 3
