@@ -498,3 +498,175 @@ def warm_up_example(config: dict[str, Any], device: torch.device) -> tuple[Any, 
         return WarmedUpModule(pretrained_model=pretrained).load_from_pretrained(SmallCnn(config["dataset"]))
 
     return _fl_server(config, _adaptive_strategy(config), FedProxServer), make_clients(FedProxClient, config, device, factory)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# more scenarios: text, evaluation-only, one-shot merging, fine-tuning, SSL, tabular alignment, segmentation
+# ---------------------------------------------------------------------------------------------------------------
+@scenario("bert_finetuning_example")
+def bert_finetuning_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """Sequence classification with a BERT encoder and dict inputs (``input_ids`` / ``attention_mask``).  The default
+    config uses ``BertConfig.tiny`` on synthetic token sequences; set ``bert_size: base`` for bert-base-cased shapes."""
+    from torch.utils.data import DataLoader
+
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.models.bert import BertConfig, BertForSequenceClassification
+    from fl4health_b200.utils.dataset import DictionaryDataset
+
+    vocab, seq_len, classes = int(config.get("vocab_size", 1000)), int(config.get("seq_len", 32)), 4
+    bert_cfg = BertConfig() if config.get("bert_size") == "base" else BertConfig.tiny(vocab)
+
+    def dataset(n: int, seed: int) -> DictionaryDataset:
+        gen = torch.Generator().manual_seed(seed)
+        labels = torch.randint(0, classes, (n,), generator=gen)
+        ids = torch.randint(10, vocab, (n, seq_len), generator=gen)
+        ids[:, 1] = labels + 1  # a label-revealing token: makes the synthetic task learnable
+        lengths = torch.randint(seq_len // 2, seq_len + 1, (n,), generator=gen)
+        mask = (torch.arange(seq_len)[None, :] < lengths[:, None]).long()
+        return DictionaryDataset({"input_ids": list(ids), "attention_mask": list(mask)}, labels)
+
+    def customise(client: Any) -> None:
+        def loaders(cfg: dict[str, Any]) -> tuple[Any, Any]:
+            seed = config["seed"] + client.client_index
+            return (DataLoader(dataset(int(config["samples_per_client"]), seed), batch_size=config["batch_size"], shuffle=True),
+                    DataLoader(dataset(int(config["val_samples_per_client"]), 10_000 + seed), batch_size=config["batch_size"]))
+
+        client.get_data_loaders = loaders
+
+    factory = lambda: BertForSequenceClassification(bert_cfg, classes)  # noqa: E731
+    clients = make_clients(BasicClient, {**config, "optimizer": "adamw", "learning_rate": config.get("learning_rate", 1e-3)}, device,
+                           factory, customise)
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), clients
+
+
+@scenario("dp_scaffold_example")
+def dp_scaffold_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    from fl4health_b200.client_managers.poisson_sampling_manager import PoissonSamplingClientManager
+    from fl4health_b200.clients.scaffold_client import DPScaffoldClient
+    from fl4health_b200.privacy.dp_engine import GradSampleModule, ModuleValidator
+    from fl4health_b200.servers.scaffold_server import DPScaffoldServer
+    from fl4health_b200.strategies.scaffold import OpacusScaffold
+
+    fn = _dp_fn(config)
+    factory = lambda: SmallCnn(config["dataset"], batch_norm=True)  # noqa: E731
+    torch.manual_seed(config["seed"])
+    template = GradSampleModule(ModuleValidator.fix(factory()))
+    kwargs = {k: v for k, v in strategy_kwargs(config, fn).items() if k not in ("min_fit_clients", "min_evaluate_clients")}
+    strategy = OpacusScaffold(model=template, fraction_fit=1.0, fraction_evaluate=1.0, learning_rate=1.0, **kwargs)
+    server = DPScaffoldServer(PoissonSamplingClientManager(), {"n_server_rounds": config["n_server_rounds"]},
+                              noise_multiplier=config.get("noise_multiplier", 0.5), batch_size=config["batch_size"],
+                              num_server_rounds=config["n_server_rounds"], strategy=strategy, local_steps=config["local_steps"])
+    return server, make_clients(DPScaffoldClient, config, device, factory)
+
+
+@scenario("fl_plus_local_ft_example")
+def fl_plus_local_ft_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """FedAvg, then each client fine-tunes the final global model locally for a few steps at shutdown time."""
+    from fl4health_b200.clients.basic_client import BasicClient
+
+    class FineTuningClient(ExampleClientMixin, BasicClient):
+        def shutdown(self) -> None:
+            if getattr(self, "initialized", False):
+                self.train_by_steps(int(self.example_config.get("local_ft_steps", 4)), current_round=None)
+                loss, metrics = self.validate()
+                self.fine_tuned_result = (loss, metrics)
+            super().shutdown()
+
+    clients = make_clients(FineTuningClient, config, device, lambda: SmallCnn(config["dataset"]))
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), clients
+
+
+@scenario("fedsimclr_example")
+def fedsimclr_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """Federated SimCLR pre-training: ``SslTensorDataset`` makes (view, view') pairs, ``NtXentLoss`` is the criterion."""
+    from examples.common import client_datasets
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.engine.data import BatchedTensorLoader
+    from fl4health_b200.losses.contrastive_loss import NtXentLoss
+    from fl4health_b200.model_bases.fedsimclr_base import FedSimClrModel
+    from fl4health_b200.utils.dataset import SslTensorDataset
+
+    def augment(x: torch.Tensor) -> torch.Tensor:
+        return x + 0.1 * torch.randn_like(x)
+
+    def customise(client: Any) -> None:
+        def loaders(cfg: dict[str, Any]) -> tuple[Any, Any]:
+            train, val = client_datasets(config, client.client_index)
+            ssl = lambda ds: SslTensorDataset(ds.data, None, transform=None, target_transform=augment)  # noqa: E731
+            return BatchedTensorLoader(ssl(train), config["batch_size"], shuffle=True), BatchedTensorLoader(ssl(val), config["batch_size"])
+
+        client.get_data_loaders = loaders
+        client.get_criterion = lambda cfg: NtXentLoss(client.device)
+        # the "target" is the second view: embed it with the same model before the loss
+        client.transform_target = lambda target: client.model(target)
+
+    factory = lambda: FedSimClrModel(FeatureCnn(config["dataset"]), nn.Linear(FeatureCnn.out_dim, 32), pretrain=True)  # noqa: E731
+    clients = make_clients(BasicClient, config, device, factory, customise, metrics=[])
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), clients
+
+
+@scenario("feature_alignment_example")
+def feature_alignment_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """Tabular clients with heterogeneous columns aligned through ``TabularFeatureAlignmentServer`` (synthetic EHR-like
+    frames; the reference uses a MIMIC-III sample)."""
+    import numpy as np
+    import pandas as pd
+
+    from fl4health_b200.clients.tabular_data_client import TabularDataClient
+    from fl4health_b200.engine.data import BatchedTensorLoader
+    from fl4health_b200.servers.tabular_feature_alignment_server import TabularFeatureAlignmentServer
+    from fl4health_b200.utils.dataset import TensorDataset
+
+    def frame(seed: int, drop: str | None) -> pd.DataFrame:
+        rng = np.random.default_rng(seed)
+        n = int(config["samples_per_client"])
+        age, smoker = rng.normal(60, 12, n), rng.integers(0, 2, n)
+        df = pd.DataFrame({"patient_id": np.arange(n) + 10_000 * seed, "age": age, "smoker": smoker,
+                           "admission": rng.choice(["emergency", "elective", "urgent"], n),
+                           "mortality": ((age > 62) ^ (smoker == 1)).astype(int)})
+        return df.drop(columns=[drop]) if drop else df
+
+    class Client(TabularDataClient):
+        def get_data_frame(self, cfg: dict[str, Any]) -> pd.DataFrame:
+            return frame(config["seed"] + self.client_index, "admission" if self.client_index % 2 else None)
+
+        def get_data_loaders(self, cfg: dict[str, Any]) -> tuple[Any, Any]:
+            x = torch.from_numpy(np.asarray(self.aligned_features, dtype=np.float32))
+            y = torch.from_numpy(np.asarray(self.aligned_targets)).long().reshape(-1)
+            split = int(0.8 * len(x))
+            return (BatchedTensorLoader(TensorDataset(x[:split], y[:split]), config["batch_size"], shuffle=True),
+                    BatchedTensorLoader(TensorDataset(x[split:], y[split:]), config["batch_size"]))
+
+        def get_model(self, cfg: dict[str, Any]) -> nn.Module:
+            return nn.Sequential(nn.Linear(self.input_dimension, 32), nn.ReLU(), nn.Linear(32, self.output_dimension))
+
+        def get_criterion(self, cfg: dict[str, Any]) -> nn.Module:
+            return nn.CrossEntropyLoss()
+
+        def get_optimizer(self, cfg: dict[str, Any]) -> torch.optim.Optimizer:
+            return torch.optim.SGD(self.model.parameters(), lr=config["learning_rate"])
+
+    clients = []
+    for index in range(int(config["n_clients"])):
+        client = Client(Path(config["data_dir"]), [Accuracy()], device, id_column="patient_id", targets="mortality", client_name=f"client_{index}")
+        client.client_index = index
+        clients.append(client)
+
+    def initialize_parameters(input_dim: int, output_dim: int) -> Any:
+        torch.manual_seed(config["seed"])
+        return _initial_parameters(nn.Sequential(nn.Linear(input_dim, 32), nn.ReLU(), nn.Linear(32, output_dim)))
+
+    kwargs = {k: v for k, v in strategy_kwargs(config).items() if k not in ("on_fit_config_fn", "on_evaluate_config_fn")}
+    fl_config = {"n_server_rounds": config["n_server_rounds"], "batch_size": config["batch_size"], "local_steps": config["local_steps"]}
+    return TabularFeatureAlignmentServer(SimpleClientManager(), fl_config, initialize_parameters, BasicFedAvg(**kwargs)), clients
+
+
+@scenario("mr_mtl_example_flexible")
+def mr_mtl_example_flexible(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    from fl4health_b200.clients.flexible import FlexibleClient
+    from fl4health_b200.mixins import PersonalizedMode, make_it_personal
+    from fl4health_b200.servers.adaptive_constraint_servers.mrmtl_server import MrMtlServer
+
+    client_cls = make_it_personal(type("ExampleFlexible", (ExampleClientMixin, FlexibleClient), {}), PersonalizedMode.MR_MTL)
+    clients = make_clients(client_cls, config, device, lambda: SmallCnn(config["dataset"]))
+    return _fl_server(config, _adaptive_strategy({**config, "adapt_loss_weight": False}), MrMtlServer), clients
