@@ -21,6 +21,26 @@ _WORKSPACES: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
 _ACC_STRIDE = 4096  # floats; must match kAccStride in bn_act.cu (supports C <= 2048)
 
 
+_CLUSTER = {"size": int(os.environ.get("FL4H_BN_CLUSTER_SIZE", "16"))}
+
+
+def _cluster_bytes() -> int:
+    """Activations up to this size take the single-cluster kernels (``csrc/bn_cluster.cu``); 0 disables them."""
+    return int(os.environ.get("FL4H_BN_CLUSTER_MAX_BYTES", str(2 << 20)))
+
+
+def _try_cluster(launch) -> bool:  # noqa: ANN001
+    """Run ``launch(cluster_size)``; on a launch failure retry once with the portable cluster size, then give up."""
+    for size in dict.fromkeys((_CLUSTER["size"], 8)):
+        if size < 1:
+            return False
+        if launch(size) == 0:
+            _CLUSTER["size"] = size
+            return True
+    _CLUSTER["size"] = 0  # this device / driver cannot launch the cluster kernels: stop trying
+    return False
+
+
 def _allow_fused() -> int:
     """One cooperative kernel per direction (default) vs the two-kernel chain (``FL4H_BN_FUSED=0``, for A/B runs)."""
     return 0 if os.environ.get("FL4H_BN_FUSED", "1") == "0" else 1
@@ -82,6 +102,21 @@ class _BatchNormAct(torch.autograd.Function):
         y = torch.empty_like(x)  # preserves channels-last strides
         stream = _lib.stream_ptr(x.device)
         is_bf16 = 1 if x.dtype == torch.bfloat16 else 0
+        use_cluster = training and lib.fl4h_bn_cluster_supported(ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int64(_cluster_bytes()),
+                                                                 ctypes.c_int(x.element_size())) == 1 and _CLUSTER["size"] > 0
+        if use_cluster:
+            stats = torch.empty(4, c, dtype=torch.float32, device=x.device)
+            done = _try_cluster(lambda size: lib.fl4h_bn_fwd_train_cluster(
+                _lib.ptr(x), _lib.ptr(residual), _lib.ptr(y), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(weight), _lib.ptr(bias),
+                _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(nbt), ctypes.c_float(momentum if momentum is not None else 0.0),
+                ctypes.c_float(eps), _lib.ptr(stats[0]), _lib.ptr(stats[1]), ctypes.c_int(is_bf16), ctypes.c_int(1 if relu else 0),
+                ctypes.c_int(size), stream))
+            if done:
+                _lib.count_launches(1)
+                ctx.save_for_backward(x, y, weight, stats)
+                ctx.relu, ctx.has_res, ctx.has_bias = relu, residual is not None, bias is not None
+                ctx.training = True
+                return y
         if training:
             acc, counter = _workspace(x.device, c)
             stats = torch.empty(4, c, dtype=torch.float32, device=x.device)  # mean, invstd, scale, shift
@@ -131,6 +166,16 @@ class _BatchNormAct(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         grads = torch.empty(2, c, dtype=torch.float32, device=x.device)
+        if _CLUSTER["size"] > 0 and lib.fl4h_bn_cluster_supported(ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int64(_cluster_bytes()),
+                                                                  ctypes.c_int(x.element_size())) == 1:
+            done = _try_cluster(lambda size: lib.fl4h_bn_bwd_cluster(
+                _lib.ptr(dy), _lib.ptr(y), _lib.ptr(x), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(weight), _lib.ptr(stats[0]),
+                _lib.ptr(stats[1]), _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(grads[0]), _lib.ptr(grads[1]),
+                ctypes.c_int(1 if x.dtype == torch.bfloat16 else 0), ctypes.c_int(1 if ctx.relu else 0), ctypes.c_int(size),
+                _lib.stream_ptr(x.device)))
+            if done:
+                _lib.count_launches(1)
+                return dx, dres, (grads[0] if weight is not None else None), (grads[1] if ctx.has_bias else None), None, None, None, None, None, None, None
         coef = torch.empty(3, c, dtype=torch.float32, device=x.device)
         acc, counter = _workspace(x.device, c)
         err = lib.fl4h_bn_bwd(

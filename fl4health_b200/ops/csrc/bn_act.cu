@@ -24,48 +24,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bn_common.cuh"
+
 namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int kThreads = 256;
 
-template <typename T> struct Vec8;
-
-template <> struct Vec8<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(p);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-            v[2 * k] = f.x;
-            v[2 * k + 1] = f.y;
-        }
-    }
-    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-            w[k] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-};
-
-template <> struct Vec8<float> {
-    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
-    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-};
-
-__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
+using fl4h_bn::Vec8;
+using fl4h_bn::load8f;
 
 // Shared tail of both reduction kernels: fold the per-thread pairs (a, b) over the CTA's rows, RED them into
 // acc[0..C) / acc[C..2C), and elect the last CTA.  Returns true in every thread of the last CTA.
