@@ -277,8 +277,9 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
     float* acc = acc2 + par * kAccStride;
     if (blockIdx.x == 0) {
-        float* other = acc2 + (par ^ 1u) * kAccStride;
-        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+        // re-zero the WHOLE buffer the previous launch used: it may have been a layer with more channels than this one
+        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
+        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int LP = C >> 3, RP = blockDim.x / LP;
     const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
@@ -402,8 +403,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
     float* acc = acc2 + par * kAccStride;
     if (blockIdx.x == 0) {
-        float* other = acc2 + (par ^ 1u) * kAccStride;
-        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+        // re-zero the WHOLE buffer the previous launch used: it may have been a layer with more channels than this one
+        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
+        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int LP = C >> 3, RP = blockDim.x / LP;
     const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
