@@ -3,6 +3,7 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
+import os
 from fl4health_b200.ops.tc_gemm import linear_bias_act
 
 def timed(fn, iters=30):
@@ -18,13 +19,16 @@ def timed(fn, iters=30):
     return start.elapsed_time(end) / iters
 
 dev = torch.device("cuda")
-print(f"{'M':>6} {'N':>6} {'K':>6} | {'tcgen05 ms':>10} {'TFLOP/s':>8} | {'cuBLAS ms':>10} {'TFLOP/s':>8} | fused bias+relu vs cuBLAS+2 kernels")
+print(f"{'M':>6} {'N':>6} {'K':>6} | tcgen05 TFLOP/s: v0 (1 tile/CTA)  v1 (persistent 128x128)  v2 (persistent 128x256) | cuBLAS+bias+relu TFLOP/s")
 for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (16384, 4096, 1024)]:
     x = torch.randn(m, k, device=dev).bfloat16()
     w = torch.randn(n, k, device=dev).bfloat16()
     b = torch.randn(n, device=dev)
     bb = b.bfloat16()
-    ours = timed(lambda: linear_bias_act(x, w, b, True))
-    lib = timed(lambda: torch.relu(torch.nn.functional.linear(x, w, bb)))
     flops = 2.0 * m * n * k
-    print(f"{m:6d} {n:6d} {k:6d} | {ours:10.4f} {flops / ours / 1e9:8.1f} | {lib:10.4f} {flops / lib / 1e9:8.1f} |")
+    ours = []
+    for variant in ("0", "1", "2"):
+        os.environ["FL4H_TC_VARIANT"] = variant
+        ours.append(flops / timed(lambda: linear_bias_act(x, w, b, True)) / 1e9)
+    lib = timed(lambda: torch.relu(torch.nn.functional.linear(x, w, bb)))
+    print(f"{m:6d} {n:6d} {k:6d} | {ours[0]:10.1f} {ours[1]:10.1f} {ours[2]:10.1f} | {flops / lib / 1e9:8.1f}")

@@ -74,12 +74,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both operands K-major.
-__host__ __device__ constexpr uint32_t make_instr_desc() {
+__host__ __device__ constexpr uint32_t make_instr_desc(int n = BN) {
     return (1u << 4)                    // c_format  = F32
            | (1u << 7)                  // a_format  = BF16
            | (1u << 10)                 // b_format  = BF16
            | (0u << 15) | (0u << 16)    // a_major = b_major = K
-           | (uint32_t(BN >> 3) << 17)  // n_dim
+           | (uint32_t(n >> 3) << 17)   // n_dim
            | (uint32_t(BM >> 4) << 24); // m_dim
 }
 
@@ -220,19 +220,202 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
 }
 
-inline CUresult make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols /*K, contiguous*/) {
+inline CUresult make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols /*K, contiguous*/,
+                                int box_rows = BM) {
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};                    // bytes between rows
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(BM)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t elem_strides[2] = {1, 1};
     return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2: persistent, 128 x kBN tiles (kBN = 256 doubles the math per shared-memory byte), double-buffered TMEM
+// accumulators so the epilogue of tile i overlaps the main loop of tile i + 1.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int kBN>
+struct V2 {
+    static constexpr int kStagesV2 = 4;
+    static constexpr int kATile = BM * BK * 2;
+    static constexpr int kBTile = kBN * BK * 2;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kTmemColsV2 = 2 * kBN;           // two accumulator buffers
+    static constexpr int kSmemV2 = kStagesV2 * kStageBytes + 256 + 1024;
+};
+
+template <int kBN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                            __nv_bfloat16* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu) {
+    using Cfg = V2<kBN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStagesV2 * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStagesV2;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStagesV2;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + kBN - 1) / kBN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStagesV2; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar + a, 1);
+            mbar_init(tmem_empty_bar + a, 4);                 // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemColsV2));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer: one continuous ring across all of this CTA's tiles =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;   // concurrent CTAs share the W tile (L2 reuse)
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int stage = it % Cfg::kStagesV2;
+                    const uint32_t phase = (it / Cfg::kStagesV2) & 1;
+                    uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
+                    tma_load_2d(a_dst, &tma_a, kb * BK, m_blk * BM, full_bar + stage);
+                    tma_load_2d(a_dst + Cfg::kATile, &tma_b, kb * BK, n_blk * kBN, full_bar + stage);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_instr_desc(kBN);
+            uint32_t it = 0, local_tile = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+                const uint32_t acc = local_tile & 1, use = local_tile >> 1;
+                mbar_wait(tmem_empty_bar + acc, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kBN;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int stage = it % Cfg::kStagesV2;
+                    const uint32_t phase = (it / Cfg::kStagesV2) & 1;
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t b_addr = a_addr + Cfg::kATile;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + stage);
+                }
+                umma_commit(tmem_full_bar + acc);
+            }
+        }
+    } else if (warp >= 4) {  // ===== epilogue warps =====
+        const int quarter = warp & 3;
+        uint32_t local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+            const uint32_t acc = local_tile & 1, use = local_tile >> 1;
+            mbar_wait(tmem_full_bar + acc, use & 1);
+            tc_fence_after();
+            const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN + static_cast<uint32_t>(c0), v);
+                const int col0 = n_blk * kBN + c0;
+                if (row < M && col0 < N) {
+                    __nv_bfloat16* out = C + static_cast<int64_t>(row) * N + col0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = col0 + q * 8;
+                        if (col >= N) break;
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float x = __uint_as_float(v[q * 8 + j]);
+                            if (bias != nullptr && col + j < N) x += bias[col + j];
+                            if (relu) x = x > 0.f ? x : 0.f;
+                            f[j] = x;
+                        }
+                        if (col + 8 <= N) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                w[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(out + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        } else {
+                            for (int j = 0; col + j < N; ++j) out[q * 8 + j] = __float2bfloat16(f[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + acc);     // this warp's quarter of the buffer is free again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemColsV2));
+    }
+}
+
+template <int kBN>
+int launch_persistent(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int sms,
+                      cudaStream_t stream) {
+    using Cfg = V2<kBN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(tc_linear_persistent_kernel<kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemV2);
+        if (err != cudaSuccess) return static_cast<int>(err);
+        configured = true;
+    }
+    CUtensorMap map_a, map_b;
+    CUresult res = make_tensor_map(&map_a, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM);
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    res = make_tensor_map(&map_b, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K), kBN);
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    const int tiles = ((M + BM - 1) / BM) * ((N + kBN - 1) / kBN);
+    const int grid = tiles < sms ? tiles : sms;
+    tc_linear_persistent_kernel<kBN><<<grid, kThreads, Cfg::kSmemV2, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c), bias, M, N, K, relu);
+    return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace
 
 extern "C" {
+
+// variant: 0 = one 128x128 tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256
+int fl4h_tc_linear_v(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int variant,
+                     cudaStream_t stream);
 
 // returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding
 int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu,
@@ -251,6 +434,19 @@ int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     tc_linear_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c), bias, M, N, K, relu);
     return static_cast<int>(cudaGetLastError());
+}
+
+int fl4h_tc_linear_v(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int variant,
+                     cudaStream_t stream) {
+    static int sms = 0;
+    if (sms == 0) {
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    }
+    if (variant == 1) return launch_persistent<128>(a, w, c, bias, M, N, K, relu, sms, stream);
+    if (variant == 2) return launch_persistent<256>(a, w, c, bias, M, N, K, relu, sms, stream);
+    return fl4h_tc_linear(a, w, c, bias, M, N, K, relu, stream);
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@ the path validation and inference take, and the one that carries the bias/activa
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F_nn
@@ -36,15 +37,25 @@ def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch
     return (torch.relu(out) if relu else out).to(x.dtype)
 
 
-def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool) -> torch.Tensor:
+def pick_variant(m: int, n: int) -> int:
+    """0: one 128x128 tile per CTA; 1: persistent 128x128 (double-buffered TMEM); 2: persistent 128x256.
+    ``FL4H_TC_VARIANT`` forces one; by default wide outputs take the 256-wide tile (twice the math per smem byte)."""
+    forced = os.environ.get("FL4H_TC_VARIANT")
+    if forced is not None:
+        return int(forced)
+    return 2 if n >= 256 else 1
+
+
+def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool, variant: int | None = None) -> torch.Tensor:
     lib = _lib.load(True)
     m, k = x2d.shape
     n = weight.shape[0]
+    variant = pick_variant(m, n) if variant is None else variant
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x2d.device)
     bias32 = None if bias is None else (bias if bias.dtype == torch.float32 else bias.float()).contiguous()
-    err = lib.fl4h_tc_linear(
+    err = lib.fl4h_tc_linear_v(
         _lib.ptr(x2d), _lib.ptr(weight), _lib.ptr(out), _lib.ptr(bias32), ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k),
-        ctypes.c_int(1 if relu else 0), _lib.stream_ptr(x2d.device),
+        ctypes.c_int(1 if relu else 0), ctypes.c_int(variant), _lib.stream_ptr(x2d.device),
     )
     if err != 0:
         raise RuntimeError(f"fl4h_tc_linear failed ({'CUresult ' + str(-err) if err < 0 else 'cudaError ' + str(err)})")

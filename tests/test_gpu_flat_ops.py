@@ -409,9 +409,13 @@ def test_overlapped_wgrad_matches_stock_conv_backward(graphed: bool, monkeypatch
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 512), (32, 16, 512), (300, 200, 136), (4096, 1024, 1024)])
 @pytest.mark.parametrize("relu,with_bias", [(False, False), (True, True)])
-def test_tcgen05_linear_matches_reference(shape, relu, with_bias) -> None:
-    """tc_gemm.cu (TMA -> tcgen05.mma -> TMEM -> epilogue) vs an fp32 reference, ragged tiles included."""
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_tcgen05_linear_matches_reference(shape, relu, with_bias, variant, monkeypatch) -> None:
+    """tc_gemm.cu (TMA -> tcgen05.mma -> TMEM -> epilogue) vs an fp32 reference, ragged tiles included; variants:
+    one tile per CTA / persistent 128x128 / persistent 128x256 with double-buffered TMEM accumulators."""
     from fl4health_b200.ops.tc_gemm import kernel_eligible, linear_bias_act, linear_bias_act_reference
+
+    monkeypatch.setenv("FL4H_TC_VARIANT", variant)
 
     m, n, k = shape
     if n % 8:
