@@ -66,17 +66,19 @@ class PayloadSpec:
     @staticmethod
     def of(arrays: NDArrays) -> PayloadSpec:
         entries: list[tuple[tuple[int, ...], str, Any]] = []
+        flat = getattr(arrays, "flat", None)
+        layout = getattr(arrays, "layout", None)
+        whole = flat is not None and layout is not None and len(arrays) == len(layout.state_keys)
         for arr in arrays:
             if isinstance(arr, torch.Tensor):
-                inline = arr.detach().cpu().numpy() if arr.numel() <= 8 and arr.dim() == 0 else None
+                # whole-arena payloads reduce their scalar entries on the device (int_flat): no by-value copies, which
+                # would cost a D2H sync per entry per round and make the spec differ from round to round
+                inline = arr.detach().cpu().numpy() if (not whole and arr.numel() <= 8 and arr.dim() == 0) else None
                 entries.append((tuple(arr.shape), str(arr.dtype), inline))
             else:
                 np_arr = np.asarray(arr)
                 small = np_arr.dtype.kind in ("U", "S", "O") or np_arr.size <= 64
                 entries.append((tuple(np_arr.shape), f"numpy.{np_arr.dtype}", np_arr if small else None))
-        flat = getattr(arrays, "flat", None)
-        layout = getattr(arrays, "layout", None)
-        whole = flat is not None and layout is not None and len(arrays) == len(layout.state_keys)
         return PayloadSpec(entries, int(flat.numel()) if whole else None)
 
 
@@ -191,6 +193,41 @@ class SpmdContext:
         out: list[Any] = [None] * self.world_size
         dist.all_gather_object(out, obj)
         return out
+
+    def exchange_round_meta(self, kind: str, meta: dict[str, Any] | None) -> list[dict[str, Any] | None]:
+        """Per-round result metadata of every rank (sample counts, losses, metric dicts).
+
+        The first exchange of each ``kind`` pickles the dicts (``all_gather_object``) and caches their *schema*: the
+        numeric keys, and every non-numeric entry (payload spec, status code) by value.  Later rounds send only the
+        numbers: one fixed-size float64 ``all_gather`` (a single ~10 us NCCL call + one D2H read instead of two pickled
+        object collectives).  Any rank whose metadata no longer fits the cached schema (error, new metric key, changed
+        spec) raises a flag that makes every rank fall back to the pickled exchange for that round."""
+        if self.world_size == 1:
+            return [meta]
+        cache = self.__dict__.setdefault("_meta_schemas", {})
+        schema = cache.get(kind)
+        if schema is not None:
+            vector = _encode_meta(meta, schema["local"])
+            width = schema["width"]
+            send = torch.full((width + 1,), float("nan"), dtype=torch.float64)
+            if vector is not None and len(vector) == width:
+                send[0] = 1.0
+                send[1:] = torch.tensor(vector, dtype=torch.float64)
+            else:
+                send[0] = -1.0
+            send = send.to(self.device)
+            gathered = torch.empty(self.world_size * (width + 1), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(gathered, send)
+            table = gathered.view(self.world_size, width + 1).cpu()
+            if bool((table[:, 0] > 0).all()):
+                return [_decode_meta(table[r, 1:].tolist(), schema["all"][r]) for r in range(self.world_size)]
+        all_meta = self.all_gather_object(meta)
+        templates = [_meta_template(m) for m in all_meta]
+        if all(t is not None for t in templates) and len({t["width"] for t in templates}) == 1:  # type: ignore[index]
+            cache[kind] = {"local": templates[self.rank], "all": templates, "width": templates[0]["width"]}  # type: ignore[index]
+        else:
+            cache.pop(kind, None)
+        return all_meta
 
     def broadcast_object(self, obj: Any, src: int = 0) -> Any:
         if self.world_size == 1:
@@ -339,6 +376,56 @@ class SpmdClientProxy(ClientProxy):
         return super().reconnect(ins, timeout, group_id)
 
 
+def _is_number(value: Any) -> bool:
+    return isinstance(value, (int, float)) and not isinstance(value, bool)
+
+
+def _meta_template(meta: dict[str, Any] | None) -> dict[str, Any] | None:
+    """Schema of a metadata dict: which (possibly nested under "metrics") entries are numbers, everything else by value."""
+    if meta is None or "error" in meta:
+        return None
+    numeric: list[tuple[str, str | None, type]] = []
+    constants: dict[str, Any] = {}
+    for key, value in meta.items():
+        if key == "metrics" and isinstance(value, dict):
+            if not all(_is_number(v) for v in value.values()):
+                return None
+            numeric.extend(("metrics", k, type(v)) for k, v in value.items())
+        elif _is_number(value):
+            numeric.append((key, None, type(value)))
+        else:
+            constants[key] = value
+    import pickle
+
+    return {"numeric": numeric, "constants": constants, "constants_key": pickle.dumps(constants), "width": len(numeric)}
+
+
+def _encode_meta(meta: dict[str, Any] | None, template: dict[str, Any]) -> list[float] | None:
+    if meta is None or "error" in meta:
+        return None
+    current = _meta_template(meta)
+    if current is None or [n[:2] for n in current["numeric"]] != [n[:2] for n in template["numeric"]]:
+        return None
+    if current["constants_key"] != template["constants_key"]:
+        return None
+    return [float(meta[key] if sub is None else meta[key][sub]) for key, sub, _ in template["numeric"]]
+
+
+def _decode_meta(values: list[float], template: dict[str, Any]) -> dict[str, Any]:
+    meta: dict[str, Any] = dict(template["constants"])
+    if any(key == "metrics" for key, _, _ in template["numeric"]):
+        meta["metrics"] = {}
+    for value, (key, sub, kind) in zip(values, template["numeric"]):
+        cast = int(round(value)) if kind is int else float(value)
+        if sub is None:
+            meta[key] = cast
+        else:
+            meta[key][sub] = cast
+    if "metrics" in template["constants"]:
+        meta["metrics"] = template["constants"]["metrics"]
+    return meta
+
+
 class SpmdTransport:
     """``fit_clients`` / ``evaluate_clients`` / ``poll_clients`` across ranks."""
 
@@ -371,7 +458,7 @@ class SpmdTransport:
             meta = {"n": res.num_examples, "metrics": res.metrics, "spec": local_arrays.spec, "code": res.status.code}  # type: ignore[attr-defined]
         elif err is not None:
             meta = {"error": err}
-        all_meta = self.ctx.all_gather_object(meta)
+        all_meta = self.ctx.exchange_round_meta("fit", meta)
         results: list = []
         failures: list = []
         for proxy, _ in client_instructions:
@@ -397,7 +484,7 @@ class SpmdTransport:
             meta = {"loss": res.loss, "n": res.num_examples, "metrics": res.metrics, "code": res.status.code}
         elif err is not None:
             meta = {"error": err}
-        all_meta = self.ctx.all_gather_object(meta)
+        all_meta = self.ctx.exchange_round_meta("evaluate", meta)
         results: list = []
         failures: list = []
         for proxy, _ in client_instructions:
