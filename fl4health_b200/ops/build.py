@@ -76,7 +76,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{out}")
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-cudart", "shared", "-o", str(LIB_PATH), *map(str, objs), "-lcuda"]
+    # no -lcuda: driver entry points are resolved at run time (cudaGetDriverEntryPoint) so the library loads on
+    # driver-less build machines
+    link = [nvcc, "-shared", "-cudart", "shared", "-o", str(LIB_PATH), *map(str, objs)]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

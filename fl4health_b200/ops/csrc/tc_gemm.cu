@@ -220,13 +220,34 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
 }
 
+// cuTensorMapEncodeTiled is a driver-API entry point; resolve it through the runtime so the library does not link against
+// libcuda (it must still dlopen on driver-less build machines).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
+            status == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        }
+    }
+    return fn;
+}
+
 inline CUresult make_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols /*K, contiguous*/,
                                 int box_rows = BM) {
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) return CUDA_ERROR_NOT_SUPPORTED;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};                    // bytes between rows
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t elem_strides[2] = {1, 1};
-    return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                                   elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
