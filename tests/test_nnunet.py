@@ -172,3 +172,19 @@ def test_nnunet_utils() -> None:
     wrapper = NnUNetDataLoaderWrapper(ToyAugmenter(0, True), "2d", set_len=3)
     batches = list(wrapper)
     assert len(batches) == 3 and set(batches[0][1]) == {"0-16x16", "1-8x8"} and len(list(wrapper)) == 3
+
+
+def test_flexible_nnunet_client_trains_like_the_plain_one() -> None:
+    from fl4health_b200.clients.flexible.nnunet import FlexibleNnunetClient
+
+    def run(cls):
+        set_all_random_seeds(8)
+        clients = [cls(torch.device("cpu"), 999, fold=0, backend=ToyBackend(i), client_name=f"n{i}", verbose=False) for i in range(2)]
+        strategy = BasicFedAvg(min_fit_clients=2, min_evaluate_clients=2, min_available_clients=2, on_fit_config_fn=_cfg,
+                               on_evaluate_config_fn=_cfg, fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
+                               evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn)
+        server = NnunetServer(SimpleClientManager(), {"n_server_rounds": 2, "nnunet_config": "2d"}, _cfg, strategy)
+        return [v for _, v in run_simulation(server, clients, 2).losses_distributed]
+
+    plain, flexible = run(NnunetClient), run(FlexibleNnunetClient)
+    assert all(a == pytest.approx(b, rel=1e-5) for a, b in zip(plain, flexible))
