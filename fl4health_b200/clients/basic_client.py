@@ -39,6 +39,7 @@ from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics.base_metrics import TEST_LOSS_KEY, TEST_NUM_EXAMPLES_KEY, Metric
 from fl4health_b200.metrics.metric_managers import MetricManager
 from fl4health_b200.parallel.arena import ParameterArena, arena_of, attach_arena
+from fl4health_b200.utils import tracing
 from fl4health_b200.parameter_exchange.full_exchanger import FullParameterExchanger
 from fl4health_b200.parameter_exchange.parameter_exchanger_base import ParameterExchanger
 from fl4health_b200.reporting.base_reporter import BaseReporter
@@ -203,17 +204,19 @@ class BasicClient:
                 loaded = self._load_client_state()
                 log(INFO, "Successfully loaded client state." if loaded else "Client state was not loaded.")
 
-        self.set_parameters(parameters, config, fitting_round=True)
+        with tracing.phase("pull_parameters"):
+            self.set_parameters(parameters, config, fitting_round=True)
         self.update_before_train(current_server_round)
 
         fit_start_time = datetime.datetime.now()
-        if local_epochs is not None:
-            loss_dict, metrics = self.train_by_epochs(local_epochs, current_server_round)
-            local_steps = len(self.train_loader) * local_epochs
-        elif local_steps is not None:
-            loss_dict, metrics = self.train_by_steps(local_steps, current_server_round)
-        else:
-            raise ValueError("Must specify either local_epochs or local_steps in the Config.")
+        with tracing.phase("local_train"):
+            if local_epochs is not None:
+                loss_dict, metrics = self.train_by_epochs(local_epochs, current_server_round)
+                local_steps = len(self.train_loader) * local_epochs
+            elif local_steps is not None:
+                loss_dict, metrics = self.train_by_steps(local_steps, current_server_round)
+            else:
+                raise ValueError("Must specify either local_epochs or local_steps in the Config.")
         fit_end_time = datetime.datetime.now()
 
         self.update_after_train(local_steps, loss_dict, config)
@@ -235,6 +238,7 @@ class BasicClient:
                 "fit_round_end": str(fit_end_time),
                 "fit_step": self.total_steps,
                 "fit_epoch": self.total_epochs,
+                **({"device_phase_ms": tracing.phase_report()} if tracing.tracing_enabled() else {}),
             },
             current_server_round,
         )
@@ -251,8 +255,10 @@ class BasicClient:
         current_server_round = narrow_dict_type(config, "current_server_round", int)
         pack_losses_with_val_metrics = set_pack_losses_with_val_metrics(config)
 
-        self.set_parameters(parameters, config, fitting_round=False)
-        loss, metrics = self.validate(pack_losses_with_val_metrics)
+        with tracing.phase("pull_parameters"):
+            self.set_parameters(parameters, config, fitting_round=False)
+        with tracing.phase("evaluate"):
+            loss, metrics = self.validate(pack_losses_with_val_metrics)
         end_time = datetime.datetime.now()
 
         self._maybe_checkpoint(loss, metrics, CheckpointMode.POST_AGGREGATION)

@@ -8,6 +8,7 @@ from typing import Any
 
 from fl4health_b200.common.history import History
 from fl4health_b200.common.logger import log
+from fl4health_b200.utils import tracing
 from fl4health_b200.common.typing import Code, GetParametersIns, Parameters, ReconnectIns, Scalar
 from fl4health_b200.servers.client_manager import ClientManager
 from fl4health_b200.servers.transport import (
@@ -105,7 +106,8 @@ class Server:
             client_instructions, max_workers=self.max_workers, timeout=timeout, group_id=server_round
         )
         log(INFO, "aggregate_fit: received %s results and %s failures", len(results), len(failures))
-        parameters_aggregated, metrics_aggregated = self.strategy.aggregate_fit(server_round, results, failures)
+        with tracing.phase("aggregate"):
+            parameters_aggregated, metrics_aggregated = self.strategy.aggregate_fit(server_round, results, failures)
         return parameters_aggregated, metrics_aggregated, (results, failures)
 
     def disconnect_all_clients(self, timeout: float | None) -> None:
