@@ -53,6 +53,19 @@ def side_stream(device: torch.device) -> torch.cuda.Stream:
         return st.side[index]
 
 
+def branch_stream(device: torch.device) -> torch.cuda.Stream:
+    """Second side stream for *forward* branch parallelism (e.g. a ResNet block's downsample path).  Autograd runs
+    each backward node on the stream its forward ran on and inserts the cross-stream syncs itself, so a branch issued
+    here overlaps the main path in both directions."""
+    st = _state()
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    with _LOCK:
+        key = -1 - index
+        if key not in st.side:
+            st.side[key] = torch.cuda.Stream(device=device)
+        return st.side[key]
+
+
 def fork(device: torch.device) -> torch.cuda.Stream:
     side = side_stream(device)
     side.wait_stream(torch.cuda.current_stream(device))

@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from fl4health_b200.engine import streams
 from fl4health_b200.models.fused_layers import BatchNormAct2d, Conv2dOverlapWgrad, bn_act
 
 
@@ -30,7 +31,23 @@ class BasicBlock(nn.Module):
             )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        identity = x if self.downsample is None else self.downsample(x)
+        if self.downsample is None:
+            out = bn_act(self.bn1, self.conv1(x))
+            return bn_act(self.bn2, self.conv2(out), residual=x)
+        if x.is_cuda and streams.overlap_enabled():
+            # the projection shortcut is independent of conv1/bn1/conv2: run it on a side stream (its backward follows it
+            # there), joining right before the residual add; both branches are small enough to share the 148 SMs
+            main = torch.cuda.current_stream(x.device)
+            side = streams.branch_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                identity = self.downsample(x)
+            x.record_stream(side)
+            out = self.conv2(bn_act(self.bn1, self.conv1(x)))
+            main.wait_stream(side)
+            identity.record_stream(main)
+            return bn_act(self.bn2, out, residual=identity)
+        identity = self.downsample(x)
         out = bn_act(self.bn1, self.conv1(x))
         return bn_act(self.bn2, self.conv2(out), residual=identity)
 

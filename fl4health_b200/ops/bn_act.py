@@ -26,7 +26,10 @@ _CLUSTER = {"size": int(os.environ.get("FL4H_BN_CLUSTER_SIZE", "16"))}
 
 def _cluster_bytes() -> int:
     """Activations up to this size take the single-cluster kernels (``csrc/bn_cluster.cu``); 0 disables them."""
-    return int(os.environ.get("FL4H_BN_CLUSTER_MAX_BYTES", str(2 << 20)))
+    # default 0: measured on B200 the 16-CTA cluster kernels (16-29 us) lose to the grid-wide cooperative kernels
+    # (11-15 us) at every ResNet-18/CIFAR layer size -- cluster scheduling plus the serial DSMEM partial reads cost more
+    # than the global-memory barrier they replace.  Kept for experiments (FL4H_BN_CLUSTER_MAX_BYTES=<bytes>).
+    return int(os.environ.get("FL4H_BN_CLUSTER_MAX_BYTES", "0"))
 
 
 def _try_cluster(launch) -> bool:  # noqa: ANN001
@@ -78,6 +81,12 @@ def kernel_eligible(x: torch.Tensor, residual: torch.Tensor | None, momentum: fl
     if training and running_mean is not None and momentum is None:
         return False  # cumulative moving average: stock path
     if not training and running_mean is None:
+        return False
+    if running_mean is not None and running_mean.dtype != torch.float32:
+        return False  # the kernels keep statistics in fp32 (a model cast wholesale to bf16 takes the stock path)
+    if training and os.environ.get("FL4H_DETERMINISTIC", "0") == "1":
+        # the grid-wide kernels accumulate with fp32 RED atomics (order varies run to run): deterministic mode takes the
+        # (deterministic) ATen path for training statistics
         return False
     return True
 
