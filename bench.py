@@ -135,6 +135,7 @@ def main() -> None:
     from fl4health_b200.servers.client_manager import SimpleClientManager
     from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
     from fl4health_b200.utils.dataset import TensorDataset
+    from fl4health_b200.utils import tracing
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     os.environ["FL4H_COLLECTIVES"] = args.collectives
@@ -208,6 +209,7 @@ def main() -> None:
                 if sampler is not None:
                     sampler.start()
                 ops.reset_launch_count()
+                tracing.phase_report(reset=True)  # FL4H_TRACE=1 diagnostics cover the timed rounds only
                 marks["start"] = torch.cuda.Event(enable_timing=True)
                 marks["start"].record()
                 marks["wall0"] = time.perf_counter()
@@ -280,6 +282,10 @@ def main() -> None:
             "note": "per round: every train/val batch copied from pinned host memory; loss+accuracy scalars read back",
         }
     if ctx.rank == 0:
+        if tracing.tracing_enabled():  # FL4H_TRACE=1: device milliseconds per round phase (diagnostic, stderr)
+            torch.cuda.synchronize()
+            report = tracing.phase_report()
+            print(json.dumps({k: round(v["mean_ms"], 4) for k, v in report.items()}), file=sys.stderr)
         print(json.dumps(result))
     ctx.shutdown()
 

@@ -11,6 +11,7 @@ import torch
 
 from examples.common import describe, load_example_config
 from examples.scenarios import SCENARIOS
+import examples.extra_scenarios  # noqa: F401  (registers the remaining scenarios)
 from fl4health_b200.simulation import run_simulation
 from fl4health_b200.utils.random import set_all_random_seeds
 

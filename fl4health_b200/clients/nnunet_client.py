@@ -194,6 +194,8 @@ class NnunetClient(BasicClient):
         self.plans: dict[str, Any]
 
     # ------------------------------------------------------------------------------------------ set-up
+    defer_global_model_creation = True  # the network only exists once ``setup_client`` has prepared the experiment
+
     def setup_client(self, config: Config) -> None:
         self.nnunet_config = NnunetConfig(narrow_dict_type(config, "nnunet_config", str))
         self.plans = pickle.loads(narrow_dict_type(config, "nnunet_plans", bytes))
@@ -293,6 +295,9 @@ class NnunetClient(BasicClient):
         return pred * mask.expand(-1, pred.shape[1], *mask.shape[2:]), target
 
     def update_metric_manager(self, preds: TorchPredType, target: TorchTargetType, metric_manager: MetricManager) -> None:
+        # personalised wrappers prefix the twin models' outputs with "global-" / "local-": metrics follow the personal
+        # (local) model; without prefixes both steps are no-ops (parity: clients/flexible/nnunet.py:799-803)
+        preds = {k.removeprefix("local-"): v for k, v in preds.items() if not k.startswith("global")}
         m_pred = convert_deep_supervision_dict_to_list(preds)[0] if len(preds) > 1 else next(iter(preds.values()))
         if isinstance(target, torch.Tensor):
             m_target = target

@@ -5,6 +5,7 @@ personal model); the mixin clones it for the global model."""
 
 from __future__ import annotations
 
+import copy
 from logging import INFO, WARNING
 from typing import Any
 
@@ -43,8 +44,10 @@ class DittoPersonalizedMixin(AdaptiveDriftConstrainedMixin):
 
     # ------------------------------------------------------------------------------------------ set-up
     def get_global_model(self, config: Config) -> nn.Module:
-        """Same architecture as the personal model (a fresh instance from the user's ``get_model``)."""
-        return self.get_model(config)  # type: ignore[attr-defined]
+        """Same architecture as the personal model (a fresh instance from the user's ``get_model``; clients whose
+        ``get_model`` hands out one shared instance — nnU-Net's prepared experiment — get a deep copy)."""
+        model = self.get_model(config)  # type: ignore[attr-defined]
+        return copy.deepcopy(model) if model is getattr(self, "model", None) else model
 
     def _copy_optimizer_with_new_params(self, original_optimizer: Optimizer) -> Optimizer:
         """An optimizer of the same class and hyper-parameters (first param group) over the global model."""
@@ -81,7 +84,9 @@ class DittoPersonalizedMixin(AdaptiveDriftConstrainedMixin):
         self.optimizers = optimizers
 
     def setup_client(self, config: Config) -> None:
-        if self.global_model is None:
+        # clients that can only build their model inside their own setup_client (``defer_global_model_creation``) get
+        # the global twin created on demand by ``get_optimizer`` instead
+        if self.global_model is None and not getattr(self, "defer_global_model_creation", False):
             self.global_model = self._place_model(self.get_global_model(config))  # type: ignore[attr-defined]
             log(INFO, f"Global model set: {type(self.global_model).__name__}")
         super().setup_client(config)  # type: ignore[misc]

@@ -3,8 +3,8 @@
 // Why: for the <= 2 MB activation tensors of a CIFAR-scale network, the grid-wide kernels in bn_act.cu cost 11-16 us
 // each no matter how little data they touch -- their critical path is a chain of global-memory round trips (load,
 // RED atomics + fence, grid-barrier arrive, poll, read totals, store).  A single cluster of 8-16 CTAs keeps the whole
-// dependency on chip: per-CTA partial sums live in shared memory, every CTA reads its peers' partials through
-// distributed shared memory (DSMEM), and the only synchronisation is the hardware cluster barrier.  The tile each
+// dependency on chip: every CTA pushes its partial sums into all peers' shared memory with DSMEM reductions
+// (red.shared::cluster), and the only synchronisation is the hardware cluster barrier.  The tile each
 // thread normalises stays in registers between the two phases (forward) so x is read exactly once.
 //
 // Layout / mapping are those of bn_act.cu: x is [M, C] with C contiguous (NHWC), C % 8 == 0, one thread owns 8
@@ -29,10 +29,13 @@ constexpr int kCacheRegs = 64;  // registers per thread spent on the tile kept b
 template <typename T> constexpr int fwd_cache() { return kCacheRegs / Vec8<T>::kRawRegs; }
 template <typename T> constexpr int bwd_cache() { return kCacheRegs / (2 * Vec8<T>::kRawRegs); }
 
-// smem layout (floats): [0, 2C) this CTA's partial sums | [2C, 2C + 2*RP*C) block-reduction scratch, later reused for
+// smem layout (floats): [0, 2C) cluster-wide totals (pushed by all CTAs) | [2C, 2C + 2*RP*C) block-reduction scratch, later reused for
 // the per-channel coefficients (<= 3C floats) | shift values [C] (forward only).
-__device__ __forceinline__ void block_partials(const float (&a)[8], const float (&b)[8], int C, int LP, int RP, int lane, int ty,
-                                               float* partial, float* scratch) {
+// Push variant: every CTA adds its per-channel partials into EVERY peer's `totals` array with asynchronous DSMEM
+// reductions (red.shared::cluster) -- S pipelined fire-and-forget operations per value instead of S dependent remote
+// loads on the critical path.  `totals` must have been zeroed cluster-wide before (barrier_arrive / barrier_wait).
+__device__ __forceinline__ void block_partials_push(cg::cluster_group& cluster, const float (&a)[8], const float (&b)[8], int C,
+                                                    int LP, int RP, int lane, int ty, float* totals, float* scratch) {
     if (ty < RP) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -41,26 +44,18 @@ __device__ __forceinline__ void block_partials(const float (&a)[8], const float 
         }
     }
     __syncthreads();
+    const unsigned S = cluster.num_blocks();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sa = 0.f, sb = 0.f;
         for (int t = 0; t < RP; ++t) {
             sa += scratch[(t * 2 + 0) * C + c];
             sb += scratch[(t * 2 + 1) * C + c];
         }
-        partial[c] = sa;
-        partial[C + c] = sb;
-    }
-}
-
-// Sum the S per-CTA partials of channel c through DSMEM (every CTA computes the totals redundantly: no second hop).
-__device__ __forceinline__ void cluster_totals(cg::cluster_group& cluster, float* partial, int C, int c, float& a, float& b) {
-    const unsigned S = cluster.num_blocks();
-    a = 0.f;
-    b = 0.f;
-    for (unsigned r = 0; r < S; ++r) {
-        const float* remote = cluster.map_shared_rank(partial, r);
-        a += remote[c];
-        b += remote[C + c];
+        for (unsigned r = 0; r < S; ++r) {
+            float* remote = cluster.map_shared_rank(totals, r);
+            atomicAdd(remote + c, sa);
+            atomicAdd(remote + C + c, sb);
+        }
     }
 }
 
@@ -79,6 +74,9 @@ bn_fwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __r
     const unsigned rank = cluster.block_rank();
 
     for (int c = threadIdx.x; c < C; c += blockDim.x) kshift[c] = running_mean != nullptr ? running_mean[c] : 0.f;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) partial[c] = 0.f;   // cluster-wide totals land here
+    __syncthreads();
+    cluster.barrier_arrive();                              // "my totals are zeroed" -- waited for just before the push
     const int64_t r0 = (int64_t)rank * rows_per_cta;
     const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
     constexpr int kFwdCache = fwd_cache<T>();
@@ -127,12 +125,12 @@ bn_fwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __r
             }
         }
     }
-    block_partials(s, q, C, LP, RP, lane, ty, partial, scratch);
-    cluster.sync();                                        // every CTA's partials are visible cluster-wide
+    cluster.barrier_wait();
+    block_partials_push(cluster, s, q, C, LP, RP, lane, ty, partial, scratch);
+    cluster.sync();                                        // all pushes have landed in every CTA's totals
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float sd, sq;
-        cluster_totals(cluster, partial, C, c, sd, sq);
+        const float sd = partial[c], sq = partial[C + c];
         const float k0 = kshift[c];
         const float md = sd * inv_m;
         const float mean = k0 + md;
@@ -209,6 +207,9 @@ bn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T
     float* partial = smem;
     float* scratch = smem + 2 * C;
     const unsigned rank = cluster.block_rank();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) partial[c] = 0.f;
+    __syncthreads();
+    cluster.barrier_arrive();
     const int64_t r0 = (int64_t)rank * rows_per_cta;
     const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
     constexpr int kBwdCache = bwd_cache<T>();
@@ -257,12 +258,12 @@ bn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T
             }
         }
     }
-    block_partials(sg, sgx, C, LP, RP, lane, ty, partial, scratch);
+    cluster.barrier_wait();
+    block_partials_push(cluster, sg, sgx, C, LP, RP, lane, ty, partial, scratch);
     cluster.sync();
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a, b;
-        cluster_totals(cluster, partial, C, c, a, b);
+        const float a = partial[c], b = partial[C + c];
         scratch[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd[c];
         scratch[C + c] = a * inv_m;
         scratch[2 * C + c] = b * inv_m;

@@ -48,6 +48,7 @@ from fl4health_b200.common.typing import (
     ndarrays_to_parameters,
 )
 from fl4health_b200.servers.client_proxy import ClientProxy, InProcessClientProxy
+from fl4health_b200.utils import tracing
 
 _CONTEXT: SpmdContext | None = None
 
@@ -149,9 +150,43 @@ class SpmdContext:
         self.collective_backend = collective_backend or os.environ.get("FL4H_COLLECTIVES", "auto")
         self.fused: Any = None  # ops.p2p.FusedCollectives when peer memory is available
         self.timings: dict[str, float] = {}
+        self.mailbox: Any = None  # runtime.mailbox.ShmMailbox when every rank lives on this host
         _CONTEXT = self
+        if self.world_size > 1 and os.environ.get("FL4H_SHM_MAILBOX", "1") != "0":
+            self._open_mailbox()
 
     # -- lifecycle ---------------------------------------------------------------------------------------------
+    def _open_mailbox(self) -> None:
+        """Host-side shared-memory mailbox for the per-round metadata (single-node jobs only; every failure mode
+        falls back to the collective exchange — the decision is agreed on by all ranks)."""
+        import socket
+
+        from fl4health_b200.runtime import mailbox as mbox
+
+        name = mbox.default_name()
+        box, ok = None, mbox.load_runtime() is not None
+        try:
+            if ok and self.rank == 0:
+                box = mbox.ShmMailbox(name, self.world_size, 0, create=True)
+        except RuntimeError:
+            ok = False
+        infos = self.all_gather_object((socket.gethostname(), ok, name))  # doubles as "rank 0 has created the segment"
+        name = infos[0][2]
+        usable = all(flag for _, flag, _ in infos) and len({host for host, _, _ in infos}) == 1
+        if usable and self.rank != 0:
+            try:
+                box = mbox.ShmMailbox(name, self.world_size, self.rank)
+            except RuntimeError:
+                box = None
+        opened = self.all_gather_object(box is not None)
+        if self.rank == 0 and box is not None:
+            box.unlink()  # every rank that could open it has: drop the name so a crash cannot leak the segment
+        if all(opened):
+            self.mailbox = box
+            log(INFO, "round metadata travels through the shared-memory mailbox (no device collective, no stream sync)")
+        elif box is not None:
+            box.close()
+
     def enable_fused_collectives(self) -> bool:
         """Try to set up peer-mapped symmetric memory + the fused kernels; fall back to NCCL when unavailable."""
         if self.fused is not None:
@@ -175,6 +210,9 @@ class SpmdContext:
         if self.fused is not None:
             self.fused.close()
             self.fused = None
+        if self.mailbox is not None:
+            self.mailbox.close()
+            self.mailbox = None
         if self.world_size > 1 and dist.is_initialized():
             dist.destroy_process_group()
         _CONTEXT = None
@@ -199,14 +237,20 @@ class SpmdContext:
 
         The first exchange of each ``kind`` pickles the dicts (``all_gather_object``) and caches their *schema*: the
         numeric keys, and every non-numeric entry (payload spec, status code) by value.  Later rounds send only the
-        numbers: one fixed-size float64 ``all_gather`` (a single ~10 us NCCL call + one D2H read instead of two pickled
-        object collectives).  Any rank whose metadata no longer fits the cached schema (error, new metric key, changed
+        numbers — through the host shared-memory mailbox when all ranks share a node (microseconds, no device work, no
+        stream synchronisation), otherwise as one fixed-size float64 ``all_gather`` (one NCCL call + one D2H read).  Any rank whose metadata no longer fits the cached schema (error, new metric key, changed
         spec) raises a flag that makes every rank fall back to the pickled exchange for that round."""
         if self.world_size == 1:
             return [meta]
         cache = self.__dict__.setdefault("_meta_schemas", {})
         schema = cache.get(kind)
-        if schema is not None:
+        if schema is not None and self.mailbox is not None and schema["width"] + 1 <= self.mailbox.capacity:
+            vector = _encode_meta(meta, schema["local"])
+            ok = vector is not None and len(vector) == schema["width"]
+            records = self.mailbox.all_gather([1.0, *vector] if ok else [-1.0])  # type: ignore[misc]
+            if all(len(rec) == schema["width"] + 1 and rec[0] > 0 for rec in records):
+                return [_decode_meta(records[r][1:].tolist(), schema["all"][r]) for r in range(self.world_size)]
+        elif schema is not None:
             vector = _encode_meta(meta, schema["local"])
             width = schema["width"]
             send = torch.full((width + 1,), float("nan"), dtype=torch.float64)
@@ -251,7 +295,8 @@ class SpmdContext:
         """``out = epilogue(sum_r coef[r] * flat_r)`` on every rank.  ``local`` is this rank's flat buffer (or None
         when the rank was not sampled: it then contributes zeros)."""
         if self.fused is not None and local is not None and self.fused.owns(local) and all(c >= 0 for c in coef_by_rank):
-            return self.fused.aggregate(local, coef_by_rank, out=out, epilogue=epilogue)
+            with tracing.phase("agg_collective"):
+                return self.fused.aggregate(local, coef_by_rank, out=out, epilogue=epilogue)
         from fl4health_b200.ops import flat as flat_ops
 
         target = out if (out is not None and not epilogue) else torch.empty(numel, dtype=torch.float32, device=self.device)
@@ -260,7 +305,8 @@ class SpmdContext:
         else:  # pre-scale by this client's FedAvg weight (one streaming kernel), then sum across ranks
             flat_ops.weighted_sum(target, [local[:numel]], [coef_by_rank[self.rank]])
         if self.world_size > 1:
-            dist.all_reduce(target, op=dist.ReduceOp.SUM)
+            with tracing.phase("agg_collective"):
+                dist.all_reduce(target, op=dist.ReduceOp.SUM)
         if epilogue:
             result = out if out is not None else torch.empty_like(target)
             flat_ops.weighted_sum(result, [target], [1.0], **epilogue)
@@ -458,7 +504,8 @@ class SpmdTransport:
             meta = {"n": res.num_examples, "metrics": res.metrics, "spec": local_arrays.spec, "code": res.status.code}  # type: ignore[attr-defined]
         elif err is not None:
             meta = {"error": err}
-        all_meta = self.ctx.exchange_round_meta("fit", meta)
+        with tracing.phase("exchange_meta"):
+            all_meta = self.ctx.exchange_round_meta("fit", meta)
         results: list = []
         failures: list = []
         for proxy, _ in client_instructions:
@@ -484,7 +531,8 @@ class SpmdTransport:
             meta = {"loss": res.loss, "n": res.num_examples, "metrics": res.metrics, "code": res.status.code}
         elif err is not None:
             meta = {"error": err}
-        all_meta = self.ctx.exchange_round_meta("evaluate", meta)
+        with tracing.phase("exchange_meta"):
+            all_meta = self.ctx.exchange_round_meta("evaluate", meta)
         results: list = []
         failures: list = []
         for proxy, _ in client_instructions:

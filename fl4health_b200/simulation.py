@@ -30,6 +30,8 @@ def run_simulation(
     register_clients(server, clients)
     history, _ = server.fit(num_rounds=num_rounds, timeout=timeout)
     if shutdown:
-        server.disconnect_all_clients(timeout=timeout)
-        server.shutdown()
+        if hasattr(server, "disconnect_all_clients"):
+            server.disconnect_all_clients(timeout=timeout)
+        if hasattr(server, "shutdown"):  # evaluation-only servers have no reporters / state to flush
+            server.shutdown()
     return history

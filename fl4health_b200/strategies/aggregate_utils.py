@@ -130,7 +130,10 @@ def _spmd_weighted_combine(
             if ctx.world_size > 1:
                 import torch.distributed as dist
 
-                dist.all_reduce(ints)
+                from fl4health_b200.utils import tracing
+
+                with tracing.phase("agg_int_buffers"):
+                    dist.all_reduce(ints)
             ints = ints.to(torch.int64)
             out.int_flat = ints
             cursor = 0

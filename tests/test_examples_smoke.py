@@ -7,6 +7,7 @@ from examples.run import main
 from examples.scenarios import SCENARIOS
 
 ONE_ROUND = {"fedpca_example"}
+ONE_SHOT = {"federated_eval_example", "model_merge_example"}  # a single evaluation / merge pass: metrics, no per-round losses
 
 
 @pytest.mark.parametrize("scenario", sorted(SCENARIOS))
@@ -15,6 +16,9 @@ def test_example_scenario_runs(scenario: str, tmp_path, monkeypatch) -> None:
     rounds = 1 if scenario in ONE_ROUND else 2
     summary = main([scenario, "--rounds", str(rounds), "--clients", "2", "--device", "cpu", "--config", _tiny_config(tmp_path, scenario)])
     assert summary["scenario"] == scenario
+    if scenario in ONE_SHOT:
+        assert summary["metrics"] and all(v == v for v in summary["metrics"].values())
+        return
     assert len(summary["losses"]) == rounds
     assert all(loss == loss for _, loss in summary["losses"])  # no NaNs
 
