@@ -35,6 +35,7 @@ from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, NDArrays, Scalar
 from fl4health_b200.engine.fused_optim import _FlatOptimizer, translate_optimizer
 from fl4health_b200.engine.graph_runner import GraphStepRunner
+from fl4health_b200.engine.modes import set_training
 from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics.base_metrics import TEST_LOSS_KEY, TEST_NUM_EXAMPLES_KEY, Metric
 from fl4health_b200.metrics.metric_managers import MetricManager
@@ -206,7 +207,8 @@ class BasicClient:
 
         with tracing.phase("pull_parameters"):
             self.set_parameters(parameters, config, fitting_round=True)
-        self.update_before_train(current_server_round)
+        with tracing.phase("update_before_train"):
+            self.update_before_train(current_server_round)
 
         fit_start_time = datetime.datetime.now()
         with tracing.phase("local_train"):
@@ -219,7 +221,8 @@ class BasicClient:
                 raise ValueError("Must specify either local_epochs or local_steps in the Config.")
         fit_end_time = datetime.datetime.now()
 
-        self.update_after_train(local_steps, loss_dict, config)
+        with tracing.phase("update_after_train"):
+            self.update_after_train(local_steps, loss_dict, config)
 
         if self._should_evaluate_after_fit(evaluate_after_fit):
             validation_loss, validation_metrics = self.validate(pack_losses_with_val_metrics)
@@ -246,7 +249,8 @@ class BasicClient:
         if self.checkpoint_and_state_module.state_checkpointer is not None:
             self._save_client_state()
 
-        return self.get_parameters(config), self.num_train_samples, metrics
+        with tracing.phase("push_parameters"):
+            return self.get_parameters(config), self.num_train_samples, metrics
 
     def evaluate(self, parameters: NDArrays, config: Config) -> tuple[float, int, dict[str, Scalar]]:
         if not self.initialized:
@@ -435,7 +439,7 @@ class BasicClient:
     def train_by_epochs(
         self, epochs: int, current_round: int | None = None
     ) -> tuple[dict[str, float], dict[str, Scalar]]:
-        self.model.train()
+        set_training(self.model, True)
         steps_this_round = 0
         report_data: dict[str, Any] = {"round": current_round}
         step_reports = self._step_reports_enabled()
@@ -491,7 +495,7 @@ class BasicClient:
     def train_by_steps(
         self, steps: int, current_round: int | None = None
     ) -> tuple[dict[str, float], dict[str, Scalar]]:
-        self.model.train()
+        set_training(self.model, True)
         self.train_loss_meter.clear()
         self.train_metric_manager.clear()
         self._log_header_str(current_round)
@@ -539,7 +543,7 @@ class BasicClient:
         self, loss_meter: LossMeter, metric_manager: MetricManager, include_losses_in_metrics: bool = False
     ) -> tuple[float, dict[str, Scalar]]:
         assert self.num_validation_steps is not None, "num_validation_steps must be defined to use this function"
-        self.model.eval()
+        set_training(self.model, False)
         metric_manager.clear()
         loss_meter.clear()
         if self.val_iterator is None:
@@ -560,7 +564,7 @@ class BasicClient:
         logging_mode: LoggingMode = LoggingMode.VALIDATION, include_losses_in_metrics: bool = False,
     ) -> tuple[float, dict[str, Scalar]]:
         assert logging_mode in (LoggingMode.VALIDATION, LoggingMode.TEST, LoggingMode.EARLY_STOP_VALIDATION)
-        self.model.eval()
+        set_training(self.model, False)
         metric_manager.clear()
         loss_meter.clear()
         with torch.no_grad():

@@ -81,6 +81,7 @@ class Parameters:
     # arena metadata (optional): one contiguous buffer backing every entry of ``tensors``.
     flat: Any = None
     layout: Any = None
+    int_flat: Any = None  # all integer entries as one int64 tensor (see ``NDArrays.int_flat``)
 
 
 def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
@@ -89,6 +90,7 @@ def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
         tensor_type="torch",
         flat=getattr(ndarrays, "flat", None),
         layout=getattr(ndarrays, "layout", None),
+        int_flat=getattr(ndarrays, "int_flat", None),
     )
 
 
@@ -96,7 +98,9 @@ def parameters_to_ndarrays(parameters: Parameters) -> NDArrays:
     tagged = getattr(parameters, "_arrays", None)
     if tagged is not None:  # SPMD transport: keep ownership tags / remote placeholders intact
         return tagged
-    return NDArrays(parameters.tensors, flat=parameters.flat, layout=parameters.layout)
+    arrays = NDArrays(parameters.tensors, flat=parameters.flat, layout=parameters.layout)
+    arrays.int_flat = getattr(parameters, "int_flat", None)
+    return arrays
 
 
 def to_numpy(array: NDArray) -> np.ndarray:

@@ -74,7 +74,7 @@ class FusedCollectives:
                 raise RuntimeError(f"GPU {device_index} cannot access peer {peer}")
         self.slots: list[_Slot] = []
         self.epoch = 0
-        self._result_by_numel: dict[int, _Slot] = {}
+        self._result_by_numel: dict[int, tuple[_Slot, torch.Tensor]] = {}
         self._flags = self._alloc_slot(2 * MAX_RANKS * 4)
         self._exchange(self._flags)
         ctx.barrier()
@@ -133,11 +133,12 @@ class FusedCollectives:
         slot.peer_ptrs = peer_ptrs
 
     def result_buffer(self, numel: int) -> torch.Tensor:
-        slot = self._result_by_numel.get(numel)
-        if slot is None:
+        entry = self._result_by_numel.get(numel)
+        if entry is None:
             slot = self._alloc_slot(numel * 4)
-            self._result_by_numel[numel] = slot
-        return slot.tensor[: numel * 4].view(torch.float32)
+            entry = (slot, slot.tensor[: numel * 4].view(torch.float32))  # ONE tensor object: view caches key on it
+            self._result_by_numel[numel] = entry
+        return entry[1]
 
     # -- kernels ----------------------------------------------------------------------------------------------
     def _peer_args(self, contrib: torch.Tensor, result: torch.Tensor, coef_by_rank: list[float]) -> _PeerArgs:

@@ -265,7 +265,8 @@ class ParameterArena:
         if names is None:
             cache_key = (base.data_ptr(), base.numel())
             cached = self._views_cache.get(cache_key)
-            if cached is not None and cached.flat is base:
+            # same address + size + dtype while the cache keeps the old storage alive => same memory: reuse the views
+            if cached is not None and cached.flat.dtype == base.dtype and cached.flat.device == base.device:
                 fresh = NDArrays(cached, flat=base, layout=self)  # shallow copy: callers may mutate the list
                 fresh.int_flat = self.int_flat if region is None else None
                 return fresh

@@ -46,6 +46,7 @@ from fl4health_b200.common.typing import (
     Parameters,
     Status,
     ndarrays_to_parameters,
+    parameters_to_ndarrays,
 )
 from fl4health_b200.servers.client_proxy import ClientProxy, InProcessClientProxy
 from fl4health_b200.utils import tracing
@@ -114,6 +115,7 @@ def _sliced_with_tags(source: Any, start: int | None, stop: int | None) -> NDArr
         part.materialized = source.materialized  # type: ignore[attr-defined]
     else:
         part = _LocalPayload(base, flat=base.flat, layout=base.layout)
+        part.int_flat = base.int_flat
         part.ctx, part.rank, part.spec = source.ctx, source.rank, spec  # type: ignore[attr-defined]
     return part
 
@@ -370,6 +372,7 @@ class _LocalPayload(NDArrays):
 
 def _tag_local(arrays: NDArrays, ctx: SpmdContext) -> NDArrays:
     tagged = _LocalPayload(arrays, flat=getattr(arrays, "flat", None), layout=getattr(arrays, "layout", None))
+    tagged.int_flat = getattr(arrays, "int_flat", None)
     tagged.ctx, tagged.rank, tagged.spec = ctx, ctx.rank, PayloadSpec.of(arrays)  # type: ignore[attr-defined]
     return tagged
 
@@ -500,7 +503,7 @@ class SpmdTransport:
         local_arrays: NDArrays | None = None
         meta: dict[str, Any] | None = None
         if res is not None:
-            local_arrays = _tag_local(NDArrays(res.parameters.tensors, flat=res.parameters.flat, layout=res.parameters.layout), self.ctx)
+            local_arrays = _tag_local(parameters_to_ndarrays(res.parameters), self.ctx)
             meta = {"n": res.num_examples, "metrics": res.metrics, "spec": local_arrays.spec, "code": res.status.code}  # type: ignore[attr-defined]
         elif err is not None:
             meta = {"error": err}

@@ -29,6 +29,9 @@ def tracing_enabled() -> bool:
 def phase(name: str) -> Iterator[None]:
     cuda = torch.cuda.is_available()
     timed = tracing_enabled()
+    annotate = torch.autograd.profiler.record_function(f"fl4h:{name}") if torch.autograd._profiler_enabled() else None
+    if annotate is not None:  # shows up as a user annotation on torch.profiler / kineto timelines
+        annotate.__enter__()
     if cuda:
         torch.cuda.nvtx.range_push(f"fl4h:{name}")
     if timed:
@@ -42,6 +45,8 @@ def phase(name: str) -> Iterator[None]:
             _PENDING[name].append((start, end))
         if cuda:
             torch.cuda.nvtx.range_pop()
+        if annotate is not None:
+            annotate.__exit__(None, None, None)
 
 
 def phase_report(reset: bool = False) -> dict[str, dict[str, float]]:
