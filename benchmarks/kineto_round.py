@@ -104,3 +104,14 @@ for key, total in sorted(busy_by.items(), key=lambda kv: -kv[1]):
 print("largest gaps (us, host phase, offset ms):")
 for gap, key, off in sorted(big, reverse=True)[:25]:
     print(f"  {gap:8.1f}  {key:28s} @ {off/1e3:8.3f}")
+# what the host was doing inside the largest steady-state gaps (second profiled round onwards)
+host = sorted((e for e in trace if e.get("cat") in ("cpu_op", "cuda_runtime", "cuda_driver", "user_annotation") and "dur" in e), key=lambda e: e["ts"])
+t0 = merged[0][0]
+steady = [g for g in sorted(big, reverse=True) if g[2] > span / ROUNDS][:8]
+for gap, key, off in steady:
+    a, b = t0 + off, t0 + off + gap
+    inside = [e for e in host if e["ts"] < b and e["ts"] + e["dur"] > a and e["dur"] > 4]
+    inside.sort(key=lambda e: -e["dur"])
+    print(f"--- gap {gap:.0f} us in {key} @ {off/1e3:.3f} ms: host events overlapping it")
+    for e in inside[:14]:
+        print(f"      {e['dur']:8.1f} us  [{e['cat']}] {e['name'][:90]}  (starts {e['ts']-a:+.0f} us)")

@@ -98,7 +98,8 @@ class Accuracy(Metric):
 
     def compute(self, name: str | None = None) -> Metrics:
         assert self.correct is not None and self.total is not None, "No updates were recorded"
-        return {self._key(name): float(self.correct.item()) / float(self.total.item())}
+        correct, total = torch.stack((self.correct.to(torch.float64), self.total.to(torch.float64))).tolist()  # one D2H
+        return {self._key(name): correct / total}
 
     def clear(self) -> None:
         if self.correct is not None and self.total is not None:

@@ -12,6 +12,7 @@ reference reduces per layer with ``functools.reduce(np.add, ...)`` over NumPy ar
 from __future__ import annotations
 
 from collections.abc import Sequence
+from typing import Any
 
 import numpy as np
 import torch
@@ -54,6 +55,29 @@ def _result_buffer(layout: object, like: torch.Tensor) -> torch.Tensor:
     return ring[-1]
 
 
+def _merge_int_flats(int_flats: Sequence[torch.Tensor], coefficients: Sequence[float]) -> torch.Tensor:
+    """``trunc(sum_k c_k * ints_k)`` over the clients' packed integer state: 2 tiny kernels per client, no host→device
+    coefficient tensor (this runs right after the fit synchronisation point, i.e. with an idle GPU)."""
+    acc = int_flats[0].to(torch.float64).mul_(float(coefficients[0]))
+    for ints, coef in zip(int_flats[1:], coefficients[1:]):
+        acc.add_(ints.to(torch.float64), alpha=float(coef))
+    return acc.to(torch.int64)
+
+
+def _scatter_int_views(out: NDArrays, layout: Any, merged: torch.Tensor) -> None:
+    """Point the integer entries of ``out`` at slices of ``merged`` (one ``split`` + cached positions / shapes)."""
+    plan = getattr(layout, "_int_scatter_plan", None)
+    if plan is None:
+        positions = [i for i, key in enumerate(layout.state_keys) if key in layout.int_state]
+        states = [layout.int_state[layout.state_keys[i]] for i in positions]
+        plan = (positions, [t.numel() for t in states], [t.shape for t in states], [t.dtype for t in states])
+        layout._int_scatter_plan = plan
+    positions, sizes, shapes, dtypes = plan
+    out.int_flat = merged
+    for idx, piece, shape, dtype in zip(positions, merged.split(sizes), shapes, dtypes):
+        out[idx] = piece.view(shape) if dtype == merged.dtype else piece.view(shape).to(dtype)
+
+
 def _is_meta_array(arr: NDArray) -> bool:
     return isinstance(arr, np.ndarray) and arr.dtype.kind in ("U", "S", "O")
 
@@ -72,16 +96,7 @@ def weighted_combine(arrays: Sequence[NDArrays], coefficients: Sequence[float]) 
         # integer state (e.g. num_batches_tracked) is not in the flat buffer: average it like the reference does
         int_flats = [getattr(nds.layout, "int_flat", None) for nds in arrays]
         if layout.int_state and all(f is not None for f in int_flats):
-            stacked = torch.stack([f.to(torch.float64) for f in int_flats])  # [K, n_int]
-            weights = torch.tensor(list(coefficients), dtype=torch.float64, device=stacked.device).unsqueeze(1)
-            merged = (stacked * weights).sum(dim=0).to(torch.int64)
-            out.int_flat = merged
-            cursor = 0
-            for idx, key in enumerate(layout.state_keys):
-                if key in layout.int_state:
-                    numel = layout.int_state[key].numel()
-                    out[idx] = merged[cursor : cursor + numel].view(layout.int_state[key].shape)
-                    cursor += numel
+            _scatter_int_views(out, layout, _merge_int_flats(int_flats, coefficients))
         else:
             out.int_flat = None
             for idx, key in enumerate(layout.state_keys):
@@ -134,13 +149,7 @@ def _spmd_weighted_combine(
 
                 with tracing.phase("agg_int_buffers"):
                     dist.all_reduce(ints)
-            ints = ints.to(torch.int64)
-            out.int_flat = ints
-            cursor = 0
-            for i in int_idx:
-                numel = out[i].numel()
-                out[i] = ints[cursor : cursor + numel].view(out[i].shape).to(out[i].dtype)
-                cursor += numel
+            _scatter_int_views(out, layout, ints.to(torch.int64))
         return out
     # non-arena payloads: pack the tensor entries into one temporary flat buffer, reduce, unpack
     assert epilogue is None, "server-optimizer epilogues need arena-backed payloads in SPMD mode"

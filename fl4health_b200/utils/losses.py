@@ -16,12 +16,26 @@ from typing import Generic, TypeVar
 import torch
 
 
+def read_scalars(tensors: dict[str, torch.Tensor]) -> dict[str, float]:
+    """Host values of several 0-d tensors with ONE device→host transfer (a ``.item()`` per entry costs a copy and a
+    stream synchronisation each; right after a local-training phase the GPU sits idle for all of them)."""
+    values = list(tensors.values())
+    if len(values) > 1 and all(v.is_cuda and v.device == values[0].device for v in values):
+        host = torch.stack([v.detach().reshape(()).to(torch.float64) for v in values]).tolist()
+        return dict(zip(tensors.keys(), host))
+    return {key: float(val.item()) for key, val in tensors.items()}
+
+
 class Losses(ABC):
     def __init__(self, additional_losses: dict[str, torch.Tensor] | None = None) -> None:
         self.additional_losses: dict[str, torch.Tensor] = additional_losses if additional_losses else {}
 
     def as_dict(self) -> dict[str, float]:
-        return {key: float(val.item()) for key, val in self.additional_losses.items()}
+        return read_scalars(self._named_scalars())
+
+    def _named_scalars(self) -> dict[str, torch.Tensor]:
+        """The tensors ``as_dict`` reports, under their reporting keys."""
+        return dict(self.additional_losses)
 
     def _flat_items(self) -> dict[str, torch.Tensor]:
         """All scalar tensors of this container under unique keys (used by the meter)."""
@@ -52,9 +66,9 @@ class EvaluationLosses(Losses):
         super().__init__(additional_losses)
         self.checkpoint = checkpoint
 
-    def as_dict(self) -> dict[str, float]:
-        out = super().as_dict()
-        out["checkpoint"] = float(self.checkpoint.item())
+    def _named_scalars(self) -> dict[str, torch.Tensor]:
+        out = super()._named_scalars()
+        out["checkpoint"] = self.checkpoint
         return out
 
     def _flat_items(self) -> dict[str, torch.Tensor]:
@@ -78,9 +92,9 @@ class TrainingLosses(Losses):
         super().__init__(additional_losses)
         self.backward: dict[str, torch.Tensor] = backward if isinstance(backward, dict) else {"backward": backward}
 
-    def as_dict(self) -> dict[str, float]:
-        out = super().as_dict()
-        out.update({key: float(loss.item()) for key, loss in self.backward.items()})
+    def _named_scalars(self) -> dict[str, torch.Tensor]:
+        out = super()._named_scalars()
+        out.update(self.backward)
         return out
 
     def _flat_items(self) -> dict[str, torch.Tensor]:
