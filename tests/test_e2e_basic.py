@@ -3,6 +3,7 @@
 import json
 from pathlib import Path
 
+import pytest
 import torch
 
 from fl4health_b200.checkpointing.checkpointer import BestLossTorchModuleCheckpointer, LatestTorchModuleCheckpointer
@@ -126,3 +127,39 @@ def test_resume_from_server_and_client_state(tmp_path: Path) -> None:
     resumed = run_simulation(server, clients, num_rounds=3)
     assert [r for r, _ in resumed.losses_distributed] == [1, 2, 3]
     assert abs(resumed.losses_distributed[0][1] - reference.losses_distributed[0][1]) < 1e-6
+
+
+def test_fault_injection_then_resume(tmp_path: Path, monkeypatch: pytest.MonkeyPatch) -> None:
+    """``FL4H_FAULT_AFTER_ROUND=2`` pre-empts the server after round 2 (state saved); a fresh process-equivalent
+    (new server + clients over the same state directory) finishes rounds 3..4 and keeps the first two rounds' history
+    (fault injection to test resume)."""
+    from fl4health_b200.checkpointing.client_module import ClientCheckpointAndStateModule
+    from fl4health_b200.checkpointing.state_checkpointer import ClientStateCheckpointer
+
+    state_dir = tmp_path / "state"
+    state_dir.mkdir()
+
+    def build():
+        set_all_random_seeds(13)
+        module = BaseServerCheckpointAndStateModule(
+            model=Net(), parameter_exchanger=FullParameterExchanger(), state_checkpointer=ServerStateCheckpointer(state_dir))
+        server = FlServer(SimpleClientManager(), {"n_server_rounds": 4}, _strategy(), checkpoint_and_state_module=module,
+                          on_init_parameters_config_fn=fit_config_fn(), server_name="srv")
+        clients = make_clients(2)
+        for c in clients:
+            c.checkpoint_and_state_module = ClientCheckpointAndStateModule(state_checkpointer=ClientStateCheckpointer(state_dir))
+        return server, clients
+
+    monkeypatch.setenv("FL4H_FAULT_AFTER_ROUND", "2")
+    server, clients = build()
+    with pytest.raises(SystemExit, match="fault injected after round 2"):
+        run_simulation(server, clients, num_rounds=4)
+    first_two = list(server.history.losses_distributed)
+    assert [r for r, _ in first_two] == [1, 2]
+
+    monkeypatch.delenv("FL4H_FAULT_AFTER_ROUND")
+    server, clients = build()
+    resumed = run_simulation(server, clients, num_rounds=4)
+    assert [r for r, _ in resumed.losses_distributed] == [1, 2, 3, 4]
+    assert resumed.losses_distributed[:2] == first_two  # rounds 1-2 come from the restored history, not a re-run
+    assert clients[0].total_steps == 4 * 5  # step counters restored: 2 rounds before the fault + 2 after
