@@ -20,7 +20,8 @@ def timed(fn, iters=30):
 
 dev = torch.device("cuda")
 print(f"{'M':>6} {'N':>6} {'K':>6} | tcgen05 TFLOP/s: v0 (1 tile/CTA)  v1 (persistent 128x128)  v2 (persistent 128x256) | cuBLAS+bias+relu TFLOP/s")
-for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (16384, 4096, 1024)]:
+for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (16384, 4096, 1024),
+                (4096, 2304, 768), (4096, 768, 768), (4096, 3072, 768), (4096, 768, 3072)]:  # last four: BERT-base, 32 x 128 tokens
     x = torch.randn(m, k, device=dev).bfloat16()
     w = torch.randn(n, k, device=dev).bfloat16()
     b = torch.randn(n, device=dev)

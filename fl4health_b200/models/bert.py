@@ -4,8 +4,8 @@ randomly initialised or loaded from a local state dict with HF-compatible shapes
 
 Inputs follow the HF convention and arrive as a dict (``input_ids``, ``attention_mask``[, ``token_type_ids``]), which
 exercises the clients' dict-input path.  Attention uses ``scaled_dot_product_attention`` (flash kernels on CUDA); the
-feed-forward and classifier projections are ``LinearAct`` modules, i.e. the tcgen05 GEMM with fused bias(+ReLU)
-epilogue when running in bf16 on a B200.
+attention, feed-forward and classifier projections are ``LinearAct`` modules, i.e. the tcgen05 GEMM with fused
+bias(+GELU / ReLU) epilogue when running in bf16 on a B200.
 """
 
 from __future__ import annotations
@@ -29,7 +29,7 @@ class BertConfig:
     type_vocab_size: int = 2
     layer_norm_eps: float = 1e-12
     hidden_dropout_prob: float = 0.1
-    activation: str = "gelu"  # "relu" fuses the activation into the first feed-forward GEMM's epilogue
+    activation: str = "gelu"  # "gelu" (erf, as HF BERT) or "relu": fused into the first feed-forward GEMM's epilogue
 
     @classmethod
     def tiny(cls, vocab_size: int = 1000) -> BertConfig:
@@ -57,12 +57,12 @@ class BertLayer(nn.Module):
     def __init__(self, cfg: BertConfig) -> None:
         super().__init__()
         self.num_heads = cfg.num_attention_heads
-        self.qkv = nn.Linear(cfg.hidden_size, 3 * cfg.hidden_size)
-        self.attn_out = nn.Linear(cfg.hidden_size, cfg.hidden_size)
+        self.qkv = LinearAct(cfg.hidden_size, 3 * cfg.hidden_size)
+        self.attn_out = LinearAct(cfg.hidden_size, cfg.hidden_size)
         self.attn_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        fused_relu = cfg.activation == "relu"
-        self.ffn_in = LinearAct(cfg.hidden_size, cfg.intermediate_size, relu=fused_relu)
-        self.act = nn.Identity() if fused_relu else nn.GELU()
+        assert cfg.activation in ("gelu", "relu")
+        self.ffn_in = LinearAct(cfg.hidden_size, cfg.intermediate_size, activation=cfg.activation)  # activation in the epilogue
+        self.act = nn.Identity()
         self.ffn_out = LinearAct(cfg.intermediate_size, cfg.hidden_size)
         self.ffn_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
         self.dropout = nn.Dropout(cfg.hidden_dropout_prob)

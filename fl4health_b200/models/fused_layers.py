@@ -3,6 +3,8 @@
 
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -93,17 +95,37 @@ class Conv2dOverlapWgrad(nn.Conv2d):
 
 
 class LinearAct(nn.Linear):
-    """``nn.Linear`` (+ optional fused ReLU) whose bf16 CUDA forward is the hand-written tcgen05 / TMEM / TMA GEMM with
-    the bias + activation epilogue (``ops/csrc/tc_gemm.cu``); identical parameters and state-dict keys."""
+    """``nn.Linear`` (+ optional fused ReLU / GELU) whose bf16 CUDA forward is the hand-written tcgen05 / TMEM / TMA GEMM
+    with the bias + activation epilogue (``ops/csrc/tc_gemm.cu``); identical parameters and state-dict keys.
+    ``activation``: ``None | "relu" | "gelu"`` (``relu=True`` is the older spelling of ``activation="relu"``)."""
 
-    def __init__(self, in_features: int, out_features: int, bias: bool = True, relu: bool = False, device=None, dtype=None) -> None:  # noqa: ANN001
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, relu: bool = False, device=None, dtype=None,  # noqa: ANN001
+                 activation: str | None = None) -> None:
         super().__init__(in_features, out_features, bias, device=device, dtype=dtype)
-        self.relu = relu
+        assert activation in (None, "none", "relu", "gelu")
+        self.relu = "relu" if relu else (activation or "none")
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002
         if torch.is_autocast_enabled() and input.is_cuda and input.dtype != self.weight.dtype == torch.bfloat16:
             input = input.to(torch.bfloat16)  # master-weight mode: weights already bf16, activations follow autocast
-        return linear_bias_act(input, self.weight, self.bias, self.relu)
+        if self._use_kernel(input):
+            return linear_bias_act(input, self.weight, self.bias, self.relu)
+        out = nn.functional.linear(input, self.weight, self.bias)
+        return torch.relu(out) if self.relu == "relu" else (nn.functional.gelu(out) if self.relu == "gelu" else out)
+
+    def _use_kernel(self, input: torch.Tensor) -> bool:  # noqa: A002
+        """``FL4H_TC_LINEAR``: ``always`` | ``never`` | ``auto`` (default).  ``auto`` sends the layer through the
+        hand-written kernel where it is the faster choice on B200: whenever an activation is fused into the epilogue
+        (saves a full elementwise pass over the output: BERT-base FFN-in, 30 us vs 19 + 15 us for library GEMM + GELU,
+        in situ) and for large plain GEMMs (>= 2048 in every dimension, on par with the library); mid-sized plain
+        GEMMs stay on the library, whose 2-CTA tiles are ~1.3x faster there (``profiles/README.md``)."""
+        policy = os.environ.get("FL4H_TC_LINEAR", "auto")
+        if policy == "never" or not input.is_cuda:
+            return False
+        if policy == "always" or self.relu != "none":
+            return True
+        rows = input.numel() // max(input.shape[-1], 1)
+        return min(rows, self.in_features, self.out_features) >= 2048
 
     def extra_repr(self) -> str:
-        return super().extra_repr() + f", relu={self.relu}"
+        return super().extra_repr() + f", activation={self.relu}"

@@ -105,9 +105,111 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Epilogue of one 32-column chunk of an accumulator row: (+bias) -> optional store of the pre-activation (what a GELU
+// backward needs) -> activation -> bf16, 16-byte stores.
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_BIAS_BF16 = 0x100 };  // flag: persistent variants only
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == ACT_RELU) return x > 0.f ? x : 0.f;
+    if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));  // exact (erf) GELU, as nn.GELU()
+    return x;
+}
+
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&f)[8], int valid) {
+    if (valid >= 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)                        // unrolled + predicated: keeps f[] in registers
+            if (j < valid) dst[j] = __float2bfloat16(f[j]);
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], __nv_bfloat16* __restrict__ C,
+                                               __nv_bfloat16* __restrict__ pre, const float* __restrict__ bias, int row,
+                                               int col0, int N, int act) {
+    const int64_t base = static_cast<int64_t>(row) * N + col0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                          // 4 x 8 columns -> 16-byte stores
+        const int col = col0 + q * 8;
+        if (col >= N) break;
+        float z[8], f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float x = __uint_as_float(v[q * 8 + j]);
+            if (bias != nullptr && col + j < N) x += bias[col + j];
+            z[j] = x;
+            f[j] = apply_act(x, act);
+        }
+        store8_bf16(C + base + q * 8, f, N - col);
+        if (pre != nullptr) store8_bf16(pre + base + q * 8, z, N - col);
+    }
+}
+
+// Same epilogue with the 32x32 block transposed through a warp-private shared-memory buffer, so that every global
+// store instruction writes 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.  With one
+// thread per accumulator row, the direct version issues 16-byte partial-sector writes only: measured on B200 that
+// costs ~10-15 us per 128x256 tile, i.e. the epilogue -- not the tensor pipe -- bounds every GEMM with K <= 1024.
+constexpr int kStageStride = 80;                            // 64 B of payload + 16 B pad: conflict-free 16-byte writes
+constexpr int kStageBytesPerWarp = 32 * kStageStride;
+
+__device__ __forceinline__ void stage_and_store(const float (&f)[32], uint8_t* stage, __nv_bfloat16* __restrict__ dst, int row_base,
+                                                int lane, int col0, int M, int N) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(stage + lane * kStageStride + q * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+    const int seg = lane & 3, col = col0 + seg * 8;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * kStageStride + seg * 16);
+        const int grow = row_base + r;
+        if (grow < M && col < N) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(grow) * N + col) = val;
+    }
+    __syncwarp();
+}
+
+// `bias_s`: this tile's bias slice staged in shared memory by the caller (nullptr = no bias), indexed from the chunk's
+// first column.  Reading it from global here instead put ~40 % of the epilogue's stall samples on the first FADD after
+// each LDG (ncu source view, 4096x2304x768).
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], uint8_t* stage, __nv_bfloat16* __restrict__ C,
+                                                      __nv_bfloat16* __restrict__ pre, const float* bias_s,
+                                                      int row_base, int lane, int col0, int M, int N, int act) {
+    float z[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float4 b4 = bias_s != nullptr ? *reinterpret_cast<const float4*>(bias_s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        z[j] = __uint_as_float(v[j]) + b4.x;
+        z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+        z[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+        z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+    }
+    if (pre != nullptr) stage_and_store(z, stage, pre, row_base, lane, col0, M, N);
+    if (act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = apply_act(z[j], act);
+    }
+    stage_and_store(z, stage, C, row_base, lane, col0, M, N);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 __nv_bfloat16* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu) {
+                 __nv_bfloat16* __restrict__ C, __nv_bfloat16* __restrict__ pre, const float* __restrict__ bias, int M, int N,
+                 int K, int act) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
@@ -184,33 +286,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t acc[32];
             tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), acc);
             const int col0 = n_blk * BN + c0;
-            if (row < M && col0 < N) {
-                __nv_bfloat16* out = C + static_cast<int64_t>(row) * N + col0;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {              // 4 x 8 columns -> 16-byte stores
-                    const int col = col0 + v * 8;
-                    if (col >= N) break;
-                    float f[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float x = __uint_as_float(acc[v * 8 + j]);
-                        if (bias != nullptr && col + j < N) x += bias[col + j];
-                        if (relu) x = x > 0.f ? x : 0.f;
-                        f[j] = x;
-                    }
-                    if (col + 8 <= N) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            w[j] = *reinterpret_cast<uint32_t*>(&h);
-                        }
-                        *reinterpret_cast<uint4*>(out + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-                    } else {
-                        for (int j = 0; col + j < N; ++j) out[v * 8 + j] = __float2bfloat16(f[j]);
-                    }
-                }
-            }
+            if (row < M && col0 < N) epilogue_chunk(acc, C, pre, bias, row, col0, N, act);
         }
     }
     tc_fence_before();
@@ -268,14 +344,19 @@ struct V2 {
     static constexpr int kBTile = kBN * BK * 2;
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kTmemColsV2 = 2 * kBN;           // two accumulator buffers
-    static constexpr int kSmemV2 = kStagesV2 * kStageBytes + 256 + 1024;
+    static constexpr int kStagingOffset = kStagesV2 * kStageBytes + 256;       // after the barriers
+    static constexpr int kBiasOffset = kStagingOffset + 4 * kStageBytesPerWarp;  // per epilogue warp: kBN floats
+    static constexpr int kSmemV2 = kBiasOffset + 4 * kBN * 4 + 1024;            // + staging + bias + alignment slack
 };
 
 template <int kBN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                            __nv_bfloat16* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu) {
+                            __nv_bfloat16* __restrict__ C, __nv_bfloat16* __restrict__ pre, const float* __restrict__ bias, int M, int N,
+                 int K, int act) {
     using Cfg = V2<kBN>;
+    const bool bias_bf16 = (act & ACT_BIAS_BF16) != 0;      // `bias` points at bf16 values (master-weight mode)
+    act &= 0xff;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStagesV2 * Cfg::kStageBytes);
@@ -361,41 +442,29 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
             const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
             const uint32_t acc = local_tile & 1, use = local_tile >> 1;
+            // this tile's bias slice -> shared memory, issued BEFORE waiting for the accumulator so the global-load
+            // latency hides behind the mainloop
+            float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOffset) + quarter * kBN;
+            if (bias != nullptr) {
+                for (int c = lane; c < kBN; c += 32) {
+                    const int col = n_blk * kBN + c;
+                    float b = 0.f;
+                    if (col < N) b = bias_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[col]) : bias[col];
+                    bias_s[c] = b;
+                }
+                __syncwarp();
+            }
             mbar_wait(tmem_full_bar + acc, use & 1);
             tc_fence_after();
-            const int row = m_blk * BM + quarter * 32 + lane;
+            const int row_base = m_blk * BM + quarter * 32;
+            uint8_t* stage = smem + Cfg::kStagingOffset + quarter * kStageBytesPerWarp;
 #pragma unroll 1
             for (int c0 = 0; c0 < kBN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN + static_cast<uint32_t>(c0), v);
                 const int col0 = n_blk * kBN + c0;
-                if (row < M && col0 < N) {
-                    __nv_bfloat16* out = C + static_cast<int64_t>(row) * N + col0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int col = col0 + q * 8;
-                        if (col >= N) break;
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float x = __uint_as_float(v[q * 8 + j]);
-                            if (bias != nullptr && col + j < N) x += bias[col + j];
-                            if (relu) x = x > 0.f ? x : 0.f;
-                            f[j] = x;
-                        }
-                        if (col + 8 <= N) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                                w[j] = *reinterpret_cast<uint32_t*>(&h);
-                            }
-                            *reinterpret_cast<uint4*>(out + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-                        } else {
-                            for (int j = 0; col + j < N; ++j) out[q * 8 + j] = __float2bfloat16(f[j]);
-                        }
-                    }
-                }
+                if (row_base < M && col0 < N)
+                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + c0 : nullptr, row_base, lane, col0, M, N, act);
             }
             tc_fence_before();
             __syncwarp();
@@ -410,8 +479,8 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
 }
 
 template <int kBN>
-int launch_persistent(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int sms,
-                      cudaStream_t stream) {
+int launch_persistent(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act,
+                      int sms, cudaStream_t stream) {
     using Cfg = V2<kBN>;
     static bool configured = false;
     if (!configured) {
@@ -426,7 +495,8 @@ int launch_persistent(const void* a, const void* w, void* c, const float* bias, 
     if (res != CUDA_SUCCESS) return -static_cast<int>(res);
     const int tiles = ((M + BM - 1) / BM) * ((N + kBN - 1) / kBN);
     const int grid = tiles < sms ? tiles : sms;
-    tc_linear_persistent_kernel<kBN><<<grid, kThreads, Cfg::kSmemV2, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c), bias, M, N, K, relu);
+    tc_linear_persistent_kernel<kBN><<<grid, kThreads, Cfg::kSmemV2, stream>>>(
+        map_a, map_b, static_cast<__nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(pre), bias, M, N, K, act);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -434,13 +504,21 @@ int launch_persistent(const void* a, const void* w, void* c, const float* bias, 
 
 extern "C" {
 
-// variant: 0 = one 128x128 tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256
-int fl4h_tc_linear_v(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int variant,
-                     cudaStream_t stream);
-
-// returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding
-int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu,
-                   cudaStream_t stream) {
+// act: 0 none, 1 ReLU, 2 GELU(erf); | 0x100 = `bias` holds bf16 instead of fp32 (variants 1 and 2 only).
+// `pre` (optional, [M, N] bf16) receives x.W^T + b BEFORE the activation.
+// variant: 0 = one 128x128 tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256.
+// Returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding.
+int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act,
+                      int variant, cudaStream_t stream) {
+    static int sms = 0;
+    if (sms == 0) {
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    }
+    if (variant == 1) return launch_persistent<128>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (variant == 2) return launch_persistent<256>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (act & ACT_BIAS_BF16) return static_cast<int>(cudaErrorInvalidValue);
     static bool configured = false;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -453,21 +531,18 @@ int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int
     res = make_tensor_map(&map_b, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K));
     if (res != CUDA_SUCCESS) return -static_cast<int>(res);
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    tc_linear_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c), bias, M, N, K, relu);
+    tc_linear_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c),
+                                                             static_cast<__nv_bfloat16*>(pre), bias, M, N, K, act);
     return static_cast<int>(cudaGetLastError());
 }
 
 int fl4h_tc_linear_v(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int variant,
                      cudaStream_t stream) {
-    static int sms = 0;
-    if (sms == 0) {
-        int device = 0;
-        cudaGetDevice(&device);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    }
-    if (variant == 1) return launch_persistent<128>(a, w, c, bias, M, N, K, relu, sms, stream);
-    if (variant == 2) return launch_persistent<256>(a, w, c, bias, M, N, K, relu, sms, stream);
-    return fl4h_tc_linear(a, w, c, bias, M, N, K, relu, stream);
+    return fl4h_tc_linear_ex(a, w, c, nullptr, bias, M, N, K, relu ? ACT_RELU : ACT_NONE, variant, stream);
+}
+
+int fl4h_tc_linear(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, cudaStream_t stream) {
+    return fl4h_tc_linear_ex(a, w, c, nullptr, bias, M, N, K, relu ? ACT_RELU : ACT_NONE, 0, stream);
 }
 
 }  // extern "C"

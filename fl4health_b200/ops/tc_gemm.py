@@ -18,7 +18,7 @@ from fl4health_b200.ops import _lib
 
 
 def kernel_eligible(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> bool:
-    if not (x.is_cuda and weight.is_cuda) or _lib.load() is None:
+    if not (x.is_cuda and weight.is_cuda) or _lib.load() is None or os.environ.get("FL4H_TC_DISABLE") == "1":
         return False
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         return False
@@ -32,9 +32,20 @@ def kernel_eligible(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
     return bias is None or (bias.is_cuda and bias.numel() == n)
 
 
-def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool) -> torch.Tensor:
+ACTIVATIONS = {"none": 0, "relu": 1, "gelu": 2}
+
+
+def _act_code(act: bool | str | None) -> int:
+    if isinstance(act, bool) or act is None:
+        return 1 if act else 0
+    return ACTIVATIONS[act]
+
+
+def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool | str) -> torch.Tensor:
     out = F_nn.linear(x.float(), weight.float(), None if bias is None else bias.float())
-    return (torch.relu(out) if relu else out).to(x.dtype)
+    code = _act_code(relu)
+    out = torch.relu(out) if code == 1 else (F_nn.gelu(out) if code == 2 else out)
+    return out.to(x.dtype)
 
 
 def pick_variant(m: int, n: int) -> int:
@@ -46,49 +57,70 @@ def pick_variant(m: int, n: int) -> int:
     return 2 if n >= 256 else 1
 
 
-def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool, variant: int | None = None) -> torch.Tensor:
+def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, act: bool | int, variant: int | None = None,
+            want_pre: bool = False) -> torch.Tensor | tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load(True)
     m, k = x2d.shape
     n = weight.shape[0]
     variant = pick_variant(m, n) if variant is None else variant
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x2d.device)
-    bias32 = None if bias is None else (bias if bias.dtype == torch.float32 else bias.float()).contiguous()
-    err = lib.fl4h_tc_linear_v(
-        _lib.ptr(x2d), _lib.ptr(weight), _lib.ptr(out), _lib.ptr(bias32), ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k),
-        ctypes.c_int(1 if relu else 0), ctypes.c_int(variant), _lib.stream_ptr(x2d.device),
+    pre = torch.empty_like(out) if want_pre else None
+    code = int(act)
+    if bias is None or bias.dtype == torch.float32:
+        bias_arg = bias
+    elif bias.dtype == torch.bfloat16 and variant in (1, 2):  # master-weight mode: read the bf16 bias in the kernel
+        bias_arg, code = bias, code | 0x100
+    else:
+        bias_arg = bias.float()
+    if bias_arg is not None and not bias_arg.is_contiguous():
+        bias_arg = bias_arg.contiguous()
+    err = lib.fl4h_tc_linear_ex(
+        _lib.ptr(x2d), _lib.ptr(weight), _lib.ptr(out), _lib.ptr(pre), _lib.ptr(bias_arg), ctypes.c_int(m), ctypes.c_int(n),
+        ctypes.c_int(k), ctypes.c_int(code), ctypes.c_int(variant), _lib.stream_ptr(x2d.device),
     )
     if err != 0:
         raise RuntimeError(f"fl4h_tc_linear failed ({'CUresult ' + str(-err) if err < 0 else 'cudaError ' + str(err)})")
     _lib.count_launches(1)
-    return out
+    return (out, pre) if want_pre else out
 
 
 class _LinearBiasAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):  # noqa: ANN001, ANN205
+    def forward(ctx, x, weight, bias, act):  # noqa: ANN001, ANN205
         x2d = x.reshape(-1, x.shape[-1])
         if not x2d.is_contiguous():
             x2d = x2d.contiguous()
-        out = _launch(x2d, weight, bias, relu)
-        ctx.save_for_backward(x2d, weight, out if relu else None)
-        ctx.relu, ctx.has_bias, ctx.in_shape = relu, bias is not None, x.shape
+        needs_grad = any(ctx.needs_input_grad[:3])
+        if act == 2 and needs_grad:  # GELU backward needs the pre-activation: the epilogue stores it alongside
+            out, pre = _launch(x2d, weight, bias, act, want_pre=True)
+            ctx.save_for_backward(x2d, weight, pre)
+        else:
+            out = _launch(x2d, weight, bias, act)
+            ctx.save_for_backward(x2d, weight, out if act == 1 else None)
+        ctx.act, ctx.has_bias, ctx.in_shape = act, bias is not None, x.shape
         ctx.bias_dtype = None if bias is None else bias.dtype
         return out.reshape(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, grad_out):  # noqa: ANN001, ANN205
-        x2d, weight, out = ctx.saved_tensors
+        x2d, weight, aux = ctx.saved_tensors
         g = grad_out.reshape(-1, grad_out.shape[-1])
-        if ctx.relu:
-            g = g * (out > 0).to(g.dtype)
+        if ctx.act == 1:
+            g = g * (aux > 0).to(g.dtype)
+        elif ctx.act == 2:
+            g = torch.ops.aten.gelu_backward(g.contiguous(), aux)
         grad_x = (g @ weight).reshape(ctx.in_shape) if ctx.needs_input_grad[0] else None
         grad_w = g.t() @ x2d if ctx.needs_input_grad[1] else None
-        grad_b = g.float().sum(dim=0).to(ctx.bias_dtype) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        grad_b = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:  # one reduction kernel (fp32 accumulation inside) when dtypes agree
+            grad_b = g.sum(dim=0) if ctx.bias_dtype == g.dtype else g.sum(dim=0, dtype=torch.float32).to(ctx.bias_dtype)
         return grad_x, grad_w, grad_b, None
 
 
-def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False) -> torch.Tensor:
+def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, relu: bool | str = False) -> torch.Tensor:
+    """``relu``: False / True (ReLU) or one of ``"none" | "relu" | "gelu"`` (exact erf GELU)."""
+    code = _act_code(relu)
     if kernel_eligible(x, weight, bias):
-        return _LinearBiasAct.apply(x, weight, bias, relu)
+        return _LinearBiasAct.apply(x, weight, bias, code)
     out = F_nn.linear(x, weight, bias)
-    return torch.relu(out) if relu else out
+    return torch.relu(out) if code == 1 else (F_nn.gelu(out) if code == 2 else out)

@@ -442,3 +442,93 @@ def test_tcgen05_linear_matches_reference(shape, relu, with_bias, variant, monke
     (pre * (y.detach() > 0).float() if relu else pre).backward(g.float())
     assert torch.allclose(x.grad.float(), xr.grad, rtol=3e-2, atol=3e-2)
     assert torch.allclose(w.grad.float(), wr.grad, rtol=3e-2, atol=3e-2 * (m ** 0.5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(256, 384, 512), (300, 200, 136), (2048, 3072, 768)])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_tcgen05_linear_gelu_epilogue(shape, variant, monkeypatch) -> None:
+    """GELU (erf) epilogue of tc_gemm.cu: the forward matches an fp32 reference, the pre-activation stored by the same
+    epilogue feeds an exact GELU backward, and a no-grad call does not write the pre-activation at all."""
+    from fl4health_b200.ops.tc_gemm import linear_bias_act, linear_bias_act_reference
+
+    monkeypatch.setenv("FL4H_TC_VARIANT", variant)
+    m, n, k = shape
+    torch.manual_seed(m * 3 + n)
+    dev = torch.device("cuda")
+    x = torch.randn(m, k, device=dev).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(n, k, device=dev) / k ** 0.5).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(n, device=dev)
+    y = linear_bias_act(x, w, b, "gelu")
+    ref = linear_bias_act_reference(x.detach(), w.detach(), b, "gelu").float()
+    assert torch.allclose(y.float(), ref, rtol=2e-2, atol=2e-2), (y.float() - ref).abs().max()
+    with torch.no_grad():
+        y_inf = linear_bias_act(x, w, b, "gelu")
+    assert torch.equal(y_inf, y.detach())
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    torch.nn.functional.gelu(torch.nn.functional.linear(xr, wr, b)).backward(g.float())
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=4e-2, atol=4e-2), (x.grad.float() - xr.grad).abs().max()
+    assert torch.allclose(w.grad.float(), wr.grad, rtol=4e-2, atol=4e-2 * (m ** 0.5))
+
+
+@pytest.mark.gpu
+def test_bert_layer_fused_matches_stock_modules(monkeypatch) -> None:
+    """A BERT encoder whose projections run through the tcgen05 kernel (fused bias / GELU) vs the same weights through
+    stock nn.Linear + nn.GELU in fp32: logits and every parameter gradient agree to bf16 accuracy."""
+    from fl4health_b200 import ops
+    from fl4health_b200.models.bert import BertConfig, BertForSequenceClassification
+
+    monkeypatch.setenv("FL4H_TC_LINEAR", "always")  # default "auto" keeps mid-sized plain GEMMs on the library
+    torch.manual_seed(7)
+    dev = torch.device("cuda")
+    cfg = BertConfig(vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024,
+                     max_position_embeddings=64, hidden_dropout_prob=0.0)
+    model = BertForSequenceClassification(cfg, 8).to(dev)
+    ref = BertForSequenceClassification(cfg, 8).to(dev)
+    ref.load_state_dict(model.state_dict())
+    ids = torch.randint(0, 512, (16, 64), device=dev)
+    mask = (torch.arange(64, device=dev)[None, :] < torch.randint(32, 65, (16, 1), device=dev)).long()
+    labels = torch.randint(0, 8, (16,), device=dev)
+    model = model.to(torch.bfloat16)
+    before = ops.launch_count()
+    logits = model(ids, mask)
+    assert ops.launch_count() - before == 2 * 4 + 2  # qkv, attn_out, ffn_in, ffn_out per layer + pooler + classifier
+    monkeypatch.setenv("FL4H_TC_LINEAR", "auto")
+    before = ops.launch_count()
+    with torch.no_grad():
+        auto_logits = model(ids, mask)
+    assert ops.launch_count() - before == 2  # auto: only the GEMMs with a fused activation (ffn_in) at this size
+    assert torch.allclose(auto_logits.float(), logits.float(), rtol=5e-2, atol=5e-2)
+    monkeypatch.setenv("FL4H_TC_LINEAR", "always")
+    torch.nn.functional.cross_entropy(logits.float(), labels).backward()
+    ref_logits = ref(ids, mask)
+    torch.nn.functional.cross_entropy(ref_logits, labels).backward()
+    assert torch.allclose(logits.float(), ref_logits, rtol=5e-2, atol=5e-2), (logits.float() - ref_logits).abs().max()
+    for (name, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        cos = torch.nn.functional.cosine_similarity(p.grad.float().flatten(), q.grad.flatten(), dim=0)
+        assert cos > 0.98, (name, float(cos))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_tcgen05_linear_bf16_bias(variant, monkeypatch) -> None:
+    """Master-weight mode hands the kernel a bf16 bias: the persistent variants read it as is (no cast kernel), the
+    one-tile variant goes through an fp32 copy; both match the fp32 reference and produce a bf16 bias gradient."""
+    from fl4health_b200.ops.tc_gemm import linear_bias_act, linear_bias_act_reference
+
+    monkeypatch.setenv("FL4H_TC_VARIANT", variant)
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    x = torch.randn(512, 256, device=dev).to(torch.bfloat16)
+    w = (torch.randn(384, 256, device=dev) / 16).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(384, device=dev).to(torch.bfloat16).requires_grad_(True)
+    y = linear_bias_act(x, w, b, "gelu")
+    ref = linear_bias_act_reference(x, w.detach(), b.detach(), "gelu").float()
+    assert torch.allclose(y.float(), ref, rtol=2e-2, atol=2e-2)
+    y.sum().backward()
+    assert b.grad is not None and b.grad.dtype == torch.bfloat16 and w.grad.dtype == torch.bfloat16
+    br = b.detach().float().requires_grad_(True)
+    torch.nn.functional.gelu(torch.nn.functional.linear(x.float(), w.detach().float(), br)).sum().backward()
+    assert torch.allclose(b.grad.float(), br.grad, rtol=5e-2, atol=0.5)
