@@ -114,18 +114,18 @@ class LinearAct(nn.Linear):
         return torch.relu(out) if self.relu == "relu" else (nn.functional.gelu(out) if self.relu == "gelu" else out)
 
     def _use_kernel(self, input: torch.Tensor) -> bool:  # noqa: A002
-        """``FL4H_TC_LINEAR``: ``always`` | ``never`` | ``auto`` (default).  ``auto`` sends the layer through the
-        hand-written kernel where it is the faster choice on B200: whenever an activation is fused into the epilogue
-        (saves a full elementwise pass over the output: BERT-base FFN-in, 30 us vs 19 + 15 us for library GEMM + GELU,
-        in situ) and for large plain GEMMs (>= 2048 in every dimension, on par with the library); mid-sized plain
-        GEMMs stay on the library, whose 2-CTA tiles are ~1.3x faster there (``profiles/README.md``)."""
+        """``FL4H_TC_LINEAR``: ``always`` | ``never`` | ``auto`` (default).  ``auto`` uses the hand-written kernel where
+        it is the faster choice on B200 (``profiles/README.md``, tcgen05 table): a fused activation on a GEMM of at
+        least 4096^3 work (1236 vs 1154 TFLOP/s with ReLU, 1078 vs 1047 with GELU at 4096^3 against library GEMM + an
+        elementwise pass).  Smaller problems stay on the library: its 2-CTA tiles reach 930-970 TFLOP/s at BERT-base
+        shapes (K = 768) where this 1-CTA kernel reaches 575-580, so even a free activation does not pay for it."""
         policy = os.environ.get("FL4H_TC_LINEAR", "auto")
         if policy == "never" or not input.is_cuda:
             return False
-        if policy == "always" or self.relu != "none":
+        if policy == "always":
             return True
         rows = input.numel() // max(input.shape[-1], 1)
-        return min(rows, self.in_features, self.out_features) >= 2048
+        return self.relu != "none" and rows * self.in_features * self.out_features >= 4096 ** 3
 
     def extra_repr(self) -> str:
         return super().extra_repr() + f", activation={self.relu}"

@@ -109,9 +109,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 // backward needs) -> activation -> bf16, 16-byte stores.
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_BIAS_BF16 = 0x100 };  // flag: persistent variants only
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one reciprocal, one exp2, a degree-5
+// Horner chain -- about a third of libdevice erff's instructions.  With erff the GELU epilogue of a 128x256 tile was
+// instruction-bound at ~5 us against a 3.2 us mainloop at K = 768 (ncu: 13 M instructions for 4096x3072x768).
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = exp2f(-1.4426950408889634f * ax * ax);
+    return copysignf(1.f - p * t * e, x);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == ACT_RELU) return x > 0.f ? x : 0.f;
-    if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));  // exact (erf) GELU, as nn.GELU()
+    if (act == ACT_GELU) return 0.5f * x * (1.f + erf_as(x * 0.70710678118654752f));  // erf GELU, as nn.GELU()
     return x;
 }
 
@@ -337,7 +351,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int kBN>
+template <int kBN, int kEpi = 4>
 struct V2 {
     static constexpr int kStagesV2 = 4;
     static constexpr int kATile = BM * BK * 2;
@@ -345,16 +359,19 @@ struct V2 {
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kTmemColsV2 = 2 * kBN;           // two accumulator buffers
     static constexpr int kStagingOffset = kStagesV2 * kStageBytes + 256;       // after the barriers
-    static constexpr int kBiasOffset = kStagingOffset + 4 * kStageBytesPerWarp;  // per epilogue warp: kBN floats
-    static constexpr int kSmemV2 = kBiasOffset + 4 * kBN * 4 + 1024;            // + staging + bias + alignment slack
+    static constexpr int kEpiWarps = kEpi;                // 4 (one per TMEM lane quarter) or 8 (two per quarter, half the columns each)
+    static constexpr int kThreadsV2 = 32 * (4 + kEpiWarps);
+    static constexpr int kColsPerEpiWarp = kBN / (kEpiWarps / 4);
+    static constexpr int kBiasOffset = kStagingOffset + kEpiWarps * kStageBytesPerWarp;  // per epilogue warp: its bias slice
+    static constexpr int kSmemV2 = kBiasOffset + kEpiWarps * kColsPerEpiWarp * 4 + 1024;  // + staging + bias + alignment slack
 };
 
-template <int kBN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kBN, int kEpi>
+__global__ void __launch_bounds__(V2<kBN, kEpi>::kThreadsV2, 1)
 tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                             __nv_bfloat16* __restrict__ C, __nv_bfloat16* __restrict__ pre, const float* __restrict__ bias, int M, int N,
                  int K, int act) {
-    using Cfg = V2<kBN>;
+    using Cfg = V2<kBN, kEpi>;
     const bool bias_bf16 = (act & ACT_BIAS_BF16) != 0;      // `bias` points at bf16 values (master-weight mode)
     act &= 0xff;
     extern __shared__ uint8_t smem_raw[];
@@ -381,7 +398,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar + a, 1);
-            mbar_init(tmem_empty_bar + a, 4);                 // one arrival per epilogue warp
+            mbar_init(tmem_empty_bar + a, Cfg::kEpiWarps);    // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -436,18 +453,18 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                 umma_commit(tmem_full_bar + acc);
             }
         }
-    } else if (warp >= 4) {  // ===== epilogue warps =====
-        const int quarter = warp & 3;
+    } else if (warp >= 4) {  // ===== epilogue warps: warp e owns TMEM lanes [32 (e % 4), +32) x columns [half * kBN/2, +kBN/2) =====
+        const int epi = warp - 4, quarter = epi & 3, col_begin = (epi >> 2) * Cfg::kColsPerEpiWarp;
         uint32_t local_tile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
             const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
             const uint32_t acc = local_tile & 1, use = local_tile >> 1;
-            // this tile's bias slice -> shared memory, issued BEFORE waiting for the accumulator so the global-load
+            // this warp's bias slice -> shared memory, issued BEFORE waiting for the accumulator so the global-load
             // latency hides behind the mainloop
-            float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOffset) + quarter * kBN;
+            float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOffset) + epi * Cfg::kColsPerEpiWarp;
             if (bias != nullptr) {
-                for (int c = lane; c < kBN; c += 32) {
-                    const int col = n_blk * kBN + c;
+                for (int c = lane; c < Cfg::kColsPerEpiWarp; c += 32) {
+                    const int col = n_blk * kBN + col_begin + c;
                     float b = 0.f;
                     if (col < N) b = bias_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[col]) : bias[col];
                     bias_s[c] = b;
@@ -457,14 +474,15 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             mbar_wait(tmem_full_bar + acc, use & 1);
             tc_fence_after();
             const int row_base = m_blk * BM + quarter * 32;
-            uint8_t* stage = smem + Cfg::kStagingOffset + quarter * kStageBytesPerWarp;
+            uint8_t* stage = smem + Cfg::kStagingOffset + epi * kStageBytesPerWarp;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kBN; c0 += 32) {
+            for (int c0 = col_begin; c0 < col_begin + Cfg::kColsPerEpiWarp; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN + static_cast<uint32_t>(c0), v);
                 const int col0 = n_blk * kBN + c0;
                 if (row_base < M && col0 < N)
-                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + c0 : nullptr, row_base, lane, col0, M, N, act);
+                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) : nullptr, row_base, lane, col0,
+                                          M, N, act);
             }
             tc_fence_before();
             __syncwarp();
@@ -478,13 +496,13 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     }
 }
 
-template <int kBN>
+template <int kBN, int kEpi>
 int launch_persistent(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act,
                       int sms, cudaStream_t stream) {
-    using Cfg = V2<kBN>;
+    using Cfg = V2<kBN, kEpi>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(tc_linear_persistent_kernel<kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemV2);
+        cudaError_t err = cudaFuncSetAttribute(tc_linear_persistent_kernel<kBN, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemV2);
         if (err != cudaSuccess) return static_cast<int>(err);
         configured = true;
     }
@@ -495,7 +513,7 @@ int launch_persistent(const void* a, const void* w, void* c, void* pre, const fl
     if (res != CUDA_SUCCESS) return -static_cast<int>(res);
     const int tiles = ((M + BM - 1) / BM) * ((N + kBN - 1) / kBN);
     const int grid = tiles < sms ? tiles : sms;
-    tc_linear_persistent_kernel<kBN><<<grid, kThreads, Cfg::kSmemV2, stream>>>(
+    tc_linear_persistent_kernel<kBN, kEpi><<<grid, Cfg::kThreadsV2, Cfg::kSmemV2, stream>>>(
         map_a, map_b, static_cast<__nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(pre), bias, M, N, K, act);
     return static_cast<int>(cudaGetLastError());
 }
@@ -506,7 +524,7 @@ extern "C" {
 
 // act: 0 none, 1 ReLU, 2 GELU(erf); | 0x100 = `bias` holds bf16 instead of fp32 (variants 1 and 2 only).
 // `pre` (optional, [M, N] bf16) receives x.W^T + b BEFORE the activation.
-// variant: 0 = one 128x128 tile per CTA (v1), 1 = persistent 128x128, 2 = persistent 128x256.
+// variant: 0 = one 128x128 tile per CTA, 1 = persistent 128x128, 2 = persistent 128x256, 3 = 128x256 with 8 epilogue warps.
 // Returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding.
 int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act,
                       int variant, cudaStream_t stream) {
@@ -516,8 +534,9 @@ int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const fl
         cudaGetDevice(&device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     }
-    if (variant == 1) return launch_persistent<128>(a, w, c, pre, bias, M, N, K, act, sms, stream);
-    if (variant == 2) return launch_persistent<256>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (variant == 1) return launch_persistent<128, 4>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (variant == 2) return launch_persistent<256, 4>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (variant == 3) return launch_persistent<256, 8>(a, w, c, pre, bias, M, N, K, act, sms, stream);
     if (act & ACT_BIAS_BF16) return static_cast<int>(cudaErrorInvalidValue);
     static bool configured = false;
     if (!configured) {

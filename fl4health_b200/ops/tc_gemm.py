@@ -48,13 +48,18 @@ def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch
     return out.to(x.dtype)
 
 
-def pick_variant(m: int, n: int) -> int:
-    """0: one 128x128 tile per CTA; 1: persistent 128x128 (double-buffered TMEM); 2: persistent 128x256.
-    ``FL4H_TC_VARIANT`` forces one; by default wide outputs take the 256-wide tile (twice the math per smem byte)."""
+def pick_variant(m: int, n: int, k: int = 0) -> int:
+    """0: one 128x128 tile per CTA; 1: persistent 128x128 (double-buffered TMEM); 2: persistent 128x256, 4 epilogue
+    warps; 3: persistent 128x256, 8 epilogue warps.  ``FL4H_TC_VARIANT`` forces one.  Measured on B200
+    (``benchmarks/tc_gemm_bench.py``): with K <= 4096 the epilogue is on the critical path and the 8-warp version wins
+    (580 vs 452 TFLOP/s at 4096x2304x768, 1038 vs 762 at 16384x4096x1024); at 8192^3 the 4-warp version does
+    (1326 vs 1208)."""
     forced = os.environ.get("FL4H_TC_VARIANT")
     if forced is not None:
         return int(forced)
-    return 2 if n >= 256 else 1
+    if n < 256:
+        return 1
+    return 3 if 0 < k <= 4096 else 2
 
 
 def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, act: bool | int, variant: int | None = None,
@@ -62,13 +67,13 @@ def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, 
     lib = _lib.load(True)
     m, k = x2d.shape
     n = weight.shape[0]
-    variant = pick_variant(m, n) if variant is None else variant
+    variant = pick_variant(m, n, k) if variant is None else variant
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x2d.device)
     pre = torch.empty_like(out) if want_pre else None
     code = int(act)
     if bias is None or bias.dtype == torch.float32:
         bias_arg = bias
-    elif bias.dtype == torch.bfloat16 and variant in (1, 2):  # master-weight mode: read the bf16 bias in the kernel
+    elif bias.dtype == torch.bfloat16 and variant in (1, 2, 3):  # master-weight mode: read the bf16 bias in the kernel
         bias_arg, code = bias, code | 0x100
     else:
         bias_arg = bias.float()
