@@ -13,7 +13,7 @@ from typing import Any
 import torch
 from torch import nn
 
-from examples.common import ExampleClientMixin, client_datasets, make_config_fn, strategy_kwargs
+from examples.common import ExampleClientMixin, client_datasets, strategy_kwargs
 from examples.models import SmallCnn
 from examples.scenarios import _adaptive_strategy, _dict_optimizers, _dp_fn, _fl_server, make_clients, scenario
 from fl4health_b200.engine.data import BatchedTensorLoader

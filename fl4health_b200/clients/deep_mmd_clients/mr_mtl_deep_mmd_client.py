@@ -13,7 +13,6 @@ from fl4health_b200.common.typing import Config, Scalar
 from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.reporting.base_reporter import BaseReporter
-from fl4health_b200.utils.client import clone_and_freeze_model
 from fl4health_b200.utils.losses import EvaluationLosses, LossMeterType, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 from fl4health_b200.clients._mmd_feature_alignment import DeepMmdMixin

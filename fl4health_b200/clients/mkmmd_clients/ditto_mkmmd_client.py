@@ -9,12 +9,12 @@ from pathlib import Path
 import torch
 
 from fl4health_b200.checkpointing.client_module import ClientCheckpointAndStateModule
-from fl4health_b200.common.typing import Config, Scalar
+from fl4health_b200.common.typing import Config
 from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.utils.client import clone_and_freeze_model
-from fl4health_b200.utils.losses import EvaluationLosses, LossMeterType, TrainingLosses
+from fl4health_b200.utils.losses import LossMeterType, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 from fl4health_b200.clients._mmd_feature_alignment import MkMmdMixin
 from fl4health_b200.clients.ditto_client import DittoClient
