@@ -2,19 +2,22 @@
 # compute-sanitizer sweep over every hand-written kernel.  Run on a GPU box:
 #   gpurun --timeout 1500 -- 'bash tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'
 # memcheck: out-of-bounds / misaligned accesses; racecheck: shared-memory hazards; synccheck: invalid barrier usage.
+# CUDA-graph capture tests are excluded: the sanitizer's own legacy-stream activity invalidates stream capture
+# (cudaErrorStreamCaptureImplicit), which is not a kernel error.
 # The kernel numerics tests are the workload (small shapes, every code path).  Cooperative / cluster launches and the
 # tcgen05 kernel are included; the multi-GPU fused collectives need `--gpus 2` and are covered by tests/test_multigpu_fused.py.
 set -u
 cd "$(dirname "$0")/.."
 TESTS="tests/test_gpu_flat_ops.py"
-FILTER=${FILTER:-"not (4096 or shape3 or 2048 or bert or resnet)"}   # skip the largest shapes: the sanitizers slow kernels down 10-100x
+FILTER=${FILTER:-"not (4096 or shape3 or 2048 or bert or resnet or overlapped_wgrad)"}   # skip the largest shapes: the sanitizers slow kernels down 10-100x
 PER_TOOL_TIMEOUT=${PER_TOOL_TIMEOUT:-420}
 status=0
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
   echo "=== compute-sanitizer --tool $tool ==="
   FL4H_NO_AUTOBUILD=1 timeout $PER_TOOL_TIMEOUT compute-sanitizer --tool "$tool" --error-exitcode 9 --print-limit 20 \
-    python -m pytest $TESTS -m gpu -q -x -k "$FILTER" -p no:cacheprovider 2>&1 | tail -15
-  rc=${PIPESTATUS[0]}
+    python -m pytest $TESTS -m gpu -q -k "$FILTER" -p no:cacheprovider -p no:faulthandler > "${OUT_DIR:-gpurun_out}/sanitize_$tool.full.log" 2>&1
+  rc=$?
+  grep -E "^=========|passed|failed" "${OUT_DIR:-gpurun_out}/sanitize_$tool.full.log" | grep -v "^=========     " | tail -40
   echo "--- $tool exit code: $rc"
   [ "$rc" -ne 0 ] && status=$rc
 done
