@@ -37,7 +37,7 @@ def _spin():
         _SPIN[0] @ _SPIN[1]
 
 dev = torch.device("cuda")
-print(f"{'M':>6} {'N':>6} {'K':>6} | tcgen05 TFLOP/s: v0 (1 tile/CTA)  v1 (persistent 128x128)  v2 (persistent 128x256)  v3 (v2, 8 epilogue warps) | GELU epilogue | library")
+print(f"{'M':>6} {'N':>6} {'K':>6} | tcgen05 TFLOP/s: v0 (1 tile/CTA)  v1 (persistent 128x128)  v2 (persistent 128x256)  v3 (v2, 8 epilogue warps)  v4 (CTA pair) | GELU epilogue | library")
 for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (16384, 4096, 1024),
                 (4096, 2304, 768), (4096, 768, 768), (4096, 3072, 768), (4096, 768, 3072)]:  # last four: BERT-base, 32 x 128 tokens
     x = torch.randn(m, k, device=dev).bfloat16()
@@ -46,7 +46,7 @@ for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 
     bb = b.bfloat16()
     flops = 2.0 * m * n * k
     ours = []
-    for variant in ("0", "1", "2", "3"):
+    for variant in ("0", "1", "2", "3", "4"):
         os.environ["FL4H_TC_VARIANT"] = variant
         ours.append(flops / timed(lambda: linear_bias_act(x, w, b, True)) / 1e9)
     lib = timed(lambda: torch.relu(torch.nn.functional.linear(x, w, bb)))
@@ -54,7 +54,9 @@ for m, n, k in [(256, 512, 512), (1024, 1024, 1024), (4096, 4096, 4096), (8192, 
     gelu2 = flops / timed(lambda: linear_bias_act(x, w, b, "gelu")) / 1e9
     os.environ["FL4H_TC_VARIANT"] = "3"
     gelu3 = flops / timed(lambda: linear_bias_act(x, w, b, "gelu")) / 1e9
+    os.environ["FL4H_TC_VARIANT"] = "4"
+    gelu4 = flops / timed(lambda: linear_bias_act(x, w, b, "gelu")) / 1e9
     lib_gemm = timed(lambda: torch.nn.functional.linear(x, w, bb))
     lib_gelu = timed(lambda: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, bb)))
-    print(f"{m:6d} {n:6d} {k:6d} | {ours[0]:8.1f} {ours[1]:8.1f} {ours[2]:8.1f} {ours[3]:8.1f} | gelu v2 {gelu2:7.1f} v3 {gelu3:7.1f} | "
+    print(f"{m:6d} {n:6d} {k:6d} | {ours[0]:8.1f} {ours[1]:8.1f} {ours[2]:8.1f} {ours[3]:8.1f} {ours[4]:8.1f} | gelu v2 {gelu2:7.1f} v3 {gelu3:7.1f} v4 {gelu4:7.1f} | "
           f"lib gemm+bias {flops / lib_gemm / 1e9:7.1f}  +relu {flops / lib / 1e9:7.1f}  +gelu {flops / lib_gelu / 1e9:7.1f}")

@@ -518,13 +518,230 @@ int launch_persistent(const void* a, const void* w, void* c, void* pre, const fl
     return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v4: CTA pair (thread-block cluster of 2, `tcgen05.mma.cta_group::2`).  One 256 x 256 output tile per pair: each CTA
+// holds its own 128 rows of A and HALF of the W tile (128 of the 256 output columns) in shared memory; the leader's
+// single MMA thread issues M = 256 instructions that run on both SMs' tensor cores, each SM reading the other's half
+// of W over the pair's shared-memory path.  Per k-block a CTA now loads 32 KB instead of 48 KB (the L2 -> SM stream is
+// what bounds the 1-CTA kernel at ~58 % of the tensor peak), and 5 stages fit instead of 4.
+//
+// Synchronisation (all mbarriers at identical offsets in both CTAs):
+//   full[s]        lives in the LEADER: both CTAs' TMA loads complete_tx on it (peer bit of the address cleared);
+//   empty[s]       in each CTA: `tcgen05.commit ... multicast::cluster` from the leader releases both producers;
+//   tmem_full[a]   in each CTA: multicast commit, each CTA's epilogue warps wait locally;
+//   tmem_empty[a]  in the LEADER: epilogue warps of both CTAs arrive (remote arrive from CTA 1).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;              // shared::cluster address of the same offset in CTA rank 0
+
+struct P2 {
+    static constexpr int kBN = 256, kHalfN = 128;
+    static constexpr int kStagesP = 5;
+    static constexpr int kATile = BM * BK * 2;               // this CTA's 128 rows of A
+    static constexpr int kBTile = kHalfN * BK * 2;           // this CTA's half of the W tile
+    static constexpr int kStageBytes = kATile + kBTile;      // 32 KiB
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kThreadsP = 32 * (4 + kEpiWarps);
+    static constexpr int kColsPerEpiWarp = kBN / 2;
+    static constexpr int kBarrierOffset = kStagesP * kStageBytes;
+    static constexpr int kStagingOffset = kBarrierOffset + 256;
+    static constexpr int kBiasOffset = kStagingOffset + kEpiWarps * kStageBytesPerWarp;
+    static constexpr int kSmemP = kBiasOffset + kEpiWarps * kColsPerEpiWarp * 4 + 1024;
+    static constexpr int kTmemColsP = 512;                   // two 256-column accumulator buffers = all of TMEM
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_instr_desc_pair() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P2::kBN >> 3) << 17) | (uint32_t(256 >> 4) << 24);  // M = 256
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2::kThreadsP, 1)
+tc_linear_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                      __nv_bfloat16* __restrict__ C, __nv_bfloat16* __restrict__ pre, const float* __restrict__ bias, int M, int N,
+                      int K, int act) {
+    const bool bias_bf16 = (act & ACT_BIAS_BF16) != 0;
+    act &= 0xff;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P2::kBarrierOffset);
+    uint64_t* empty_bar = full_bar + P2::kStagesP;
+    uint64_t* tmem_full_bar = empty_bar + P2::kStagesP;       // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2], used in the leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + P2::kBN - 1) / P2::kBN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < P2::kStagesP; ++s) {
+            mbar_init(full_bar + s, 1);                      // leader: one expect_tx arrival covering both CTAs' bytes
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar + a, 1);
+            mbar_init(tmem_empty_bar + a, 2 * P2::kEpiWarps);  // every epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(P2::kTmemColsP));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                       // both CTAs' barriers are initialised, TMEM is allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs): own A rows, own half of W =====
+            uint32_t it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+                const int row_b = n_blk * P2::kBN + static_cast<int>(rank) * P2::kHalfN;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int stage = it % P2::kStagesP;
+                    const uint32_t phase = (it / P2::kStagesP) & 1;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * P2::kStageBytes);
+                    uint8_t* a_dst = smem + stage * P2::kStageBytes;
+                    tma_load_2d_pair(a_dst, &tma_a, kb * BK, row_a, full_bar + stage);
+                    tma_load_2d_pair(a_dst + P2::kATile, &tma_b, kb * BK, row_b, full_bar + stage);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer: leader CTA only =====
+            constexpr uint32_t idesc = make_instr_desc_pair();
+            uint32_t it = 0, local_tile = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+                const uint32_t acc = local_tile & 1, use = local_tile >> 1;
+                mbar_wait(tmem_empty_bar + acc, (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * P2::kBN;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int stage = it % P2::kStagesP;
+                    const uint32_t phase = (it / P2::kStagesP) & 1;
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * P2::kStageBytes);
+                    const uint32_t b_addr = a_addr + P2::kATile;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16_pair(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(empty_bar + stage);     // both CTAs' copies of this stage are free again
+                }
+                umma_commit_pair(tmem_full_bar + acc);       // both CTAs' epilogues may read their accumulator half
+            }
+        }
+    } else if (warp >= 4) {  // ===== epilogue (both CTAs): rows [rank * 128, +128) of the pair's 256 x 256 tile =====
+        const int epi = warp - 4, quarter = epi & 3, col_begin = (epi >> 2) * P2::kColsPerEpiWarp;
+        uint32_t local_tile = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+            const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+            const uint32_t acc = local_tile & 1, use = local_tile >> 1;
+            float* bias_s = reinterpret_cast<float*>(smem + P2::kBiasOffset) + epi * P2::kColsPerEpiWarp;
+            if (bias != nullptr) {
+                for (int c = lane; c < P2::kColsPerEpiWarp; c += 32) {
+                    const int col = n_blk * P2::kBN + col_begin + c;
+                    float b = 0.f;
+                    if (col < N) b = bias_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[col]) : bias[col];
+                    bias_s[c] = b;
+                }
+                __syncwarp();
+            }
+            mbar_wait(tmem_full_bar + acc, use & 1);
+            tc_fence_after();
+            const int row_base = m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
+            uint8_t* stage = smem + P2::kStagingOffset + epi * kStageBytesPerWarp;
+#pragma unroll 1
+            for (int c0 = col_begin; c0 < col_begin + P2::kColsPerEpiWarp; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * P2::kBN + static_cast<uint32_t>(c0), v);
+                const int col0 = n_blk * P2::kBN + c0;
+                if (row_base < M && col0 < N)
+                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) : nullptr, row_base, lane, col0,
+                                          M, N, act);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tmem_empty_bar + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                       // neither CTA may free TMEM / exit while the peer still uses it
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(P2::kTmemColsP));
+    }
+}
+
+int launch_pair(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act, int sms,
+                cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(tc_linear_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::kSmemP);
+        if (err != cudaSuccess) return static_cast<int>(err);
+        configured = true;
+    }
+    CUtensorMap map_a, map_b;
+    CUresult res = make_tensor_map(&map_a, a, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM);
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    res = make_tensor_map(&map_b, w, static_cast<uint64_t>(N), static_cast<uint64_t>(K), P2::kHalfN);
+    if (res != CUDA_SUCCESS) return -static_cast<int>(res);
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + P2::kBN - 1) / P2::kBN);
+    int pairs = sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    tc_linear_pair_kernel<<<2 * pairs, P2::kThreadsP, P2::kSmemP, stream>>>(
+        map_a, map_b, static_cast<__nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(pre), bias, M, N, K, act);
+    return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace
 
 extern "C" {
 
 // act: 0 none, 1 ReLU, 2 GELU(erf); | 0x100 = `bias` holds bf16 instead of fp32 (variants 1 and 2 only).
 // `pre` (optional, [M, N] bf16) receives x.W^T + b BEFORE the activation.
-// variant: 0 = one 128x128 tile per CTA, 1 = persistent 128x128, 2 = persistent 128x256, 3 = 128x256 with 8 epilogue warps.
+// variant: 0 = one 128x128 tile per CTA, 1 = persistent 128x128, 2 = persistent 128x256, 3 = 128x256 with 8 epilogue warps, 4 = CTA pair (cta_group::2), 256x256 per pair.
 // Returns 0 on success; >0 cudaError; <0 = -CUresult of the tensor-map encoding.
 int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const float* bias, int M, int N, int K, int act,
                       int variant, cudaStream_t stream) {
@@ -537,6 +754,7 @@ int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const fl
     if (variant == 1) return launch_persistent<128, 4>(a, w, c, pre, bias, M, N, K, act, sms, stream);
     if (variant == 2) return launch_persistent<256, 4>(a, w, c, pre, bias, M, N, K, act, sms, stream);
     if (variant == 3) return launch_persistent<256, 8>(a, w, c, pre, bias, M, N, K, act, sms, stream);
+    if (variant == 4) return launch_pair(a, w, c, pre, bias, M, N, K, act, sms, stream);
     if (act & ACT_BIAS_BF16) return static_cast<int>(cudaErrorInvalidValue);
     static bool configured = false;
     if (!configured) {

@@ -50,7 +50,8 @@ def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch
 
 def pick_variant(m: int, n: int, k: int = 0) -> int:
     """0: one 128x128 tile per CTA; 1: persistent 128x128 (double-buffered TMEM); 2: persistent 128x256, 4 epilogue
-    warps; 3: persistent 128x256, 8 epilogue warps.  ``FL4H_TC_VARIANT`` forces one.  Measured on B200
+    warps; 3: persistent 128x256, 8 epilogue warps; 4: CTA pair (``tcgen05.mma.cta_group::2``), 256x256 tile per pair.
+    ``FL4H_TC_VARIANT`` forces one.  Measured on B200
     (``benchmarks/tc_gemm_bench.py``): with K <= 4096 the epilogue is on the critical path and the 8-warp version wins
     (580 vs 452 TFLOP/s at 4096x2304x768, 1038 vs 762 at 16384x4096x1024); at 8192^3 the 4-warp version does
     (1326 vs 1208)."""
@@ -73,7 +74,7 @@ def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, 
     code = int(act)
     if bias is None or bias.dtype == torch.float32:
         bias_arg = bias
-    elif bias.dtype == torch.bfloat16 and variant in (1, 2, 3):  # master-weight mode: read the bf16 bias in the kernel
+    elif bias.dtype == torch.bfloat16 and variant in (1, 2, 3, 4):  # master-weight mode: read the bf16 bias in the kernel
         bias_arg, code = bias, code | 0x100
     else:
         bias_arg = bias.float()

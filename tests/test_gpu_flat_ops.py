@@ -409,7 +409,7 @@ def test_overlapped_wgrad_matches_stock_conv_backward(graphed: bool, monkeypatch
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 512), (32, 16, 512), (300, 200, 136), (4096, 1024, 1024)])
 @pytest.mark.parametrize("relu,with_bias", [(False, False), (True, True)])
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
 def test_tcgen05_linear_matches_reference(shape, relu, with_bias, variant, monkeypatch) -> None:
     """tc_gemm.cu (TMA -> tcgen05.mma -> TMEM -> epilogue) vs an fp32 reference, ragged tiles included; variants:
     one tile per CTA / persistent 128x128 / persistent 128x256 with double-buffered TMEM accumulators."""
@@ -446,7 +446,7 @@ def test_tcgen05_linear_matches_reference(shape, relu, with_bias, variant, monke
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(256, 384, 512), (300, 200, 136), (2048, 3072, 768)])
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
 def test_tcgen05_linear_gelu_epilogue(shape, variant, monkeypatch) -> None:
     """GELU (erf) epilogue of tc_gemm.cu: the forward matches an fp32 reference, the pre-activation stored by the same
     epilogue feeds an exact GELU backward, and a no-grad call does not write the pre-activation at all."""
@@ -512,7 +512,7 @@ def test_bert_layer_fused_matches_stock_modules(monkeypatch) -> None:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
 def test_tcgen05_linear_bf16_bias(variant, monkeypatch) -> None:
     """Master-weight mode hands the kernel a bf16 bias: the persistent variants read it as is (no cast kernel), the
     one-tile variant goes through an fp32 copy; both match the fp32 reference and produce a bf16 bias gradient."""
