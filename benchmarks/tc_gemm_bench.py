@@ -6,20 +6,29 @@ import torch
 import os
 from fl4health_b200.ops.tc_gemm import linear_bias_act
 
-def timed(fn, iters=40, repeats=3):
+def timed(fn, iters=20, repeats=3):
     """Best of `repeats` blocks of `iters` back-to-back calls (CUDA events).  The first version of this script measured
     each configuration once, cold: the SM clock was still ramping during the first configurations of every shape and
     the ORDER of the columns changed the ranking.  `_spin` keeps the clocks up between configurations."""
     best = float("inf")
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    # the calls are captured in a CUDA graph: small problems are otherwise HOST-bound (ctypes call + two tensor-map
+    # encodes + autograd.Function cost ~23 us per call -- every small shape used to report the same "23 us kernel")
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
     for _ in range(repeats):
         _spin()
-        for _ in range(5):
-            fn()
+        graph.replay()
         torch.cuda.synchronize()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        for _ in range(iters):
-            fn()
+        graph.replay()
         end.record()
         torch.cuda.synchronize()
         best = min(best, start.elapsed_time(end) / iters)

@@ -115,17 +115,23 @@ class LinearAct(nn.Linear):
 
     def _use_kernel(self, input: torch.Tensor) -> bool:  # noqa: A002
         """``FL4H_TC_LINEAR``: ``always`` | ``never`` | ``auto`` (default).  ``auto`` uses the hand-written kernel where
-        it is the faster choice on B200 (``profiles/README.md``, tcgen05 table): a fused activation on a GEMM of at
-        least 4096^3 work (1236 vs 1154 TFLOP/s with ReLU, 1078 vs 1047 with GELU at 4096^3 against library GEMM + an
-        elementwise pass).  Smaller problems stay on the library: its 2-CTA tiles reach 930-970 TFLOP/s at BERT-base
-        shapes (K = 768) where this 1-CTA kernel reaches 575-580, so even a free activation does not pay for it."""
+        it is the faster choice on B200 (``profiles/README.md``, tcgen05 table, CUDA-graph timed):
+
+        * fused **ReLU** on any layer with >= 256 outputs and >= 1024 rows: 903 vs 681 TFLOP/s at 4096x2304x768,
+          1341 vs 839 at 16384x4096x1024, 1400 vs 1349 at 4096^3 against library GEMM + an elementwise pass;
+        * fused **GELU** from 4096^3 of work up (1294 vs 1119): below that the erf chain makes the epilogue longer than
+          a K = 768 mainloop and library GEMM + GELU pass wins (623 vs 493 at 4096x3072x768);
+        * plain linears stay on the library (this kernel reaches 84-100 % of it: 903 vs 1073 at 4096x2304x768, 1504 vs
+          1490 at 8192^3)."""
         policy = os.environ.get("FL4H_TC_LINEAR", "auto")
         if policy == "never" or not input.is_cuda:
             return False
         if policy == "always":
             return True
         rows = input.numel() // max(input.shape[-1], 1)
-        return self.relu != "none" and rows * self.in_features * self.out_features >= 4096 ** 3
+        if self.relu == "relu":
+            return self.out_features >= 256 and rows >= 1024
+        return self.relu == "gelu" and rows * self.in_features * self.out_features >= 4096 ** 3
 
     def extra_repr(self) -> str:
         return super().extra_repr() + f", activation={self.relu}"

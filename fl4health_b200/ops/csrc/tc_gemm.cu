@@ -170,11 +170,38 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], __nv_bfl
 // store instruction writes 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.  With one
 // thread per accumulator row, the direct version issues 16-byte partial-sector writes only: measured on B200 that
 // costs ~10-15 us per 128x256 tile, i.e. the epilogue -- not the tensor pipe -- bounds every GEMM with K <= 1024.
+// Phase timestamps of CTA 0 (SM clock), read back with fl4h_tc_debug_read: a handful of global stores per launch.
+//   [0] kernel entry  [1] setup done (barriers, TMEM)  [2] first operands landed  [3 + t] MMA issue of tile t done (t < 8)
+//   [16 + 2t] accumulator of tile t visible to the epilogue  [17 + 2t] epilogue of tile t done  [40] last TMA issued  [41] exit
+//   [42..46] first chunk of tile 0, epilogue warp 0: TMEM load done / bias+activation done / staged / read back / stored
+__device__ long long g_tc_phase_clock[48];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0) g_tc_phase_clock[(slot)] = clock64(); } while (0)
+
 constexpr int kStageStride = 80;                            // 64 B of payload + 16 B pad: conflict-free 16-byte writes
 constexpr int kStageBytesPerWarp = 32 * kStageStride;
 
-__device__ __forceinline__ void stage_and_store(const float (&f)[32], uint8_t* stage, __nv_bfloat16* __restrict__ dst, int row_base,
-                                                int lane, int col0, int M, int N) {
+// Explicit shared-space accesses.  The staging / bias buffers are carved out of the dynamically aligned `smem` pointer,
+// for which the compiler had emitted GENERIC loads and stores (`LD.E.128 ... [R.64+0x30100]`, long-scoreboard class): one
+// 32x32 epilogue chunk took ~2.0 us of pure latency (phase timestamps, 4096x2304x768).
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void stage_and_store(const float (&f)[32], uint32_t stage, __nv_bfloat16* __restrict__ dst, int row_base,
+                                                int lane, int col0, int M, int N, bool stamp = false) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t w[4];
@@ -183,41 +210,51 @@ __device__ __forceinline__ void stage_and_store(const float (&f)[32], uint8_t* s
             __nv_bfloat162 h = __floats2bfloat162_rn(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
             w[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(stage + lane * kStageStride + q * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        sts128(stage + lane * kStageStride + q * 16, w[0], w[1], w[2], w[3]);
     }
     __syncwarp();
+    if (stamp) TC_STAMP(45);
     const int seg = lane & 3, col = col0 + seg * 8;
+    uint4 val[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) val[it] = lds128(stage + (it * 8 + (lane >> 2)) * kStageStride + seg * 16);
+    if (stamp) TC_STAMP(46);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2);
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * kStageStride + seg * 16);
-        const int grow = row_base + r;
-        if (grow < M && col < N) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(grow) * N + col) = val;
+        const int grow = row_base + it * 8 + (lane >> 2);
+        if (grow < M && col < N) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(grow) * N + col) = val[it];
     }
     __syncwarp();
+    if (stamp) TC_STAMP(47);
 }
 
 // `bias_s`: this tile's bias slice staged in shared memory by the caller (nullptr = no bias), indexed from the chunk's
 // first column.  Reading it from global here instead put ~40 % of the epilogue's stall samples on the first FADD after
 // each LDG (ncu source view, 4096x2304x768).
-__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], uint8_t* stage, __nv_bfloat16* __restrict__ C,
-                                                      __nv_bfloat16* __restrict__ pre, const float* bias_s,
-                                                      int row_base, int lane, int col0, int M, int N, int act) {
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], uint32_t stage, __nv_bfloat16* __restrict__ C,
+                                                      __nv_bfloat16* __restrict__ pre, uint32_t bias_s /* shared address, 0 = none */,
+                                                      int row_base, int lane, int col0, int M, int N, int act, bool stamp = false) {
     float z[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        float4 b4 = bias_s != nullptr ? *reinterpret_cast<const float4*>(bias_s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 b4 = bias_s != 0 ? lds128f(bias_s + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         z[j] = __uint_as_float(v[j]) + b4.x;
         z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
         z[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
         z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
     }
     if (pre != nullptr) stage_and_store(z, stage, pre, row_base, lane, col0, M, N);
-    if (act != ACT_NONE) {
+    // activation branch hoisted out of the element loop by hand: with the per-element `if (act == ...)` the compiler
+    // kept a predicated GELU chain in the ReLU path (phase timestamps: 1.3 us of "bias + ReLU" per 32x32 chunk)
+    if (act == ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = apply_act(z[j], act);
+        for (int j = 0; j < 32; ++j) z[j] = fmaxf(z[j], 0.f);
+    } else if (act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = 0.5f * z[j] * (1.f + erf_as(z[j] * 0.70710678118654752f));
     }
-    stage_and_store(z, stage, C, row_base, lane, col0, M, N);
+    if (stamp) TC_STAMP(44);
+    stage_and_store(z, stage, C, row_base, lane, col0, M, N, stamp);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -374,6 +411,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     using Cfg = V2<kBN, kEpi>;
     const bool bias_bf16 = (act & ACT_BIAS_BF16) != 0;      // `bias` points at bf16 values (master-weight mode)
     act &= 0xff;
+    if (threadIdx.x == 0) TC_STAMP(0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStagesV2 * Cfg::kStageBytes);
@@ -410,6 +448,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    if (threadIdx.x == 0) TC_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer: one continuous ring across all of this CTA's tiles =====
@@ -426,6 +465,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                     tma_load_2d(a_dst + Cfg::kATile, &tma_b, kb * BK, n_blk * kBN, full_bar + stage);
                 }
             }
+            TC_STAMP(40);
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
@@ -441,6 +481,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                     const uint32_t phase = (it / Cfg::kStagesV2) & 1;
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after();
+                    if (it == 0) TC_STAMP(2);
                     const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t b_addr = a_addr + Cfg::kATile;
 #pragma unroll
@@ -451,6 +492,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                     umma_commit(empty_bar + stage);
                 }
                 umma_commit(tmem_full_bar + acc);
+                if (local_tile < 8) TC_STAMP(3 + local_tile);
             }
         }
     } else if (warp >= 4) {  // ===== epilogue warps: warp e owns TMEM lanes [32 (e % 4), +32) x columns [half * kBN/2, +kBN/2) =====
@@ -461,32 +503,37 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             const uint32_t acc = local_tile & 1, use = local_tile >> 1;
             // this warp's bias slice -> shared memory, issued BEFORE waiting for the accumulator so the global-load
             // latency hides behind the mainloop
-            float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOffset) + epi * Cfg::kColsPerEpiWarp;
+            const uint32_t bias_s = smem_u32(smem + Cfg::kBiasOffset) + epi * Cfg::kColsPerEpiWarp * 4;
             if (bias != nullptr) {
                 for (int c = lane; c < Cfg::kColsPerEpiWarp; c += 32) {
                     const int col = n_blk * kBN + col_begin + c;
                     float b = 0.f;
                     if (col < N) b = bias_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[col]) : bias[col];
-                    bias_s[c] = b;
+                    sts32f(bias_s + c * 4, b);
                 }
                 __syncwarp();
             }
             mbar_wait(tmem_full_bar + acc, use & 1);
             tc_fence_after();
+            if (epi == 0 && lane == 0 && local_tile < 8) TC_STAMP(16 + 2 * local_tile);
             const int row_base = m_blk * BM + quarter * 32;
-            uint8_t* stage = smem + Cfg::kStagingOffset + epi * kStageBytesPerWarp;
+            const uint32_t stage = smem_u32(smem + Cfg::kStagingOffset) + epi * kStageBytesPerWarp;
 #pragma unroll 1
             for (int c0 = col_begin; c0 < col_begin + Cfg::kColsPerEpiWarp; c0 += 32) {
                 uint32_t v[32];
+                const bool stamp = epi == 0 && lane == 0 && local_tile == 0 && c0 == col_begin;
+                if (stamp) TC_STAMP(42);
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN + static_cast<uint32_t>(c0), v);
+                if (stamp) TC_STAMP(43);
                 const int col0 = n_blk * kBN + c0;
                 if (row_base < M && col0 < N)
-                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) : nullptr, row_base, lane, col0,
-                                          M, N, act);
+                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) * 4 : 0u, row_base, lane, col0,
+                                          M, N, act, stamp);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar + acc);     // this warp's quarter of the buffer is free again
+            if (epi == 0 && lane == 0 && local_tile < 8) TC_STAMP(17 + 2 * local_tile);
         }
     }
     tc_fence_before();
@@ -494,6 +541,7 @@ tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemColsV2));
     }
+    if (threadIdx.x == 0) TC_STAMP(41);
 }
 
 template <int kBN, int kEpi>
@@ -678,27 +726,27 @@ tc_linear_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
             const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
             const uint32_t acc = local_tile & 1, use = local_tile >> 1;
-            float* bias_s = reinterpret_cast<float*>(smem + P2::kBiasOffset) + epi * P2::kColsPerEpiWarp;
+            const uint32_t bias_s = smem_u32(smem + P2::kBiasOffset) + epi * P2::kColsPerEpiWarp * 4;
             if (bias != nullptr) {
                 for (int c = lane; c < P2::kColsPerEpiWarp; c += 32) {
                     const int col = n_blk * P2::kBN + col_begin + c;
                     float b = 0.f;
                     if (col < N) b = bias_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[col]) : bias[col];
-                    bias_s[c] = b;
+                    sts32f(bias_s + c * 4, b);
                 }
                 __syncwarp();
             }
             mbar_wait(tmem_full_bar + acc, use & 1);
             tc_fence_after();
             const int row_base = m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
-            uint8_t* stage = smem + P2::kStagingOffset + epi * kStageBytesPerWarp;
+            const uint32_t stage = smem_u32(smem + P2::kStagingOffset) + epi * kStageBytesPerWarp;
 #pragma unroll 1
             for (int c0 = col_begin; c0 < col_begin + P2::kColsPerEpiWarp; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * P2::kBN + static_cast<uint32_t>(c0), v);
                 const int col0 = n_blk * P2::kBN + c0;
                 if (row_base < M && col0 < N)
-                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) : nullptr, row_base, lane, col0,
+                    epilogue_chunk_staged(v, stage, C, pre, bias != nullptr ? bias_s + (c0 - col_begin) * 4 : 0u, row_base, lane, col0,
                                           M, N, act);
             }
             tc_fence_before();
@@ -771,6 +819,11 @@ int fl4h_tc_linear_ex(const void* a, const void* w, void* c, void* pre, const fl
     tc_linear_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, static_cast<__nv_bfloat16*>(c),
                                                              static_cast<__nv_bfloat16*>(pre), bias, M, N, K, act);
     return static_cast<int>(cudaGetLastError());
+}
+
+// Copies the 48 phase timestamps of the last persistent-variant launch (CTA 0, SM clock cycles) to `out`.
+int fl4h_tc_debug_read(long long* out) {
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_tc_phase_clock, sizeof(long long) * 48));
 }
 
 int fl4h_tc_linear_v(const void* a, const void* w, void* c, const float* bias, int M, int N, int K, int relu, int variant,

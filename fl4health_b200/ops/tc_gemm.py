@@ -50,17 +50,16 @@ def linear_bias_act_reference(x: torch.Tensor, weight: torch.Tensor, bias: torch
 
 def pick_variant(m: int, n: int, k: int = 0) -> int:
     """0: one 128x128 tile per CTA; 1: persistent 128x128 (double-buffered TMEM); 2: persistent 128x256, 4 epilogue
-    warps; 3: persistent 128x256, 8 epilogue warps; 4: CTA pair (``tcgen05.mma.cta_group::2``), 256x256 tile per pair.
-    ``FL4H_TC_VARIANT`` forces one.  Measured on B200
-    (``benchmarks/tc_gemm_bench.py``): with K <= 4096 the epilogue is on the critical path and the 8-warp version wins
-    (580 vs 452 TFLOP/s at 4096x2304x768, 1038 vs 762 at 16384x4096x1024); at 8192^3 the 4-warp version does
-    (1326 vs 1208)."""
+    warps; 3: persistent 128x256, 8 epilogue warps; 4: CTA pair (``tcgen05.mma.cta_group::2``), 256x256 tile per pair,
+    8 epilogue warps per CTA.  ``FL4H_TC_VARIANT`` forces one.  Measured on B200 with the calls captured in a CUDA graph
+    (``benchmarks/tc_gemm_bench.py``): the pair kernel is the fastest or tied at every shape with N >= 256
+    (903 vs 896 (v3) vs 798 (v2) TFLOP/s at 4096x2304x768; 1504 vs 1406 vs 1418 at 8192^3)."""
     forced = os.environ.get("FL4H_TC_VARIANT")
     if forced is not None:
         return int(forced)
     if n < 256:
         return 1
-    return 3 if 0 < k <= 4096 else 2
+    return 3 if m <= 128 else 4
 
 
 def _launch(x2d: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, act: bool | int, variant: int | None = None,
