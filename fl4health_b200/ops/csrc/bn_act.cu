@@ -265,6 +265,12 @@ __device__ __forceinline__ void red_partials(const float (&a)[8], const float (&
     }
 }
 
+// Phase timestamps of CTA 0 of the fused forward kernel (SM clock), read back with fl4h_bn_debug_read:
+//   [0] entry  [1] shift values staged  [2] tile loaded + per-thread sums  [3] block reduce + RED atomics issued
+//   [4] grid barrier passed  [5] totals read, scale/shift ready  [6] normalised tile stored
+__device__ long long g_bn_phase_clock[16];
+#define BN_STAMP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_bn_phase_clock[(slot)] = clock64(); } while (0)
+
 template <typename T, bool kRelu, bool kRes>
 __global__ void __launch_bounds__(kThreads)
 bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t M, int C, int rows_per_cta,
@@ -272,6 +278,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
                     float* running_var, int64_t* nbt, float momentum, float eps, float* mean_out, float* invstd_out,
                     float* acc2, unsigned* parity) {
     cg::grid_group grid = cg::this_grid();
+    BN_STAMP(0);
     extern __shared__ float smem[];            // [4096] reduce scratch (later scale|shift) + [C] shift values
     float* kshift = smem + 4096;
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
@@ -284,7 +291,6 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     const int LP = C >> 3, RP = blockDim.x / LP;
     const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
     for (int c = threadIdx.x; c < C; c += blockDim.x) kshift[c] = running_mean != nullptr ? running_mean[c] : 0.f;
-    __syncthreads();
     float shift[8], s[8], q[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; shift[k] = 0.f; }
@@ -292,6 +298,17 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
     const bool cached = rows_per_cta <= kCacheRows * RP;   // uniform: the whole tile stays in registers
     float tile[kCacheRows][8];
+    // The tile loads do not depend on the shift values: issue them BEFORE the barrier that publishes `kshift`, so the
+    // running-mean fetch (a dependent ~1 us global round trip, phase timestamps) overlaps the tile's own L2 latency.
+    if (ty < RP && cached) {
+#pragma unroll
+        for (int it = 0; it < kCacheRows; ++it) {
+            const int64_t r = r0 + ty + (int64_t)it * RP;
+            if (r < r1) Vec8<T>::load(x + r * C + lane * 8, tile[it]);
+        }
+    }
+    __syncthreads();
+    BN_STAMP(1);
     if (ty < RP) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) shift[k] = kshift[lane * 8 + k];
@@ -300,7 +317,6 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
             for (int it = 0; it < kCacheRows; ++it) {
                 const int64_t r = r0 + ty + (int64_t)it * RP;
                 if (r < r1) {
-                    Vec8<T>::load(x + r * C + lane * 8, tile[it]);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float d = tile[it][k] - shift[k];
@@ -322,8 +338,11 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
             }
         }
     }
+    BN_STAMP(2);
     red_partials(s, q, C, LP, RP, lane, ty, acc, smem);
+    BN_STAMP(3);
     grid.sync();
+    BN_STAMP(4);
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float sd = __ldcg(acc + c), sq = __ldcg(acc + C + c);
@@ -347,6 +366,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
         }
     }
     __syncthreads();
+    BN_STAMP(5);
     if (ty < RP) {
         float sc[8], sh[8];
 #pragma unroll
@@ -386,6 +406,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
             }
         }
     }
+    BN_STAMP(6);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *parity = par ^ 1u;
         if (nbt != nullptr) *nbt += 1;
@@ -414,20 +435,63 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
     for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; mu[k] = 0.f; is[k] = 0.f; }
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+    // Common case (every ResNet-18 / CIFAR layer): the CTA's tile is <= kBwdCacheRows rows per thread.  dy and x stay in
+    // registers PACKED as loaded (4 registers per 8 bf16) between the two phases and the ReLU mask shrinks to 8 bits per
+    // row, so phase 2 reads nothing from memory and all phase-1 loads are in flight at once (the row loop below it issues
+    // one row's loads per iteration: ~0.7 us of L2 latency per iteration, twice).
+    constexpr int kBwdCacheRows = 8;
+    constexpr bool kCanCache = Vec8<T>::kRawRegs == 4;
+    const bool cached = kCanCache && rows_per_cta <= kBwdCacheRows * RP;
+    typename Vec8<T>::Raw graw[kCanCache ? kBwdCacheRows : 1], xraw[kCanCache ? kBwdCacheRows : 1];
+    uint32_t mask_lo = 0u, mask_hi = 0u;                   // bit (8 * (it % 4) + k) of lo (it < 4) / hi: y > 0
     if (ty < RP) {
         load8f(mean + lane * 8, mu);
         load8f(invstd + lane * 8, is);
-        for (int64_t r = r0 + ty; r < r1; r += RP) {
-            float g[8], xv[8], yv[8];
-            const int64_t off = r * C + lane * 8;
-            Vec8<T>::load(dy + off, g);
-            Vec8<T>::load(x + off, xv);
-            if (kRelu) Vec8<T>::load(y + off, yv);
+        if (cached) {
+            typename Vec8<T>::Raw yraw[kCanCache ? kBwdCacheRows : 1];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
-                sg[k] += gi;
-                sgx[k] = fmaf(gi, (xv[k] - mu[k]) * is[k], sgx[k]);
+            for (int it = 0; it < kBwdCacheRows; ++it) {
+                const int64_t r = r0 + ty + (int64_t)it * RP;
+                if (r < r1) {
+                    const int64_t off = r * C + lane * 8;
+                    graw[it] = Vec8<T>::load_raw(dy + off);
+                    xraw[it] = Vec8<T>::load_raw(x + off);
+                    if (kRelu) yraw[it] = Vec8<T>::load_raw(y + off);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < kBwdCacheRows; ++it) {
+                const int64_t r = r0 + ty + (int64_t)it * RP;
+                if (r < r1) {
+                    float g[8], xv[8], yv[8];
+                    Vec8<T>::unpack(graw[it], g);
+                    Vec8<T>::unpack(xraw[it], xv);
+                    if (kRelu) Vec8<T>::unpack(yraw[it], yv);
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool on = !kRelu || yv[k] > 0.f;
+                        bits |= (on ? 1u : 0u) << k;
+                        const float gi = on ? g[k] : 0.f;
+                        sg[k] += gi;
+                        sgx[k] = fmaf(gi, (xv[k] - mu[k]) * is[k], sgx[k]);
+                    }
+                    if (it < 4) mask_lo |= bits << (8 * it); else mask_hi |= bits << (8 * (it - 4));
+                }
+            }
+        } else {
+            for (int64_t r = r0 + ty; r < r1; r += RP) {
+                float g[8], xv[8], yv[8];
+                const int64_t off = r * C + lane * 8;
+                Vec8<T>::load(dy + off, g);
+                Vec8<T>::load(x + off, xv);
+                if (kRelu) Vec8<T>::load(y + off, yv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+                    sg[k] += gi;
+                    sgx[k] = fmaf(gi, (xv[k] - mu[k]) * is[k], sgx[k]);
+                }
             }
         }
     }
@@ -453,20 +517,42 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
             mg[k] = smem[C + lane * 8 + k];
             mgx[k] = smem[2 * C + lane * 8 + k];
         }
-        for (int64_t r = r0 + ty; r < r1; r += RP) {   // second read of the tile comes from L2
-            float g[8], xv[8], yv[8];
-            const int64_t off = r * C + lane * 8;
-            Vec8<T>::load(dy + off, g);
-            Vec8<T>::load(x + off, xv);
-            if (kRelu) Vec8<T>::load(y + off, yv);
+        if (cached) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
-                g[k] = gi;
-                xv[k] = a[k] * (gi - mg[k] - (xv[k] - mu[k]) * is[k] * mgx[k]);
+            for (int it = 0; it < kBwdCacheRows; ++it) {
+                const int64_t r = r0 + ty + (int64_t)it * RP;
+                if (r < r1) {
+                    float g[8], xv[8];
+                    Vec8<T>::unpack(graw[it], g);
+                    Vec8<T>::unpack(xraw[it], xv);
+                    const uint32_t bits = (it < 4 ? mask_lo >> (8 * it) : mask_hi >> (8 * (it - 4))) & 0xffu;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float gi = ((bits >> k) & 1u) ? g[k] : 0.f;
+                        g[k] = gi;
+                        xv[k] = a[k] * (gi - mg[k] - (xv[k] - mu[k]) * is[k] * mgx[k]);
+                    }
+                    const int64_t off = r * C + lane * 8;
+                    Vec8<T>::store(dx + off, xv);
+                    if (kRes) Vec8<T>::store(dres + off, g);
+                }
             }
-            Vec8<T>::store(dx + off, xv);
-            if (kRes) Vec8<T>::store(dres + off, g);
+        } else {
+            for (int64_t r = r0 + ty; r < r1; r += RP) {   // second read of the tile comes from L2
+                float g[8], xv[8], yv[8];
+                const int64_t off = r * C + lane * 8;
+                Vec8<T>::load(dy + off, g);
+                Vec8<T>::load(x + off, xv);
+                if (kRelu) Vec8<T>::load(y + off, yv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gi = (!kRelu || yv[k] > 0.f) ? g[k] : 0.f;
+                    g[k] = gi;
+                    xv[k] = a[k] * (gi - mg[k] - (xv[k] - mu[k]) * is[k] * mgx[k]);
+                }
+                Vec8<T>::store(dx + off, xv);
+                if (kRes) Vec8<T>::store(dres + off, g);
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *parity = par ^ 1u;
@@ -497,6 +583,11 @@ inline int apply_grid(int64_t nvec) {
 }  // namespace
 
 extern "C" {
+
+// Copies the 16 phase timestamps (CTA 0, SM clock cycles) of the last fused forward launch to `out`.
+int fl4h_bn_debug_read(long long* out) {
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_bn_phase_clock, sizeof(long long) * 16));
+}
 
 int fl4h_bn_supported(int64_t M, int C) { return (C % 8 == 0 && C / 8 <= kThreads && M >= 1) ? 1 : 0; }
 
