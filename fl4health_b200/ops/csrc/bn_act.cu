@@ -246,17 +246,37 @@ constexpr int kCacheRows = 8;
 
 __device__ __forceinline__ void red_partials(const float (&a)[8], const float (&b)[8], int C, int LP, int RP, int lane, int ty,
                                              float* acc, float* smem) {
-    if (ty < RP) {
+    // Stage 1 (power-of-two LP < 32, i.e. C in {64, 128} ... ): the 32 / LP row-threads of a warp that own the same 8
+    // channels combine through shuffles, so the shared-memory stage holds RP / (32 / LP) rows instead of RP and the
+    // serial per-channel loop below shrinks by the same factor (32 -> 8 iterations at C = 64).
+    const bool fold = (LP & (LP - 1)) == 0 && LP < 32 && (blockDim.x % 32) == 0;
+    float a2[8], b2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a2[k] = a[k]; b2[k] = b[k]; }
+    int group = 1;
+    if (fold) {
+        group = 32 / LP;
+        for (int off = LP; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], off);
+                b2[k] += __shfl_xor_sync(0xffffffffu, b2[k], off);
+            }
+        }
+    }
+    const int rows = (RP + group - 1) / group;
+    if (ty < RP && (ty % group) == 0) {
+        const int row = ty / group;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            smem[(ty * 2 + 0) * C + lane * 8 + k] = a[k];
-            smem[(ty * 2 + 1) * C + lane * 8 + k] = b[k];
+            smem[(row * 2 + 0) * C + lane * 8 + k] = a2[k];
+            smem[(row * 2 + 1) * C + lane * 8 + k] = b2[k];
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sa = 0.f, sb = 0.f;
-        for (int t = 0; t < RP; ++t) {
+        for (int t = 0; t < rows; ++t) {
             sa += smem[(t * 2 + 0) * C + c];
             sb += smem[(t * 2 + 1) * C + c];
         }
@@ -283,11 +303,6 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     float* kshift = smem + 4096;
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
     float* acc = acc2 + par * kAccStride;
-    if (blockIdx.x == 0) {
-        // re-zero the WHOLE buffer the previous launch used: it may have been a layer with more channels than this one
-        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
-        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     const int LP = C >> 3, RP = blockDim.x / LP;
     const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
     for (int c = threadIdx.x; c < C; c += blockDim.x) kshift[c] = running_mean != nullptr ? running_mean[c] : 0.f;
@@ -406,6 +421,12 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
             }
         }
     }
+    // Off the critical path (CTA 0 used to do this BEFORE loading its tile, delaying everyone at the grid barrier): re-zero
+    // the WHOLE accumulator buffer the previous launch used -- it may have been a layer with more channels than this one.
+    if (blockIdx.x == 0) {
+        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
+        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     BN_STAMP(6);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *parity = par ^ 1u;
@@ -423,11 +444,6 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
     extern __shared__ float smem[];            // max(4096, 3C) floats: reduce scratch, later a | mean(g) | mean(g xhat)
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
     float* acc = acc2 + par * kAccStride;
-    if (blockIdx.x == 0) {
-        // re-zero the WHOLE buffer the previous launch used: it may have been a layer with more channels than this one
-        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
-        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     const int LP = C >> 3, RP = blockDim.x / LP;
     const int lane = threadIdx.x % LP, ty = threadIdx.x / LP;
     float sg[8], sgx[8], mu[8], is[8];
@@ -554,6 +570,10 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
                 if (kRes) Vec8<T>::store(dres + off, g);
             }
         }
+    }
+    if (blockIdx.x == 0) {  // see the forward kernel: zero the other parity's accumulators after the useful work
+        float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
+        for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *parity = par ^ 1u;
 }
