@@ -441,7 +441,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
                     const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
                     float* acc2, unsigned* parity) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ float smem[];            // max(4096, 3C) floats: reduce scratch, later a | mean(g) | mean(g xhat)
+    BN_STAMP(8);                               // backward: [8] entry [9] tile loaded + sums [10] block reduce + REDs [11] barrier
+    extern __shared__ float smem[];            //           [12] totals staged [13] dx (and dres) stored
+    // smem: max(4096, 3C) floats: reduce scratch, later a | mean(g) | mean(g xhat)
     const unsigned par = *reinterpret_cast<volatile unsigned*>(parity) & 1u;
     float* acc = acc2 + par * kAccStride;
     const int LP = C >> 3, RP = blockDim.x / LP;
@@ -511,8 +513,11 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
             }
         }
     }
+    BN_STAMP(9);
     red_partials(sg, sgx, C, LP, RP, lane, ty, acc, smem);
+    BN_STAMP(10);
     grid.sync();
+    BN_STAMP(11);
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float a = __ldcg(acc + c), b = __ldcg(acc + C + c);
@@ -525,6 +530,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
         }
     }
     __syncthreads();
+    BN_STAMP(12);
     if (ty < RP) {
         float a[8], mg[8], mgx[8];
 #pragma unroll
@@ -571,6 +577,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* 
             }
         }
     }
+    BN_STAMP(13);
     if (blockIdx.x == 0) {  // see the forward kernel: zero the other parity's accumulators after the useful work
         float4* other = reinterpret_cast<float4*>(acc2 + (par ^ 1u) * kAccStride);
         for (int c = threadIdx.x; c < kAccStride / 4; c += blockDim.x) other[c] = make_float4(0.f, 0.f, 0.f, 0.f);
