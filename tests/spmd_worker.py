@@ -46,10 +46,11 @@ def main() -> None:
                       on_init_parameters_config_fn=fit_config_fn())
     fused_mode = os.environ.get("FL4H_COLLECTIVES", "auto")
     build_spmd_federation(ctx, server, client, fused=True if fused_mode == "fused" else (False if fused_mode == "nccl" or ctx.device.type != "cuda" else None))
+    used_mailbox = ctx.mailbox is not None
     history, _ = server.fit(num_rounds=2)
     state = {k: v.detach().cpu().double().sum().item() for k, v in client.model.state_dict().items()}
     if ctx.rank == 0:
-        Path(out_path).write_text(json.dumps({"losses": history.losses_distributed, "state": state}))
+        Path(out_path).write_text(json.dumps({"losses": history.losses_distributed, "state": state, "mailbox": used_mailbox}))
     ctx.barrier()
     ctx.shutdown()
 

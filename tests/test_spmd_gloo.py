@@ -21,9 +21,9 @@ from tests.helpers import fit_config_fn, make_clients
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _launch(tmp_path: Path, strategy: str, port: int) -> dict:
+def _launch(tmp_path: Path, strategy: str, port: int, **extra_env: str) -> dict:
     out = tmp_path / f"{strategy}.json"
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", FL4H_LOG_LEVEL="ERROR")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", FL4H_LOG_LEVEL="ERROR", **extra_env)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "spmd_worker.py"), str(out), strategy]
     proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
@@ -57,9 +57,14 @@ def _local(strategy_name: str) -> dict:
     return {"losses": history.losses_distributed, "state": state}
 
 
-@pytest.mark.parametrize("strategy,port", [("fedavg", 29611), ("fedadam", 29612)])
-def test_spmd_matches_single_process(tmp_path: Path, strategy: str, port: int) -> None:
-    spmd = _launch(tmp_path, strategy, port)
+@pytest.mark.parametrize("strategy,port,mailbox", [("fedavg", 29611, "1"), ("fedadam", 29612, "1"), ("fedavg", 29613, "0")])
+def test_spmd_matches_single_process(tmp_path: Path, strategy: str, port: int, mailbox: str) -> None:
+    """``mailbox``: per-round metadata through the shared-memory mailbox (default) or, with ``FL4H_SHM_MAILBOX=0``,
+    through the fixed-size float64 all-gather — both must reproduce the single-process federation."""
+    spmd = _launch(tmp_path, strategy, port, FL4H_SHM_MAILBOX=mailbox)
+    from fl4health_b200.runtime.mailbox import load_runtime
+
+    assert spmd["mailbox"] == (mailbox == "1" and load_runtime() is not None)
     local = _local(strategy)
     for (r1, l1), (r2, l2) in zip(spmd["losses"], local["losses"]):
         assert r1 == r2 and abs(l1 - l2) < 1e-5, (spmd["losses"], local["losses"])
