@@ -111,8 +111,10 @@ __device__ __forceinline__ void sgd_update4(float4& w, float4 g, float4& m, cons
     for (int i = 0; i < 4; ++i) {
         float gi = gp[i];
         if (kHasCv) gi += cp[i];                       // SCAFFOLD: g += (c - c_i), precomputed at broadcast time
-        if (kHasAnchor) gi += mu * (wp[i] - ap[i]);    // FedProx/Ditto/MR-MTL: analytic grad of mu/2 |w - w_t|^2
-        gi += wd * wp[i];
+        // zero coefficients are skipped like torch.optim does: 0 * inf is NaN, and FedPM's scores are legitimately
+        // +-inf after a Bayesian aggregate of 0 or 1 (sigmoid_inverse)
+        if (kHasAnchor && mu != 0.f) gi += mu * (wp[i] - ap[i]);    // FedProx/Ditto/MR-MTL: analytic grad of mu/2 |w - w_t|^2
+        if (wd != 0.f) gi += wd * wp[i];
         float buf = first ? gi : mom * mp[i] + (1.f - damp) * gi;
         mp[i] = buf;
         float upd = (mom != 0.f) ? (nesterov ? gi + mom * buf : buf) : gi;
@@ -188,8 +190,8 @@ adamw_step_kernel(float* __restrict__ w, const void* __restrict__ grad, float* _
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float gi = gp[k] * gscale;
-            if (kHasAnchor) gi += mu * (wp[k] - ap[k]);
-            if (decoupled) wp[k] *= (1.f - lr * wd); else gi += wd * wp[k];
+            if (kHasAnchor && mu != 0.f) gi += mu * (wp[k] - ap[k]);
+            if (wd != 0.f) { if (decoupled) wp[k] *= (1.f - lr * wd); else gi += wd * wp[k]; }
             mp[k] = b1 * mp[k] + (1.f - b1) * gi;
             vp[k] = b2 * vp[k] + (1.f - b2) * gi * gi;
             float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;

@@ -120,8 +120,8 @@ mt_step_kernel(const __grid_constant__ MtTable t, float* __restrict__ w, float* 
                 for (int k = 0; k < 4; ++k) {
                     if (e + k >= numel) continue;
                     float gi = gp[k] * gscale;
-                    if (anchor) gi += mu * (wp[k] - ap[k]);
-                    if (decoupled) wp[k] *= (1.f - lr * wd); else gi += wd * wp[k];
+                    if (anchor && mu != 0.f) gi += mu * (wp[k] - ap[k]);
+                    if (wd != 0.f) { if (decoupled) wp[k] *= (1.f - lr * wd); else gi += wd * wp[k]; }
                     mp[k] = b1 * mp[k] + (1.f - b1) * gi;
                     vp[k] = b2 * vp[k] + (1.f - b2) * gi * gi;
                     wp[k] -= step_size * mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps);
@@ -136,8 +136,8 @@ mt_step_kernel(const __grid_constant__ MtTable t, float* __restrict__ w, float* 
                     if (e + k >= numel) continue;
                     float gi = gp[k] * gscale;
                     if (cv) gi += cp[k];
-                    if (anchor) gi += mu * (wp[k] - ap[k]);
-                    gi += wd * wp[k];
+                    if (anchor && mu != 0.f) gi += mu * (wp[k] - ap[k]);
+                    if (wd != 0.f) gi += wd * wp[k];
                     const float buf = first ? gi : mom * mp[k] + (1.f - damp) * gi;
                     mp[k] = buf;
                     wp[k] -= lr * ((mom != 0.f) ? (nesterov ? gi + mom * buf : buf) : gi);

@@ -80,9 +80,11 @@ def sgd_step_reference(w, grad, momentum_buf, hp, anchor=None, cv=None, shadow=N
     g = grad[:n].to(torch.float32) * h[HP_GSCALE]
     if cv is not None:
         g = g + cv[:n]
-    if anchor is not None:
+    # zero coefficients are skipped (as torch.optim does): 0 * inf would be NaN and FedPM scores may be +-inf
+    if anchor is not None and mu != 0.0:
         g = g + mu * (w - anchor[:n])
-    g = g + wd * w
+    if wd != 0.0:
+        g = g + wd * w
     if mom != 0.0:
         assert momentum_buf is not None
         if first:
@@ -129,12 +131,13 @@ def adamw_step_reference(w, grad, exp_avg, exp_avg_sq, hp, anchor=None, shadow=N
     lr, wd, mu, b1, b2, eps, step = h[HP_LR], h[HP_WD], h[HP_MU], h[HP_B1], h[HP_B2], h[HP_EPS], h[HP_STEP]
     n = w.numel()
     g = grad[:n].to(torch.float32) * h[HP_GSCALE]
-    if anchor is not None:
+    if anchor is not None and mu != 0.0:
         g = g + mu * (w - anchor[:n])
-    if decoupled:
-        w.mul_(1.0 - lr * wd)
-    else:
-        g = g + wd * w
+    if wd != 0.0:
+        if decoupled:
+            w.mul_(1.0 - lr * wd)
+        else:
+            g = g + wd * w
     exp_avg[:n].mul_(b1).add_(g, alpha=1.0 - b1)
     exp_avg_sq[:n].mul_(b2).addcmul_(g, g, value=1.0 - b2)
     bc1, bc2 = 1.0 - b1**step, 1.0 - b2**step

@@ -532,3 +532,29 @@ def test_tcgen05_linear_bf16_bias(variant, monkeypatch) -> None:
     br = b.detach().float().requires_grad_(True)
     torch.nn.functional.gelu(torch.nn.functional.linear(x.float(), w.detach().float(), br)).sum().backward()
     assert torch.allclose(b.grad.float(), br.grad, rtol=5e-2, atol=0.5)
+
+
+@pytest.mark.gpu
+def test_optimizer_kernels_keep_infinite_parameters_finite_free_of_nan():
+    """FedPM scores are legitimately +-inf after a Bayesian aggregate of exactly 0 or 1 (sigmoid_inverse).  With zero
+    weight decay / drift weight the kernels must skip those terms like torch.optim does (0 * inf = NaN otherwise)."""
+    dev = torch.device("cuda")
+    w = torch.tensor([float("inf"), -float("inf"), 1.0, -2.0] * 8, device=dev)
+    g = torch.full_like(w, 0.25)
+    anchor = torch.zeros_like(w)
+    hp = _hp(HP_LR=0.5)
+    F.sgd_step(w, g, None, hp, anchor)
+    assert not torch.isnan(w).any() and torch.isinf(w[0]) and torch.isinf(w[1])
+    assert torch.allclose(w[2:4], torch.tensor([0.875, -2.125], device=dev))
+    ref = torch.tensor([float("inf"), -float("inf"), 1.0, -2.0] * 8)
+    F.sgd_step_reference(ref, g.cpu(), None, hp.cpu(), anchor.cpu())
+    assert not torch.isnan(ref).any() and torch.allclose(ref[2:4], w[2:4].cpu())
+    # table (multi-tensor) kernel, the path master-weight mode uses
+    from fl4health_b200.ops.multi_tensor import TableEntry, mt_step
+
+    master = torch.tensor([float("inf"), -float("inf"), 1.0, -2.0] * 8, device=dev)
+    momentum = torch.zeros_like(master)
+    grad = torch.full_like(master, 0.25)
+    mt_step([TableEntry(grad, 0, master.numel())], False, master, momentum, None, _hp(HP_LR=0.5, HP_MOM=0.9, HP_FIRST=1.0),
+            anchor=torch.zeros_like(master))
+    assert not torch.isnan(master).any() and torch.isinf(master[0]) and torch.allclose(master[2:4], w[2:4])

@@ -87,3 +87,21 @@ def test_int_flat_survives_parameters_round_trip() -> None:
     back = parameters_to_ndarrays(ndarrays_to_parameters(arrays))
     assert back.int_flat is arrays.int_flat
     assert parameters_to_ndarrays(ndarrays_to_parameters([torch.zeros(2)])).int_flat is None
+
+
+def test_optimizer_references_skip_zero_coefficients_on_infinite_parameters() -> None:
+    """0 * inf = NaN: with zero weight decay / drift weight the terms are skipped (torch.optim semantics), so FedPM's
+    +-inf scores (sigmoid_inverse of an aggregate of exactly 0 or 1) survive a local step."""
+    from fl4health_b200.ops import flat as F
+
+    w = torch.tensor([float("inf"), -float("inf"), 1.0, -2.0])
+    hp = F.make_hyper_params("cpu")
+    hp[F.HP_LR] = 0.5
+    F.sgd_step_reference(w, torch.full((4,), 0.25), None, hp, anchor=torch.zeros(4))
+    assert not torch.isnan(w).any() and torch.isinf(w[:2]).all() and torch.allclose(w[2:], torch.tensor([0.875, -2.125]))
+    w = torch.tensor([float("inf"), 1.0, -2.0, 0.5])
+    m, v = torch.zeros(4), torch.zeros(4)
+    hp = F.make_hyper_params("cpu")
+    hp[F.HP_LR], hp[F.HP_B1], hp[F.HP_B2], hp[F.HP_EPS] = 0.1, 0.9, 0.999, 1e-8
+    F.adamw_step_reference(w, torch.full((4,), 0.25), m, v, hp, anchor=torch.zeros(4))
+    assert not torch.isnan(w).any() and torch.isinf(w[0])
