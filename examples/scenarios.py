@@ -85,7 +85,7 @@ def fedopt_example(config: dict[str, Any], device: torch.device) -> tuple[Any, l
 
     template = SmallCnn(config["dataset"])
     torch.manual_seed(config["seed"])
-    strategy = FedAdam(initial_parameters=_initial_parameters(SmallCnn(config["dataset"])), eta=config.get("server_learning_rate", 0.05),
+    strategy = FedAdam(initial_parameters=_initial_parameters(SmallCnn(config["dataset"])), eta=config.get("server_learning_rate", 0.005),
                        **strategy_kwargs(config))
     del template
     return _fl_server(config, strategy), make_clients(BasicClient, config, device, lambda: SmallCnn(config["dataset"]))
@@ -110,7 +110,7 @@ def flash_example(config: dict[str, Any], device: torch.device) -> tuple[Any, li
 
     config = {**config, "local_epochs": config.get("local_epochs", 2), "local_steps": None}
     fn = make_config_fn(config, gamma=config.get("gamma", 0.01))
-    strategy = Flash(initial_parameters=None, eta=config.get("server_learning_rate", 0.05), **strategy_kwargs(config, fn))
+    strategy = Flash(initial_parameters=None, eta=config.get("server_learning_rate", 0.005), **strategy_kwargs(config, fn))
     return _fl_server(config, strategy, config_fn=fn), make_clients(FlashClient, config, device, lambda: SmallCnn(config["dataset"]))
 
 
