@@ -60,6 +60,8 @@ from fl4health_b200.utils.losses import EvaluationLosses, LossMeter, LossMeterTy
 from fl4health_b200.utils.random import generate_hash
 from fl4health_b200.utils.typing import LogLevel, TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 
+EXPECTED_OUTPUT_TUPLE_SIZE = 2  # a model may return (predictions, features)
+
 
 class BasicClient:
     def __init__(

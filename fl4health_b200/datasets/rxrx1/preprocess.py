@@ -28,6 +28,15 @@ def filter_and_save_data(metadata: pd.DataFrame, top_sirna_ids: list[int], cell_
     keep.to_csv(output_path, index=False)
 
 
+def save_to_pkl(data: torch.Tensor, output_path: str) -> None:
+    """Pickle one tensor (the reference's per-image storage, ``rxrx1/preprocess.py:74-83``; kept for tools that still
+    write that layout — this package stores one tensor file per (client, split) instead)."""
+    import pickle
+
+    with open(output_path, "wb") as handle:
+        pickle.dump(data, handle)
+
+
 def load_image(row: dict[Hashable, Any], root: Path) -> torch.Tensor:
     """``[3, H, W]`` float tensor in [0, 1] assembled from the per-channel PNGs of one (experiment, plate, well, site)."""
     import numpy as np

@@ -80,14 +80,47 @@ SOURCES: dict[str, _Source] = {
 }
 
 
+def _image_path(source: _Source, row: pd.Series) -> str:
+    return os.path.join(*source.image_prefix, str(row[source.image_column]) + source.image_suffix)
+
+
+def _label(source: _Source, row: pd.Series) -> str:
+    return source.label_map[row[source.label_column]]
+
+
+# Public per-dataset helpers with the reference's names (preprocess_skin.py:120-152, 194-225, 253-300): views over SOURCES.
+def ham_image_path_func(row: pd.Series) -> str:
+    return _image_path(SOURCES["HAM10000"], row)
+
+
+def ham_label_map_func(row: pd.Series) -> str:
+    return _label(SOURCES["HAM10000"], row)
+
+
+def pad_image_path_func(row: pd.Series) -> str:
+    return _image_path(SOURCES["PAD-UFES-20"], row)
+
+
+def pad_label_map_func(row: pd.Series) -> str:
+    return _label(SOURCES["PAD-UFES-20"], row)
+
+
+def derm7pt_image_path_func(row: pd.Series) -> str:
+    return _image_path(SOURCES["Derm7pt"], row)
+
+
+def derm7pt_label_map_func(row: pd.Series) -> str:
+    return _label(SOURCES["Derm7pt"], row)
+
+
 def _preprocess_source(data_path: str, source: _Source, official_columns: list[str]) -> None:
     folder = os.path.join(data_path, source.folder)
     frame = pd.read_csv(os.path.join(folder, source.metadata))
     for client_name, row_filter in source.clients.items():
         process_client_data(
             row_filter(frame).reset_index(drop=True), client_name, folder,
-            lambda row, s=source: os.path.join(*s.image_prefix, str(row[s.image_column]) + s.image_suffix),
-            lambda row, s=source: s.label_map[row[s.label_column]], source.original_columns, official_columns,
+            lambda row, s=source: _image_path(s, row), lambda row, s=source: _label(s, row), source.original_columns,
+            official_columns,
         )
 
 

@@ -17,11 +17,40 @@ import pandas as pd
 from pandas.api.types import is_bool_dtype, is_integer_dtype, is_numeric_dtype, is_object_dtype, is_string_dtype
 
 from fl4health_b200.feature_alignment.constants import (
+    FEATURE_TYPES,
     FEATURE_MAPPING_ATTR,
     FEATURE_TYPE_ATTR,
     ORDINAL_MAX_CATEGORIES,
     FeatureType,
 )
+
+
+def valid_feature_type(type: FeatureType, raise_error: bool = True) -> bool:  # noqa: A002
+    """Whether ``type`` is one of the feature types a column can be converted to (parity: handle_types.py:393-414)."""
+    if type in FEATURE_TYPES:
+        return True
+    if raise_error:
+        raise ValueError(f"Feature type '{type.value}' not in {', '.join(t.value for t in FEATURE_TYPES)}.")
+    return False
+
+
+def _type_to_dtype(type: FeatureType) -> str | None:  # noqa: A002
+    if type in (FeatureType.STRING, FeatureType.NUMERIC):
+        return None  # the caller keeps its own string length / numeric precision
+    if type in (FeatureType.BINARY, FeatureType.CATEGORICAL_INDICATOR, FeatureType.ORDINAL):
+        return "category"
+    if valid_feature_type(type, raise_error=True):
+        raise ValueError("Supported type has no corresponding datatype.")
+    return None
+
+
+def to_dtype(series: pd.Series, type: FeatureType) -> pd.Series:  # noqa: A002
+    """``series`` with the pandas dtype that goes with the feature type (categorical for binary / ordinal / indicator
+    columns, untouched otherwise; parity: handle_types.py:448-467)."""
+    dtype = _type_to_dtype(type)
+    if dtype is None or series.dtype == dtype:
+        return series
+    return series.astype(dtype)
 
 
 def get_unique(values: np.ndarray | pd.Series, unique: np.ndarray | None = None) -> np.ndarray:

@@ -20,6 +20,8 @@ from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.metrics.metrics_utils import threshold_tensor
 from fl4health_b200.metrics.utils import align_pred_and_target_shapes
 
+MAX_COUNT_TENSOR_DIMS = 2  # count tensors are never more than 2-dimensional
+
 N_LABELS_BINARY = 2
 
 

@@ -29,6 +29,7 @@ from fl4health_b200.parameter_exchange.parameter_exchanger_base import Parameter
 from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerAdaptiveConstraint
 from fl4health_b200.utils.losses import TrainingLosses
 from fl4health_b200.utils.typing import TorchInputType, TorchPredType, TorchTargetType
+from fl4health_b200.mixins.core_protocols import AdaptiveDriftConstrainedProtocol  # noqa: F401  (import-path parity)
 
 
 class AdaptiveDriftConstrainedMixin(BaseFlexibleMixin):

@@ -88,3 +88,44 @@ class FlexibleClientProtocol(FlexibleClientProtocolPreSetup, Protocol):
     def compute_evaluation_loss(
         self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
     ) -> EvaluationLosses: ...
+
+
+@runtime_checkable
+class AdaptiveDriftConstrainedProtocol(FlexibleClientProtocol, Protocol):
+    """What ``AdaptiveDriftConstrainedMixin`` adds to / expects from the client (adaptive_drift_constrained.py:23-32)."""
+
+    loss_for_adaptation: float
+    drift_penalty_tensors: list[torch.Tensor] | None
+    drift_penalty_weight: float | None
+    penalty_loss_function: Any
+    parameter_exchanger: Any
+
+    def compute_penalty_loss(self) -> torch.Tensor: ...
+
+    def setup_client_and_return_all_model_parameters(self, config: Config) -> NDArrays: ...
+
+
+@runtime_checkable
+class DittoPersonalizedProtocol(AdaptiveDriftConstrainedProtocol, Protocol):
+    """(personalized/ditto.py:30-44)"""
+
+    global_model: nn.Module | None
+    optimizer_keys: list[str]
+
+    def get_global_model(self, config: Config) -> nn.Module: ...
+
+    def _copy_optimizer_with_new_params(self, original_optimizer: Optimizer) -> Optimizer: ...
+
+    def set_initial_global_tensors(self) -> None: ...
+
+    def safe_global_model(self) -> nn.Module: ...
+
+
+@runtime_checkable
+class MrMtlPersonalizedProtocol(AdaptiveDriftConstrainedProtocol, Protocol):
+    """(personalized/mr_mtl.py:27-32)"""
+
+    initial_global_model: nn.Module | None
+    initial_global_tensors: list[torch.Tensor]
+
+    def get_global_model(self, config: Config) -> nn.Module: ...

@@ -20,6 +20,7 @@ from fl4health_b200.parameter_exchange.full_exchanger import FullParameterExchan
 from fl4health_b200.utils.config import narrow_dict_type
 from fl4health_b200.utils.losses import EvaluationLosses, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
+from fl4health_b200.mixins.core_protocols import DittoPersonalizedProtocol  # noqa: F401  (import-path parity)
 
 
 class DittoPersonalizedMixin(AdaptiveDriftConstrainedMixin):

@@ -13,6 +13,7 @@ from fl4health_b200.common.typing import Config, NDArrays, Scalar
 from fl4health_b200.mixins.adaptive_drift_constrained import AdaptiveDriftConstrainedMixin
 from fl4health_b200.utils.losses import TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchPredType, TorchTargetType
+from fl4health_b200.mixins.core_protocols import MrMtlPersonalizedProtocol  # noqa: F401  (import-path parity)
 
 
 class MrMtlPersonalizedMixin(AdaptiveDriftConstrainedMixin):

@@ -8,6 +8,8 @@ from enum import Enum
 import torch
 from torch import nn
 
+EXPECTED_MAX_PRED_N_DIMS = 2  # [batch, classes] predictions per ensemble member
+
 
 class EnsembleAggregationMode(Enum):
     VOTE = "VOTE"

@@ -8,6 +8,8 @@ from pathlib import Path
 import torch
 from torch import nn
 
+DEFAULT_PROJECTION_HEAD = nn.Identity()
+
 
 class FedSimClrModel(nn.Module):
     def __init__(

@@ -12,6 +12,8 @@ from torch.nn.parameter import Parameter
 
 from fl4health_b200.common.logger import log
 
+TWO_D_TENSOR_SHAPE_LENGTH = 2
+
 
 class PcaModule(nn.Module):
     def __init__(self, low_rank: bool = False, full_svd: bool = False, rank_estimation: int = 6) -> None:

@@ -20,13 +20,18 @@ from torch import nn
 
 from fl4health_b200.checkpointing.server_module import NnUnetServerCheckpointAndStateModule
 from fl4health_b200.common.logger import log
-from fl4health_b200.common.typing import Code, Config, GetPropertiesIns, Parameters, Scalar
+from fl4health_b200.common.typing import Code, Config, EvaluateIns, FitIns, GetPropertiesIns, Parameters, Scalar
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.servers.base_server import FlServer
 from fl4health_b200.servers.client_manager import ClientManager
+from fl4health_b200.servers.client_proxy import ClientProxy
 from fl4health_b200.strategies.strategy import Strategy
 from fl4health_b200.utils.config import narrow_dict_type
 from fl4health_b200.utils.nnunet_utils import NnunetConfig
+
+FIT_CFG_FN = Callable[[int, Parameters, ClientManager], list[tuple[ClientProxy, FitIns]]]
+EVAL_CFG_FN = Callable[[int, Parameters, ClientManager], list[tuple[ClientProxy, EvaluateIns]]]
+CFG_FN = FIT_CFG_FN | EVAL_CFG_FN
 
 CFG_FN = Callable[..., Any]
 ModelBuilder = Callable[[dict, NnunetConfig, int, int, bool], nn.Module]

@@ -16,6 +16,8 @@ from fl4health_b200.servers.client_proxy import ClientProxy
 from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
 from fl4health_b200.utils.functions import decode_and_pseudo_sort_results
 
+EVALUATE_FN_TYPE = Callable[[int, NDArrays, dict[str, Scalar]], tuple[float, dict[str, Scalar]] | None] | None
+
 MINIMUM_PCA_CLIENTS = 2
 
 

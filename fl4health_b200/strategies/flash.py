@@ -22,6 +22,8 @@ from fl4health_b200.common.typing import (
 from fl4health_b200.servers.client_proxy import ClientProxy
 from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
 
+EVALUATE_FN_TYPE = Callable[[int, NDArrays, dict[str, Scalar]], tuple[float, dict[str, Scalar]] | None] | None
+
 
 class Flash(BasicFedAvg):
     def __init__(

@@ -1,0 +1,77 @@
+"""Small public names kept for import-path parity with the reference (found by diffing module-level public names)."""
+
+import pandas as pd
+import pytest
+import torch
+
+from fl4health_b200.feature_alignment.constants import FeatureType
+from fl4health_b200.feature_alignment.handle_types import to_dtype, valid_feature_type
+
+
+def test_handle_types_helpers() -> None:
+    assert valid_feature_type(FeatureType.ORDINAL)
+    assert not valid_feature_type(FeatureType.CATEGORICAL_INDICATOR, raise_error=False)
+    with pytest.raises(ValueError, match="categorical_indicator"):
+        valid_feature_type(FeatureType.CATEGORICAL_INDICATOR)
+    series = pd.Series([0, 1, 1, 0])
+    assert str(to_dtype(series, FeatureType.BINARY).dtype) == "category"
+    assert to_dtype(series, FeatureType.NUMERIC) is series
+    strings = pd.Series(["a", "b"])
+    assert to_dtype(strings, FeatureType.STRING) is strings  # strings keep whatever dtype the caller chose
+
+
+def test_skin_cancer_path_and_label_functions() -> None:
+    from fl4health_b200.datasets.skin_cancer import preprocess_skin as ps
+
+    ham = pd.Series({"image_id": "ISIC_0001", "dx": "akiec"})
+    assert ps.ham_image_path_func(ham).endswith("HAM10000/ISIC_0001.jpg") and ps.ham_label_map_func(ham) == "AK"
+    pad = pd.Series({"img_id": "PAT_1.png", "diagnostic": "SEK"})
+    assert ps.pad_image_path_func(pad).endswith("PAD-UFES-20/PAT_1.png") and ps.pad_label_map_func(pad) == "BKL"
+    derm = pd.Series({"derm": "a/b.jpg", "diagnosis": "melanoma (in situ)"})
+    assert ps.derm7pt_image_path_func(derm).endswith("Derm7pt/images/a/b.jpg") and ps.derm7pt_label_map_func(derm) == "MEL"
+
+
+def test_rxrx1_save_to_pkl(tmp_path) -> None:
+    import pickle
+
+    from fl4health_b200.datasets.rxrx1.preprocess import save_to_pkl
+
+    save_to_pkl(torch.arange(6).view(2, 3), str(tmp_path / "t.pkl"))
+    assert torch.equal(pickle.load(open(tmp_path / "t.pkl", "rb")), torch.arange(6).view(2, 3))
+
+
+def test_protocol_compliance_decorator_and_protocol_names() -> None:
+    from fl4health_b200.clients.flexible.base import FlexibleClient
+    from fl4health_b200.mixins.adaptive_drift_constrained import AdaptiveDriftConstrainedProtocol
+    from fl4health_b200.mixins.personalized.ditto import DittoPersonalizedProtocol
+    from fl4health_b200.mixins.personalized.mr_mtl import MrMtlPersonalizedProtocol
+    from fl4health_b200.mixins.personalized.utils import ensure_protocol_compliance
+
+    assert issubclass(DittoPersonalizedProtocol, AdaptiveDriftConstrainedProtocol)
+    assert issubclass(MrMtlPersonalizedProtocol, AdaptiveDriftConstrainedProtocol)
+
+    class NotAClient:
+        @ensure_protocol_compliance
+        def method(self) -> int:
+            return 1
+
+    with pytest.raises(TypeError, match="Protocol requirements not met"):
+        NotAClient().method()
+
+    class Flex(FlexibleClient):
+        @ensure_protocol_compliance
+        def method(self) -> int:
+            return 2
+
+    assert Flex.method(Flex.__new__(Flex)) == 2
+
+
+def test_constants_exist() -> None:
+    from fl4health_b200.clients.basic_client import EXPECTED_OUTPUT_TUPLE_SIZE
+    from fl4health_b200.model_bases.ensemble_base import EXPECTED_MAX_PRED_N_DIMS
+    from fl4health_b200.model_bases.masked_layers.masked_normalization_layers import BATCH_NORM_1D_INPUT_LENGTHS
+    from fl4health_b200.model_bases.pca import TWO_D_TENSOR_SHAPE_LENGTH
+    from fl4health_b200.servers.nnunet_server import EVAL_CFG_FN, FIT_CFG_FN  # noqa: F401
+
+    assert (EXPECTED_OUTPUT_TUPLE_SIZE, EXPECTED_MAX_PRED_N_DIMS, TWO_D_TENSOR_SHAPE_LENGTH) == (2, 2, 2)
+    assert BATCH_NORM_1D_INPUT_LENGTHS == {2, 3}
