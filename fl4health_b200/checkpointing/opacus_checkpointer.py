@@ -45,7 +45,7 @@ class OpacusCheckpointer(FunctionTorchModuleCheckpointer):
     def load_checkpoint(self, path_to_checkpoint: str | None = None) -> nn.Module:
         raise NotImplementedError(
             "When loading from Opacus checkpointers, you need to provide a model into which state is loaded. "
-            "Please use load_best_checkpoint instead"
+            "Please use load_best_checkpoint_into_model instead"
         )
 
     def load_best_checkpoint(self, model: nn.Module, target_is_grad_sample_module: bool = False) -> None:
@@ -57,6 +57,11 @@ class OpacusCheckpointer(FunctionTorchModuleCheckpointer):
         elif not wrapped_keys and target_is_grad_sample_module:
             state = {f"_module.{k}": v for k, v in state.items()}
         model.load_state_dict({k: torch.as_tensor(v) for k, v in state.items()}, strict=True)
+
+
+    def load_best_checkpoint_into_model(self, target_model: nn.Module, target_is_grad_sample_module: bool = False) -> None:
+        """The reference's name for ``load_best_checkpoint`` (``opacus_checkpointer.py:89-107``)."""
+        self.load_best_checkpoint(target_model, target_is_grad_sample_module)
 
 
 class LatestOpacusCheckpointer(OpacusCheckpointer):

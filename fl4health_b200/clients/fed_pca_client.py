@@ -38,7 +38,7 @@ class _PcaExchanger(FullParameterExchanger):
 class FedPCAClient:
     def __init__(self, data_path: Path, device: torch.device, model_save_dir: Path, client_name: str | None = None,
                  metrics: Sequence[Metric] | None = None) -> None:
-        self.client_name = generate_hash() if client_name is None else client_name
+        self.client_name = self.generate_hash() if client_name is None else client_name
         self.model: PcaModule
         self.initialized = False
         self.data_path = data_path
@@ -49,6 +49,10 @@ class FedPCAClient:
         self.num_train_samples: int
         self.num_val_samples: int
         self.parameter_exchanger: ParameterExchanger = _PcaExchanger()
+
+    def generate_hash(self, length: int = 8) -> str:
+        """Unique id used as the client name when none is given (parity: ``fed_pca_client.py:44-55``)."""
+        return generate_hash(length)
 
     def get_parameters(self, config: Config) -> NDArrays:
         if not self.initialized:

@@ -101,22 +101,28 @@ class Nnunetv2Backend:
         self.always_preprocess, self.n_dataload_processes = always_preprocess, n_dataload_processes
         self.trainer_kwargs = trainer_kwargs or {}
 
+    # The four steps below carry the names of the reference client's methods (``nnunet_client.py:388-560``); the client
+    # exposes them too and simply forwards to its backend.
+    def maybe_extract_fingerprint(self) -> None:
+        from nnunetv2.experiment_planning.plan_and_preprocess_api import extract_fingerprints  # type: ignore[import-not-found]
+        from nnunetv2.paths import nnUNet_preprocessed  # type: ignore[import-not-found]
+
+        fingerprint = Path(nnUNet_preprocessed) / self.dataset_name / "dataset_fingerprint.json"
+        if self.always_preprocess or not fingerprint.exists():
+            extract_fingerprints(dataset_ids=[self.dataset_id])
+
     def plan(self) -> dict[str, Any]:
         from nnunetv2.experiment_planning.experiment_planners.default_experiment_planner import ExperimentPlanner  # type: ignore[import-not-found]
-        from nnunetv2.experiment_planning.plan_and_preprocess_api import extract_fingerprints  # type: ignore[import-not-found]
 
-        extract_fingerprints(dataset_ids=[self.dataset_id])
+        self.maybe_extract_fingerprint()
         plans = ExperimentPlanner(dataset_name_or_id=self.dataset_id, plans_name="temp_plans").plan_experiment()
         plans["plans_name"] = self.dataset_name + "_plans"
         return plans
 
-    def prepare(self, plans: dict[str, Any], config: NnunetConfig, fold: int | str, batch_size: int | None, device: torch.device) -> PreparedExperiment:
-        from batchgenerators.utilities.file_and_folder_operations import load_json, save_json  # type: ignore[import-not-found]
-        from nnunetv2.experiment_planning.plan_and_preprocess_api import preprocess_dataset  # type: ignore[import-not-found]
+    def create_plans(self, plans: dict[str, Any], batch_size: int | None = None) -> dict[str, Any]:
+        """Localise the federation's plans to this client's dataset and save them next to the preprocessed data."""
+        from batchgenerators.utilities.file_and_folder_operations import save_json  # type: ignore[import-not-found]
         from nnunetv2.paths import nnUNet_preprocessed  # type: ignore[import-not-found]
-        from nnunetv2.training.nnUNetTrainer.nnUNetTrainer import nnUNetTrainer  # type: ignore[import-not-found]
-
-        from fl4health_b200.utils.nnunet_utils import NnUNetDataLoaderWrapper
 
         local = dict(plans)
         local["source_plans_name"] = plans.get("plans_name", "plans")
@@ -129,10 +135,28 @@ class Nnunetv2Backend:
         plans_path = Path(nnUNet_preprocessed) / self.dataset_name / f"{local['plans_name']}.json"
         plans_path.parent.mkdir(parents=True, exist_ok=True)
         save_json(local, str(plans_path), sort_keys=False)
-        identifier = (self.data_identifier or local["plans_name"]) + "_" + config.value
-        if self.always_preprocess or not (plans_path.parent / identifier).exists():
-            preprocess_dataset(dataset_id=self.dataset_id, plans_identifier=local["plans_name"], configurations=[config.value],
+        return local
+
+    def maybe_preprocess(self, local_plans: dict[str, Any], config: NnunetConfig) -> None:
+        from nnunetv2.experiment_planning.plan_and_preprocess_api import preprocess_dataset  # type: ignore[import-not-found]
+        from nnunetv2.paths import nnUNet_preprocessed  # type: ignore[import-not-found]
+
+        identifier = (self.data_identifier or local_plans["plans_name"]) + "_" + config.value
+        if self.always_preprocess or not (Path(nnUNet_preprocessed) / self.dataset_name / identifier).exists():
+            preprocess_dataset(dataset_id=self.dataset_id, plans_identifier=local_plans["plans_name"], configurations=[config.value],
                                num_processes=[self.n_dataload_processes or 4])
+
+    def prepare(self, plans: dict[str, Any], config: NnunetConfig, fold: int | str, batch_size: int | None, device: torch.device) -> PreparedExperiment:
+        from batchgenerators.utilities.file_and_folder_operations import load_json  # type: ignore[import-not-found]
+        from nnunetv2.paths import nnUNet_preprocessed  # type: ignore[import-not-found]
+        from nnunetv2.training.nnUNetTrainer.nnUNetTrainer import nnUNetTrainer  # type: ignore[import-not-found]
+
+        from fl4health_b200.utils.nnunet_utils import NnUNetDataLoaderWrapper
+
+        self.maybe_extract_fingerprint()
+        local = self.create_plans(plans, batch_size)
+        self.maybe_preprocess(local, config)
+        plans_path = Path(nnUNet_preprocessed) / self.dataset_name / f"{local['plans_name']}.json"
         dataset_json = load_json(str(plans_path.parent / "dataset.json"))
         trainer = nnUNetTrainer(plans=local, configuration=config.value, fold=fold, dataset_json=dataset_json, device=device,
                                 **self.trainer_kwargs)
@@ -203,6 +227,27 @@ class NnunetClient(BasicClient):
         self.experiment = self.backend.prepare(self.plans, self.nnunet_config, self.fold,
                                                int(batch_size) if batch_size is not None else None, self.device)
         super().setup_client(config)
+
+    # reference-named steps, forwarded to the backend when it has them (the injected test / example backends do not)
+    def maybe_extract_fingerprint(self) -> None:
+        step = getattr(self.backend, "maybe_extract_fingerprint", None)
+        if step is not None:
+            step()
+
+    def create_plans(self, config: Config) -> dict[str, Any]:
+        plans = pickle.loads(narrow_dict_type(config, "nnunet_plans", bytes))
+        step = getattr(self.backend, "create_plans", None)
+        batch_size = config.get("batch_size")
+        return step(plans, int(batch_size) if batch_size is not None else None) if step is not None else plans
+
+    def maybe_preprocess(self, nnunet_config: NnunetConfig) -> None:
+        step = getattr(self.backend, "maybe_preprocess", None)
+        if step is not None:
+            step(self.create_plans({"nnunet_plans": pickle.dumps(self.plans)}), nnunet_config)
+
+    def empty_cache(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.empty_cache()
 
     def get_model(self, config: Config) -> nn.Module:
         return self.experiment.network

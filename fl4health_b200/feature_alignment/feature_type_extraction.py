@@ -37,6 +37,11 @@ class FeatureMeta:
     def get_type(self) -> FeatureType:
         return self.type_
 
+    def update(self, meta: list[tuple[str, Any]]) -> None:
+        """Set several meta attributes at once: ``[(attribute name, value), ...]`` (feature_type_extraction.py:107-115)."""
+        for name, value in meta:
+            setattr(self, name, value)
+
 
 class Features:
     def __init__(self, data: pd.DataFrame, features: str | list[str], by: str | list[str] | None,

@@ -125,6 +125,26 @@ class MkMmdLoss(torch.nn.Module):
         a, b, c, d = kernels.unbind(dim=pairing_dim + 1)
         return a + b - c - d
 
+    # Per-kernel / from-distances entry points with the reference's names (``mkmmd_loss.py:152-199``); each is a view of
+    # ``_h_from_distances``, which evaluates all bandwidths in one pass.
+    def compute_h_u_from_inner_products(self, inner_products: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+        """``inner_products``: [4, n, n] squared distances; ``gamma``: shape (1,).  Returns [1, n, n]."""
+        assert gamma.shape == (1,)
+        a, b, c, d = torch.exp(-inner_products / gamma).unbind(dim=0)
+        return (a + b - c - d).unsqueeze(0)
+
+    def compute_h_u_from_inner_products_linear(self, inner_products: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+        """``inner_products``: [n/2, 4] squared distances of the quadruples.  Returns [1, n/2]."""
+        assert gamma.shape == (1,)
+        a, b, c, d = torch.exp(-inner_products / gamma).unbind(dim=1)
+        return (a + b - c - d).unsqueeze(0)
+
+    def compute_all_h_u_from_inner_products(self, inner_product_all_samples: torch.Tensor) -> torch.Tensor:
+        return self._h_from_distances(inner_product_all_samples, 0)  # [K, n, n]
+
+    def compute_all_h_u_from_inner_products_linear(self, inner_product_quadruples: torch.Tensor) -> torch.Tensor:
+        return self._h_from_distances(inner_product_quadruples, 1)  # [K, n/2]
+
     def compute_all_h_u_all_samples(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return self._h_from_distances(self.compute_euclidean_inner_products(x, y), 0)  # [K, n, n]
 
@@ -155,9 +175,12 @@ class MkMmdLoss(torch.nn.Module):
         delta = self.form_h_u_delta_w_i(all_h_u_per_v_i)
         return (delta @ delta.t()) / delta.shape[1]
 
+    def form_kernel_samples_minus_expectation(self, all_h_u_per_sample: torch.Tensor, hat_d_per_kernel: torch.Tensor) -> torch.Tensor:
+        return all_h_u_per_sample - hat_d_per_kernel.reshape(-1, 1, 1)
+
     def compute_hat_q_k(self, all_h_u_per_sample: torch.Tensor, hat_d_per_kernel: torch.Tensor) -> torch.Tensor:
         k, n, _ = all_h_u_per_sample.shape
-        centered = (all_h_u_per_sample - hat_d_per_kernel.reshape(k, 1, 1)).reshape(k, -1)
+        centered = self.form_kernel_samples_minus_expectation(all_h_u_per_sample, hat_d_per_kernel).reshape(k, -1)
         return (centered @ centered.t()) / (n * n - 1.0)
 
     def beta_with_extreme_kernel_base_values(

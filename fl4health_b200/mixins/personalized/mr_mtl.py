@@ -31,6 +31,14 @@ class MrMtlPersonalizedMixin(AdaptiveDriftConstrainedMixin):
             self.initial_global_model = self._place_model(self.get_global_model(config), with_grad=False)  # type: ignore[attr-defined]
         super().setup_client(config)  # type: ignore[misc]
 
+    def get_optimizer(self, config: Config) -> Any:
+        """Hook kept from the reference (``mr_mtl.py:94-109``): a last chance to create the anchor model when a wrapped
+        client builds its optimizer before ``setup_client`` ran; returns whatever the wrapped client returns."""
+        if self.initial_global_model is None:
+            self.initial_global_model = self._place_model(self.get_global_model(config), with_grad=False)  # type: ignore[attr-defined]
+            log(INFO, f"initial_global_model set: {type(self.initial_global_model).__name__} within `get_optimizer`")
+        return super().get_optimizer(config=config)  # type: ignore[misc]
+
     def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
         assert self.initial_global_model is not None and self.parameter_exchanger is not None  # type: ignore[attr-defined]
         server_model_state, self.drift_penalty_weight = self.parameter_exchanger.unpack_parameters(parameters)  # type: ignore[attr-defined]

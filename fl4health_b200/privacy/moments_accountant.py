@@ -13,19 +13,43 @@ from collections.abc import Sequence
 import numpy as np
 
 from fl4health_b200.privacy import rdp
+from fl4health_b200.privacy.dp_events import (
+    DpEvent,
+    GaussianDpEvent,
+    NeighborRel,
+    PoissonSampledDpEvent,
+    SampledWithoutReplacementDpEvent,
+    SelfComposedDpEvent,
+)
 
 
 class SamplingStrategy(ABC):
+    neighbor_relation: NeighborRel
+
     @abstractmethod
     def rdp_per_update(self, noise_multiplier: float, orders: Sequence[float]) -> np.ndarray:
         raise NotImplementedError
+
+    @abstractmethod
+    def get_dp_event(self, noise_event: DpEvent) -> DpEvent:
+        """The sampled mechanism as a plain-data event (parity: ``moments_accountant.py:26-61``)."""
+        raise NotImplementedError
+
+    def composed_event(self, noise_multiplier: float, updates: int) -> DpEvent:
+        """``updates`` self-compositions of the sampled Gaussian mechanism: what the accountant charges for."""
+        return SelfComposedDpEvent(self.get_dp_event(GaussianDpEvent(noise_multiplier)), updates)
 
 
 class PoissonSampling(SamplingStrategy):
     """Each element participates independently with probability ``sampling_ratio`` (add/remove-one neighbours)."""
 
+    neighbor_relation = NeighborRel.ADD_OR_REMOVE_ONE
+
     def __init__(self, sampling_ratio: float) -> None:
         self.sampling_ratio = sampling_ratio
+
+    def get_dp_event(self, noise_event: DpEvent) -> DpEvent:
+        return PoissonSampledDpEvent(self.sampling_ratio, noise_event)
 
     def rdp_per_update(self, noise_multiplier: float, orders: Sequence[float]) -> np.ndarray:
         return rdp.rdp_poisson_subsampled_gaussian(self.sampling_ratio, noise_multiplier, orders)
@@ -34,9 +58,14 @@ class PoissonSampling(SamplingStrategy):
 class FixedSamplingWithoutReplacement(SamplingStrategy):
     """Exactly ``sample_size`` of ``population_size`` elements per update (replace-one neighbours)."""
 
+    neighbor_relation = NeighborRel.REPLACE_ONE
+
     def __init__(self, population_size: int, sample_size: int) -> None:
         self.population_size = population_size
         self.sample_size = sample_size
+
+    def get_dp_event(self, noise_event: DpEvent) -> DpEvent:
+        return SampledWithoutReplacementDpEvent(self.population_size, self.sample_size, noise_event)
 
     def rdp_per_update(self, noise_multiplier: float, orders: Sequence[float]) -> np.ndarray:
         return rdp.rdp_sample_wor_gaussian(self.sample_size / self.population_size, noise_multiplier, orders)

@@ -54,12 +54,11 @@ class InstanceLevelDpServer(FlServer):
         self.setup_privacy_accountant_and_log(timeout)
         return super().fit(num_rounds=num_rounds, timeout=timeout)
 
-    def setup_privacy_accountant_and_log(self, timeout: float | None) -> None:
-        """Also used (unbound) by ``DPScaffoldServer``."""
+    def setup_privacy_accountant(self, sample_counts: list[int]) -> None:
+        """Build the FL accountant from the polled per-client training-set sizes (parity:
+        ``instance_level_dp_server.py:131-169``).  With a step budget the epoch count charged is the largest any client
+        can reach (ceil(steps * batch / smallest dataset)), so the privacy loss is never under-estimated."""
         assert isinstance(self._client_manager, PoissonSamplingClientManager), "instance-level DP requires Poisson client sampling"
-        sample_counts = self.poll_clients_for_sample_counts(timeout)
-        num_clients = len(sample_counts)
-        total_samples = sum(sample_counts)
         if self.local_epochs is not None:
             epochs_per_round = self.local_epochs
         else:
@@ -67,9 +66,15 @@ class InstanceLevelDpServer(FlServer):
             epochs_per_round = max(ceil(self.local_steps * self.batch_size / max(min(sample_counts), 1)), 1)
         self.accountant = FlInstanceLevelAccountant(
             client_sampling_rate=self.strategy.fraction_fit, noise_multiplier=self.noise_multiplier,
-            epochs_per_round=epochs_per_round, client_batch_sizes=[self.batch_size] * num_clients,
+            epochs_per_round=epochs_per_round, client_batch_sizes=[self.batch_size] * len(sample_counts),
             client_dataset_sizes=sample_counts,
         )
+
+    def setup_privacy_accountant_and_log(self, timeout: float | None) -> None:
+        """Also used (unbound) by ``DPScaffoldServer``."""
+        sample_counts = self.poll_clients_for_sample_counts(timeout)
+        total_samples = sum(sample_counts)
+        InstanceLevelDpServer.setup_privacy_accountant(self, sample_counts)
         target_delta = self.delta if self.delta is not None else 1.0 / total_samples
         epsilon = self.accountant.get_epsilon(self.num_server_rounds, target_delta)
         log(INFO, f"Model privacy after full training will be ({epsilon}, {target_delta})")

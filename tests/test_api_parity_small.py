@@ -75,3 +75,30 @@ def test_constants_exist() -> None:
 
     assert (EXPECTED_OUTPUT_TUPLE_SIZE, EXPECTED_MAX_PRED_N_DIMS, TWO_D_TENSOR_SHAPE_LENGTH) == (2, 2, 2)
     assert BATCH_NORM_1D_INPUT_LENGTHS == {2, 3}
+
+
+def test_dp_events_and_mkmmd_decomposition_helpers() -> None:
+    from fl4health_b200.losses.mkmmd_loss import MkMmdLoss
+    from fl4health_b200.privacy.dp_events import GaussianDpEvent, NeighborRel, PoissonSampledDpEvent, SelfComposedDpEvent
+    from fl4health_b200.privacy.moments_accountant import FixedSamplingWithoutReplacement, PoissonSampling
+
+    event = PoissonSampling(0.25).composed_event(1.5, 40)
+    assert event == SelfComposedDpEvent(PoissonSampledDpEvent(0.25, GaussianDpEvent(1.5)), 40)
+    assert FixedSamplingWithoutReplacement(100, 10).neighbor_relation is NeighborRel.REPLACE_ONE
+    assert FixedSamplingWithoutReplacement(100, 10).get_dp_event(GaussianDpEvent(1.0)).sample_size == 10
+
+    torch.manual_seed(0)
+    loss = MkMmdLoss(device=torch.device("cpu"), gammas=torch.tensor([0.5, 2.0, 8.0]))
+    x, y = torch.randn(8, 5), torch.randn(8, 5) + 0.5
+    distances = loss.compute_euclidean_inner_products(x, y)
+    all_h = loss.compute_all_h_u_from_inner_products(distances)
+    assert torch.allclose(all_h, loss.compute_all_h_u_all_samples(x, y))
+    per_kernel = torch.cat([loss.compute_h_u_from_inner_products(distances, g.reshape(1)) for g in loss.gammas])
+    assert torch.allclose(per_kernel, all_h, atol=1e-6)
+    quads = loss.compute_euclidean_inner_products_linear(loss.construct_quadruples(x, y))
+    lin = loss.compute_all_h_u_from_inner_products_linear(quads)
+    assert torch.allclose(lin, loss.compute_all_h_u_linear(x, y))
+    assert torch.allclose(torch.cat([loss.compute_h_u_from_inner_products_linear(quads, g.reshape(1)) for g in loss.gammas]), lin, atol=1e-6)
+    hat_d = loss.compute_hat_d_per_kernel(all_h)
+    centred = loss.form_kernel_samples_minus_expectation(all_h, hat_d)
+    assert centred.shape == all_h.shape and torch.allclose(centred.reshape(3, -1).mean(dim=1), torch.zeros(3), atol=1e-6)
