@@ -85,7 +85,8 @@ class Nnunetv2Backend:
     """Default backend over the optional ``nnunetv2`` package."""
 
     def __init__(self, dataset_id: int, data_identifier: str | None = None, plans_identifier: str | None = None,
-                 always_preprocess: bool = False, n_dataload_processes: int | None = None, trainer_kwargs: dict | None = None) -> None:
+                 always_preprocess: bool = False, n_dataload_processes: int | None = None, trainer_kwargs: dict | None = None,
+                 trainer_class: type | None = None) -> None:
         try:
             import nnunetv2  # type: ignore[import-not-found]  # noqa: F401
         except ImportError as exc:
@@ -100,6 +101,7 @@ class Nnunetv2Backend:
         self.data_identifier, self.plans_identifier = data_identifier, plans_identifier
         self.always_preprocess, self.n_dataload_processes = always_preprocess, n_dataload_processes
         self.trainer_kwargs = trainer_kwargs or {}
+        self.trainer_class = trainer_class  # an nnUNetTrainer subclass; None = the stock trainer
 
     # The four steps below carry the names of the reference client's methods (``nnunet_client.py:388-560``); the client
     # exposes them too and simply forwards to its backend.
@@ -158,8 +160,9 @@ class Nnunetv2Backend:
         self.maybe_preprocess(local, config)
         plans_path = Path(nnUNet_preprocessed) / self.dataset_name / f"{local['plans_name']}.json"
         dataset_json = load_json(str(plans_path.parent / "dataset.json"))
-        trainer = nnUNetTrainer(plans=local, configuration=config.value, fold=fold, dataset_json=dataset_json, device=device,
-                                **self.trainer_kwargs)
+        trainer_cls = self.trainer_class if self.trainer_class is not None else nnUNetTrainer
+        trainer = trainer_cls(plans=local, configuration=config.value, fold=fold, dataset_json=dataset_json, device=device,
+                              **self.trainer_kwargs)
         trainer.initialize()
         train_gen, val_gen = trainer.get_dataloaders()
         labels = trainer.label_manager
@@ -195,8 +198,13 @@ class NnunetClient(BasicClient):
         client_name: str | None = None,
         backend: NnunetBackend | None = None,
         engine_options: EngineOptions | None = None,
+        nnunet_trainer_class: type | None = None,
+        nnunet_trainer_class_kwargs: dict[str, Any] | None = None,
     ) -> None:
-        """Config keys required from the server: ``nnunet_config`` (str) and — unless this client is asked to create
+        """``nnunet_trainer_class`` / ``nnunet_trainer_class_kwargs``: an ``nnUNetTrainer`` subclass (and extra constructor
+        arguments) for the default backend, as in the reference (``nnunet_client.py:71-150``).
+
+        Config keys required from the server: ``nnunet_config`` (str) and — unless this client is asked to create
         them — ``nnunet_plans`` (pickled dict).  ``compile`` is accepted for API parity; the engine's CUDA-graph capture
         replaces ``torch.compile`` here."""
         super().__init__(
@@ -209,7 +217,8 @@ class NnunetClient(BasicClient):
         self.verbose = verbose
         self.compile = compile
         self.backend: NnunetBackend = backend if backend is not None else Nnunetv2Backend(
-            dataset_id, data_identifier, plans_identifier, always_preprocess, n_dataload_processes)
+            dataset_id, data_identifier, plans_identifier, always_preprocess, n_dataload_processes,
+            trainer_kwargs=nnunet_trainer_class_kwargs, trainer_class=nnunet_trainer_class)
         self.dataset_name = self.backend.dataset_name
         self.stream2debug = StreamToLogger(LOGGER, DEBUG)
         self.grad_scaler = torch.amp.GradScaler("cuda", enabled=device.type == "cuda")

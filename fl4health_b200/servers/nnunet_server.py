@@ -63,6 +63,19 @@ def nnunetv2_model_builder(plans: dict, config: NnunetConfig, num_input_channels
     )
 
 
+def _trainer_model_builder(trainer_class: type) -> ModelBuilder:
+    def build(plans: dict, config: NnunetConfig, num_input_channels: int, num_segmentation_heads: int, deep_supervision: bool) -> nn.Module:
+        from nnunetv2.utilities.plans_handling.plans_handler import PlansManager  # type: ignore[import-not-found]
+
+        configuration = PlansManager(plans).get_configuration(config.value)
+        return trainer_class.build_network_architecture(
+            configuration.network_arch_class_name, configuration.network_arch_init_kwargs,
+            configuration.network_arch_init_kwargs_req_import, num_input_channels, num_segmentation_heads, deep_supervision,
+        )
+
+    return build
+
+
 class NnunetServer(FlServer):
     def __init__(
         self,
@@ -76,7 +89,10 @@ class NnunetServer(FlServer):
         accept_failures: bool = True,
         model_builder: ModelBuilder = nnunetv2_model_builder,
         global_deep_supervision: bool = False,
+        nnunet_trainer_class: type | None = None,
     ) -> None:
+        """``nnunet_trainer_class``: an ``nnUNetTrainer`` subclass whose ``build_network_architecture`` builds the global
+        model (the reference's knob, ``nnunet_server.py:54-110``); ignored when a custom ``model_builder`` is given."""
         if checkpoint_and_state_module is not None:
             assert isinstance(checkpoint_and_state_module, NnUnetServerCheckpointAndStateModule), (
                 "checkpoint_and_state_module must have type NnUnetServerCheckpointAndStateModule")
@@ -88,6 +104,8 @@ class NnunetServer(FlServer):
             on_init_parameters_config_fn=on_init_parameters_config_fn, server_name=server_name,
             accept_failures=accept_failures,
         )
+        if nnunet_trainer_class is not None and model_builder is nnunetv2_model_builder:
+            model_builder = _trainer_model_builder(nnunet_trainer_class)
         self.model_builder = model_builder
         self.global_deep_supervision = global_deep_supervision
         self.nnunet_config = NnunetConfig(self.fl_config["nnunet_config"])

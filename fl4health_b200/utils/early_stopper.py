@@ -21,7 +21,11 @@ class EarlyStopper:
         patience: int | None = 1,
         interval_steps: int = 5,
         snapshot_dir: Path | None = None,
+        train_loop_checkpoint_dir: Path | None = None,
     ) -> None:
+        """``train_loop_checkpoint_dir`` is the reference's name for ``snapshot_dir`` (``early_stopper.py:14-60``)."""
+        if snapshot_dir is None:
+            snapshot_dir = train_loop_checkpoint_dir
         self.client = client
         self.patience = patience
         self.count_down = patience
