@@ -117,6 +117,8 @@ def _spmd_weighted_combine(
     from fl4health_b200.parallel.spmd import PayloadSpec
 
     ctx = next(nds.ctx for nds in arrays if getattr(nds, "ctx", None) is not None)
+    if len({nds.rank for nds in arrays}) < len(arrays):  # some rank hosts several of these clients
+        return _spmd_weighted_combine_multi(ctx, arrays, coefficients, epilogue, out_flat)
     coef_by_rank = [0.0] * ctx.world_size
     local: NDArrays | None = None
     spec: PayloadSpec | None = None
@@ -158,14 +160,81 @@ def _spmd_weighted_combine(
     sizes = [int(np.prod(s)) if len(s) else 1 for s in shapes]
     total = sum(sizes)
     packed = None
+    padded = (total + 3) // 4 * 4  # the flat kernels work on 16-byte vectors
     if local is not None:
-        packed = torch.cat([to_tensor(local[i], ctx.device).reshape(-1).to(torch.float32) for i in tensor_idx]) if tensor_idx else torch.zeros(0, device=ctx.device)
-    reduced = ctx.weighted_sum_flat(packed, coef_by_rank, total)
+        packed = torch.zeros(padded, dtype=torch.float32, device=ctx.device)
+        if tensor_idx:
+            packed[:total] = torch.cat([to_tensor(local[i], ctx.device).reshape(-1).to(torch.float32) for i in tensor_idx])
+    reduced = ctx.weighted_sum_flat(packed, coef_by_rank, padded)
     out = NDArrays([entry[2] for entry in spec.entries])
     cursor = 0
     for i, shape, size in zip(tensor_idx, shapes, sizes):
         out[i] = reduced[cursor : cursor + size].view(shape)
         cursor += size
+    return out
+
+
+_LAYOUT_HINTS: dict[int, Any] = {}  # flat_numel -> arena layout last seen on this rank (ranks whose clients sat a round out)
+
+
+def _spmd_weighted_combine_multi(
+    ctx: Any, arrays: Sequence[NDArrays], coefficients: Sequence[float], epilogue: dict | None = None,
+    out_flat: torch.Tensor | None = None,
+) -> NDArrays:
+    """``parallel/spmd_multi.py``: ranks host several clients.  Each rank folds ITS payloads into one partial sum with a
+    streaming kernel, the partials are reduced with one all-reduce (cost independent of the number of clients), then the
+    strategy epilogue runs.  Payloads that are not arena-shaped, or a rank that has never seen the layout, take the
+    always-correct route: materialise every payload everywhere and combine locally."""
+
+    spec = arrays[0].spec
+    local = [(nds, float(c)) for nds, c in zip(arrays, coefficients) if nds.rank == ctx.rank and not getattr(nds, "remote", False)]
+    layout = next((nds.layout for nds, _ in local if getattr(nds, "layout", None) is not None), None)
+    arena_shaped = spec.flat_numel is not None and all(nds.spec.flat_numel == spec.flat_numel for nds in arrays)
+    if arena_shaped and layout is not None:
+        _LAYOUT_HINTS[spec.flat_numel] = layout
+    elif arena_shaped:
+        layout = _LAYOUT_HINTS.get(spec.flat_numel)
+    # the choice below must be the same on every rank: agree on it (a rank that does not know the layout cannot rebuild the
+    # arena views, so everybody takes the packed route)
+    if ctx.all_reduce_max(0.0 if (arena_shaped and layout is not None) else 1.0) > 0.0:
+        assert epilogue is None, "server-optimizer epilogues need arena-backed payloads in SPMD mode"
+        # packed route (side payloads such as SCAFFOLD variates, models without an arena): the tensor entries of every
+        # local payload are concatenated, scaled and summed into one buffer, reduced with one all-reduce, and unpacked
+        tensor_idx = [i for i, (_, _, inline) in enumerate(spec.entries) if inline is None]
+        shapes = [spec.entries[i][0] for i in tensor_idx]
+        sizes = [int(np.prod(shape)) if len(shape) else 1 for shape in shapes]
+        total = sum(sizes)
+        packed = torch.zeros((total + 3) // 4 * 4, dtype=torch.float32, device=ctx.device)  # 16-byte vectors in the flat kernels
+        for nds, coef in local:
+            if tensor_idx:
+                packed[:total].add_(torch.cat([to_tensor(nds[i], ctx.device).reshape(-1).to(torch.float32) for i in tensor_idx]), alpha=coef)
+        reduced = ctx.weighted_sum_flat(packed, [1.0] * ctx.world_size, packed.numel())
+        out = NDArrays([entry[2] for entry in spec.entries])
+        cursor = 0
+        for i, shape, size in zip(tensor_idx, shapes, sizes):
+            out[i] = reduced[cursor : cursor + size].view(shape)
+            cursor += size
+        return out
+    numel = spec.flat_numel
+    partial = torch.zeros(numel, dtype=torch.float32, device=ctx.device)
+    if local:
+        flat_ops.weighted_sum(partial, [nds.flat[:numel] for nds, _ in local], [c for _, c in local])
+    result_flat = ctx.weighted_sum_flat(partial, [1.0] * ctx.world_size, numel, out=out_flat, epilogue=epilogue)
+    out = layout.ndarrays(region=result_flat)
+    if layout.int_state:
+        positions = [i for i, key in enumerate(layout.state_keys) if key in layout.int_state]
+        width = sum(layout.int_state[layout.state_keys[i]].numel() for i in positions)
+        ints = torch.zeros(width, dtype=torch.float64, device=ctx.device)
+        for nds, coef in local:
+            packed = getattr(nds, "int_flat", None)
+            if packed is None or packed.numel() != width:
+                packed = torch.cat([to_tensor(nds[i], ctx.device).reshape(-1) for i in positions])
+            ints.add_(packed.to(torch.float64), alpha=coef)
+        if ctx.world_size > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(ints)
+        _scatter_int_views(out, layout, ints.to(torch.int64))
     return out
 
 

@@ -86,7 +86,9 @@ class Scaffold(BasicFedAvg):
     ) -> tuple[Parameters | None, dict[str, Scalar]]:
         if not results or (not self.accept_failures and failures):
             return None, {}
-        decoded = [arrays for _, arrays, _ in decode_and_pseudo_sort_results(results)]
+        # both halves of the packed payload (weights, variate updates) go through weighted_combine, which reduces SPMD
+        # payloads with collectives: no need to broadcast every client's full payload first
+        decoded = [arrays for _, arrays, _ in decode_and_pseudo_sort_results(results, materialize=False)]
         aggregated = self.aggregate(decoded)
         weights, variate_updates = self.parameter_packer.unpack_parameters(aggregated)
         self.server_model_weights = self.compute_updated_weights(weights)

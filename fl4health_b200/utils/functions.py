@@ -62,8 +62,10 @@ def decode_and_pseudo_sort_results(
     decoded = []
     for proxy, res in ordered:
         arrays = parameters_to_ndarrays(res.parameters)
-        if materialize and getattr(arrays, "remote", False):
-            # SPMD fallback for strategies that need every client's full payload: broadcast from the owner.
+        if materialize and getattr(arrays, "ctx", None) is not None and arrays.ctx.world_size > 1:
+            # SPMD fallback for strategies that need every client's full payload: broadcast from the owner.  The OWNER
+            # has to take part too (its copy is the broadcast source) — testing `remote` alone left it out and
+            # deadlocked every strategy on this path.
             from fl4health_b200.parallel.spmd import materialize as _materialize
 
             arrays = _materialize(arrays)
