@@ -27,7 +27,10 @@ def main() -> None:
     ctx = SpmdContext()
     set_all_random_seeds(42)
     total = sum(split)
-    common = dict(min_fit_clients=total, min_evaluate_clients=total, min_available_clients=total,
+    fraction = float(os.environ.get("FL4H_TEST_FRACTION", "1.0"))
+    sampled = max(1, int(total * fraction))
+    common = dict(fraction_fit=fraction, fraction_evaluate=fraction, min_fit_clients=sampled, min_evaluate_clients=sampled,
+                  min_available_clients=total,
                   on_fit_config_fn=fit_config_fn(), on_evaluate_config_fn=fit_config_fn(),
                   fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
                   evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn)
@@ -44,11 +47,13 @@ def main() -> None:
         strategy = FedAdam(initial_parameters=ndarrays_to_parameters(arena.ndarrays()), eta=0.05, **common)
     else:
         strategy = BasicFedAvg(**common)
-    server = FlServer(SimpleClientManager(), {"n_server_rounds": 2}, strategy, on_init_parameters_config_fn=fit_config_fn())
+    rounds = int(os.environ.get("FL4H_TEST_ROUNDS", "2"))
+    server = FlServer(SimpleClientManager(), {"n_server_rounds": rounds}, strategy, on_init_parameters_config_fn=fit_config_fn())
     proxies = build_spmd_federation_multi(ctx, server, clients)
-    history, _ = server.fit(num_rounds=2)
+    history, _ = server.fit(num_rounds=rounds)
     if ctx.rank == 0:
-        state = {k: v.detach().cpu().double().sum().item() for k, v in clients[0].model.state_dict().items()}
+        trained = next((c for c in clients if getattr(c, "initialized", False)), None)
+        state = {} if trained is None else {k: v.detach().cpu().double().sum().item() for k, v in trained.model.state_dict().items()}
         Path(out_path).write_text(json.dumps({"losses": history.losses_distributed, "state": state, "clients": len(proxies)}))
     ctx.barrier()
     ctx.shutdown()

@@ -22,9 +22,9 @@ from tests.helpers import fit_config_fn, make_clients
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _launch(tmp_path: Path, strategy: str, split: str, port: int) -> dict:
+def _launch(tmp_path: Path, strategy: str, split: str, port: int, **extra_env: str) -> dict:
     out = tmp_path / f"{strategy}.json"
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", FL4H_LOG_LEVEL="ERROR")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", FL4H_LOG_LEVEL="ERROR", **extra_env)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "spmd_multi_worker.py"), str(out), strategy, split]
     proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
@@ -97,3 +97,13 @@ def test_strategies_that_need_whole_payloads_run_in_spmd_and_match_simulation(sc
     for summary in spmd:
         for (r1, l1), (r2, l2) in zip(summary["losses"], local["losses"]):
             assert r1 == r2 and abs(l1 - l2) < 1e-5, (summary["losses"], local["losses"])
+
+
+def test_partial_participation_with_idle_ranks(tmp_path: Path) -> None:
+    """Half of six clients (hosted 1 + 5) are sampled each round for five rounds: rounds in which a rank has no selected
+    client — including before it has ever seen a payload — must neither deadlock nor change the collective sequence."""
+    import math
+
+    result = _launch(tmp_path, "fedavg", "1,5", 29671, FL4H_TEST_FRACTION="0.5", FL4H_TEST_ROUNDS="5")
+    assert result["clients"] == 6 and len(result["losses"]) == 5
+    assert all(math.isfinite(loss) for _, loss in result["losses"])
