@@ -128,9 +128,23 @@ def _spmd_weighted_combine(
         if nds.rank == ctx.rank:
             local = nds
     assert spec is not None
-    if spec.flat_numel is not None:
+    arena_route = spec.flat_numel is not None
+    if arena_route:
         layout = local.layout if local is not None else None
         local_flat = local.flat if local is not None else None
+        if layout is not None:
+            _LAYOUT_HINTS[spec.flat_numel] = layout
+        if len(arrays) < ctx.world_size:
+            # Partial participation (fraction / Poisson sampling): a rank whose client sat this round out contributes
+            # weight 0 from its own arena, whose layout it knows from an earlier round — that also keeps the fused
+            # peer-memory kernel's launch decision identical on every rank.  If some rank has never seen the layout,
+            # everybody takes the packed route below (one agreement collective, only in this mode).
+            hint = layout if layout is not None else _LAYOUT_HINTS.get(spec.flat_numel)
+            if ctx.all_reduce_max(0.0 if hint is not None else 1.0) > 0.0:
+                arena_route = False
+            elif layout is None:
+                layout, local_flat = hint, hint.flat[: spec.flat_numel]
+    if arena_route:
         if out_flat is None and local_flat is not None and layout is not None and ctx.fused is None:
             out_flat = _result_buffer(layout, local_flat)
         result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.flat_numel, out=out_flat, epilogue=epilogue)
@@ -153,8 +167,8 @@ def _spmd_weighted_combine(
                     dist.all_reduce(ints)
             _scatter_int_views(out, layout, ints.to(torch.int64))
         return out
-    # non-arena payloads: pack the tensor entries into one temporary flat buffer, reduce, unpack
-    assert epilogue is None, "server-optimizer epilogues need arena-backed payloads in SPMD mode"
+    # non-arena payloads (or no agreed layout): pack the tensor entries into one temporary flat buffer, reduce, unpack
+    assert epilogue is None, "server-optimizer epilogues need arena-backed payloads (seen by every rank) in SPMD mode"
     tensor_idx = [i for i, (_, _, inline) in enumerate(spec.entries) if inline is None]
     shapes = [spec.entries[i][0] for i in tensor_idx]
     sizes = [int(np.prod(s)) if len(s) else 1 for s in shapes]

@@ -107,3 +107,13 @@ def test_partial_participation_with_idle_ranks(tmp_path: Path) -> None:
     result = _launch(tmp_path, "fedavg", "1,5", 29671, FL4H_TEST_FRACTION="0.5", FL4H_TEST_ROUNDS="5")
     assert result["clients"] == 6 and len(result["losses"]) == 5
     assert all(math.isfinite(loss) for _, loss in result["losses"])
+
+
+def test_one_client_per_rank_with_partial_participation(tmp_path: Path) -> None:
+    """One client per rank, half of them sampled per round: the rank that sits a round out contributes weight 0 from its
+    own arena (or, before it has ever produced a payload, everybody agrees on the packed route) instead of raising."""
+    import math
+
+    result = _launch(tmp_path, "fedavg", "1,1", 29672, FL4H_TEST_FRACTION="0.5", FL4H_TEST_ROUNDS="6")
+    assert result["clients"] == 2 and len(result["losses"]) == 6
+    assert all(math.isfinite(loss) for _, loss in result["losses"])
