@@ -131,9 +131,11 @@ class NnunetServer(FlServer):
         if checkpointer_exists:
             log(INFO, "\tThis client's local dataset will be used to determine the number of input and output channels")
         client = self._client_manager.sample(1)[0]
-        response = client.get_properties(GetPropertiesIns(config=config), timeout=timeout, group_id=0)
-        if response.status.code != Code.OK:
+        # through the transport: under SPMD the rank that hosts this client answers and every rank receives the reply
+        answered, failed = self.transport.poll_clients([(client, GetPropertiesIns(config=config))], None, timeout)
+        if failed or not answered or answered[0][1].status.code != Code.OK:
             raise RuntimeError("Failed to successfully receive properties from client")
+        response = answered[0][1]
         properties = response.properties
         self.nnunet_plans_bytes = narrow_dict_type(properties, "nnunet_plans", bytes) if plans_bytes is None else plans_bytes
         assert isinstance(self.nnunet_plans_bytes, bytes)
