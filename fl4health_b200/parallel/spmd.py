@@ -446,7 +446,9 @@ def _meta_template(meta: dict[str, Any] | None) -> dict[str, Any] | None:
             constants[key] = value
     import pickle
 
-    return {"numeric": numeric, "constants": constants, "constants_key": pickle.dumps(constants), "width": len(numeric)}
+    has_metrics = isinstance(meta.get("metrics"), dict)  # an EMPTY metrics dict leaves no numeric entry behind
+    return {"numeric": numeric, "constants": constants, "constants_key": pickle.dumps(constants), "width": len(numeric),
+            "has_metrics": has_metrics}
 
 
 def _encode_meta(meta: dict[str, Any] | None, template: dict[str, Any]) -> list[float] | None:
@@ -462,7 +464,7 @@ def _encode_meta(meta: dict[str, Any] | None, template: dict[str, Any]) -> list[
 
 def _decode_meta(values: list[float], template: dict[str, Any]) -> dict[str, Any]:
     meta: dict[str, Any] = dict(template["constants"])
-    if any(key == "metrics" for key, _, _ in template["numeric"]):
+    if template.get("has_metrics") or any(key == "metrics" for key, _, _ in template["numeric"]):
         meta["metrics"] = {}
     for value, (key, sub, kind) in zip(values, template["numeric"]):
         cast = int(round(value)) if kind is int else float(value)

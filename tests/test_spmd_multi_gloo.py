@@ -117,3 +117,10 @@ def test_one_client_per_rank_with_partial_participation(tmp_path: Path) -> None:
     result = _launch(tmp_path, "fedavg", "1,1", 29672, FL4H_TEST_FRACTION="0.5", FL4H_TEST_ROUNDS="6")
     assert result["clients"] == 2 and len(result["losses"]) == 6
     assert all(math.isfinite(loss) for _, loss in result["losses"])
+
+
+def test_clients_without_metrics_survive_the_cached_metadata_schema() -> None:
+    """A client with no metrics sends an EMPTY metrics dict: from round 2 on the numbers-only metadata exchange has to
+    rebuild that (empty) dict instead of dropping the key."""
+    (summary,) = _run_scenario_spmd("ae_example", 29673)
+    assert len(summary["losses"]) == 2 and summary["metrics"] == {}
