@@ -66,6 +66,8 @@ class AdaptiveDriftConstraintClient(BasicClient):
     def get_parameters(self, config: Config) -> NDArrays:
         if not self.initialized:
             return self.setup_client_and_return_all_model_parameters(config)
+        if self.initial_parameters_requested(config):  # already set up by a properties poll: plain model state, unpacked
+            return FullParameterExchanger().push_parameters(self.model, config=config)
         assert self.model is not None and self.parameter_exchanger is not None and self.loss_for_adaptation is not None
         model_weights = self.parameter_exchanger.push_parameters(self.model, config=config)
         return self.parameter_exchanger.pack_parameters(model_weights, self.loss_for_adaptation)

@@ -173,6 +173,13 @@ class BasicClient:
         self.setup_client(config)
         return FullParameterExchanger().push_parameters(self.model, config=config)
 
+    def initial_parameters_requested(self, config: Config) -> bool:
+        """True when ``get_parameters`` is the server's request for INITIAL parameters (round 0 of
+        ``on_init_parameters_config_fn``) reaching a client that has already been set up — a properties poll (nnU-Net plan
+        negotiation, tabular feature alignment) may have initialised it.  Clients that pack side information into their
+        regular payload must answer this request with the plain model state, exactly like an uninitialised client."""
+        return self.initialized and config.get("current_server_round") == 0
+
     def shutdown(self) -> None:
         self.reports_manager.report({"shutdown": str(datetime.datetime.now())})
         self.reports_manager.shutdown()

@@ -25,6 +25,7 @@ from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.utils.config import narrow_dict_type
 from fl4health_b200.utils.losses import EvaluationLosses, LossMeterType, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
+from fl4health_b200.parameter_exchange.full_exchanger import FullParameterExchanger
 
 
 class DittoClient(AdaptiveDriftConstraintClient):
@@ -74,6 +75,8 @@ class DittoClient(AdaptiveDriftConstraintClient):
     def get_parameters(self, config: Config) -> NDArrays:
         if not self.initialized:
             return self.setup_client_and_return_all_model_parameters(config)
+        if self.initial_parameters_requested(config):  # already set up by a properties poll: plain model state, unpacked
+            return FullParameterExchanger().push_parameters(self.model, config=config)
         assert self.global_model is not None and self.parameter_exchanger is not None
         weights = self.parameter_exchanger.push_parameters(self.global_model, config=config)
         return self.parameter_exchanger.pack_parameters(weights, self.loss_for_adaptation)

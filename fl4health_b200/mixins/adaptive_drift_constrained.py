@@ -51,6 +51,8 @@ class AdaptiveDriftConstrainedMixin(BaseFlexibleMixin):
     def get_parameters(self, config: Config) -> NDArrays:
         if not self.initialized:  # type: ignore[attr-defined]
             return self.setup_client_and_return_all_model_parameters(config)
+        if self.initial_parameters_requested(config):  # type: ignore[attr-defined]
+            return FullParameterExchanger().push_parameters(self.model, config=config)  # type: ignore[attr-defined]
         assert self.model is not None and self.parameter_exchanger is not None  # type: ignore[attr-defined]
         weights = self.parameter_exchanger.push_parameters(self.model, config=config)  # type: ignore[attr-defined]
         return self.parameter_exchanger.pack_parameters(weights, self.loss_for_adaptation)  # type: ignore[attr-defined]

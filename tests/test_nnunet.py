@@ -188,3 +188,20 @@ def test_flexible_nnunet_client_trains_like_the_plain_one() -> None:
 
     plain, flexible = run(NnunetClient), run(FlexibleNnunetClient)
     assert all(a == pytest.approx(b, rel=1e-5) for a, b in zip(plain, flexible))
+
+
+def test_initial_parameter_request_after_a_properties_poll_is_unpacked() -> None:
+    """Plan negotiation sets the polled client up; if the server then asks THE SAME client for the initial parameters
+    (round 0), a personalised client must answer with the plain model state, not with its packed (weights + loss) payload
+    — otherwise the strategy appends the drift weight a second time and every client fails to unpack."""
+    from fl4health_b200.clients.flexible.nnunet import FlexibleNnunetClient
+    from fl4health_b200.mixins.personalized import PersonalizedMode, make_it_personal
+
+    cls = make_it_personal(FlexibleNnunetClient, PersonalizedMode.DITTO)
+    client = cls(torch.device("cpu"), 999, fold=0, backend=ToyBackend(0), verbose=False)
+    config = {**_cfg(0), "nnunet_plans": pickle.dumps(ToyBackend(0).plan())}
+    client.get_properties(dict(config))
+    assert client.initialized
+    n_state = len(client.model.state_dict())
+    assert len(client.get_parameters(dict(config))) == n_state  # round 0 = initial-parameter request
+    assert len(client.get_parameters({**config, "current_server_round": 1})) == n_state + 1  # regular payload: + loss
