@@ -458,3 +458,182 @@ def client_level_dp_weighted_example(config: dict[str, Any], device: torch.devic
                                        server_noise_multiplier=0.05, num_server_rounds=config["n_server_rounds"],
                                        on_init_parameters_config_fn=lambda r: fn(0))
     return server, make_clients(NumpyClippingClient, config, device, lambda: nn.Sequential(nn.Linear(features, 2)), customise)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second stages and sub-variants of the representation-learning examples
+# ---------------------------------------------------------------------------------------------------------------
+def _flat_dim(config: dict[str, Any]) -> int:
+    return 28 * 28 if config["dataset"] == "mnist" else 3 * 32 * 32
+
+
+@scenario("fedprox_vae_example")
+def fedprox_vae_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """ae_examples/fedprox_vae_example: the VAE of ``ae_example`` trained with FedProx (adaptive proximal weight)."""
+    from fl4health_b200.clients.fed_prox_client import FedProxClient
+    from fl4health_b200.model_bases.autoencoders_base import VariationalAe
+    from fl4health_b200.preprocessing.autoencoders.loss import VaeLoss
+    from fl4health_b200.servers.adaptive_constraint_servers.fedprox_server import FedProxServer
+    from fl4health_b200.utils.dataset_converter import AutoEncoderDatasetConverter
+
+    in_dim, latent = _flat_dim(config), 16
+
+    class Encoder(nn.Module):
+        def __init__(self) -> None:
+            super().__init__()
+            self.body = nn.Sequential(nn.Flatten(), nn.Linear(in_dim, 64), nn.ReLU())
+            self.mu, self.logvar = nn.Linear(64, latent), nn.Linear(64, latent)
+
+        def forward(self, x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+            h = self.body(x)
+            return self.mu(h), self.logvar(h)
+
+    class FlatVaeLoss(VaeLoss):
+        def forward(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+            return super().forward(preds, target.flatten(1))
+
+    def customise(client: Any) -> None:
+        def loaders(cfg: dict[str, Any]) -> tuple[Any, Any]:
+            train, val = client_datasets(config, client.client_index)
+            convert = lambda ds: AutoEncoderDatasetConverter().convert_dataset(ds)  # noqa: E731
+            return BatchedTensorLoader(convert(train), config["batch_size"], shuffle=True), BatchedTensorLoader(convert(val), config["batch_size"])
+
+        client.get_data_loaders = loaders
+        client.get_criterion = lambda cfg: FlatVaeLoss(latent, nn.MSELoss(reduction="sum"))
+
+    factory = lambda: VariationalAe(Encoder(), nn.Sequential(nn.Linear(latent, 64), nn.ReLU(), nn.Linear(64, in_dim)))  # noqa: E731
+    clients = make_clients(FedProxClient, config, device, factory, customise, metrics=[])
+    return _fl_server(config, _adaptive_strategy(config), FedProxServer), clients
+
+
+def _pretrain_and_save(model: nn.Module, path: Path) -> None:
+    path.parent.mkdir(parents=True, exist_ok=True)
+    torch.save(model, path)
+
+
+class _CondEncoder(nn.Module):
+    """Module-level (picklable: the dimensionality-reduction processors ``torch.load`` whole models) CVAE encoder."""
+
+    def __init__(self, in_dim: int, n_conditions: int, latent: int) -> None:
+        super().__init__()
+        self.body = nn.Sequential(nn.Linear(in_dim + n_conditions, 32), nn.ReLU())
+        self.mu, self.logvar = nn.Linear(32, latent), nn.Linear(32, latent)
+
+    def forward(self, x: torch.Tensor, condition: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        h = self.body(torch.cat((x.flatten(1), condition), dim=-1))
+        return self.mu(h), self.logvar(h)
+
+
+class _CondDecoder(nn.Module):
+    def __init__(self, in_dim: int, n_conditions: int, latent: int) -> None:
+        super().__init__()
+        self.body = nn.Linear(latent + n_conditions, in_dim)
+
+    def forward(self, z: torch.Tensor, condition: torch.Tensor) -> torch.Tensor:
+        return self.body(torch.cat((z, condition), dim=-1))
+
+
+@scenario("cvae_dim_example")
+def cvae_dim_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """ae_examples/cvae_dim_example: a (here: freshly initialised and saved) CVAE encoder reduces every sample to its
+    latent code under a fixed client condition (``CvaeFixedConditionProcessor``); a small classifier is federated on
+    the codes."""
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.model_bases.autoencoders_base import ConditionalVae
+    from fl4health_b200.preprocessing.autoencoders.dim_reduction import CvaeFixedConditionProcessor
+    from fl4health_b200.utils.dataset import TensorDataset
+
+    in_dim, latent, n_conditions = _flat_dim(config), 8, int(config["n_clients"])
+    out = Path(config.get("checkpoint_dir", "examples_out/cvae_dim"))
+
+    torch.manual_seed(config["seed"])
+    _pretrain_and_save(ConditionalVae(_CondEncoder(in_dim, n_conditions, latent), _CondDecoder(in_dim, n_conditions, latent)), out / "cvae.pt")
+
+    def customise(client: Any) -> None:
+        condition = torch.nn.functional.one_hot(torch.tensor(client.client_index), n_conditions).float()
+        processor = CvaeFixedConditionProcessor(out / "cvae.pt", condition, device=torch.device("cpu"), return_mu_only=True)
+
+        def reduce(ds: TensorDataset) -> TensorDataset:
+            return TensorDataset(processor(ds.data.reshape(len(ds.data), -1).float()), ds.targets)
+
+        def loaders(cfg: dict[str, Any]) -> tuple[Any, Any]:
+            train, val = client_datasets(config, client.client_index)
+            return BatchedTensorLoader(reduce(train), config["batch_size"], shuffle=True), BatchedTensorLoader(reduce(val), config["batch_size"])
+
+        client.get_data_loaders = loaders
+
+    factory = lambda: nn.Sequential(nn.Linear(latent, 32), nn.ReLU(), nn.Linear(32, 10))  # noqa: E731
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), make_clients(BasicClient, config, device, factory, customise)
+
+
+@scenario("fedpca_dim_reduction_example")
+def fedpca_dim_reduction_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """fedpca_examples/dim_reduction: a saved ``PcaModule`` (what ``fedpca_example`` / perform_pca produces) projects the
+    data onto its leading components (``PcaPreprocessor``); a classifier is federated on the projections."""
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.model_bases.pca import PcaModule
+    from fl4health_b200.preprocessing.pca_preprocessor import PcaPreprocessor
+    from fl4health_b200.utils.dataset import TensorDataset
+
+    components = int(config.get("new_dimension", 16))
+    out = Path(config.get("checkpoint_dir", "examples_out/fedpca_dim_reduction"))
+    # stage 1 stand-in: principal components of one reference shard, saved the way FedPCAClient / the server do
+    reference, _ = client_datasets(config, 0)
+    pca = PcaModule(low_rank=False, full_svd=False, rank_estimation=components)
+    principal_components, singular_values = pca(reference.data.reshape(len(reference.data), -1).float(), center_data=True)
+    pca.set_principal_components(principal_components, singular_values)
+    _pretrain_and_save(pca, out / "pca.pt")
+
+    def customise(client: Any) -> None:
+        def loaders(cfg: dict[str, Any]) -> tuple[Any, Any]:
+            train, val = client_datasets(config, client.client_index)
+            flat = lambda ds: TensorDataset(ds.data.reshape(len(ds.data), -1).float(), ds.targets)  # noqa: E731
+            reducer = PcaPreprocessor(out / "pca.pt")
+            return (BatchedTensorLoader(reducer.reduce_dimension(components, flat(train)), config["batch_size"], shuffle=True),
+                    BatchedTensorLoader(reducer.reduce_dimension(components, flat(val)), config["batch_size"]))
+
+        client.get_data_loaders = loaders
+
+    factory = lambda: nn.Sequential(nn.Linear(components, 32), nn.ReLU(), nn.Linear(32, 10))  # noqa: E731
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), make_clients(BasicClient, config, device, factory, customise)
+
+
+@scenario("fedsimclr_finetuning_example")
+def fedsimclr_finetuning_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """fedsimclr_example/fedsimclr_finetuning_example: the encoder saved by the pre-training stage is loaded with
+    ``FedSimClrModel.load_pretrained_model`` (``pretrain=False``: encoder → prediction head) and fine-tuned with labels."""
+    from examples.models import FeatureCnn
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.model_bases.fedsimclr_base import FedSimClrModel
+
+    out = Path(config.get("checkpoint_dir", "examples_out/fedsimclr"))
+    torch.manual_seed(config["seed"])
+    pretrained = FedSimClrModel(FeatureCnn(config["dataset"]), nn.Linear(FeatureCnn.out_dim, 32), nn.Linear(FeatureCnn.out_dim, 10),
+                                pretrain=True)  # stands in for the checkpoint written by `fedsimclr_example`
+    _pretrain_and_save(pretrained, out / "pretrained.pt")
+    factory = lambda: FedSimClrModel.load_pretrained_model(out / "pretrained.pt")  # noqa: E731
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), make_clients(BasicClient, config, device, factory)
+
+
+@scenario("warmed_up_fenda_example")
+def warmed_up_fenda_example(config: dict[str, Any], device: torch.device) -> tuple[Any, list[Any]]:
+    """warm_up_example/warmed_up_fenda: both feature extractors of a FENDA model start from a pretrained plain CNN; the
+    weights mapping renames ``features.*`` to ``first_feature_extractor.*`` / ``second_feature_extractor.*``."""
+    from examples.models import ConcatHead, FeatureCnn
+    from fl4health_b200.clients.fenda_client import FendaClient
+    from fl4health_b200.model_bases.fenda_base import FendaModel
+    from fl4health_b200.preprocessing.warmed_up_module import WarmedUpModule
+
+    import json
+
+    out = Path(config.get("checkpoint_dir", "examples_out/warmed_up_fenda"))
+    torch.manual_seed(config["seed"] + 1)
+    pretrained = SmallCnn(config["dataset"])
+    out.mkdir(parents=True, exist_ok=True)
+    (out / "weights_mapping.json").write_text(json.dumps({"first_feature_extractor": "features", "second_feature_extractor": "features"}))
+
+    def factory() -> nn.Module:
+        model = FendaModel(FeatureCnn(config["dataset"]), FeatureCnn(config["dataset"]), ConcatHead())
+        return WarmedUpModule(pretrained_model=pretrained, weights_mapping_path=out / "weights_mapping.json").load_from_pretrained(model)
+
+    return _fl_server(config, BasicFedAvg(**strategy_kwargs(config))), make_clients(FendaClient, config, device, factory)
