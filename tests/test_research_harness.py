@@ -142,3 +142,28 @@ def test_command_line_round_trip(tmp_path, capsys) -> None:  # type: ignore[no-u
     assert sorted(printed) == ["lr_0.01_lam_0.5", "lr_0.01_lam_2.0"]
     folder, _ = main(["best", "--dir", str(tmp_path / "o" / "synthetic" / "mr_mtl")])
     assert folder.name in printed
+
+
+@pytest.mark.parametrize("method, n_clients", [("fedavg", 2), ("ditto", 4)])
+def test_spmd_run_matches_the_in_process_simulation(method: str, n_clients: int, tmp_path) -> None:  # type: ignore[no-untyped-def]
+    """``torchrun … -m research.run train --spmd`` (gloo, 2 ranks; 1 or 2 clients per rank) reproduces the simulation."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    common = ["--task", "synthetic", "--method", method, "--rounds", "2", "--local-steps", "2", "--samples-per-client", "100", "--no-checkpoint",
+              "--device", "cpu", "--task-kwargs", f"n_clients={n_clients}"]
+    from research.run import main
+
+    (reference,) = main(["train", *common, "--artifact-dir", str(tmp_path / "sim")])
+    port = 29700 + (os.getpid() + n_clients) % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           "-m", "research.run", "train", *common, "--artifact-dir", str(tmp_path / "spmd"), "--spmd"]
+    env = {**os.environ, "FL4H_LOG_LEVEL": "ERROR", "PYTHONPATH": str(root)}
+    proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [line for line in proc.stdout.splitlines() if line.startswith("[{")]
+    assert len(lines) == 1  # rank 0 reports
+    assert json.loads(lines[0])[0]["best_aggregated_loss"] == pytest.approx(reference["best_aggregated_loss"], rel=1e-5)
