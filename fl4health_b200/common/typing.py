@@ -11,16 +11,16 @@ from __future__ import annotations
 from collections.abc import Callable
 from dataclasses import dataclass, field
 from enum import Enum
-from typing import Any, Union
+from typing import Any
 
 import numpy as np
 import torch
 
-Scalar = Union[bool, bytes, float, int, str]
+Scalar = bool | bytes | float | int | str
 Config = dict[str, Scalar]
 Metrics = dict[str, Scalar]
 Properties = dict[str, Scalar]
-NDArray = Union[np.ndarray, torch.Tensor]
+NDArray = np.ndarray | torch.Tensor
 MetricsAggregationFn = Callable[[list[tuple[int, Metrics]]], Metrics]
 
 

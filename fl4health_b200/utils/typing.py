@@ -5,7 +5,7 @@ from __future__ import annotations
 import logging
 from collections.abc import Callable
 from enum import Enum
-from typing import TYPE_CHECKING, Union
+from typing import TYPE_CHECKING
 
 import torch
 from torch import nn
@@ -15,15 +15,15 @@ from fl4health_b200.common.typing import EvaluateRes, FitRes, NDArrays
 if TYPE_CHECKING:
     from fl4health_b200.servers.client_proxy import ClientProxy
 
-TorchInputType = Union[torch.Tensor, dict[str, torch.Tensor]]
-TorchTargetType = Union[torch.Tensor, dict[str, torch.Tensor]]
+TorchInputType = torch.Tensor | dict[str, torch.Tensor]
+TorchTargetType = torch.Tensor | dict[str, torch.Tensor]
 TorchPredType = dict[str, torch.Tensor]
 TorchFeatureType = dict[str, torch.Tensor]
 TorchTransformFunction = Callable[[torch.Tensor], torch.Tensor]
-LayerSelectionFunction = Callable[[nn.Module, Union[nn.Module, None]], tuple[NDArrays, list[str]]]
+LayerSelectionFunction = Callable[[nn.Module, nn.Module | None], tuple[NDArrays, list[str]]]
 
-FitFailures = list[Union[tuple["ClientProxy", FitRes], BaseException]]
-EvaluateFailures = list[Union[tuple["ClientProxy", EvaluateRes], BaseException]]
+FitFailures = list["tuple[ClientProxy, FitRes] | BaseException"]
+EvaluateFailures = list["tuple[ClientProxy, EvaluateRes] | BaseException"]
 
 
 class LogLevel(Enum):
