@@ -16,6 +16,30 @@ from fl4health_b200.simulation import run_simulation
 from fl4health_b200.utils.random import set_all_random_seeds
 
 
+def _replicated(clients: list, ctx, ranks_per_client: int):  # noqa: ANN001, ANN202
+    """This rank's replica of client ``rank // G``: same client index (hence the same data), a 1/G shard of it, and
+    gradient averaging inside the group (``fl4health_b200.parallel.client_group``)."""
+    from fl4health_b200.engine.data import BatchedTensorLoader
+    from fl4health_b200.parallel.client_group import ClientGroup, ReplicatedClientMixin, shard_dataset
+
+    group = ClientGroup.from_world(ctx.rank, ctx.world_size, ranks_per_client)
+    client = clients[ctx.rank]
+    client.__class__ = type(f"Replicated{type(client).__name__}", (ReplicatedClientMixin, type(client)), {})
+    client.client_group, client.client_index = group, group.client_index
+    client.client_name = f"{client.client_name}.replica{group.group_rank}"
+    make_loaders = client.get_data_loaders
+
+    def sharded_loaders(config):  # noqa: ANN001, ANN202
+        train, val = make_loaders(config)
+        shard = lambda loader, shuffle: BatchedTensorLoader(  # noqa: E731
+            shard_dataset(loader.dataset, group, seed=11), max(loader.batch_size // group.group_size, 1), shuffle=shuffle,
+            placement="device" if ctx.device.type == "cuda" else "host", device=ctx.device)
+        return shard(train, True), shard(val, False)
+
+    client.get_data_loaders = sharded_loaders
+    return client
+
+
 def main(argv: list[str] | None = None) -> dict:
     parser = argparse.ArgumentParser(description=__doc__)
     parser.add_argument("scenario", choices=sorted(SCENARIOS), nargs="?")
@@ -26,6 +50,8 @@ def main(argv: list[str] | None = None) -> dict:
     parser.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     parser.add_argument("--spmd", action="store_true", help="one client per rank (launch with torch.distributed.run)")
     parser.add_argument("--clients-per-rank", type=int, default=1, help="with --spmd: host this many clients on every rank")
+    parser.add_argument("--ranks-per-client", type=int, default=1,
+                        help="with --spmd: every client spans this many GPUs (replicas on disjoint data shards, gradients averaged per step)")
     args = parser.parse_args(argv)
     if args.list or args.scenario is None:
         print("\n".join(sorted(SCENARIOS)))
@@ -40,7 +66,10 @@ def main(argv: list[str] | None = None) -> dict:
         per_rank = max(1, args.clients_per_rank)
         config["n_clients"] = ctx.world_size * per_rank
         server, clients = SCENARIOS[args.scenario](config, ctx.device)
-        if per_rank == 1:
+        if args.ranks_per_client > 1:
+            assert per_rank == 1, "--ranks-per-client and --clients-per-rank are mutually exclusive"
+            build_spmd_federation(ctx, server, _replicated(clients, ctx, args.ranks_per_client))
+        elif per_rank == 1:
             build_spmd_federation(ctx, server, clients[ctx.rank])
         else:  # more clients than GPUs: every rank hosts a contiguous block of them
             from fl4health_b200.parallel.spmd_multi import build_spmd_federation_multi

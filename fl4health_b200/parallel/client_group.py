@@ -1,0 +1,133 @@
+"""A client that spans several GPUs (intra-client data parallelism).
+
+The reference only ever reaches this through one example — ``examples/fedllm_example`` launches each *client* with
+``torchrun --nproc_per_node=2`` and lets DeepSpeed shard it (``client.py:104-106``, ``run_client_zero_3.slrm:72``) while
+the library itself is unaware.  Here the notion is part of the SPMD runtime:
+
+* the world of ``W`` ranks is cut into consecutive groups of ``G`` ranks; every group is ONE federated client
+  (``ClientGroup``), every rank of the group holds a full replica of the client's model and a disjoint shard of its
+  data (``shard_dataset``);
+* ``ReplicatedClientMixin`` averages the gradients over the group between backward and the optimizer step (one
+  collective on the flat arena gradient — the arena makes the "bucket" the whole model), so all replicas take the
+  same step on the union batch;
+* the federation layer needs no change: each replica reports its shard's sample count, and because the replicas of a
+  client are identical, the sample-weighted aggregate over all ``W`` ranks equals the client-weighted aggregate over
+  the ``W / G`` clients (``Σ_r n_r w_r = Σ_k (Σ_{r∈k} n_r) w_k``).  Metrics aggregate the same way.
+
+Buffers that are not parameters (batch-norm running statistics) are per-replica during a round — each replica sees
+its own shard — and are merged by the round-end aggregate like any other exchanged tensor.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+from fl4health_b200.parallel.arena import arena_of
+from fl4health_b200.utils.dataset import TensorDataset
+
+
+@dataclass
+class ClientGroup:
+    """This rank's place in the client it belongs to."""
+
+    client_index: int
+    group_rank: int
+    group_size: int
+    process_group: Any  # torch.distributed.ProcessGroup | None (None when group_size == 1 or the world is one rank)
+
+    @classmethod
+    def from_world(cls, rank: int, world_size: int, group_size: int) -> ClientGroup:
+        """Consecutive ranks form a client (ranks ``[k*G, (k+1)*G)`` -> client ``k``): neighbours share an NVSwitch
+        domain anyway, and the layout keeps ``rank // G`` as the client index.  Collective over the WORLD: every rank
+        must call it (``new_group`` requires all ranks to create all groups in the same order)."""
+        if world_size % group_size != 0:
+            raise ValueError(f"world size {world_size} is not a multiple of the client group size {group_size}")
+        mine = None
+        if group_size > 1 and world_size > 1:
+            for start in range(0, world_size, group_size):
+                group = dist.new_group(list(range(start, start + group_size)))
+                if start <= rank < start + group_size:
+                    mine = group
+        return cls(rank // group_size, rank % group_size, group_size, mine)
+
+    def all_reduce_mean(self, tensor: torch.Tensor) -> torch.Tensor:
+        if self.process_group is not None:
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.process_group)
+            tensor.div_(self.group_size)
+        return tensor
+
+
+def shard_dataset(dataset: TensorDataset, group: ClientGroup, seed: int = 0) -> TensorDataset:
+    """Replica ``r`` of ``G`` keeps samples ``perm[r::G]`` of a seeded permutation: disjoint, equal-sized up to one."""
+    assert dataset.targets is not None
+    if group.group_size == 1:
+        return dataset
+    order = torch.randperm(len(dataset.data), generator=torch.Generator().manual_seed(seed))
+    usable = len(order) - len(order) % group.group_size  # equal shards: every replica takes the same number of steps
+    mine = order[:usable][group.group_rank::group.group_size]
+    return TensorDataset(dataset.data[mine], dataset.targets[mine], dataset.transform, dataset.target_transform, dataset.batch_transform)
+
+
+class ReplicatedClientMixin:
+    """Combine as ``class C(ReplicatedClientMixin, SomeClient)`` and set ``client.client_group``.
+
+    ``transform_gradients`` is the hook every client calls between ``backward()`` and ``optimizer.step()``
+    (``basic_client.py`` ``train_step``); clients that already use it (SCAFFOLD's control-variate correction, DP
+    clipping) compose through ``super()``: their correction is applied to the local gradient first, then the
+    replicas are averaged.
+    """
+
+    client_group: ClientGroup | None = None
+
+    def transform_gradients(self, losses: Any) -> None:
+        super().transform_gradients(losses)  # type: ignore[misc]
+        group = self.client_group
+        if group is None or group.process_group is None:
+            return
+        for model in self._replicated_models():
+            average_gradients(model, group)
+
+    def _replicated_models(self) -> list[torch.nn.Module]:
+        models = [self.model]  # type: ignore[attr-defined]
+        twin = getattr(self, "global_model", None)  # Ditto-style clients train a second model in the same step
+        if isinstance(twin, torch.nn.Module):
+            models.append(twin)
+        return models
+
+
+def average_gradients(model: torch.nn.Module, group: ClientGroup) -> None:
+    """Mean of the gradients over the group.  One collective when the gradients live in the arena's flat buffer;
+    otherwise the per-parameter gradients are coalesced into one temporary."""
+    arena = arena_of(model)
+    flat = getattr(arena, "grad", None) if arena is not None else None
+    params = [p for p in model.parameters() if p.requires_grad]
+    if flat is not None and params and all(p.grad is not None and _is_view_of(p.grad, flat) for p in params):
+        group.all_reduce_mean(flat)
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if len(grads) != len(params):  # a parameter unused on this replica must still take part: the collective is by position
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in params]
+    if not grads:
+        return
+    by_dtype: dict[torch.dtype, list[torch.Tensor]] = {}
+    for g in grads:
+        by_dtype.setdefault(g.dtype, []).append(g)
+    for bucket in by_dtype.values():
+        coalesced = torch.cat([g.reshape(-1) for g in bucket])
+        group.all_reduce_mean(coalesced)
+        offset = 0
+        for g in bucket:
+            g.copy_(coalesced[offset:offset + g.numel()].view_as(g))
+            offset += g.numel()
+
+
+def _is_view_of(tensor: torch.Tensor, base: torch.Tensor) -> bool:
+    start, end = base.data_ptr(), base.data_ptr() + base.numel() * base.element_size()
+    return tensor.device == base.device and start <= tensor.data_ptr() < end

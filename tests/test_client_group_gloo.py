@@ -1,0 +1,88 @@
+"""Clients spanning several ranks (``fl4health_b200.parallel.client_group``): gradient averaging equals full-batch
+training, shards are disjoint, and a 2-rank client behaves like the single-process client on the union of its data."""
+
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from fl4health_b200.parallel.client_group import ClientGroup, ReplicatedClientMixin, average_gradients, shard_dataset
+from fl4health_b200.utils.dataset import TensorDataset
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_shards_are_disjoint_equal_and_cover_the_data() -> None:
+    data = TensorDataset(torch.arange(23).float().view(-1, 1), torch.arange(23))
+    groups = [ClientGroup(0, r, 3, None) for r in range(3)]
+    shards = [shard_dataset(data, g, seed=4) for g in groups]
+    assert [len(s.data) for s in shards] == [7, 7, 7]
+    merged = torch.cat([s.targets for s in shards])
+    assert len(set(merged.tolist())) == 21  # disjoint; 23 % 3 samples dropped so that replicas stay in lock-step
+    assert shard_dataset(data, ClientGroup(0, 0, 1, None)) is data
+    assert all(torch.equal(a.targets, b.targets) for a, b in zip(shards, [shard_dataset(data, g, seed=4) for g in groups]))
+    with pytest.raises(ValueError):
+        ClientGroup.from_world(0, 6, 4)
+    solo = ClientGroup.from_world(3, 8, 1)
+    assert (solo.client_index, solo.group_rank, solo.process_group) == (3, 0, None)
+
+
+def test_single_rank_group_leaves_gradients_alone() -> None:
+    model = torch.nn.Linear(3, 2)
+    model(torch.randn(4, 3)).sum().backward()
+    before = [p.grad.clone() for p in model.parameters()]
+    average_gradients(model, ClientGroup(0, 0, 1, None))
+    assert all(torch.equal(a, p.grad) for a, p in zip(before, model.parameters()))
+
+    class Base:
+        calls = 0
+
+        def transform_gradients(self, losses) -> None:  # type: ignore[no-untyped-def]
+            Base.calls += 1
+
+    class Client(ReplicatedClientMixin, Base):
+        pass
+
+    client = Client()
+    client.model = model
+    client.transform_gradients(None)  # composes through super() even without a group
+    assert Base.calls == 1
+
+
+def _launch(tmp_path: Path, world: int, group_size: int, port: int) -> list[dict]:
+    out = tmp_path / f"w{world}g{group_size}"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "client_group_worker.py"), str(out), str(group_size)]
+    proc = subprocess.run(cmd, env={**os.environ, "FL4H_LOG_LEVEL": "ERROR"}, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    return [json.loads(Path(f"{out}.rank{r}").read_text()) for r in range(world)]
+
+
+def test_two_rank_client_matches_the_single_rank_client_on_the_union_batch(tmp_path: Path) -> None:
+    base = 29900 + os.getpid() % 50
+    (solo,) = _launch(tmp_path, world=1, group_size=1, port=base)
+    replicas = _launch(tmp_path, world=2, group_size=2, port=base + 1)
+    # both replicas hold the same parameters before every aggregate (they took identical, averaged steps) ...
+    assert all(r["grad_error"] < 1e-6 for r in replicas)  # averaged shard gradients == union-batch gradient
+    for key in ("1", "2"):
+        assert replicas[0]["pre_aggregate"][key] == pytest.approx(replicas[1]["pre_aggregate"][key], rel=1e-9)
+    # ... each trains on half of the client's data, and the federated losses are finite and improving
+    assert [r["train_samples"] for r in replicas] == [64, 64] and solo["train_samples"] == 128
+    losses = [v for _, v in replicas[0]["losses"]]
+    assert losses[1] < losses[0] and all(torch.isfinite(torch.tensor(v)) for v in losses)
+    assert replicas[0]["losses"] == replicas[1]["losses"]
+
+
+def test_four_ranks_two_clients_of_two_replicas(tmp_path: Path) -> None:
+    results = _launch(tmp_path, world=4, group_size=2, port=29960 + os.getpid() % 30)
+    assert [r["client"] for r in results] == [0, 0, 1, 1]
+    for a, b in ((0, 1), (2, 3)):  # replicas of one client agree; the two clients (different data) do not
+        assert results[a]["pre_aggregate"]["1"] == pytest.approx(results[b]["pre_aggregate"]["1"], rel=1e-9)
+    assert results[0]["pre_aggregate"]["1"] != pytest.approx(results[2]["pre_aggregate"]["1"], rel=1e-6)
+    assert all(r["losses"] == results[0]["losses"] for r in results)
