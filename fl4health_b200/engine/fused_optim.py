@@ -310,8 +310,8 @@ class FlatAdamW(_FlatOptimizer):
 
 def translate_optimizer(optimizer: Optimizer, arena: ParameterArena) -> Optimizer:
     """Stock SGD / Adam / AdamW -> flat fused equivalent.  Anything else (or exotic flags) is returned unchanged."""
-    if isinstance(optimizer, _FlatOptimizer):
-        return optimizer
+    if isinstance(optimizer, _FlatOptimizer) or getattr(optimizer, "fl4h_keep_stock", False):
+        return optimizer  # (ZeRO-1 shards keep the stock optimizer: the flat companions are arena-length by construction)
     kind = type(optimizer)
     if kind not in (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW) or (arena.grad is None and arena.shadow is None):
         return optimizer

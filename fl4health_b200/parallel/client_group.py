@@ -83,6 +83,21 @@ class ReplicatedClientMixin:
 
     client_group: ClientGroup | None = None
 
+    def setup_client(self, config: Any) -> None:
+        group = self.client_group
+        engine = getattr(self, "engine", None)
+        if group is not None and group.process_group is not None and engine is not None and getattr(engine, "cuda_graphs", False):
+            # the gradient collective sits inside train_step, i.e. inside the captured region; NCCL calls can be
+            # captured, but that path has not been validated on hardware yet, so replicated clients run eagerly
+            from dataclasses import replace
+            from logging import WARNING
+
+            from fl4health_b200.common.logger import log
+
+            log(WARNING, "client spans several ranks: CUDA-graph capture of the training step is disabled for it")
+            self.engine = replace(engine, cuda_graphs=False)
+        super().setup_client(config)  # type: ignore[misc]
+
     def transform_gradients(self, losses: Any) -> None:
         super().transform_gradients(losses)  # type: ignore[misc]
         group = self.client_group
@@ -131,3 +146,91 @@ def average_gradients(model: torch.nn.Module, group: ClientGroup) -> None:
 def _is_view_of(tensor: torch.Tensor, base: torch.Tensor) -> bool:
     start, end = base.data_ptr(), base.data_ptr() + base.numel() * base.element_size()
     return tensor.device == base.device and start <= tensor.data_ptr() < end
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ZeRO-1: optimizer state sharded over the replicas of a client
+# --------------------------------------------------------------------------------------------------------------------
+def partition_parameters(params: list[torch.nn.Parameter], group_size: int) -> list[list[int]]:
+    """Greedy balance by element count (largest first, to the least loaded replica); deterministic, so every replica
+    computes the same ownership table.  Returns, per replica, the indices into ``params`` it owns."""
+    owned: list[list[int]] = [[] for _ in range(group_size)]
+    load = [0] * group_size
+    for index in sorted(range(len(params)), key=lambda i: (-params[i].numel(), i)):
+        target = min(range(group_size), key=lambda r: (load[r], r))
+        owned[target].append(index)
+        load[target] += params[index].numel()
+    return [sorted(indices) for indices in owned]
+
+
+class Zero1ClientMixin(ReplicatedClientMixin):
+    """``ReplicatedClientMixin`` + optimizer-state sharding: every replica keeps momentum / Adam moments only for the
+    parameters it owns (1/G of the model), steps those, and the owners then broadcast the new values inside the group.
+
+    The user's ``get_optimizer`` is unchanged: the optimizer it returns is rebuilt over the owned subset with the same
+    class and per-group hyper-parameters (and kept as a stock ``torch.optim`` optimizer, see ``get_optimizer``).  With
+    fp32 masters in the arena the *masters* are what is broadcast, and the bf16 compute shadow is refreshed afterwards.
+    """
+
+    def get_optimizer(self, config: Any) -> Any:
+        optimizer = super().get_optimizer(config)  # type: ignore[misc]
+        group = self.client_group
+        if group is None or group.process_group is None:
+            return optimizer
+        if isinstance(optimizer, dict):
+            raise NotImplementedError("Zero1ClientMixin shards single-optimizer clients; multi-optimizer clients use ReplicatedClientMixin")
+        model: torch.nn.Module = self.model  # type: ignore[attr-defined]
+        trainable = [p for p in model.parameters() if p.requires_grad]
+        table = partition_parameters(trainable, group.group_size)
+        mine = {id(trainable[i]) for i in table[group.group_rank]}
+        new_groups = []
+        for param_group in optimizer.param_groups:
+            kept = [p for p in param_group["params"] if id(p) in mine]
+            if kept:
+                new_groups.append({**{k: v for k, v in param_group.items() if k != "params"}, "params": kept})
+        if not new_groups:  # more replicas than tensors: this replica owns nothing but still needs a valid optimizer
+            new_groups = [{**{k: v for k, v in optimizer.param_groups[0].items() if k != "params"}, "params": [torch.nn.Parameter(torch.zeros(()))]}]
+        names = {id(p): name for name, p in model.named_parameters()}
+        self._zero1_owned_names = [[names[id(trainable[i])] for i in indices] for indices in table]
+        self._zero1_foreign = [trainable[i] for r, indices in enumerate(table) if r != group.group_rank for i in indices]
+        sharded = type(optimizer)(new_groups, **{k: v for k, v in optimizer.defaults.items() if k in type(optimizer).__init__.__code__.co_varnames})
+        # The fused flat optimizers index arena-length companion buffers (momentum / moments at the parameter's arena
+        # offset), which would allocate the full state on every replica; the stock optimizer over the owned subset is
+        # what actually divides the state memory by G.  (A compact companion layout for the fused kernels is future work.)
+        sharded.fl4h_keep_stock = True  # type: ignore[attr-defined]
+        return sharded
+
+    def update_after_step(self, step: int, current_round: int | None = None) -> None:
+        group = self.client_group
+        if group is not None and group.process_group is not None and hasattr(self, "_zero1_owned_names"):
+            self._zero1_sync_parameters(group)
+        super().update_after_step(step, current_round)  # type: ignore[misc]
+
+    @torch.no_grad()
+    def _zero1_sync_parameters(self, group: ClientGroup) -> None:
+        model: torch.nn.Module = self.model  # type: ignore[attr-defined]
+        arena = arena_of(model)
+        params = dict(model.named_parameters())
+        storage = (lambda name: arena.view(name)) if arena is not None else (lambda name: params[name].data)  # fp32 masters when there are any
+        first_rank = group.client_index * group.group_size  # global rank of the group's replica 0
+        for owner, names in enumerate(self._zero1_owned_names):
+            if not names:
+                continue
+            tensors = [storage(name) for name in names]
+            coalesced = torch.cat([t.reshape(-1).float() for t in tensors])
+            dist.broadcast(coalesced, src=first_rank + owner, group=group.process_group)
+            if owner != group.group_rank:
+                offset = 0
+                for t in tensors:
+                    t.copy_(coalesced[offset:offset + t.numel()].view_as(t))
+                    offset += t.numel()
+        if arena is not None:
+            arena.refresh_shadow()
+        for p in self._zero1_foreign:  # nobody on this replica steps (or clears) these gradients
+            if p.grad is not None:
+                p.grad.zero_() if _grad_is_persistent(p, arena) else setattr(p, "grad", None)
+
+
+def _grad_is_persistent(p: torch.nn.Parameter, arena: Any) -> bool:
+    flat = getattr(arena, "grad", None) if arena is not None else None
+    return flat is not None and p.grad is not None and _is_view_of(p.grad, flat)

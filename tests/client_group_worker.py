@@ -15,7 +15,7 @@ from fl4health_b200.clients.basic_client import BasicClient  # noqa: E402
 from fl4health_b200.engine.data import BatchedTensorLoader  # noqa: E402
 from fl4health_b200.metrics import Accuracy  # noqa: E402
 from fl4health_b200.metrics.metric_aggregation import evaluate_metrics_aggregation_fn, fit_metrics_aggregation_fn  # noqa: E402
-from fl4health_b200.parallel.client_group import ClientGroup, ReplicatedClientMixin, shard_dataset  # noqa: E402
+from fl4health_b200.parallel.client_group import ClientGroup, ReplicatedClientMixin, Zero1ClientMixin, shard_dataset  # noqa: E402
 from fl4health_b200.parallel.spmd import SpmdContext, build_spmd_federation  # noqa: E402
 from fl4health_b200.servers.base_server import FlServer  # noqa: E402
 from fl4health_b200.servers.client_manager import SimpleClientManager  # noqa: E402
@@ -37,7 +37,7 @@ class GroupNormNet(torch.nn.Module):
         return self.fc(torch.flatten(x, 1))
 
 
-class ShardedClient(ReplicatedClientMixin, BasicClient):
+class _Hooks:
     data_seed = 0
 
     def get_model(self, config):  # noqa: ANN001, ANN201
@@ -58,8 +58,17 @@ class ShardedClient(ReplicatedClientMixin, BasicClient):
         return torch.optim.SGD(self.model.parameters(), lr=0.05, momentum=0.9)
 
 
+class ShardedClient(ReplicatedClientMixin, _Hooks, BasicClient):
+    pass
+
+
+class Zero1Client(Zero1ClientMixin, _Hooks, BasicClient):
+    """Same hooks, optimizer state sharded over the replicas."""
+
+
 def main() -> None:
     out_path, group_size = sys.argv[1], int(sys.argv[2])
+    client_cls = Zero1Client if os.environ.get("FL4H_TEST_ZERO1") == "1" else ShardedClient
     ctx = SpmdContext()
     group = ClientGroup.from_world(ctx.rank, ctx.world_size, group_size)
 
@@ -70,7 +79,7 @@ def main() -> None:
     strategy = BasicFedAvg(min_fit_clients=n, min_evaluate_clients=n, min_available_clients=n, on_fit_config_fn=fn, on_evaluate_config_fn=fn,
                            fit_metrics_aggregation_fn=fit_metrics_aggregation_fn, evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn)
     server = FlServer(SimpleClientManager(), {"n_server_rounds": 2}, strategy, on_init_parameters_config_fn=fn)
-    client = ShardedClient(Path("."), [Accuracy()], ctx.device, client_name=f"client{group.client_index}.replica{group.group_rank}")
+    client = client_cls(Path("."), [Accuracy()], ctx.device, client_name=f"client{group.client_index}.replica{group.group_rank}")
     client.client_group, client.data_seed = group, group.client_index
     build_spmd_federation(ctx, server, client)
 
@@ -97,7 +106,11 @@ def main() -> None:
     grad_error = max(float((p.grad - r).abs().max()) for p, r in zip(probe.parameters(), reference))
     payload = {"rank": ctx.rank, "grad_error": grad_error, "client": group.client_index, "losses": history.losses_distributed,
                "pre_aggregate": {str(k): [float(v.sum()), float(v.abs().sum())] for k, v in seen.items()},
-               "train_samples": client.num_train_samples}
+               "train_samples": client.num_train_samples, "optimizer_class": type(client.optimizers["global"]).__name__,
+               "trainable_elements": sum(p.numel() for p in client.model.parameters() if p.requires_grad),
+               "optimizer_state_elements": sum(v.numel() for state in client.optimizers["global"].state.values() for v in state.values()
+                                               if isinstance(v, torch.Tensor)) if hasattr(client.optimizers["global"], "state") else -1,
+               "final": [float(v) for v in torch.cat([p.detach().double().flatten() for p in client.model.parameters()])[:50]]}
     Path(f"{out_path}.rank{ctx.rank}").write_text(json.dumps(payload))
     ctx.barrier()
     ctx.shutdown()

@@ -55,11 +55,11 @@ def test_single_rank_group_leaves_gradients_alone() -> None:
     assert Base.calls == 1
 
 
-def _launch(tmp_path: Path, world: int, group_size: int, port: int) -> list[dict]:
-    out = tmp_path / f"w{world}g{group_size}"
+def _launch(tmp_path: Path, world: int, group_size: int, port: int, **extra_env: str) -> list[dict]:
+    out = tmp_path / f"w{world}g{group_size}{'z' if extra_env else ''}"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "client_group_worker.py"), str(out), str(group_size)]
-    proc = subprocess.run(cmd, env={**os.environ, "FL4H_LOG_LEVEL": "ERROR"}, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    proc = subprocess.run(cmd, env={**os.environ, "FL4H_LOG_LEVEL": "ERROR", **extra_env}, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert proc.returncode == 0, proc.stderr[-3000:]
     return [json.loads(Path(f"{out}.rank{r}").read_text()) for r in range(world)]
 
@@ -86,3 +86,29 @@ def test_four_ranks_two_clients_of_two_replicas(tmp_path: Path) -> None:
         assert results[a]["pre_aggregate"]["1"] == pytest.approx(results[b]["pre_aggregate"]["1"], rel=1e-9)
     assert results[0]["pre_aggregate"]["1"] != pytest.approx(results[2]["pre_aggregate"]["1"], rel=1e-6)
     assert all(r["losses"] == results[0]["losses"] for r in results)
+
+
+def test_partition_is_balanced_and_deterministic() -> None:
+    from fl4health_b200.parallel.client_group import partition_parameters
+
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (100, 10, 90, 50, 45, 5)]
+    table = partition_parameters(params, 2)
+    assert sorted(i for owned in table for i in owned) == list(range(6))
+    loads = [sum(params[i].numel() for i in owned) for owned in table]
+    assert abs(loads[0] - loads[1]) <= 10 and table == partition_parameters(params, 2)
+    assert partition_parameters(params[:1], 3) == [[0], [], []]
+
+
+def test_zero1_matches_replicated_training_with_half_the_optimizer_state(tmp_path: Path) -> None:
+    base = 29850 + os.getpid() % 40
+    plain = _launch(tmp_path, world=2, group_size=2, port=base)
+    sharded = _launch(tmp_path, world=2, group_size=2, port=base + 1, FL4H_TEST_ZERO1="1")
+    # same trajectory: ownership only decides WHO computes an update, not its value
+    for key in ("1", "2"):
+        assert sharded[0]["pre_aggregate"][key] == pytest.approx(plain[0]["pre_aggregate"][key], rel=1e-6)
+        assert sharded[0]["pre_aggregate"][key] == pytest.approx(sharded[1]["pre_aggregate"][key], rel=1e-9)
+    assert sharded[0]["final"] == pytest.approx(plain[0]["final"], rel=1e-5, abs=1e-7)
+    assert [v for _, v in sharded[0]["losses"]] == pytest.approx([v for _, v in plain[0]["losses"]], rel=1e-6)
+    # momentum buffers: together the shards hold exactly one copy of the state, tensor-granular, so this tiny model (one 2560-element matrix) splits unevenly
+    shards, total = [r["optimizer_state_elements"] for r in sharded], sharded[0]["trainable_elements"]
+    assert sum(shards) == total and 0 < min(shards) and max(shards) < total and sharded[0]["optimizer_class"] == "SGD"
