@@ -112,3 +112,17 @@ def test_zero1_matches_replicated_training_with_half_the_optimizer_state(tmp_pat
     # momentum buffers: together the shards hold exactly one copy of the state, tensor-granular, so this tiny model (one 2560-element matrix) splits unevenly
     shards, total = [r["optimizer_state_elements"] for r in sharded], sharded[0]["trainable_elements"]
     assert sum(shards) == total and 0 < min(shards) and max(shards) < total and sharded[0]["optimizer_class"] == "SGD"
+
+
+@pytest.mark.parametrize("scenario", ["fedllm_example", "ditto_example"])
+def test_examples_run_with_two_ranks_per_client(scenario: str) -> None:
+    """``examples.run --spmd --ranks-per-client 2``: the LLM example the reference shards with DeepSpeed, and a client
+    that trains two models per step (both are averaged over the group)."""
+    port = 29800 + (os.getpid() + len(scenario)) % 40
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           "-m", "examples.run", scenario, "--spmd", "--ranks-per-client", "2", "--device", "cpu", "--rounds", "2"]
+    proc = subprocess.run(cmd, env={**os.environ, "FL4H_LOG_LEVEL": "ERROR"}, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    (line,) = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    losses = [v for _, v in json.loads(line)["losses"]]
+    assert len(losses) == 2 and all(torch.isfinite(torch.tensor(v)) for v in losses)
