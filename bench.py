@@ -19,9 +19,14 @@ on every rank (barrier + synchronize on both sides), max over ranks.  Two timed 
 * ``e2e``    — every batch is staged from pinned host memory (H2D inside the timed region) and every round's loss /
   metrics are read back (D2H), through the same public API.
 
-``--impl reference`` would run the unmodified reference; it cannot be installed offline (its build backend
-``hatchling`` and its core dependency ``flwr`` are absent from the image and the wheelhouse), so that arm reports
-``unavailable``.
+Precision: the headline (``value`` / ``e2e``) runs at the REFERENCE's precision — fp32 parameters, activations and
+optimizer state, PyTorch-default TF32 tensor-core math inside convolutions, fp32 Linear (the reference has no AMP
+outside nnU-Net).  The bf16 master-weight engine mode is measured afterwards in the same process and reported under
+``"bf16"`` as an extra (``--dtype bf16`` makes it the headline instead).
+
+``--impl reference`` runs the UNMODIFIED reference package (``baseline/_ref/fl4health``) through its stock path
+(``baseline/reference_arm.py``: one CPU server process + one client process per GPU, NumPy aggregation, no
+``fl4health_b200`` import anywhere on that path); see DESIGN.md §6.
 """
 
 from __future__ import annotations
@@ -51,18 +56,22 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--train-samples", type=int, default=4096)
     p.add_argument("--collectives", default="auto", choices=["auto", "nccl", "fused"])
     p.add_argument("--no-graphs", action="store_true")
-    p.add_argument("--fp32", action="store_true")
+    p.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                   help="headline precision: fp32 = the reference's (fp32 state, TF32 conv math); bf16 = master-weight mode")
+    p.add_argument("--fp32", action="store_true", help="(kept for old command lines) same as --dtype fp32")
+    p.add_argument("--skip-extra-dtype", action="store_true", help="do not also measure the other precision")
     p.add_argument("--no-master-weights", action="store_true", help="bf16 autocast over fp32 params instead of bf16 shadow params")
     p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--device", default="cuda", help="reference arm only: cpu runs its plumbing test without a GPU")
     return p.parse_args()
 
 
 def reference_arm() -> None:
-    print(json.dumps({
-        "impl": "reference",
-        "unavailable": "reference cannot be installed offline: build backend hatchling and core dependency flwr "
-                       "(plus opacus, torchmetrics, dp-accounting) are not in the image or /opt/wheelhouse",
-    }))
+    """Hand over to baseline/reference_arm.py (imports nothing from fl4health_b200; same CLI flags)."""
+    import runpy
+
+    sys.path.pop(0)  # the reference arm must not see this repo's package
+    runpy.run_path(str(Path(__file__).resolve().parent / "baseline" / "reference_arm.py"), run_name="__main__")
 
 
 class ClockSampler:
@@ -151,11 +160,15 @@ def main() -> None:
     torch.manual_seed(1234 + ctx.rank)
 
     eager_impl = args.impl == "eager"
-    engine = EngineOptions(
-        arena=not eager_impl, fused_optimizer=not eager_impl, cuda_graphs=not (args.no_graphs or eager_impl),
-        amp_dtype=None if args.fp32 else torch.bfloat16, channels_last=not eager_impl,
-        master_weights=not (eager_impl or args.fp32 or args.no_master_weights),
-    )
+    headline_dtype = "fp32" if args.fp32 else args.dtype
+
+    def engine_for(dtype: str) -> EngineOptions:
+        bf16 = dtype == "bf16"
+        return EngineOptions(
+            arena=not eager_impl, fused_optimizer=not eager_impl, cuda_graphs=not (args.no_graphs or eager_impl),
+            amp_dtype=torch.bfloat16 if bf16 else None, channels_last=not eager_impl,
+            master_weights=bf16 and not (eager_impl or args.no_master_weights),
+        )
 
     def synthetic(n: int, seed: int) -> TensorDataset:
         gen = torch.Generator().manual_seed(seed)
@@ -187,67 +200,85 @@ def main() -> None:
     def config_fn(server_round: int) -> dict:
         return {"current_server_round": server_round, "local_steps": args.local_steps, "batch_size": args.batch_size}
 
-    client = CifarResNetClient(Path("."), [Accuracy()], device, client_name=f"rank{ctx.rank}", engine_options=engine)
-    strategy = BasicFedAvg(
-        min_fit_clients=world, min_evaluate_clients=world, min_available_clients=world,
-        on_fit_config_fn=config_fn, on_evaluate_config_fn=config_fn,
-        fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
-        evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
-    )
-    server = FlServer(SimpleClientManager(), {"n_server_rounds": args.steps + args.warmup, "local_steps": args.local_steps},
-                      strategy, on_init_parameters_config_fn=config_fn, accept_failures=False)
-    build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
-
     l2_flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
 
-    def timed_fit(label: str) -> dict:
-        """Run warmup+steps rounds through FlServer.fit; time the last `steps` rounds on the device."""
-        marks: dict[str, object] = {}
-        sampler = ClockSampler(device.index) if ctx.rank == 0 else None
+    def run_federation(dtype: str, with_e2e: bool) -> tuple[dict, dict | None, EngineOptions]:
+        """Build one federation at `dtype` and time it (e2e staging first, then device-resident datasets)."""
+        engine = engine_for(dtype)
+        client = CifarResNetClient(Path("."), [Accuracy()], device, client_name=f"rank{ctx.rank}", engine_options=engine)
+        strategy = BasicFedAvg(
+            min_fit_clients=world, min_evaluate_clients=world, min_available_clients=world,
+            on_fit_config_fn=config_fn, on_evaluate_config_fn=config_fn,
+            fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
+            evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
+        )
+        server = FlServer(SimpleClientManager(), {"n_server_rounds": args.steps + args.warmup, "local_steps": args.local_steps},
+                          strategy, on_init_parameters_config_fn=config_fn, accept_failures=False)
+        build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
 
-        def on_round_end(server_round: int) -> None:
-            l2_flush.fill_(1.0)  # evict L2 between rounds (inside the timed region; ~40 us)
-            if server_round == args.warmup:
-                ctx.barrier()
-                torch.cuda.synchronize()
-                if sampler is not None:
-                    sampler.start()
-                ops.reset_launch_count()
-                tracing.phase_report(reset=True)  # FL4H_TRACE=1 diagnostics cover the timed rounds only
-                marks["start"] = torch.cuda.Event(enable_timing=True)
-                marks["start"].record()
-                marks["wall0"] = time.perf_counter()
-            elif server_round == args.warmup + args.steps:
-                marks["end"] = torch.cuda.Event(enable_timing=True)
-                marks["end"].record()
-                torch.cuda.synchronize()
-                ctx.barrier()
-                marks["wall1"] = time.perf_counter()
-                marks["launches"] = ops.launch_count()
-                if sampler is not None:
-                    marks["clocks"] = sampler.stop()
+        def timed_fit(label: str) -> dict:
+            """Run warmup+steps rounds through FlServer.fit; time the last `steps` rounds on the device."""
+            marks: dict[str, object] = {}
+            sampler = ClockSampler(device.index) if ctx.rank == 0 else None
 
-        server.round_end_hooks = [on_round_end]
-        if args.warmup == 0:
-            on_round_end(0)
-        history, _ = server.fit(num_rounds=args.warmup + args.steps)
-        ms = marks["start"].elapsed_time(marks["end"])  # type: ignore[union-attr]
-        ms = ctx.all_reduce_max(ms)
-        final_loss = history.losses_distributed[-1][1]
-        return {"label": label, "ms_total": ms, "ms_per_round": ms / args.steps, "launches": marks["launches"],
-                "clocks": marks.get("clocks"), "final_loss": final_loss,
-                "wall_s": marks["wall1"] - marks["wall0"]}  # type: ignore[operator]
+            def on_round_end(server_round: int) -> None:
+                l2_flush.fill_(1.0)  # evict L2 between rounds (inside the timed region; ~40 us)
+                if server_round == args.warmup:
+                    ctx.barrier()
+                    torch.cuda.synchronize()
+                    if sampler is not None:
+                        sampler.start()
+                    ops.reset_launch_count()
+                    tracing.phase_report(reset=True)  # FL4H_TRACE=1 diagnostics cover the timed rounds only
+                    marks["start"] = torch.cuda.Event(enable_timing=True)
+                    marks["start"].record()
+                    marks["wall0"] = time.perf_counter()
+                elif server_round == args.warmup + args.steps:
+                    marks["end"] = torch.cuda.Event(enable_timing=True)
+                    marks["end"].record()
+                    torch.cuda.synchronize()
+                    ctx.barrier()
+                    marks["wall1"] = time.perf_counter()
+                    marks["launches"] = ops.launch_count()
+                    if sampler is not None:
+                        marks["clocks"] = sampler.stop()
 
-    # ---- e2e first (pinned host datasets -> H2D every batch), then device-resident ----------------------------
-    e2e = None
-    if not args.skip_e2e:
-        CifarResNetClient.placement = "pinned"
-        e2e = timed_fit("e2e")
-        # re-create loaders for the device-resident run (graphs and model state are reused)
-        CifarResNetClient.placement = "device"
-        client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
-        client.train_iterator = None
-    main_run = timed_fit("device")
+            server.round_end_hooks = [on_round_end]
+            if args.warmup == 0:
+                on_round_end(0)
+            history, _ = server.fit(num_rounds=args.warmup + args.steps)
+            ms = marks["start"].elapsed_time(marks["end"])  # type: ignore[union-attr]
+            ms = ctx.all_reduce_max(ms)
+            final_loss = history.losses_distributed[-1][1]
+            return {"label": label, "ms_total": ms, "ms_per_round": ms / args.steps, "launches": marks["launches"],
+                    "clocks": marks.get("clocks"), "final_loss": final_loss,
+                    "wall_s": marks["wall1"] - marks["wall0"]}  # type: ignore[operator]
+
+        # ---- e2e first (pinned host datasets -> H2D every batch), then device-resident ------------------------
+        e2e_run = None
+        if with_e2e:
+            CifarResNetClient.placement = "pinned"
+            e2e_run = timed_fit("e2e")
+            # re-create loaders for the device-resident run (graphs and model state are reused)
+            CifarResNetClient.placement = "device"
+            client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
+            client.train_iterator = None
+        device_run = timed_fit("device")
+        if tracing.tracing_enabled() and ctx.rank == 0:  # FL4H_TRACE=1: device ms per round phase (diagnostic, stderr)
+            torch.cuda.synchronize()
+            report = tracing.phase_report()
+            print(json.dumps({"dtype": dtype, **{k: round(v["mean_ms"], 4) for k, v in report.items()}}), file=sys.stderr)
+        return device_run, e2e_run, engine
+
+    main_run, e2e, engine = run_federation(headline_dtype, with_e2e=not args.skip_e2e)
+    extra = None
+    if not (args.skip_extra_dtype or eager_impl):
+        other = "bf16" if headline_dtype == "fp32" else "fp32"
+        extra_run, extra_e2e, _ = run_federation(other, with_e2e=not args.skip_e2e)
+        extra = {"dtype": other, "value": world * 1000.0 / extra_run["ms_per_round"], "ms_per_step": extra_run["ms_per_round"],
+                 "final_val_loss": extra_run["final_loss"], "gpu_launches": extra_run["launches"]}
+        if extra_e2e is not None:
+            extra["e2e"] = {"value": world * 1000.0 / extra_e2e["ms_per_round"], "ms_per_step": extra_e2e["ms_per_round"]}
 
     rounds_per_s = 1000.0 / main_run["ms_per_round"]
     bytes_in = args.local_steps * args.batch_size * (3 * 32 * 32 * 4 + 8) + args.val_batches * args.batch_size * (3 * 32 * 32 * 4 + 8)
@@ -266,7 +297,8 @@ def main() -> None:
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "fp32" if args.fp32 else "bf16",
+        "dtype": ("fp32 (fp32 params/activations/optimizer, TF32 tensor-core conv math = the reference's PyTorch defaults)"
+                  if headline_dtype == "fp32" else "bf16"),
         "data": "synthetic CIFAR-10-shaped (3x32x32, 10 classes), random-init ResNet-18",
         "impl": args.impl,
         "config": {
@@ -291,11 +323,9 @@ def main() -> None:
             "note": "per federation round, summed over ranks: every train/val batch copied from pinned host memory; "
                     "loss+accuracy scalars read back on every rank",
         }
+    if extra is not None:
+        result[extra["dtype"]] = extra  # the other precision, same federation code, measured after the headline
     if ctx.rank == 0:
-        if tracing.tracing_enabled():  # FL4H_TRACE=1: device milliseconds per round phase (diagnostic, stderr)
-            torch.cuda.synchronize()
-            report = tracing.phase_report()
-            print(json.dumps({k: round(v["mean_ms"], 4) for k, v in report.items()}), file=sys.stderr)
         print(json.dumps(result))
     ctx.shutdown()
 
