@@ -10,6 +10,17 @@
 //                 cross-GPU barrier, then the receiver-side unpack in the same kernel:
 //                 w <- g, FedProx anchor w_t <- g, bf16 compute shadow <- g, SCAFFOLD d <- c - c_i.
 //
+// Two data paths, chosen per launch:
+//   * NVLS (default when the symmetric segments are bound to an NVSwitch multicast object, see symm_mem.cu):
+//       reduce-scatter = `multimem.ld_reduce.add.v4.f32` on the multicast address (the switch pulls the K copies and
+//       returns their sum: K-1 fewer NVLink transfers into the GPU), all-gather / broadcast = `multimem.st.v4.f32`
+//       (one store leaves the GPU, the switch replicates it into every rank's copy).  The switch can only ADD, so a
+//       non-uniform weighted mean first scales this rank's contribution into a multicast-bound staging buffer
+//       (phase A of the same kernel); uniform weights are applied after the reduction instead.
+//   * P2P (deterministic mode, `FL4H_NVLS=0`, or no multicast support): fixed-rank-order `ld/st.volatile` over the
+//       unicast peer mappings.
+// The integer model buffers (BatchNorm `num_batches_tracked`) are reduced by the same launch (one warp, P2P loads).
+//
 // Synchronisation is done with flags in peer-mapped memory (release/acquire at system scope) + a grid barrier, so no
 // host round trip and no NCCL call sits between the local training kernels and the aggregate.  Kernels are launched
 // cooperatively (all CTAs co-resident: the grid barrier cannot deadlock).
@@ -38,6 +49,15 @@ struct PeerTable {
     float coef[FL4H_MAX_RANKS];
     int rank;
     int world;
+    // NVLS: multicast addresses of the contribution source and of the result buffer; `stage` is this rank's unicast
+    // view of the multicast-bound staging buffer (null: contributions are reduced in place, weights are uniform)
+    const float* mc_contrib;
+    float* mc_result;
+    float* stage;
+    // integer buffers riding along (null when the model has none): ibuf[r] = rank r's int64 values (peer-mapped)
+    const long long* ibuf[FL4H_MAX_RANKS];
+    long long* ibuf_out;
+    int n_int;
 };
 
 struct EpiArgs {
@@ -65,6 +85,21 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// NVLS: in-switch reduction / replication on a multicast address (sm_90+; SASS: MULTIMEM / RED..MULTIMEM forms)
+__device__ __forceinline__ float4 mm_ld_reduce4(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(mc)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void mm_st4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
 }
 
 // Cross-GPU barrier executed by CTA 0 (threads 0..world-1), bracketed by grid barriers by the caller.
@@ -111,6 +146,22 @@ __device__ __forceinline__ float epi_apply(int mode, const EpiArgs& ea, float av
     }
 }
 
+// Integer buffers (a handful of int64 counters): weighted mean over ranks, truncated like the reference's
+// float-average -> int64 load (fl4health/parameter_exchange/full_exchanger.py:45-47).  One warp of CTA 0, P2P loads.
+// Must run between the two peer barriers (peers' values final, nobody has overwritten them yet).
+__device__ __forceinline__ void reduce_int_buffers(const PeerTable& t) {
+    if (t.n_int == 0 || blockIdx.x != 0) return;
+    for (int i = threadIdx.x; i < t.n_int; i += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < t.world; ++k) {
+            long long v;
+            asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(v) : "l"(t.ibuf[k] + i));
+            acc += (double)t.coef[k] * (double)v;
+        }
+        t.ibuf_out[i] = (long long)acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // agg_fused: every rank owns slice [rank*slice, (rank+1)*slice) of the flat payload.
 //   wcur/m/v are LOCAL full-length buffers (only the owned slice is touched): server optimizer state is sharded by
@@ -124,6 +175,7 @@ agg_fused_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict_
     // (0) all ranks finished local training and are inside the kernel: contributions may be read.
     peer_barrier(t, 0, epoch);
     grid.sync();
+    reduce_int_buffers(t);
 
     const int64_t begin = (int64_t)t.rank * slice;
     int64_t end = begin + slice;
@@ -178,6 +230,33 @@ agg_fused_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict_
     peer_barrier(t, 1, epoch);
 }
 
+// Receiver-side unpack shared by both broadcast kernels: one read of the landed global buffer, up to four writes.
+__device__ __forceinline__ void unpack_landed(const float* g, float* __restrict__ w, float* __restrict__ anchor,
+                                              __nv_bfloat16* __restrict__ shadow, const float* __restrict__ c_server,
+                                              const float* __restrict__ c_local, float* __restrict__ cv_out,
+                                              int64_t numel) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total4 = numel >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int64_t e = i << 2;
+        const float4 gv = ld_peer4(g + e);  // volatile: written by peers during this kernel, never in L1
+        if (w) *reinterpret_cast<float4*>(w + e) = gv;
+        if (anchor) *reinterpret_cast<float4*>(anchor + e) = gv;
+        if (shadow) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(shadow + e) = packed;
+        }
+        if (cv_out) {
+            const float4 cs = *reinterpret_cast<const float4*>(c_server + e);
+            const float4 cl = *reinterpret_cast<const float4*>(c_local + e);
+            *reinterpret_cast<float4*>(cv_out + e) = make_float4(cs.x - cl.x, cs.y - cl.y, cs.z - cl.z, cs.w - cl.w);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // bcast_fused: root's `contrib[root]` buffer -> every rank's `result` buffer, then receiver-side unpack.
 // ---------------------------------------------------------------------------------------------------------------
@@ -219,27 +298,112 @@ bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restri
     peer_barrier(t, 1, epoch);
     grid.sync();
 
-    // receiver-side tail: one read of the landed global buffer, up to four writes
-    const float* g = t.result[t.rank];
-    const int64_t total4 = numel >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-        const int64_t e = i << 2;
-        const float4 gv = ld_peer4(g + e);  // volatile: written by peers during this kernel, never in L1
-        if (w) *reinterpret_cast<float4*>(w + e) = gv;
-        if (anchor) *reinterpret_cast<float4*>(anchor + e) = gv;
-        if (shadow) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
-            uint2 packed;
-            packed.x = *reinterpret_cast<uint32_t*>(&lo);
-            packed.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(shadow + e) = packed;
+    unpack_landed(t.result[t.rank], w, anchor, shadow, c_server, c_local, cv_out, numel);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// agg_nvls: the same contract as agg_fused, data path through the NVSwitch multicast object.
+//   phase A (non-uniform weights only): stage <- coef[rank] * contrib            (local HBM, full length)
+//   barrier 0
+//   phase B: slice owner: acc = multimem.ld_reduce(mc_contrib + e)  [* coef if uniform] -> epilogue
+//            -> multimem.st(mc_result + e)                                       (lands in every rank's result)
+//   barrier 1
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+agg_nvls_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__ m, float* __restrict__ v,
+                EpiArgs ea, int64_t numel, int64_t slice, uint32_t epoch, float uniform_coef) {
+    cg::grid_group grid = cg::this_grid();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t.stage != nullptr) {
+        const float c = t.coef[t.rank];
+        const float4* src = reinterpret_cast<const float4*>(t.contrib[t.rank]);
+        float4* dst = reinterpret_cast<float4*>(t.stage);
+        const int64_t total4 = numel >> 2;
+#pragma unroll 4
+        for (int64_t i = tid; i < total4; i += stride) {
+            float4 x = __ldcs(src + i);
+            dst[i] = make_float4(c * x.x, c * x.y, c * x.z, c * x.w);
         }
-        if (cv_out) {
-            const float4 cs = *reinterpret_cast<const float4*>(c_server + e);
-            const float4 cl = *reinterpret_cast<const float4*>(c_local + e);
-            *reinterpret_cast<float4*>(cv_out + e) = make_float4(cs.x - cl.x, cs.y - cl.y, cs.z - cl.z, cs.w - cl.w);
+        __threadfence_system();
+        grid.sync();
+    }
+    peer_barrier(t, 0, epoch);
+    grid.sync();
+    reduce_int_buffers(t);
+
+    const int64_t begin = (int64_t)t.rank * slice;
+    int64_t end = begin + slice;
+    if (end > numel) end = numel;
+    const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
+    constexpr int kUnroll = 4;  // 148 CTAs x 512 thr x 4 x 16 B = 4.8 MB in flight >= NVLink bandwidth-delay product
+    for (int64_t base = tid; base < n4; base += stride * kUnroll) {
+        float4 acc[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i < n4) acc[u] = mm_ld_reduce4(t.mc_contrib + begin + (i << 2));
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i >= n4) continue;
+            const int64_t e = begin + (i << 2);
+            float4 a = acc[u];
+            a.x *= uniform_coef; a.y *= uniform_coef; a.z *= uniform_coef; a.w *= uniform_coef;
+            if (ea.mode != EPI_NONE) {
+                float4 wv = *reinterpret_cast<const float4*>(wcur + e);
+                float4 mv = m ? *reinterpret_cast<const float4*>(m + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 vv = v ? *reinterpret_cast<const float4*>(v + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a.x = epi_apply(ea.mode, ea, a.x, wv.x, mv.x, vv.x);
+                a.y = epi_apply(ea.mode, ea, a.y, wv.y, mv.y, vv.y);
+                a.z = epi_apply(ea.mode, ea, a.z, wv.z, mv.z, vv.z);
+                a.w = epi_apply(ea.mode, ea, a.w, wv.w, mv.w, vv.w);
+                if (m) *reinterpret_cast<float4*>(m + e) = mv;
+                if (v) *reinterpret_cast<float4*>(v + e) = vv;
+            }
+            mm_st4(t.mc_result + e, a);
         }
     }
+    __threadfence_system();
+    grid.sync();
+    peer_barrier(t, 1, epoch);
+}
+
+// bcast_nvls: the root streams its buffer through ONE multimem.st per 16 bytes (the switch replicates it into every
+// rank's result buffer: root egress = payload, no per-peer stores), barrier, then every rank unpacks locally.
+__global__ void __launch_bounds__(kThreads, 1)
+bcast_nvls_kernel(PeerTable t, int root, float* __restrict__ w, float* __restrict__ anchor,
+                  __nv_bfloat16* __restrict__ shadow, const float* __restrict__ c_server,
+                  const float* __restrict__ c_local, float* __restrict__ cv_out, int64_t numel, uint32_t epoch) {
+    cg::grid_group grid = cg::this_grid();
+    peer_barrier(t, 0, epoch);  // everyone's result buffer may be overwritten
+    grid.sync();
+    if (t.rank == root) {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        const int64_t total4 = numel >> 2;
+        const float4* src = reinterpret_cast<const float4*>(t.contrib[root]);
+        constexpr int kUnroll = 4;
+        for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total4; base += stride * kUnroll) {
+            float4 vals[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t i = base + (int64_t)u * stride;
+                if (i < total4) vals[u] = __ldcs(src + i);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t i = base + (int64_t)u * stride;
+                if (i < total4) mm_st4(t.mc_result + (i << 2), vals[u]);
+            }
+        }
+    }
+    __threadfence_system();
+    grid.sync();
+    peer_barrier(t, 1, epoch);
+    grid.sync();
+    unpack_landed(t.result[t.rank], w, anchor, shadow, c_server, c_local, cv_out, numel);
 }
 
 template <typename Kernel>
@@ -248,8 +412,9 @@ int coop_grid(Kernel kernel) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (per_sm < 1) per_sm = 1;
-    return sms;  // one CTA per SM: plenty of bytes in flight for NVLink, leaves room for the grid barrier
+    if (per_sm < 1) return 0;  // cannot be co-resident: the caller's cooperative launch reports the error
+    return sms;  // one CTA per SM (launch bounds guarantee >= 1 resident): 512 threads x unrolled 16-byte accesses
+                 // already cover the NVLink bandwidth-delay product, and a single wave keeps the grid barrier cheap
 }
 
 }  // namespace
@@ -289,6 +454,14 @@ struct Fl4hPeerArgs {
     float coef[FL4H_MAX_RANKS];
     int rank;
     int world;
+    void* mc_contrib;   // multicast address the reduction reads (staging buffer, or the contribution itself)
+    void* mc_result;    // multicast address of the result buffer
+    void* stage;        // unicast address of this rank's staging buffer (null: reduce contributions in place)
+    void* ibuf[FL4H_MAX_RANKS];
+    void* ibuf_out;
+    int n_int;
+    int use_nvls;
+    float uniform_coef; // applied after the in-switch sum (1.0 when the staging pass already applied the weights)
 };
 
 static PeerTable make_table(const Fl4hPeerArgs* a) {
@@ -301,6 +474,12 @@ static PeerTable make_table(const Fl4hPeerArgs* a) {
     }
     t.rank = a->rank;
     t.world = a->world;
+    t.mc_contrib = reinterpret_cast<const float*>(a->mc_contrib);
+    t.mc_result = reinterpret_cast<float*>(a->mc_result);
+    t.stage = reinterpret_cast<float*>(a->stage);
+    for (int i = 0; i < FL4H_MAX_RANKS; ++i) t.ibuf[i] = reinterpret_cast<const long long*>(a->ibuf[i]);
+    t.ibuf_out = reinterpret_cast<long long*>(a->ibuf_out);
+    t.n_int = a->n_int;
     return t;
 }
 
@@ -327,6 +506,14 @@ int fl4h_agg_fused(const Fl4hPeerArgs* args, const float* wcur, float* m, float*
     int64_t slice = (numel + t.world - 1) / t.world;
     slice = (slice + 3) & ~int64_t(3);
     cudaError_t err = cudaSuccess;
+    if (args->use_nvls) {
+        if (t.mc_contrib == nullptr || t.mc_result == nullptr) return (int)cudaErrorInvalidValue;
+        auto kernel = agg_nvls_kernel;
+        const int grid = coop_grid(kernel);
+        float uniform_coef = args->uniform_coef;
+        void* kargs[] = {&t, &wcur, &m, &v, &ea, &numel, &slice, &epoch, &uniform_coef};
+        return (int)cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+    }
     DISPATCH_WORLD(t.world, {
         auto kernel = agg_fused_kernel<KW>;
         const int grid = coop_grid(kernel);
@@ -345,6 +532,13 @@ int fl4h_bcast_fused(const Fl4hPeerArgs* args, int root, float* w, float* anchor
     slice = (slice + 3) & ~int64_t(3);
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
     cudaError_t err = cudaSuccess;
+    if (args->use_nvls) {
+        if (t.mc_result == nullptr) return (int)cudaErrorInvalidValue;
+        auto kernel = bcast_nvls_kernel;
+        const int grid = coop_grid(kernel);
+        void* kargs[] = {&t, &root, &w, &anchor, &sh, &c_server, &c_local, &cv_out, &numel, &epoch};
+        return (int)cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+    }
     DISPATCH_WORLD(t.world, {
         auto kernel = bcast_fused_kernel<KW>;
         const int grid = coop_grid(kernel);

@@ -160,7 +160,10 @@ class ParameterArena:
             # integer buffers (num_batches_tracked ...) live in ONE int64 buffer so they aggregate with one op
             int_sizes = [(name, t.numel()) for name, t in self.int_state.items() if t.dtype == torch.int64]
             if int_sizes:
-                self.int_flat = torch.zeros(sum(n for _, n in int_sizes), dtype=torch.int64, device=self.device)
+                # same allocator as the float arena: in SPMD mode the counters sit in symmetric memory, so the fused
+                # aggregate kernel reduces them through peer loads in the same launch (no separate collective)
+                self.int_flat = self._alloc(sum(n for _, n in int_sizes), torch.int64, self.device)
+                self.int_flat.zero_()
                 cursor = 0
                 for name, numel in int_sizes:
                     old = self.int_state[name]

@@ -151,6 +151,7 @@ class SpmdContext:
         # which implementation reduces / broadcasts model payloads
         self.collective_backend = collective_backend or os.environ.get("FL4H_COLLECTIVES", "auto")
         self.fused: Any = None  # ops.p2p.FusedCollectives when peer memory is available
+        self.last_int_reduced: torch.Tensor | None = None
         self.timings: dict[str, float] = {}
         self.mailbox: Any = None  # runtime.mailbox.ShmMailbox when every rank lives on this host
         _CONTEXT = self
@@ -292,13 +293,25 @@ class SpmdContext:
     # -- payload collectives -----------------------------------------------------------------------------------
     def weighted_sum_flat(
         self, local: torch.Tensor | None, coef_by_rank: list[float], numel: int, out: torch.Tensor | None = None,
-        epilogue: dict[str, Any] | None = None,
+        epilogue: dict[str, Any] | None = None, int_local: torch.Tensor | None = None,
     ) -> torch.Tensor:
         """``out = epilogue(sum_r coef[r] * flat_r)`` on every rank.  ``local`` is this rank's flat buffer (or None
-        when the rank was not sampled: it then contributes zeros)."""
+        when the rank was not sampled: it then contributes zeros).
+
+        ``int_local`` (the arena's int64 counters) rides along on the fused path: the reduced values are left in
+        ``self.last_int_reduced`` (None when the caller has to reduce them itself)."""
+        self.last_int_reduced = None
         if self.fused is not None and local is not None and self.fused.owns(local) and all(c >= 0 for c in coef_by_rank):
+            int_out = None
+            if int_local is not None and self.fused.owns(int_local):
+                int_out = torch.empty_like(int_local)  # plain local memory: peers read the inputs during the kernel
+            else:
+                int_local = None
             with tracing.phase("agg_collective"):
-                return self.fused.aggregate(local, coef_by_rank, out=out, epilogue=epilogue)
+                result = self.fused.aggregate(local, coef_by_rank, out=out, epilogue=epilogue, int_local=int_local,
+                                              int_out=int_out)
+            self.last_int_reduced = int_out
+            return result
         from fl4health_b200.ops import flat as flat_ops
 
         target = out if (out is not None and not epilogue) else torch.empty(numel, dtype=torch.float32, device=self.device)

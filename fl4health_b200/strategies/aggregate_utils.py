@@ -147,24 +147,29 @@ def _spmd_weighted_combine(
     if arena_route:
         if out_flat is None and local_flat is not None and layout is not None and ctx.fused is None:
             out_flat = _result_buffer(layout, local_flat)
-        result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.flat_numel, out=out_flat, epilogue=epilogue)
+        int_flat = getattr(layout, "int_flat", None) if layout is not None else None
+        result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.flat_numel, out=out_flat, epilogue=epilogue,
+                                            int_local=int_flat)
         if layout is None:
             raise RuntimeError("rank without a local payload cannot rebuild arena views; sample all ranks or use weight 0")
         out = layout.ndarrays(region=result_flat)
         int_idx = [i for i, key in enumerate(layout.state_keys) if key in layout.int_state]
         if int_idx:
-            int_flat = getattr(layout, "int_flat", None)
-            if int_flat is not None and int_flat.numel() == sum(out[i].numel() for i in int_idx):
-                ints = int_flat.to(torch.float64) * coef_by_rank[ctx.rank]  # one tensor for all integer buffers
+            reduced = getattr(ctx, "last_int_reduced", None)
+            if reduced is not None and reduced.numel() == sum(out[i].numel() for i in int_idx):
+                ints = reduced  # the fused aggregate kernel already reduced the counters (same launch)
             else:
-                ints = torch.cat([out[i].reshape(-1).to(torch.float64) * coef_by_rank[ctx.rank] for i in int_idx])
-            if ctx.world_size > 1:
-                import torch.distributed as dist
+                if int_flat is not None and int_flat.numel() == sum(out[i].numel() for i in int_idx):
+                    ints = int_flat.to(torch.float64) * coef_by_rank[ctx.rank]  # one tensor for all integer buffers
+                else:
+                    ints = torch.cat([out[i].reshape(-1).to(torch.float64) * coef_by_rank[ctx.rank] for i in int_idx])
+                if ctx.world_size > 1:
+                    import torch.distributed as dist
 
-                from fl4health_b200.utils import tracing
+                    from fl4health_b200.utils import tracing
 
-                with tracing.phase("agg_int_buffers"):
-                    dist.all_reduce(ints)
+                    with tracing.phase("agg_int_buffers"):
+                        dist.all_reduce(ints)
             _scatter_int_views(out, layout, ints.to(torch.int64))
         return out
     # non-arena payloads (or no agreed layout): pack the tensor entries into one temporary flat buffer, reduce, unpack

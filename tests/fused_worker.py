@@ -23,7 +23,7 @@ def main() -> None:
     assert ctx.enable_fused_collectives(), "fused collectives could not be enabled"
     fused = ctx.fused
     rank, world, dev = ctx.rank, ctx.world_size, ctx.device
-    report: dict = {"world": world, "numel": numel}
+    report: dict = {"world": world, "numel": numel, "nvls": bool(fused.has_multicast)}
 
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     local = fused.allocator(numel, torch.float32, dev)
@@ -39,7 +39,20 @@ def main() -> None:
     out = fused.aggregate(local, coefs)
     torch.cuda.synchronize()
     report["agg_max_abs_err"] = float((out - ref).abs().max().item())
-    report["agg_bit_exact"] = bool(torch.equal(out, ref))
+    report["agg_bit_exact"] = bool(torch.equal(out, ref))  # guaranteed by the fixed-order P2P kernel only
+
+    # uniform weights (NVLS: arenas reduced in place, no staging pass) + integer buffers riding along
+    uni = [1.0 / world] * world
+    ref_uni = torch.zeros_like(local)
+    F.weighted_sum(ref_uni, gathered, uni)
+    ints = fused.allocator(24, torch.int64, dev)
+    ints.copy_(torch.arange(24, device=dev) * (rank + 1) + 7)
+    int_out = torch.zeros(24, dtype=torch.int64, device=dev)
+    out_uni = fused.aggregate(local, uni, int_local=ints, int_out=int_out).clone()
+    torch.cuda.synchronize()
+    report["agg_uniform_max_abs_err"] = float((out_uni - ref_uni).abs().max().item())
+    want_int = sum((torch.arange(24, dtype=torch.float64) * (r + 1) + 7) * uni[r] for r in range(world)).to(torch.int64)
+    report["int_ok"] = bool(torch.equal(int_out.cpu(), want_int))
 
     # FedAdam epilogue: compare with the single-GPU epilogue kernel on the gathered data
     cur = torch.randn(numel, generator=torch.Generator(device=dev).manual_seed(7), device=dev)
@@ -88,13 +101,25 @@ def main() -> None:
         F.bcast_unpack(scratch, w, anchor, shadow, c_server, c_local, cv)
 
     report["ms_fused_agg"] = timed(lambda: fused.aggregate(local, coefs))
+    report["ms_fused_agg_uniform"] = timed(lambda: fused.aggregate(local, uni))
     report["ms_nccl_agg"] = timed(nccl_allreduce)
     report["ms_fused_bcast"] = timed(lambda: fused.broadcast(local, root, w=w, anchor=anchor, shadow=shadow,
                                                              c_server=c_server, c_local=c_local, cv_out=cv))
     report["ms_nccl_bcast"] = timed(nccl_bcast)
-    bytes_link = numel * 4 * (world - 1) / world
-    report["fused_agg_GBps_per_dir"] = bytes_link / report["ms_fused_agg"] / 1e6
-    report["fused_bcast_GBps_per_dir"] = bytes_link / report["ms_fused_bcast"] / 1e6
+    # roofline: NVLink 5 = 900 GB/s per direction per GPU.
+    #   aggregate: NVLS moves payload*(1 + 1/K) per direction per GPU (ld_reduce pulls every rank's slice through the
+    #   switch, multimem.st pushes 1/K out and receives the whole result); P2P moves 2*payload*(K-1)/K.
+    #   broadcast: the root emits the payload once (multicast) / (K-1)/K of it per peer pair (P2P scatter+all-gather).
+    payload = numel * 4
+    agg_bytes = payload * (1 + 1 / world) if fused.has_multicast else 2 * payload * (world - 1) / world
+    bcast_bytes = payload if fused.has_multicast else payload * (world - 1) / world
+    report["payload_MB"] = payload / 1e6
+    for key, nbytes in (("ms_fused_agg", agg_bytes), ("ms_fused_agg_uniform", agg_bytes), ("ms_fused_bcast", bcast_bytes)):
+        gbps = nbytes / report[key] / 1e6
+        report[key.replace("ms_", "") + "_GBps_per_dir"] = gbps
+        report[key.replace("ms_", "") + "_frac_of_900GBps"] = gbps / 900.0
+    report["agg_lower_bound_ms"] = agg_bytes / 900e9 * 1e3
+    report["bcast_lower_bound_ms"] = bcast_bytes / 900e9 * 1e3
     if rank == 0:
         Path(out_path).write_text(json.dumps(report, indent=1))
         print(json.dumps(report))
