@@ -93,7 +93,12 @@ class AdaptiveDriftConstraintClient(BasicClient):
         dst_arena, src_arena = arena_of(constrained), arena_of(source)
         if dst_arena is not None and src_arena is not None and dst_arena.same_layout(src_arena):
             anchor = dst_arena.companion("drift_anchor")
-            flat_ops.bcast_unpack(src_arena.flat, w=None, anchor=anchor)
+            if src_arena is dst_arena and getattr(self, "anchor_from_received_model", True):
+                dst_arena.anchor_on_pull = True  # from now on the pull kernel writes the anchor itself
+            if src_arena is dst_arena and dst_arena.anchor_fresh:
+                dst_arena.anchor_fresh = False   # this pull already produced w_t
+            else:
+                flat_ops.bcast_unpack(src_arena.flat, w=None, anchor=anchor)
             return [dst_arena.view(name, anchor) for name, _ in constrained.named_parameters()]
         return [p.detach().clone() for p in source.parameters()]
 

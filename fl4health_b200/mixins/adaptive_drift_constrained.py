@@ -82,7 +82,12 @@ class AdaptiveDriftConstrainedMixin(BaseFlexibleMixin):
         arena, src_arena = arena_of(constrained), arena_of(source)
         if arena is not None and src_arena is not None and arena.same_layout(src_arena):
             anchor = arena.companion("drift_anchor")
-            flat_ops.bcast_unpack(src_arena.flat, w=None, anchor=anchor)
+            if src_arena is arena and self.anchor_from_received_model:
+                arena.anchor_on_pull = True  # from now on the pull kernel writes the anchor itself
+            if src_arena is arena and arena.anchor_fresh:
+                arena.anchor_fresh = False   # this pull already produced w_t
+            else:
+                flat_ops.bcast_unpack(src_arena.flat, w=None, anchor=anchor)
             return [arena.view(name, anchor) for name, _ in constrained.named_parameters()]
         return [p.detach().clone() for p in source.parameters()]
 

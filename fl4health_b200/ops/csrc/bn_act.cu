@@ -161,6 +161,80 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restric
     }
 }
 
+
+// Training forward when the producing convolution already reduced the batch statistics in its epilogue
+// (conv_tc.cu): `sums` = [sum | sum of squares] over all M pixels, per channel.  One streaming pass, no grid barrier:
+// every thread derives the scale/shift of its 8 channels once (the grid stride is a multiple of C/8, so a thread keeps
+// its channel group), CTA 0 does the bookkeeping (saved mean / invstd for the backward, running statistics, counter),
+// and the last CTA to finish re-zeroes `sums` for the next step (election through `done`), which keeps the buffer
+// self-resetting under CUDA-graph replay.
+template <typename T, bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_presum_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t nvec, int C, int64_t M,
+                       float* sums, const float* __restrict__ gamma, const float* __restrict__ beta, float* rmean,
+                       float* rvar, long long* nbt, float momentum, float eps, float* __restrict__ mean_out,
+                       float* __restrict__ invstd_out, unsigned* done) {
+    const int LP = C >> 3;
+    const float inv_m = 1.f / (float)M;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = (int)(first % LP) * 8;
+    float sc[8], sh[8];
+    {
+        float s[8], q[8], g[8], b[8];
+        load8f(sums + c0, s);
+        load8f(sums + C + c0, q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { g[k] = 1.f; b[k] = 0.f; }
+        if (gamma != nullptr) load8f(gamma + c0, g);
+        if (beta != nullptr) load8f(beta + c0, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float mean = s[k] * inv_m;
+            const float var = fmaxf(fmaf(-mean, mean, q[k] * inv_m), 0.f);
+            sc[k] = g[k] * rsqrtf(var + eps);
+            sh[k] = fmaf(-mean, sc[k], b[k]);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float mean = sums[c] * inv_m;
+            const float var = fmaxf(fmaf(-mean, mean, sums[C + c] * inv_m), 0.f);
+            mean_out[c] = mean;
+            invstd_out[c] = rsqrtf(var + eps);
+            if (rmean != nullptr) {
+                const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+                rmean[c] = fmaf(momentum, mean - rmean[c], rmean[c]);
+                rvar[c] = fmaf(momentum, unbiased - rvar[c], rvar[c]);
+            }
+        }
+        if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+    }
+    for (int64_t i = first; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8], r[8];
+        Vec8<T>::load(x + i * 8, v);
+        if (kRes) Vec8<T>::load(res + i * 8, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float o = fmaf(v[k], sc[k], sh[k]);
+            if (kRes) o += r[k];
+            if (kRelu) o = o > 0.f ? o : 0.f;
+            v[k] = o;
+        }
+        Vec8<T>::store(y + i * 8, v);
+    }
+    __shared__ bool is_last;
+    __syncthreads();                                       // every thread of this CTA has consumed `sums`
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(done, 1u);
+        is_last = prev == gridDim.x - 1;
+        if (is_last) *done = 0;
+    }
+    __syncthreads();
+    if (is_last)
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = 0.f;
+}
+
 template <typename T, bool kRelu>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, int64_t M, int C,
@@ -659,6 +733,24 @@ int fl4h_bn_fwd_train(const void* x, const void* res, void* y, int64_t M, int C,
         FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_FWD);
     }
 #undef LAUNCH_FWD
+    return (int)cudaGetLastError();
+}
+
+// Training forward from convolution-epilogue statistics (see bn_apply_presum_kernel).  `done` is a zero-initialised
+// election counter owned by the caller (one per `sums` buffer).
+int fl4h_bn_fwd_train_presum(const void* x, const void* res, void* y, int64_t M, int C, float* sums, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,
+                             float eps, float* mean_out, float* invstd_out, unsigned* done, int is_bf16, int relu,
+                             cudaStream_t stream) {
+    const int64_t nvec = M * C / 8;
+    const bool has_res = res != nullptr;
+    if ((C & 7) != 0 || kThreads % (C >> 3) != 0) return (int)cudaErrorInvalidValue;
+#define LAUNCH_PRESUM(T, R, S)                                                                                         \
+    bn_apply_presum_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)x, (const T*)res, (T*)y, nvec, C, \
+        M, sums, gamma, beta, running_mean, running_var, nbt, momentum, eps, mean_out, invstd_out, done)
+    if (is_bf16) FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, LAUNCH_PRESUM);
+    else FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_PRESUM);
+#undef LAUNCH_PRESUM
     return (int)cudaGetLastError();
 }
 

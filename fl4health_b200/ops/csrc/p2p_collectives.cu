@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cg = cooperative_groups;
@@ -85,6 +86,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// Phase timeline of CTA 0 of the most recent collective kernel (global timer, ns): read back with
+// fl4h_coll_debug_read.  [0] entry [1] staging pass done [2] peers arrived [3] grid released [4] main loop done
+// [5] stores fenced + grid joined [6] peers finished [7] unpack done
+__device__ unsigned long long g_coll_stamp[8];
+__device__ __forceinline__ void coll_stamp(int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_coll_stamp[slot] = t;
+    }
 }
 
 // NVLS: in-switch reduction / replication on a multicast address (sm_90+; SASS: MULTIMEM / RED..MULTIMEM forms)
@@ -310,12 +323,14 @@ bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restri
 //            -> multimem.st(mc_result + e)                                       (lands in every rank's result)
 //   barrier 1
 // ---------------------------------------------------------------------------------------------------------------
+template <int kUnroll>
 __global__ void __launch_bounds__(kThreads, 1)
 agg_nvls_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__ m, float* __restrict__ v,
                 EpiArgs ea, int64_t numel, int64_t slice, uint32_t epoch, float uniform_coef) {
     cg::grid_group grid = cg::this_grid();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    coll_stamp(0);
     if (t.stage != nullptr) {
         const float c = t.coef[t.rank];
         const float4* src = reinterpret_cast<const float4*>(t.contrib[t.rank]);
@@ -329,15 +344,18 @@ agg_nvls_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__
         __threadfence_system();
         grid.sync();
     }
+    coll_stamp(1);
     peer_barrier(t, 0, epoch);
+    coll_stamp(2);
     grid.sync();
+    coll_stamp(3);
     reduce_int_buffers(t);
 
     const int64_t begin = (int64_t)t.rank * slice;
     int64_t end = begin + slice;
     if (end > numel) end = numel;
     const int64_t n4 = (end > begin) ? ((end - begin) >> 2) : 0;
-    constexpr int kUnroll = 4;  // 148 CTAs x 512 thr x 4 x 16 B = 4.8 MB in flight >= NVLink bandwidth-delay product
+    // kUnroll x 16 B per thread in flight: 148 CTAs x 512 thr x 4 x 16 B = 4.8 MB >= NVLink bandwidth-delay product
     for (int64_t base = tid; base < n4; base += stride * kUnroll) {
         float4 acc[kUnroll];
 #pragma unroll
@@ -366,13 +384,17 @@ agg_nvls_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__
             mm_st4(t.mc_result + e, a);
         }
     }
+    coll_stamp(4);
     __threadfence_system();
     grid.sync();
+    coll_stamp(5);
     peer_barrier(t, 1, epoch);
+    coll_stamp(6);
 }
 
 // bcast_nvls: the root streams its buffer through ONE multimem.st per 16 bytes (the switch replicates it into every
 // rank's result buffer: root egress = payload, no per-peer stores), barrier, then every rank unpacks locally.
+template <int kUnroll>
 __global__ void __launch_bounds__(kThreads, 1)
 bcast_nvls_kernel(PeerTable t, int root, float* __restrict__ w, float* __restrict__ anchor,
                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ c_server,
@@ -384,7 +406,6 @@ bcast_nvls_kernel(PeerTable t, int root, float* __restrict__ w, float* __restric
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
         const int64_t total4 = numel >> 2;
         const float4* src = reinterpret_cast<const float4*>(t.contrib[root]);
-        constexpr int kUnroll = 4;
         for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total4; base += stride * kUnroll) {
             float4 vals[kUnroll];
 #pragma unroll
@@ -406,8 +427,16 @@ bcast_nvls_kernel(PeerTable t, int root, float* __restrict__ w, float* __restric
     unpack_landed(t.result[t.rank], w, anchor, shadow, c_server, c_local, cv_out, numel);
 }
 
+// Tuning knobs (read once): FL4H_NVLS_UNROLL in {2,4,8} (default 4), FL4H_COLL_GRID = CTAs (default: one per SM).
+int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v != 0) ? atoi(v) : fallback;
+}
+
 template <typename Kernel>
 int coop_grid(Kernel kernel) {
+    static int forced = env_int("FL4H_COLL_GRID", 0);
+    if (forced > 0) return forced;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -420,6 +449,10 @@ int coop_grid(Kernel kernel) {
 }  // namespace
 
 extern "C" {
+
+int fl4h_coll_debug_read(unsigned long long* out8) {
+    return (int)cudaMemcpyFromSymbol(out8, g_coll_stamp, sizeof(unsigned long long) * 8);
+}
 
 // ---- symmetric memory plumbing (CUDA IPC) -----------------------------------------------------------------------
 int fl4h_ipc_alloc(size_t bytes, void** ptr) {
@@ -508,11 +541,12 @@ int fl4h_agg_fused(const Fl4hPeerArgs* args, const float* wcur, float* m, float*
     cudaError_t err = cudaSuccess;
     if (args->use_nvls) {
         if (t.mc_contrib == nullptr || t.mc_result == nullptr) return (int)cudaErrorInvalidValue;
-        auto kernel = agg_nvls_kernel;
-        const int grid = coop_grid(kernel);
+        static int unroll = env_int("FL4H_NVLS_UNROLL", 4);
         float uniform_coef = args->uniform_coef;
         void* kargs[] = {&t, &wcur, &m, &v, &ea, &numel, &slice, &epoch, &uniform_coef};
-        return (int)cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+        void* kernel = unroll == 8 ? (void*)agg_nvls_kernel<8> : (unroll == 2 ? (void*)agg_nvls_kernel<2> : (void*)agg_nvls_kernel<4>);
+        const int grid = coop_grid(agg_nvls_kernel<4>);
+        return (int)cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
     }
     DISPATCH_WORLD(t.world, {
         auto kernel = agg_fused_kernel<KW>;
@@ -534,10 +568,11 @@ int fl4h_bcast_fused(const Fl4hPeerArgs* args, int root, float* w, float* anchor
     cudaError_t err = cudaSuccess;
     if (args->use_nvls) {
         if (t.mc_result == nullptr) return (int)cudaErrorInvalidValue;
-        auto kernel = bcast_nvls_kernel;
-        const int grid = coop_grid(kernel);
+        static int unroll = env_int("FL4H_NVLS_UNROLL", 4);
         void* kargs[] = {&t, &root, &w, &anchor, &sh, &c_server, &c_local, &cv_out, &numel, &epoch};
-        return (int)cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
+        void* kernel = unroll == 8 ? (void*)bcast_nvls_kernel<8> : (unroll == 2 ? (void*)bcast_nvls_kernel<2> : (void*)bcast_nvls_kernel<4>);
+        const int grid = coop_grid(bcast_nvls_kernel<4>);
+        return (int)cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), kargs, 0, stream);
     }
     DISPATCH_WORLD(t.world, {
         auto kernel = bcast_fused_kernel<KW>;

@@ -86,6 +86,8 @@ class ParameterArena:
         self._build_layout()
         self.flat = self._alloc(self.total, torch.float32, self.device)
         self.int_flat: torch.Tensor | None = None
+        self.anchor_on_pull = False  # drift-constrained clients: every full pull also writes regions["drift_anchor"]
+        self.anchor_fresh = False    # set by the fused pull, consumed by snapshot_drift_anchor
         self._views_cache: dict[tuple[int, int], NDArrays] = {}
         self._rehome()
         self.grad: torch.Tensor | None = None
@@ -295,9 +297,11 @@ class ParameterArena:
         keys = list(names) if names is not None else self.state_keys
         src_flat = getattr(arrays, "flat", None)
         src_layout = getattr(arrays, "layout", None)
+        self.anchor_fresh = False  # only a fused full pull (below) may vouch for the anchor region
         with torch.no_grad():
             if names is None and src_flat is not None and isinstance(src_layout, ParameterArena) and src_layout.same_layout(self):
-                if src_flat.data_ptr() != self.flat.data_ptr():
+                fused_pull = self._fused_pull(src_flat)
+                if not fused_pull and src_flat.data_ptr() != self.flat.data_ptr():
                     self.flat.copy_(src_flat, non_blocking=True)
                 src_int = getattr(arrays, "int_flat", None)
                 all_flat = self.int_flat is not None and all(t.dtype == torch.int64 for t in self.int_state.values())
@@ -308,7 +312,8 @@ class ParameterArena:
                     for idx in self._int_positions():
                         dst_int = self.int_state[self.aliases.get(keys[idx], keys[idx])]
                         dst_int.copy_(_as_tensor(arrays[idx], self.device).to(dst_int.dtype).reshape(dst_int.shape))
-                self.refresh_shadow()
+                if not fused_pull:
+                    self.refresh_shadow()
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
             for key, arr in zip(keys, arrays):
@@ -322,6 +327,30 @@ class ParameterArena:
                     dst_int = self.int_state[key]
                     dst_int.copy_(t.to(dst_int.dtype).reshape(dst_int.shape))
             self.refresh_shadow()
+
+    def _fused_pull(self, src_flat: torch.Tensor) -> bool:
+        """The server->client pull as ONE kernel (SURVEY C1 receiver side): a single read of the landed global buffer
+        writes the fp32 masters, the bf16 compute shadow and — when a drift-constrained client registered
+        ``anchor_on_pull`` — the FedProx anchor ``w_t`` (replaces copy + cast + anchor-snapshot launches; reference:
+        fl4health/parameter_exchange/full_exchanger.py:45-47 + fl4health/clients/fed_prox_client.py:18-20)."""
+        if not self.flat.is_cuda or src_flat.dtype != torch.float32 or src_flat.numel() != self.flat.numel():
+            return False
+        if src_flat.data_ptr() == self.flat.data_ptr() or self.flat.numel() % 4:
+            return False
+        shadow = self.shadow if (self.shadow is not None and self.shadow.dtype == torch.bfloat16
+                                 and self.shadow.numel() >= self.flat.numel()) else None
+        anchor = self.regions.get("drift_anchor") if self.anchor_on_pull else None
+        if anchor is not None and anchor.numel() < self.flat.numel():
+            anchor = None
+        if shadow is None and anchor is None:
+            return False  # a plain copy is already one launch
+        from fl4health_b200.ops import flat as flat_ops
+
+        flat_ops.bcast_unpack(src_flat, w=self.flat, anchor=anchor, shadow=shadow)
+        self.anchor_fresh = anchor is not None
+        if self.shadow is not None and shadow is None:
+            self.refresh_shadow()
+        return True
 
     def _int_positions(self) -> list[int]:
         cached = getattr(self, "_int_pos_cache", None)

@@ -1,0 +1,95 @@
+"""tcgen05 implicit-GEMM convolution (``ops/conv.py`` / ``csrc/conv_tc.cu``) against a plain PyTorch fp32 reference."""
+
+from __future__ import annotations
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (name, N, Cin, Cout, H, R, stride) — the ResNet-18 / CIFAR layer shapes + a non-multiple batch
+SHAPES = [
+    ("l1_3x3", 32, 64, 64, 32, 3, 1),
+    ("l2_3x3_s2", 32, 64, 128, 32, 3, 2),
+    ("l2_1x1_s2", 32, 64, 128, 32, 1, 2),
+    ("l2_3x3", 32, 128, 128, 16, 3, 1),
+    ("l3_3x3_s2", 32, 128, 256, 16, 3, 2),
+    ("l3_3x3", 32, 256, 256, 8, 3, 1),
+    ("l4_3x3_s2", 32, 256, 512, 8, 3, 2),
+    ("l4_3x3", 32, 512, 512, 4, 3, 1),
+    ("l4_1x1_s2", 32, 256, 512, 8, 1, 2),
+    ("ragged_batch", 5, 64, 64, 8, 3, 1),
+]
+
+
+def _rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    return float((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6))
+
+
+def _make(n, cin, cout, h, r, dtype):  # noqa: ANN001, ANN202
+    g = torch.Generator(device="cuda").manual_seed(n * 7 + cin + cout + h + r)
+    x = torch.randn(n, cin, h, h, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, r, r, device="cuda", generator=g) / (cin * r * r) ** 0.5).to(dtype)
+    w = w.contiguous(memory_format=torch.channels_last)
+    return x, w
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():  # noqa: ANN202
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+def test_conv_forward_and_statistics(shape, dtype) -> None:  # noqa: ANN001
+    from fl4health_b200.ops import conv
+
+    _, n, cin, cout, h, r, stride = shape
+    x, w = _make(n, cin, cout, h, r, dtype)
+    assert conv.supported(x, w, stride, (r - 1) // 2)
+    stats = torch.zeros(2, cout, device="cuda")
+    y = conv.conv2d_forward(x, w, stride, (r - 1) // 2, stats)
+    ref = F.conv2d(x.float(), w.float(), None, stride, (r - 1) // 2)
+    tol = 4e-3 if dtype == torch.float32 else 2e-2
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel_err(y, ref) < tol
+    # the epilogue statistics are those of the STORED tensor
+    yf = y.float()
+    assert torch.allclose(stats[0], yf.sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2 * yf.abs().max().item())
+    assert torch.allclose(stats[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+def test_conv_backward(shape, dtype) -> None:  # noqa: ANN001
+    from fl4health_b200.ops import conv
+
+    _, n, cin, cout, h, r, stride = shape
+    pad = (r - 1) // 2
+    x, w = _make(n, cin, cout, h, r, dtype)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, stride, pad)
+    dy = torch.randn_like(ref).to(dtype).contiguous(memory_format=torch.channels_last)
+    ref.backward(dy.float())
+    dx = conv.conv2d_dgrad(dy, conv.permute_filter_for_dgrad(w), (h, h), stride, pad)
+    dw = conv.conv2d_wgrad(x, dy, r, stride, pad)
+    tol = 4e-3 if dtype == torch.float32 else 2e-2
+    assert _rel_err(dx, xr.grad) < tol
+    assert _rel_err(dw, wr.grad) < tol
+
+
+def test_conv_autograd_matches_reference_end_to_end() -> None:
+    from fl4health_b200.ops import conv
+
+    x, w = _make(32, 64, 64, 16, 3, torch.float32)
+    x1, w1 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    x2, w2 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y1 = conv.conv2d(x1, w1, 1, 1)
+    y2 = F.conv2d(x2, w2, None, 1, 1)
+    (y1 * y1).sum().backward()
+    (y2 * y2).sum().backward()
+    assert _rel_err(y1, y2) < 4e-3 and _rel_err(x1.grad, x2.grad) < 8e-3 and _rel_err(w1.grad, w2.grad) < 8e-3

@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+# Each group in its own process under its own timeout: a hung kernel cannot take the whole box budget with it.
+mkdir -p gpurun_out/conv
+for sel in "forward and tf32" "forward and bf16" "backward and tf32" "backward and bf16" "autograd"; do
+  name=$(echo "$sel" | tr ' ' '_')
+  timeout 240 python -m pytest tests/test_gpu_conv.py -q --tb=line -k "$sel" > gpurun_out/conv/$name.log 2>&1
+  echo "== $sel rc=$?"; tail -25 gpurun_out/conv/$name.log | cut -c1-220
+done
