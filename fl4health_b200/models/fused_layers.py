@@ -9,7 +9,8 @@ import torch
 from torch import nn
 
 from fl4health_b200.engine import streams
-from fl4health_b200.ops.bn_act import batch_norm_act
+from fl4health_b200.ops import conv as tc_conv
+from fl4health_b200.ops.bn_act import batch_norm_act, presums_eligible
 from fl4health_b200.ops.tc_gemm import linear_bias_act
 
 
@@ -22,14 +23,32 @@ class BatchNormAct2d(nn.BatchNorm2d):
         super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype)
         self.relu = relu
 
-    def forward(self, x: torch.Tensor, residual: torch.Tensor | None = None) -> torch.Tensor:  # type: ignore[override]
+    def forward(self, x: torch.Tensor, residual: torch.Tensor | None = None,  # type: ignore[override]
+                presums: torch.Tensor | None = None) -> torch.Tensor:
         self._check_input_dim(x)
         return batch_norm_act(
             x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
             self.running_var if self.track_running_stats else None,
             self.num_batches_tracked if self.track_running_stats else None, self.training, self.momentum, self.eps,
-            residual=residual, relu=self.relu,
+            residual=residual, relu=self.relu, presums=presums, done=self._presum_done if presums is not None else None,
         )
+
+    # statistics produced by the preceding convolution's epilogue (ops/conv.py): a self-resetting [2, C] accumulator
+    # and the election counter of the apply kernel; plain attributes, deliberately NOT buffers (not model state)
+    _presum_buf: torch.Tensor | None = None
+    _presum_done: torch.Tensor | None = None
+
+    def presum_buffer(self, like: torch.Tensor, residual: torch.Tensor | None) -> torch.Tensor | None:
+        """The accumulator the producing convolution should reduce into, or None when this layer will not take the
+        statistics-free kernel path for this input (eval mode, unsupported dtype, deterministic mode ...)."""
+        use_batch_stats = self.training or not self.track_running_stats
+        if not presums_eligible(like, self.num_features, residual, self.momentum, use_batch_stats,
+                                self.running_mean if self.track_running_stats else None):
+            return None
+        if self._presum_buf is None or self._presum_buf.device != like.device:
+            self._presum_buf = torch.zeros(2, self.num_features, dtype=torch.float32, device=like.device)
+            self._presum_done = torch.zeros(1, dtype=torch.int32, device=like.device)
+        return self._presum_buf
 
     def extra_repr(self) -> str:
         return super().extra_repr() + f", relu={self.relu}"
@@ -45,6 +64,51 @@ def bn_act(bn: nn.Module, x: torch.Tensor, residual: torch.Tensor | None = None,
     if residual is not None:
         out = out + residual
     return torch.relu(out) if relu else out
+
+
+def conv_bn_act(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: torch.Tensor | None = None,
+                relu: bool = True) -> torch.Tensor:
+    """``relu(bn(conv(x)) + residual)``.  When ``conv`` runs on the tcgen05 kernel and ``bn`` is a ``BatchNormAct2d`` in
+    training mode, the convolution epilogue reduces the batch statistics and BatchNorm becomes a single apply pass."""
+    if isinstance(conv, TcConv2d) and isinstance(bn, BatchNormAct2d) and conv.kernel_applies(x):
+        sums = bn.presum_buffer(x, residual)
+        if sums is not None:
+            assert bn.relu == relu
+            return bn(conv(x, stats=sums), residual, presums=sums)
+    return bn_act(bn, conv(x), residual, relu)
+
+
+class _TcConvFn(torch.autograd.Function):
+    """tcgen05 implicit-GEMM convolution (``ops/conv.py``); the weight gradient runs on a side stream like the stock
+    path's (only the optimizer needs it), the data gradient stays on the critical path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding, stats):  # noqa: ANN001, ANN205
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (stride, padding)
+        return tc_conv.conv2d_forward(x, weight, stride, padding, stats)
+
+    @staticmethod
+    def backward(ctx, grad_out):  # noqa: ANN001, ANN205
+        x, weight = ctx.saved_tensors
+        stride, padding = ctx.conf
+        if grad_out.dtype != x.dtype or not grad_out.is_contiguous(memory_format=torch.channels_last):
+            grad_out = grad_out.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        grad_x = grad_w = None
+        if ctx.needs_input_grad[1]:
+            if streams.overlap_enabled():
+                main = torch.cuda.current_stream(x.device)
+                side = streams.fork(x.device)
+                with torch.cuda.stream(side):
+                    grad_w = tc_conv.conv2d_wgrad(x, grad_out, weight.shape[2], stride, padding)
+                grad_w.record_stream(main)
+                streams.defer_join(x.device, grad_out, x, weight)
+            else:
+                grad_w = tc_conv.conv2d_wgrad(x, grad_out, weight.shape[2], stride, padding)
+        if ctx.needs_input_grad[0]:
+            grad_x = tc_conv.conv2d_dgrad(grad_out, tc_conv.permute_filter_for_dgrad(weight), (x.shape[2], x.shape[3]),
+                                          stride, padding)
+        return grad_x, grad_w, None, None, None
 
 
 class _ConvOverlappedWgrad(torch.autograd.Function):
@@ -91,6 +155,28 @@ class Conv2dOverlapWgrad(nn.Conv2d):
             and (self.weight.requires_grad or input.requires_grad)
         ):
             return _ConvOverlappedWgrad.apply(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return super().forward(input)
+
+
+class TcConv2d(Conv2dOverlapWgrad):
+    """``nn.Conv2d`` (same parameters / state-dict) whose forward, data gradient and weight gradient are the hand-written
+    tcgen05 implicit-GEMM kernels (``ops/csrc/conv_tc.cu``) for the shapes they cover — bias-free square 1x1 / 3x3 filters,
+    stride 1 / 2, channels_last fp32 (TF32 math) or bf16 — and ``Conv2dOverlapWgrad`` (cuDNN) for everything else.
+    ``FL4H_TC_CONV=0`` forces the library path (A/B runs)."""
+
+    def kernel_applies(self, x: torch.Tensor) -> bool:
+        if os.environ.get("FL4H_TC_CONV", "1") == "0" or self.bias is not None or self.padding_mode != "zeros":
+            return False
+        if isinstance(self.padding, str) or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
+            return False
+        if x.dtype != self.weight.dtype:
+            return False
+        return tc_conv.supported(x, self.weight, self.stride[0], self.padding[0], self.groups, self.dilation[0])
+
+    def forward(self, input: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:  # noqa: A002
+        if self.kernel_applies(input):
+            return _TcConvFn.apply(input, self.weight, self.stride[0], self.padding[0], stats)
+        assert stats is None, "epilogue statistics requested for a shape the tcgen05 kernel does not cover"
         return super().forward(input)
 
 

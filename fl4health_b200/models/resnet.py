@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from fl4health_b200.engine import streams
-from fl4health_b200.models.fused_layers import BatchNormAct2d, Conv2dOverlapWgrad, bn_act
+from fl4health_b200.models.fused_layers import BatchNormAct2d, Conv2dOverlapWgrad, TcConv2d, bn_act, conv_bn_act
 
 
 class BasicBlock(nn.Module):
@@ -20,20 +20,21 @@ class BasicBlock(nn.Module):
 
     def __init__(self, in_planes: int, planes: int, stride: int = 1) -> None:
         super().__init__()
-        self.conv1 = Conv2dOverlapWgrad(in_planes, planes, 3, stride=stride, padding=1, bias=False)
+        # tcgen05 implicit-GEMM convolutions whose epilogue reduces the BatchNorm statistics (ops/csrc/conv_tc.cu)
+        self.conv1 = TcConv2d(in_planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn1 = BatchNormAct2d(planes, relu=True)  # bn + relu fused
-        self.conv2 = Conv2dOverlapWgrad(planes, planes, 3, stride=1, padding=1, bias=False)
+        self.conv2 = TcConv2d(planes, planes, 3, stride=1, padding=1, bias=False)
         self.bn2 = BatchNormAct2d(planes, relu=True)  # bn + residual add + relu fused
         self.downsample: nn.Module | None = None
         if stride != 1 or in_planes != planes:
             self.downsample = nn.Sequential(
-                Conv2dOverlapWgrad(in_planes, planes, 1, stride=stride, bias=False), BatchNormAct2d(planes, relu=False)
+                TcConv2d(in_planes, planes, 1, stride=stride, bias=False), BatchNormAct2d(planes, relu=False)
             )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.downsample is None:
-            out = bn_act(self.bn1, self.conv1(x))
-            return bn_act(self.bn2, self.conv2(out), residual=x)
+            out = conv_bn_act(self.conv1, self.bn1, x)
+            return conv_bn_act(self.conv2, self.bn2, out, residual=x)
         if x.is_cuda and streams.overlap_enabled():
             # the projection shortcut is independent of conv1/bn1/conv2: run it on a side stream (its backward follows it
             # there), joining right before the residual add; both branches are small enough to share the 148 SMs
@@ -41,15 +42,15 @@ class BasicBlock(nn.Module):
             side = streams.branch_stream(x.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                identity = self.downsample(x)
+                identity = conv_bn_act(self.downsample[0], self.downsample[1], x, relu=False)
             x.record_stream(side)
-            out = self.conv2(bn_act(self.bn1, self.conv1(x)))
+            out = conv_bn_act(self.conv1, self.bn1, x)
             main.wait_stream(side)
             identity.record_stream(main)
-            return bn_act(self.bn2, out, residual=identity)
-        identity = self.downsample(x)
-        out = bn_act(self.bn1, self.conv1(x))
-        return bn_act(self.bn2, self.conv2(out), residual=identity)
+            return conv_bn_act(self.conv2, self.bn2, out, residual=identity)
+        identity = conv_bn_act(self.downsample[0], self.downsample[1], x, relu=False)
+        out = conv_bn_act(self.conv1, self.bn1, x)
+        return conv_bn_act(self.conv2, self.bn2, out, residual=identity)
 
 
 class ResNet18(nn.Module):

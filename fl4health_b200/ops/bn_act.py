@@ -91,6 +91,21 @@ def kernel_eligible(x: torch.Tensor, residual: torch.Tensor | None, momentum: fl
     return True
 
 
+def presums_eligible(x_like: torch.Tensor, channels: int, residual: torch.Tensor | None, momentum: float | None,
+                     training: bool, running_mean: torch.Tensor | None) -> bool:
+    """True when ``batch_norm_act(..., presums=...)`` will take the kernel path for a tensor shaped like ``x_like``
+    with ``channels`` channels (decided BEFORE the convolution runs, so its epilogue knows whether to reduce)."""
+    if not training or not x_like.is_cuda or _lib.load() is None or x_like.dtype not in (torch.bfloat16, torch.float32):
+        return False
+    if channels % 8 != 0 or channels // 8 > 256 or 256 % (channels // 8) != 0:
+        return False
+    if residual is not None and (residual.dtype != x_like.dtype or not _is_channels_last_dense(residual)):
+        return False
+    if running_mean is not None and (momentum is None or running_mean.dtype != torch.float32):
+        return False
+    return os.environ.get("FL4H_DETERMINISTIC", "0") != "1"
+
+
 def batch_norm_act_reference(
     x: torch.Tensor, weight: torch.Tensor | None, bias: torch.Tensor | None, running_mean: torch.Tensor | None,
     running_var: torch.Tensor | None, training: bool, momentum: float, eps: float,
@@ -104,13 +119,30 @@ def batch_norm_act_reference(
 
 class _BatchNormAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu):  # noqa: ANN001, ANN205
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu,  # noqa: ANN001, ANN205
+                presums=None, done=None):
         lib = _lib.load(True)
         n, c, h, w = x.shape
         m = n * h * w
         y = torch.empty_like(x)  # preserves channels-last strides
         stream = _lib.stream_ptr(x.device)
         is_bf16 = 1 if x.dtype == torch.bfloat16 else 0
+        if training and presums is not None:
+            # the producing convolution's epilogue already reduced sum / sum-of-squares (ops/conv.py): one streaming
+            # apply pass, no statistics pass, no grid barrier; the kernel re-zeroes `presums` when it is done
+            stats = torch.empty(4, c, dtype=torch.float32, device=x.device)
+            err = lib.fl4h_bn_fwd_train_presum(
+                _lib.ptr(x), _lib.ptr(residual), _lib.ptr(y), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(presums),
+                _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(nbt),
+                ctypes.c_float(momentum if momentum is not None else 0.0), ctypes.c_float(eps), _lib.ptr(stats[0]),
+                _lib.ptr(stats[1]), _lib.ptr(done), ctypes.c_int(is_bf16), ctypes.c_int(1 if relu else 0), stream,
+            )
+            _lib.check(err, "fl4h_bn_fwd_train_presum")
+            _lib.count_launches(1)
+            ctx.save_for_backward(x, y, weight, stats)
+            ctx.relu, ctx.has_res, ctx.has_bias = relu, residual is not None, bias is not None
+            ctx.training = True
+            return y
         use_cluster = training and lib.fl4h_bn_cluster_supported(ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int64(_cluster_bytes()),
                                                                  ctypes.c_int(x.element_size())) == 1 and _CLUSTER["size"] > 0
         if use_cluster:
@@ -165,7 +197,7 @@ class _BatchNormAct(torch.autograd.Function):
             xhat = (x.float() - running_mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
             dweight = (g.float() * xhat).sum(dim=(0, 2, 3)) if weight is not None else None
             dbias = g.float().sum(dim=(0, 2, 3)) if ctx.has_bias else None
-            return dx, (g if ctx.has_res else None), dweight, dbias, None, None, None, None, None, None, None
+            return dx, (g if ctx.has_res else None), dweight, dbias, None, None, None, None, None, None, None, None, None
         x, y, weight, stats = ctx.saved_tensors
         lib = _lib.load(True)
         n, c, h, w = x.shape
@@ -184,7 +216,7 @@ class _BatchNormAct(torch.autograd.Function):
                 _lib.stream_ptr(x.device)))
             if done:
                 _lib.count_launches(1)
-                return dx, dres, (grads[0] if weight is not None else None), (grads[1] if ctx.has_bias else None), None, None, None, None, None, None, None
+                return dx, dres, (grads[0] if weight is not None else None), (grads[1] if ctx.has_bias else None), None, None, None, None, None, None, None, None, None
         coef = torch.empty(3, c, dtype=torch.float32, device=x.device)
         acc, counter = _workspace(x.device, c)
         err = lib.fl4h_bn_bwd(
@@ -197,22 +229,28 @@ class _BatchNormAct(torch.autograd.Function):
         _lib.count_launches(1 if _allow_fused() else 2)
         dweight = grads[0] if weight is not None else None
         dbias = grads[1] if ctx.has_bias else None
-        return dx, dres, dweight, dbias, None, None, None, None, None, None, None
+        return dx, dres, dweight, dbias, None, None, None, None, None, None, None, None, None
 
 
 def batch_norm_act(
     x: torch.Tensor, weight: torch.Tensor | None, bias: torch.Tensor | None, running_mean: torch.Tensor | None,
     running_var: torch.Tensor | None, num_batches_tracked: torch.Tensor | None, training: bool, momentum: float | None,
     eps: float, residual: torch.Tensor | None = None, relu: bool = True,
+    presums: torch.Tensor | None = None, done: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """``relu(batch_norm(x) + residual)`` with BatchNorm2d semantics (running stats and the batch counter are updated
-    in training mode)."""
+    in training mode).  ``presums`` ([2, C] fp32: per-channel sum / sum of squares of ``x``, e.g. from the convolution
+    epilogue) + ``done`` (int32 election counter) skip the statistics pass; only valid when ``presums_eligible``."""
     use_batch_stats = training or running_mean is None
     if kernel_eligible(x, residual, momentum, use_batch_stats, running_mean):
         if weight is not None and weight.dtype != torch.float32:
             weight, bias = weight.float(), (bias.float() if bias is not None else None)
+        if not use_batch_stats:
+            presums = done = None
         return _BatchNormAct.apply(x, residual, weight, bias, running_mean, running_var,
-                                   num_batches_tracked if use_batch_stats else None, use_batch_stats, momentum, eps, relu)
+                                   num_batches_tracked if use_batch_stats else None, use_batch_stats, momentum, eps, relu,
+                                   presums, done)
+    assert presums is None, "presums were produced but the BatchNorm kernel is not eligible: check presums_eligible first"
     if training and num_batches_tracked is not None:
         num_batches_tracked.add_(1)
     exp_factor = momentum

@@ -93,13 +93,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // MN-major: each 128-B row runs along M/N for ONE k; 8 consecutive k rows form an atom (1024 B); the next 128-B chunk
 //           along M/N sits LBO bytes away, the next group of 8 k rows SBO bytes away (canonical layout
 //           ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), cute/atom/mma_traits_sm100.hpp).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// 32-bit MN-major operands (TF32 weight gradient) need the 32-byte-atom flavour: layout = 1 (SWIZZLE_128B_BASE32B,
+//           Swizzle<2,5,2>: 32-byte chunks XOR (row & 3)), atoms of 4 k rows (512 B), filled by TMA with
+//           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  (With the plain 128B layout the tf32 MN-major MMA returned zeros.)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
     uint64_t desc = 0;
     desc |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     desc |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     desc |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     desc |= static_cast<uint64_t>(1) << 46;
-    desc |= static_cast<uint64_t>(2) << 61;
+    desc |= static_cast<uint64_t>(layout) << 61;
     return desc;
 }
 
@@ -536,8 +539,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const TapTable taps, c
 #pragma unroll
                 for (int k = 0; k < WG_KP / kRowsPerMma; ++k) {
                     const uint32_t off = k * kRowsPerMma * kRowBytes;
-                    umma<kTf32>(tmem_base, make_desc(a_addr + off, Plan::a_box, 1024), make_desc(b_addr + off, Plan::a_box, 1024), idesc,
-                                (i > 0 || k > 0) ? 1u : 0u);
+                    constexpr uint32_t layout = kTf32 ? 1u : 2u, sbo = kTf32 ? 512u : 1024u;
+                    umma<kTf32>(tmem_base, make_desc(a_addr + off, Plan::a_box, sbo, layout),
+                                make_desc(b_addr + off, Plan::a_box, sbo, layout), idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(empty_bar + stage);
             }
@@ -648,7 +652,7 @@ EncodeTiledFn encode_fn() {
 
 // 4-D map over an NHWC tensor (or a strided sub-lattice of it): dims (C, W, H, N) in elements, strides in elements.
 CUresult nhwc_map(CUtensorMap* map, const void* base, int esize, int C, int W, int H, int N, int64_t sw, int64_t sh, int64_t sn,
-                  int box_c, int bw, int bh, int bn) {
+                  int box_c, int bw, int bh, int bn, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn encode = encode_fn();
     if (encode == nullptr) return CUDA_ERROR_NOT_SUPPORTED;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -656,7 +660,7 @@ CUresult nhwc_map(CUtensorMap* map, const void* base, int esize, int C, int W, i
     cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return encode(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
@@ -829,14 +833,17 @@ int fl4h_conv_wgrad(const void* x, const void* dy, void* dw, int dtype, int N, i
     g.ntaps = ntaps;
     WgradMaps maps;
     memset(&maps, 0, sizeof(maps));
+    // MN-major operands: 16-bit types use the plain 128B swizzle, 32-bit types the 32-byte-atom variant (see make_desc)
+    const CUtensorMapSwizzle op_swizzle = dtype == 0 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     for (int i = 0; i < n_maps; ++i) {
         const char* base = reinterpret_cast<const char*>(x) + in_off[i] * esize;
-        if (nhwc_map(&maps.x[i], base, esize, cin, in_wv[i], in_hv[i], N, in_sw[i], in_sh[i], in_sn, cpb, g.pw, g.ph, g.pn) != CUDA_SUCCESS)
+        if (nhwc_map(&maps.x[i], base, esize, cin, in_wv[i], in_hv[i], N, in_sw[i], in_sh[i], in_sn, cpb, g.pw, g.ph, g.pn,
+                     op_swizzle) != CUDA_SUCCESS)
             return (int)cudaErrorInvalidValue;
     }
     for (int i = n_maps; i < 4; ++i) maps.x[i] = maps.x[0];
-    if (nhwc_map(&maps.dy, dy, esize, cout, Wo, Ho, N, cout, (int64_t)Wo * cout, (int64_t)Ho * Wo * cout, cpb, g.pw, g.ph, g.pn) !=
-        CUDA_SUCCESS)
+    if (nhwc_map(&maps.dy, dy, esize, cout, Wo, Ho, N, cout, (int64_t)Wo * cout, (int64_t)Ho * Wo * cout, cpb, g.pw, g.ph, g.pn,
+                 op_swizzle) != CUDA_SUCCESS)
         return (int)cudaErrorInvalidValue;
     if (matrix_map(&maps.dw, dw, esize, cout, dw_cols, WG_M, cpb) != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
     TapTable taps;
