@@ -47,14 +47,12 @@ def main() -> None:
             w = (torch.randn(cout, cin, r, r, device="cuda") / (cin * r * r) ** 0.5).to(dtype).contiguous(memory_format=torch.channels_last)
             y = F.conv2d(x, w, None, stride, pad)
             dy = torch.randn_like(y).contiguous(memory_format=torch.channels_last)
-            wt = conv.permute_filter_for_dgrad(w)
             stats = torch.zeros(2, cout, device="cuda")
             flops = 2 * n * (h // stride) ** 2 * cout * cin * r * r
             row = {"shape": name, "dtype": "tf32" if dtype == torch.float32 else "bf16", "gflop": round(flops / 1e9, 3)}
             row["tc_fwd_us"] = round(timed(lambda: conv.conv2d_forward(x, w, stride, pad, stats)), 2)
             row["cudnn_fwd_us"] = round(timed(lambda: F.conv2d(x, w, None, stride, pad)), 2)
-            row["tc_dgrad_us"] = round(timed(lambda: conv.conv2d_dgrad(dy, wt, (h, h), stride, pad)), 2)
-            row["tc_permute_us"] = round(timed(lambda: conv.permute_filter_for_dgrad(w)), 2)
+            row["tc_dgrad_us"] = round(timed(lambda: conv.conv2d_dgrad(dy, w, (h, h), stride, pad)), 2)
             row["cudnn_dgrad_us"] = round(timed(lambda: torch.ops.aten.convolution_backward(
                 dy, x, w, None, [stride] * 2, [pad] * 2, [1, 1], False, [0, 0], 1, [True, False, False])), 2)
             row["tc_wgrad_us"] = round(timed(lambda: conv.conv2d_wgrad(x, dy, r, stride, pad)), 2)

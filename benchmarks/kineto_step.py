@@ -12,7 +12,8 @@ device = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True
 from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics import Accuracy
-engine = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16, channels_last=True, master_weights=True)
+BF16 = os.environ.get("KINETO_DTYPE", "bf16") == "bf16"
+engine = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16 if BF16 else None, channels_last=True, master_weights=BF16)
 client = ps.Client(Path("."), [Accuracy()], device, client_name="prof", engine_options=engine)
 cfg = {"current_server_round": 1, "local_steps": 8, "batch_size": ps.BS}
 client.setup_client(cfg)

@@ -5,7 +5,9 @@ API parity: ``fl4health/clients/basic_client.py:43-1321`` — same constructor, 
 ``compute_loss_and_additional_losses``, ``transform_gradients``, ``update_before_train`` ...), the same
 ``fit``/``evaluate``/``get_parameters``/``get_properties`` protocol, report keys and config keys.
 
-What is different is *how the hooks are executed* (``EngineOptions``):
+The class is a thin API shell: the round protocol is parsed by ``engine/round_protocol.RoundPlan``, the loops live in
+``engine/local_loop`` (one schedule-driven driver instead of four hand-written loops) and the per-batch step runs through
+``engine/step_executor.StepExecutor``.  What is different is *how the hooks are executed* (``EngineOptions``):
 
 * the model's state is re-homed into a flat ``ParameterArena`` so exchange/optimizer/penalties are single kernels;
 * stock ``torch.optim`` optimizers are swapped for one-launch flat equivalents;
@@ -33,10 +35,12 @@ from torch.utils.data import DataLoader
 from fl4health_b200.checkpointing.client_module import CheckpointMode, ClientCheckpointAndStateModule
 from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, NDArrays, Scalar
-from fl4health_b200.engine.fused_optim import _FlatOptimizer, translate_optimizer
+from fl4health_b200.engine.fused_optim import translate_optimizer
 from fl4health_b200.engine.graph_runner import GraphStepRunner
-from fl4health_b200.engine.modes import set_training
+from fl4health_b200.engine.local_loop import BatchCycler, EpochSchedule, StepSchedule, run_evaluation, run_training
 from fl4health_b200.engine.options import EngineOptions
+from fl4health_b200.engine.round_protocol import RoundPlan, Stopwatch
+from fl4health_b200.engine.step_executor import StepExecutor
 from fl4health_b200.metrics.base_metrics import TEST_LOSS_KEY, TEST_NUM_EXAMPLES_KEY, Metric
 from fl4health_b200.metrics.metric_managers import MetricManager
 from fl4health_b200.parallel.arena import ParameterArena, arena_of, attach_arena
@@ -46,10 +50,7 @@ from fl4health_b200.parameter_exchange.parameter_exchanger_base import Parameter
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.reporting.reports_manager import ReportsManager
 from fl4health_b200.utils.client import (
-    check_if_batch_is_empty_and_verify_input,
     fold_loss_dict_into_metrics,
-    maybe_progress_bar,
-    move_data_to_device,
     process_and_check_validation_steps,
     set_pack_losses_with_val_metrics,
 )
@@ -61,6 +62,8 @@ from fl4health_b200.utils.random import generate_hash
 from fl4health_b200.utils.typing import LogLevel, TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 
 EXPECTED_OUTPUT_TUPLE_SIZE = 2  # a model may return (predictions, features)
+
+_SPLITS = ("train", "val", "test")
 
 
 class BasicClient:
@@ -76,13 +79,12 @@ class BasicClient:
         client_name: str | None = None,
         engine_options: EngineOptions | None = None,
     ) -> None:
-        self.data_path = data_path
+        self.data_path, self.metrics, self.progress_bar = data_path, metrics, progress_bar
         self.device = torch.device(device)
-        self.metrics = metrics
-        self.progress_bar = progress_bar
-        self.client_name = client_name if client_name is not None else generate_hash()
+        self.client_name = client_name or generate_hash()
         log(INFO, f"Client Name: {self.client_name}")
-        self.engine = engine_options if engine_options is not None else EngineOptions.from_env()
+        self.engine = engine_options or EngineOptions.from_env()
+        self._executor = StepExecutor(self.engine, self.device, self.client_name)
 
         self.checkpoint_and_state_module = checkpoint_and_state_module or ClientCheckpointAndStateModule(
             pre_aggregation=None, post_aggregation=None, state_checkpointer=None
@@ -90,20 +92,23 @@ class BasicClient:
         self.reports_manager = ReportsManager(reporters)
         self.reports_manager.initialize(id=self.client_name, name=self.client_name)
 
+        # one loss meter + metric manager per data split (train_loss_meter, val_metric_manager, ...)
+        for split in _SPLITS:
+            losses_type = TrainingLosses if split == "train" else EvaluationLosses
+            setattr(self, f"{split}_loss_meter", LossMeter[losses_type](loss_meter_type, losses_type))
+            setattr(self, f"{split}_metric_manager", MetricManager(metrics=self.metrics, metric_manager_name=split))
+
         self.initialized = False
-
-        self.train_loss_meter = LossMeter[TrainingLosses](loss_meter_type, TrainingLosses)
-        self.val_loss_meter = LossMeter[EvaluationLosses](loss_meter_type, EvaluationLosses)
-        self.test_loss_meter = LossMeter[EvaluationLosses](loss_meter_type, EvaluationLosses)
-        self.train_metric_manager = MetricManager(metrics=self.metrics, metric_manager_name="train")
-        self.val_metric_manager = MetricManager(metrics=self.metrics, metric_manager_name="val")
-        self.test_metric_manager = MetricManager(metrics=self.metrics, metric_manager_name="test")
-
         self.initial_weights: NDArrays | None = None
-        self.total_steps: int = 0
-        self.total_epochs: int = 0
+        self.total_steps = self.total_epochs = 0
+        self.num_test_samples: int | None = None
+        self.learning_rate: float | None = None
+        self.early_stopper: EarlyStopper | None = None
+        self.num_validation_steps: int | None = None
+        self._train_batches: BatchCycler | None = None
+        self._val_batches: BatchCycler | None = None
 
-        # set in setup_client
+        # bound by setup_client (declared for type checkers and subclasses)
         self.parameter_exchanger: ParameterExchanger
         self.model: nn.Module
         self.optimizers: dict[str, Optimizer]
@@ -114,62 +119,102 @@ class BasicClient:
         self.test_loader: DataLoader | None
         self.num_train_samples: int
         self.num_val_samples: int
-        self.num_test_samples: int | None = None
-        self.learning_rate: float | None = None
 
-        self.early_stopper: EarlyStopper | None = None
-        self.num_validation_steps: int | None = None
-        self.train_iterator: Iterator | None = None
-        self.val_iterator: Iterator | None = None
+    # ------------------------------------------------------------------------------------------------------------------
+    # set-up: user factories -> placed model, loaders, (fused) optimizers, schedulers, criterion, exchanger
+    # ------------------------------------------------------------------------------------------------------------------
+    def setup_client(self, config: Config) -> None:
+        self.model = self._place_model(self.get_model(config))
+        self.train_loader, self.val_loader = self.get_data_loaders(config)
+        self.test_loader = self.get_test_data_loader(config)
+        self._train_batches = self._val_batches = None
+        self._count_samples(config)
 
-        # engine state
-        self._train_runner: GraphStepRunner | None = None
-        self._train_runners: dict[Any, GraphStepRunner] = {}
-        self._val_runners: dict[Any, GraphStepRunner] = {}
+        self.set_optimizer(config)
+        self._maybe_fuse_optimizers()
+        candidates = ((key, self.get_lr_scheduler(key, config)) for key in self.optimizers)
+        self.lr_schedulers = {key: scheduler for key, scheduler in candidates if scheduler is not None}
 
-    # ==================================================================================================================
-    # protocol: parameters in / out
-    # ==================================================================================================================
-    def _maybe_checkpoint(self, loss: float, metrics: dict[str, Scalar], checkpoint_mode: CheckpointMode) -> None:
-        self.checkpoint_and_state_module.maybe_checkpoint(self.model, loss, metrics, checkpoint_mode)
+        self.criterion = self.get_criterion(config).to(self.device)
+        self.parameter_exchanger = self.get_parameter_exchanger(config)
+        self.reports_manager.report({"host_type": "client", "initialized": str(datetime.datetime.now())})
+        self.initialized = True
 
+    def _count_samples(self, config: Config) -> None:
+        def size(loader: DataLoader) -> int:
+            return len(loader.dataset)  # type: ignore[arg-type]
+
+        self.num_train_samples, self.num_val_samples = size(self.train_loader), size(self.val_loader)
+        self.num_validation_steps = process_and_check_validation_steps(config, self.val_loader)
+        if self.num_validation_steps is not None:  # capped validation: the sample count follows the cap
+            batch = self.val_loader.batch_size
+            assert batch is not None, "Validation batch size must be defined if we want to limit the number of validation steps"
+            self.num_val_samples = self.num_validation_steps * batch
+        if self.test_loader:
+            self.num_test_samples = size(self.test_loader)
+
+    def _place_model(self, model: nn.Module, with_grad: bool = True) -> nn.Module:
+        """Move a model to the device and (engine option) re-home its state into a flat arena."""
+        model = model.to(self.device)
+        options = self.engine
+        if not options.arena:
+            return model.to(memory_format=torch.channels_last) if options.channels_last else model
+        arena = attach_arena(model, self.device, with_grad=with_grad, channels_last=options.channels_last,
+                             allocator=self._arena_allocator())
+        if with_grad and options.master_weights and options.fused_optimizer and options.amp_dtype is not None:
+            arena.enable_compute_shadow(options.amp_dtype)
+        return model
+
+    def _arena_allocator(self) -> Any:
+        """Hook for the SPMD runtime: allocate arenas from peer-mapped symmetric memory."""
+        return getattr(self, "arena_allocator", None)
+
+    def _candidate_modules(self) -> list[nn.Module]:
+        """Modules whose arenas an optimizer may be operating on (clients with extra models extend this)."""
+        return [self.model]
+
+    def _arena_for_optimizer(self, optimizer: Optimizer) -> ParameterArena | None:
+        """The arena of the candidate module that owns every parameter of ``optimizer`` (None: keep the stock one)."""
+        wanted = {id(p) for group in optimizer.param_groups for p in group["params"]}
+        if not wanted:
+            return None
+        for module in self._candidate_modules():
+            arena = arena_of(module)
+            if arena is not None and wanted <= {id(p) for p in module.parameters()}:
+                return arena
+        return None
+
+    def _maybe_fuse_optimizers(self) -> None:
+        if self.engine.fused_optimizer:
+            arenas = {key: self._arena_for_optimizer(opt) for key, opt in self.optimizers.items()}
+            self.optimizers.update({key: translate_optimizer(self.optimizers[key], arena)
+                                    for key, arena in arenas.items() if arena is not None})
+
+    def set_optimizer(self, config: Config) -> None:
+        optimizer = self.get_optimizer(config)
+        assert not isinstance(optimizer, dict), "get_optimizer returned a dict: override set_optimizer to route it"
+        self.optimizers = {"global": optimizer}
+
+    def get_parameter_exchanger(self, config: Config) -> ParameterExchanger:
+        return FullParameterExchanger()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # parameters in / out
+    # ------------------------------------------------------------------------------------------------------------------
     def get_parameters(self, config: Config) -> NDArrays:
         """Arrays for the server.  Before the client is set up, this sets it up and returns ALL model state (the
         server uses it to initialise the global model)."""
         if not self.initialized:
             return self.setup_client_and_return_all_model_parameters(config)
-        assert self.model is not None and self.parameter_exchanger is not None
         self._maybe_load_saved_best_local_model_state()
         return self.parameter_exchanger.push_parameters(self.model, config=config)
-
-    def _maybe_load_saved_best_local_model_state(self) -> None:
-        if self.early_stopper is not None and self.early_stopper.patience is None:
-            log(INFO, "Loading saved best model's state before sending model to server.")
-            self.early_stopper.load_snapshot(["model"])
-
-    def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
-        """Round 1 of fitting initialises *all* weights (full exchange) whatever the exchanger; afterwards the
-        client's exchanger decides which state is overwritten."""
-        assert self.model is not None
-        current_server_round = narrow_dict_type(config, "current_server_round", int)
-        if current_server_round == 1 and fitting_round:
-            self.initialize_all_model_weights(parameters, config)
-        else:
-            assert self.parameter_exchanger is not None
-            self.parameter_exchanger.pull_parameters(parameters, self.model, config)
-
-    def initialize_all_model_weights(self, parameters: NDArrays, config: Config) -> None:
-        FullParameterExchanger().pull_parameters(parameters, self.model, config)
 
     def setup_client_and_return_all_model_parameters(self, config: Config) -> NDArrays:
         log(INFO, "Setting up client and providing full model parameters to the server for initialization")
         if not config:
-            log(
-                WARNING,
-                "This client has not yet been initialized and the config is empty. This may cause unexpected "
-                "failures, as setting up a client typically requires several configuration parameters, "
-                "including batch_size and current_server_round.",
-            )
+            log(WARNING, "This client has not yet been initialized and the config is empty. This may cause unexpected "
+                         "failures, as setting up a client typically requires several configuration parameters, "
+                         "including batch_size and current_server_round.")
         self.setup_client(config)
         return FullParameterExchanger().push_parameters(self.model, config=config)
 
@@ -180,249 +225,132 @@ class BasicClient:
         regular payload must answer this request with the plain model state, exactly like an uninitialised client."""
         return self.initialized and config.get("current_server_round") == 0
 
+    def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
+        """The very first fit installs *all* weights (full exchange) whatever the exchanger; afterwards the client's
+        exchanger decides which state is overwritten."""
+        first_fit = fitting_round and narrow_dict_type(config, "current_server_round", int) == 1
+        if first_fit:
+            self.initialize_all_model_weights(parameters, config)
+        else:
+            self.parameter_exchanger.pull_parameters(parameters, self.model, config)
+
+    def initialize_all_model_weights(self, parameters: NDArrays, config: Config) -> None:
+        FullParameterExchanger().pull_parameters(parameters, self.model, config)
+
+    def _maybe_load_saved_best_local_model_state(self) -> None:
+        stopper = self.early_stopper
+        if stopper is not None and stopper.patience is None:
+            log(INFO, "Loading saved best model's state before sending model to server.")
+            stopper.load_snapshot(["model"])
+
+    def get_properties(self, config: Config) -> dict[str, Scalar]:
+        if not self.initialized:
+            self.setup_client(config)
+        return {"num_train_samples": self.num_train_samples, "num_val_samples": self.num_val_samples}
+
     def shutdown(self) -> None:
         self.reports_manager.report({"shutdown": str(datetime.datetime.now())})
         self.reports_manager.shutdown()
 
-    # ==================================================================================================================
-    # protocol: fit / evaluate
-    # ==================================================================================================================
+    # ------------------------------------------------------------------------------------------------------------------
+    # the round protocol
+    # ------------------------------------------------------------------------------------------------------------------
     def process_config(self, config: Config) -> tuple[int | None, int | None, int, bool, bool]:
-        current_server_round = narrow_dict_type(config, "current_server_round", int)
-        if ("local_epochs" in config) and ("local_steps" in config):
-            raise ValueError("Config cannot contain both local_epochs and local_steps. Please specify only one.")
-        if "local_epochs" in config:
-            local_epochs: int | None = narrow_dict_type(config, "local_epochs", int)
-            local_steps: int | None = None
-        elif "local_steps" in config:
-            local_steps = narrow_dict_type(config, "local_steps", int)
-            local_epochs = None
-        else:
-            raise ValueError("Must specify either local_epochs or local_steps in the Config.")
-        evaluate_after_fit = bool(config.get("evaluate_after_fit", False))
-        pack_losses_with_val_metrics = set_pack_losses_with_val_metrics(config)
-        return local_epochs, local_steps, current_server_round, evaluate_after_fit, pack_losses_with_val_metrics
+        return RoundPlan.from_config(config).as_tuple()
 
     def fit(self, parameters: NDArrays, config: Config) -> tuple[NDArrays, int, dict[str, Scalar]]:
-        round_start_time = datetime.datetime.now()
-        local_epochs, local_steps, current_server_round, evaluate_after_fit, pack_losses_with_val_metrics = (
-            self.process_config(config)
-        )
+        clock = Stopwatch()
+        clock.mark("round")
+        epochs, steps, server_round, evaluate_after_fit, pack_losses = self.process_config(config)
+        state_io = self.checkpoint_and_state_module.state_checkpointer is not None
         if not self.initialized:
             self.setup_client(config)
-            if self.checkpoint_and_state_module.state_checkpointer is not None:
-                loaded = self._load_client_state()
-                log(INFO, "Successfully loaded client state." if loaded else "Client state was not loaded.")
+            if state_io:
+                log(INFO, "Successfully loaded client state." if self._load_client_state() else "Client state was not loaded.")
 
         with tracing.phase("pull_parameters"):
             self.set_parameters(parameters, config, fitting_round=True)
         with tracing.phase("update_before_train"):
-            self.update_before_train(current_server_round)
+            self.update_before_train(server_round)
 
-        fit_start_time = datetime.datetime.now()
+        clock.mark("train")
         with tracing.phase("local_train"):
-            if local_epochs is not None:
-                loss_dict, metrics = self.train_by_epochs(local_epochs, current_server_round)
-                local_steps = len(self.train_loader) * local_epochs
-            elif local_steps is not None:
-                loss_dict, metrics = self.train_by_steps(local_steps, current_server_round)
+            if epochs is not None:
+                loss_dict, metrics = self.train_by_epochs(epochs, server_round)
+                steps = len(self.train_loader) * epochs
             else:
-                raise ValueError("Must specify either local_epochs or local_steps in the Config.")
-        fit_end_time = datetime.datetime.now()
-
+                assert steps is not None
+                loss_dict, metrics = self.train_by_steps(steps, server_round)
+        clock.mark("trained")
         with tracing.phase("update_after_train"):
-            self.update_after_train(local_steps, loss_dict, config)
+            self.update_after_train(steps, loss_dict, config)
 
         if self._should_evaluate_after_fit(evaluate_after_fit):
-            validation_loss, validation_metrics = self.validate(pack_losses_with_val_metrics)
+            validation_loss, validation_metrics = self.validate(pack_losses)
             metrics.update(validation_metrics)
             self._maybe_checkpoint(validation_loss, validation_metrics, CheckpointMode.PRE_AGGREGATION)
 
-        self.reports_manager.report(
-            {
-                "fit_round_metrics": metrics,
-                "fit_round_losses": loss_dict,
-                "round": current_server_round,
-                "round_start": str(round_start_time),
-                "round_end": str(datetime.datetime.now()),
-                "fit_round_start": str(fit_start_time),
-                "fit_round_time_elapsed": round((fit_end_time - fit_start_time).total_seconds()),
-                "fit_round_end": str(fit_end_time),
-                "fit_step": self.total_steps,
-                "fit_epoch": self.total_epochs,
-                **({"device_phase_ms": tracing.phase_report()} if tracing.tracing_enabled() else {}),
-            },
-            current_server_round,
-        )
-
-        if self.checkpoint_and_state_module.state_checkpointer is not None:
+        report = {"fit_round_metrics": metrics, "fit_round_losses": loss_dict, "round": server_round,
+                  "round_start": str(clock.marks["round"]), "round_end": str(clock.mark("reported")),
+                  **clock.span("fit_round", "train", "trained"), "fit_step": self.total_steps, "fit_epoch": self.total_epochs}
+        if tracing.tracing_enabled():
+            report["device_phase_ms"] = tracing.phase_report()
+        self.reports_manager.report(report, server_round)
+        if state_io:
             self._save_client_state()
-
         with tracing.phase("push_parameters"):
             return self.get_parameters(config), self.num_train_samples, metrics
 
     def evaluate(self, parameters: NDArrays, config: Config) -> tuple[float, int, dict[str, Scalar]]:
         if not self.initialized:
             self.setup_client(config)
-        start_time = datetime.datetime.now()
-        current_server_round = narrow_dict_type(config, "current_server_round", int)
-        pack_losses_with_val_metrics = set_pack_losses_with_val_metrics(config)
-
+        clock = Stopwatch()
+        clock.mark("begin")
+        server_round = narrow_dict_type(config, "current_server_round", int)
         with tracing.phase("pull_parameters"):
             self.set_parameters(parameters, config, fitting_round=False)
         with tracing.phase("evaluate"):
-            loss, metrics = self.validate(pack_losses_with_val_metrics)
-        end_time = datetime.datetime.now()
-
+            loss, metrics = self.validate(set_pack_losses_with_val_metrics(config))
+        clock.mark("end")
         self._maybe_checkpoint(loss, metrics, CheckpointMode.POST_AGGREGATION)
         self.reports_manager.report(
-            {
-                "eval_round_metrics": metrics,
-                "eval_round_loss": loss,
-                "eval_round_start": str(start_time),
-                "eval_round_time_elapsed": round((end_time - start_time).total_seconds()),
-                "eval_round_end": str(end_time),
-                "fit_step": self.total_steps,
-                "fit_epoch": self.total_epochs,
-                "round": current_server_round,
-            },
-            current_server_round,
+            {"eval_round_metrics": metrics, "eval_round_loss": loss, **clock.span("eval_round", "begin", "end"),
+             "fit_step": self.total_steps, "fit_epoch": self.total_epochs, "round": server_round},
+            server_round,
         )
         return loss, self.num_val_samples, metrics
 
     def _should_evaluate_after_fit(self, evaluate_after_fit: bool) -> bool:
-        pre_aggregation = self.checkpoint_and_state_module.pre_aggregation
-        return evaluate_after_fit or pre_aggregation is not None
+        return evaluate_after_fit or self.checkpoint_and_state_module.pre_aggregation is not None
 
-    # ==================================================================================================================
-    # logging / reporting helpers
-    # ==================================================================================================================
-    def _log_header_str(
-        self, current_round: int | None = None, current_epoch: int | None = None,
-        logging_mode: LoggingMode = LoggingMode.TRAIN,
-    ) -> None:
-        parts = [f"Current FL Round: {current_round}"] if current_round is not None else []
-        if current_epoch is not None:
-            parts.append(f"Current Epoch: {current_epoch}")
-        log(INFO, f"{logging_mode.value} | " + "\t".join(parts))
+    def _maybe_checkpoint(self, loss: float, metrics: dict[str, Scalar], checkpoint_mode: CheckpointMode) -> None:
+        self.checkpoint_and_state_module.maybe_checkpoint(self.model, loss, metrics, checkpoint_mode)
 
-    def _log_results(
-        self, loss_dict: dict[str, float], metrics_dict: dict[str, Scalar], current_round: int | None = None,
-        current_epoch: int | None = None, logging_mode: LoggingMode = LoggingMode.TRAIN,
-    ) -> None:
-        _, client_logs = self.get_client_specific_logs(current_round, current_epoch, logging_mode)
-        lines = [f"Client {logging_mode.value} Losses: " + ", ".join(f"{k}: {v:.6f}" for k, v in loss_dict.items())]
-        if metrics_dict:
-            lines.append(
-                f"Client {logging_mode.value} Metrics: " + ", ".join(f"{k}: {v}" for k, v in metrics_dict.items())
-            )
-        log(INFO, " | ".join(lines))
-        for level, message in client_logs:
-            log(level.value, message)
-
-    def get_client_specific_logs(
-        self, current_round: int | None, current_epoch: int | None, logging_mode: LoggingMode
-    ) -> tuple[str, list[tuple[LogLevel, str]]]:
-        """Hook: extra header text + log lines (e.g. current FedProx mu)."""
-        return "", []
-
-    def get_client_specific_reports(self) -> dict[str, Any]:
-        """Hook: extra key/values merged into reporter payloads."""
-        return {}
-
-    def _step_reports_enabled(self) -> bool:
-        if self.engine.step_reports is not None:
-            return self.engine.step_reports
-        return any(getattr(r, "wants_step_reports", False) for r in self.reports_manager.reporters)
-
-    def update_metric_manager(self, preds: TorchPredType, target: TorchTargetType, metric_manager: MetricManager) -> None:
-        metric_manager.update(preds, target)
-
-    # ==================================================================================================================
-    # the per-batch step
-    # ==================================================================================================================
-    def _amp(self) -> contextlib.AbstractContextManager:
-        if self.engine.amp_dtype is not None and (self.device.type == "cuda" or self.engine.master_weights):
-            return torch.autocast(device_type=self.device.type, dtype=self.engine.amp_dtype)
-        return contextlib.nullcontext()
-
+    # ------------------------------------------------------------------------------------------------------------------
+    # one batch: the hook bodies, and the engine units wrapped around them
+    # ------------------------------------------------------------------------------------------------------------------
     def train_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
-        self.optimizers["global"].zero_grad()
+        optimizer = self.optimizers["global"]
+        optimizer.zero_grad()
         with self._amp():
             preds, features = self.predict(input)
-            target = self.transform_target(target)
-            losses = self.compute_training_loss(preds, features, target)
+            losses = self.compute_training_loss(preds, features, self.transform_target(target))
         losses.backward["backward"].backward()
         self.transform_gradients(losses)
-        self.optimizers["global"].step()
+        optimizer.step()
         return losses, preds
 
     def val_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[EvaluationLosses, TorchPredType]:
         with torch.no_grad(), self._amp():
             preds, features = self.predict(input)
-            target = self.transform_target(target)
-            losses = self.compute_evaluation_loss(preds, features, target)
+            losses = self.compute_evaluation_loss(preds, features, self.transform_target(target))
         return losses, preds
 
-    # --- engine wrappers: (train|val)_step + device-side loss/metric accumulation as one replayable unit ---------
-    def _train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
-        losses, preds = self.train_step(input, target)
-        self.train_loss_meter.accumulate(losses)
-        self.update_metric_manager(preds, target, self.train_metric_manager)
-        return losses.detach(), {key: value.detach() for key, value in preds.items()}  # type: ignore[return-value]
+    def _amp(self) -> contextlib.AbstractContextManager:
+        return self._executor.autocast()
 
-    def _sync_optimizer_hyperparams(self) -> None:
-        for optimizer in self.optimizers.values():
-            if isinstance(optimizer, _FlatOptimizer):
-                optimizer.sync_hyperparams()
-
-    def _run_train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
-        if self.engine.cuda_graphs and self.device.type == "cuda":
-            variant = self._graph_variant()
-            runner = self._train_runners.get(variant)
-            if runner is None:
-                self._evict_stale_runners(self._train_runners)
-                runner = GraphStepRunner(
-                    self._train_unit, self.device, warmup=self.engine.graph_warmup_steps,
-                    name=f"{self.client_name}/train[{variant}]", before_replay=self._sync_optimizer_hyperparams,
-                )
-                self._train_runners[variant] = runner
-                self._train_runner = runner
-            losses, preds = runner(input, target)
-        else:
-            losses, preds = self._train_unit(input, target)
-        self.train_loss_meter.mark_step()
-        return losses, preds
-
-    def _run_val_unit(
-        self, input: TorchInputType, target: TorchTargetType, loss_meter: LossMeter, metric_manager: MetricManager
-    ) -> tuple[EvaluationLosses, TorchPredType]:
-        def unit(inp: TorchInputType, tgt: TorchTargetType) -> tuple[EvaluationLosses, TorchPredType]:
-            losses, preds = self.val_step(inp, tgt)
-            loss_meter.accumulate(losses)
-            self.update_metric_manager(preds, tgt, metric_manager)
-            return losses, preds
-
-        if self.engine.cuda_graphs and self.device.type == "cuda":
-            key = (id(loss_meter), self._graph_variant())
-            runner = self._val_runners.get(key)
-            if runner is None:
-                self._evict_stale_runners(self._val_runners)
-                runner = GraphStepRunner(unit, self.device, warmup=self.engine.graph_warmup_steps,
-                                         name=f"{self.client_name}/eval")
-                self._val_runners[key] = runner
-            losses, preds = runner(input, target)
-        else:
-            losses, preds = unit(input, target)
-        loss_meter.mark_step()
-        return losses, preds
-
-    @staticmethod
-    def _evict_stale_runners(runners: dict, keep: int = 6) -> None:
-        """Captured graphs pin device memory; variants that re-bind tensors every round (MOON's frozen models) would
-        otherwise accumulate.  Oldest-first eviction keeps alternating variants (FedRep phases) resident."""
-        while len(runners) >= keep:
-            runners.pop(next(iter(runners)))
+    def _prepare_batch(self, input: TorchInputType, target: TorchTargetType) -> tuple[TorchInputType, TorchTargetType]:
+        return self._executor.stage(input, target)
 
     def _graph_variant(self) -> Any:
         """Hashable tag of everything *besides input shapes* that changes what ``train_step`` launches (e.g. FedRep's
@@ -431,315 +359,197 @@ class BasicClient:
 
     def _invalidate_graphs(self) -> None:
         """Drop captured graphs (call after anything that re-binds tensors the step reads: new model, new optimizer)."""
-        self._train_runner = None
-        self._train_runners = {}
-        self._val_runners = {}
+        self._executor.reset()
 
-    def _prepare_batch(self, input: TorchInputType, target: TorchTargetType) -> tuple[TorchInputType, TorchTargetType]:
-        input = move_data_to_device(input, self.device)
-        target = move_data_to_device(target, self.device)
-        if self.engine.channels_last and isinstance(input, torch.Tensor) and input.dim() == 4:
-            input = input.contiguous(memory_format=torch.channels_last)
-        return input, target
+    def _sync_optimizer_hyperparams(self) -> None:
+        StepExecutor.push_hyperparameters(self.optimizers)
 
-    # ==================================================================================================================
-    # training loops
-    # ==================================================================================================================
-    def train_by_epochs(
-        self, epochs: int, current_round: int | None = None
-    ) -> tuple[dict[str, float], dict[str, Scalar]]:
-        set_training(self.model, True)
-        steps_this_round = 0
-        report_data: dict[str, Any] = {"round": current_round}
-        step_reports = self._step_reports_enabled()
-        continue_training = True
-        loss_dict: dict[str, float] = {}
-        metrics: dict[str, Scalar] = {}
-        for local_epoch in range(epochs):
-            self.train_metric_manager.clear()
-            self.train_loss_meter.clear()
-            self._log_header_str(current_round, local_epoch)
-            self.update_before_epoch(epoch=local_epoch)
-            report_data.update({"fit_epoch": self.total_epochs})
-            for input, target in maybe_progress_bar(self.train_loader, self.progress_bar):
-                self.update_before_step(steps_this_round, current_round)
-                if check_if_batch_is_empty_and_verify_input(input):
-                    log(INFO, "Empty batch generated by data loader. Skipping step.")
-                    continue
-                input, target = self._prepare_batch(input, target)
-                losses, _ = self._run_train_unit(input, target)
-                self.update_after_step(steps_this_round, current_round)
-                self.update_lr_schedulers(epoch=local_epoch)
-                if step_reports:
-                    report_data.update({"fit_step_losses": losses.as_dict(), "fit_step": self.total_steps})
-                    report_data.update(self.get_client_specific_reports())
-                    self.reports_manager.report(report_data, current_round, self.total_epochs, self.total_steps)
-                self.total_steps += 1
-                steps_this_round += 1
-                if self.early_stopper is not None and self.early_stopper.should_stop(steps_this_round):
-                    log(INFO, "Early stopping criterion met. Stopping training.")
-                    self.early_stopper.load_snapshot()
-                    continue_training = False
-                    break
-            metrics = self.train_metric_manager.compute()
-            loss_dict = self.train_loss_meter.compute().as_dict()
-            report_data.update({"fit_epoch_metrics": metrics, "fit_epoch_losses": loss_dict})
-            report_data.update(self.get_client_specific_reports())
-            self.reports_manager.report(report_data, current_round, self.total_epochs)
-            self._log_results(loss_dict, metrics, current_round, local_epoch)
-            self.total_epochs += 1
-            if not continue_training:
-                break
-        return loss_dict, metrics
+    def _train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
+        """``train_step`` + device-side loss / metric accumulation: the unit that is captured and replayed."""
+        losses, preds = self.train_step(input, target)
+        self.train_loss_meter.accumulate(losses)
+        self.update_metric_manager(preds, target, self.train_metric_manager)
+        return losses.detach(), {name: tensor.detach() for name, tensor in preds.items()}  # type: ignore[return-value]
+
+    def _run_train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
+        outcome = self._executor.run_train(self._train_unit, self._graph_variant(), self._sync_optimizer_hyperparams, input, target)
+        self.train_loss_meter.mark_step()
+        return outcome
+
+    def _run_val_unit(
+        self, input: TorchInputType, target: TorchTargetType, loss_meter: LossMeter, metric_manager: MetricManager
+    ) -> tuple[EvaluationLosses, TorchPredType]:
+        def unit(batch_input: TorchInputType, batch_target: TorchTargetType) -> tuple[EvaluationLosses, TorchPredType]:
+            losses, preds = self.val_step(batch_input, batch_target)
+            loss_meter.accumulate(losses)
+            self.update_metric_manager(preds, batch_target, metric_manager)
+            return losses, preds
+
+        outcome = self._executor.run_eval(unit, (id(loss_meter), self._graph_variant()), input, target)
+        loss_meter.mark_step()
+        return outcome
+
+    # captured-graph bookkeeping, exposed for tests / profiling scripts
+    @property
+    def _train_runner(self) -> GraphStepRunner | None:
+        return self._executor.latest_train_runner
+
+    @property
+    def _train_runners(self) -> dict[Any, GraphStepRunner]:
+        return self._executor.train_runners
+
+    @property
+    def _val_runners(self) -> dict[Any, GraphStepRunner]:
+        return self._executor.eval_runners
+
+    def update_metric_manager(self, preds: TorchPredType, target: TorchTargetType, metric_manager: MetricManager) -> None:
+        metric_manager.update(preds, target)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # local training / evaluation (schedules walked by engine/local_loop)
+    # ------------------------------------------------------------------------------------------------------------------
+    def train_by_epochs(self, epochs: int, current_round: int | None = None) -> tuple[dict[str, float], dict[str, Scalar]]:
+        return run_training(self, EpochSchedule(self.train_loader, epochs), current_round)
+
+    def train_by_steps(self, steps: int, current_round: int | None = None) -> tuple[dict[str, float], dict[str, Scalar]]:
+        return run_training(self, StepSchedule(self._train_source(), steps), current_round)
+
+    def _train_source(self) -> BatchCycler:
+        if self._train_batches is None or self._train_batches.loader is not self.train_loader:
+            self._train_batches = BatchCycler(self.train_loader)
+        return self._train_batches
 
     def _next_train_batch(self) -> tuple[TorchInputType, TorchTargetType]:
-        if self.train_iterator is None:
-            self.train_iterator = iter(self.train_loader)
-        try:
-            return next(self.train_iterator)
-        except StopIteration:
-            self.train_iterator = iter(self.train_loader)
-            return next(self.train_iterator)
+        return self._train_source().draw()
 
-    def train_by_steps(
-        self, steps: int, current_round: int | None = None
-    ) -> tuple[dict[str, float], dict[str, Scalar]]:
-        set_training(self.model, True)
-        self.train_loss_meter.clear()
-        self.train_metric_manager.clear()
-        self._log_header_str(current_round)
-        report_data: dict[str, Any] = {"round": current_round}
-        step_reports = self._step_reports_enabled()
-        for step in maybe_progress_bar(range(steps), self.progress_bar):
-            self.update_before_step(step, current_round)
-            input, target = self._next_train_batch()
-            if check_if_batch_is_empty_and_verify_input(input):
-                log(INFO, "Empty batch generated by data loader. Skipping step.")
-                continue
-            input, target = self._prepare_batch(input, target)
-            losses, _ = self._run_train_unit(input, target)
-            self.update_after_step(step, current_round)
-            self.update_lr_schedulers(step=step)
-            if step_reports:
-                report_data.update({"fit_step_losses": losses.as_dict(), "fit_step": self.total_steps})
-                report_data.update(self.get_client_specific_reports())
-                self.reports_manager.report(report_data, current_round, None, self.total_steps)
-            self.total_steps += 1
-            if self.early_stopper is not None and self.early_stopper.should_stop(step):
-                log(INFO, "Early stopping criterion met. Stopping training.")
-                self.early_stopper.load_snapshot()
-                break
-        loss_dict = self.train_loss_meter.compute().as_dict()
-        metrics = self.train_metric_manager.compute()
-        self._log_results(loss_dict, metrics, current_round)
-        return loss_dict, metrics
+    @property
+    def train_iterator(self) -> Iterator | None:
+        """Position inside the training loader (step mode); assigning None rewinds it."""
+        return None if self._train_batches is None else self._train_batches._it
 
-    # ==================================================================================================================
-    # validation
-    # ==================================================================================================================
-    def _finish_validation(
-        self, loss_meter: LossMeter, metric_manager: MetricManager, logging_mode: LoggingMode,
-        include_losses_in_metrics: bool,
-    ) -> tuple[float, dict[str, Scalar]]:
-        loss_dict = loss_meter.compute().as_dict()
-        metrics = metric_manager.compute()
-        self._log_results(loss_dict, metrics, logging_mode=logging_mode)
-        if include_losses_in_metrics:
-            fold_loss_dict_into_metrics(metrics, loss_dict, logging_mode)
-        return loss_dict["checkpoint"], metrics
-
-    def _validate_by_steps(
-        self, loss_meter: LossMeter, metric_manager: MetricManager, include_losses_in_metrics: bool = False
-    ) -> tuple[float, dict[str, Scalar]]:
-        assert self.num_validation_steps is not None, "num_validation_steps must be defined to use this function"
-        set_training(self.model, False)
-        metric_manager.clear()
-        loss_meter.clear()
-        if self.val_iterator is None:
-            self.val_iterator = iter(self.val_loader)
-        with torch.no_grad():
-            for _ in maybe_progress_bar(range(self.num_validation_steps), self.progress_bar):
-                try:
-                    input, target = next(self.val_iterator)
-                except StopIteration:
-                    self.val_iterator = iter(self.val_loader)
-                    input, target = next(self.val_iterator)
-                input, target = self._prepare_batch(input, target)
-                self._run_val_unit(input, target, loss_meter, metric_manager)
-        return self._finish_validation(loss_meter, metric_manager, LoggingMode.VALIDATION, include_losses_in_metrics)
-
-    def _fully_validate_or_test(
-        self, loader: DataLoader, loss_meter: LossMeter, metric_manager: MetricManager,
-        logging_mode: LoggingMode = LoggingMode.VALIDATION, include_losses_in_metrics: bool = False,
-    ) -> tuple[float, dict[str, Scalar]]:
-        assert logging_mode in (LoggingMode.VALIDATION, LoggingMode.TEST, LoggingMode.EARLY_STOP_VALIDATION)
-        set_training(self.model, False)
-        metric_manager.clear()
-        loss_meter.clear()
-        with torch.no_grad():
-            for input, target in maybe_progress_bar(loader, self.progress_bar):
-                input, target = self._prepare_batch(input, target)
-                self._run_val_unit(input, target, loss_meter, metric_manager)
-        return self._finish_validation(loss_meter, metric_manager, logging_mode, include_losses_in_metrics)
+    @train_iterator.setter
+    def train_iterator(self, value: Iterator | None) -> None:
+        if value is None:
+            self._train_batches = None
+        else:
+            self._train_source()._it = value
 
     def validate(self, include_losses_in_metrics: bool = False) -> tuple[float, dict[str, Scalar]]:
         if self.num_validation_steps is None:
-            val_loss, val_metrics = self._fully_validate_or_test(
-                self.val_loader, self.val_loss_meter, self.val_metric_manager,
-                include_losses_in_metrics=include_losses_in_metrics,
-            )
+            batches: Any = self.val_loader
         else:
-            val_loss, val_metrics = self._validate_by_steps(
-                self.val_loss_meter, self.val_metric_manager, include_losses_in_metrics=include_losses_in_metrics
-            )
+            if self._val_batches is None or self._val_batches.loader is not self.val_loader:
+                self._val_batches = BatchCycler(self.val_loader)
+            batches = self._val_batches.take(self.num_validation_steps)
+        val_loss, val_metrics = self._fully_validate_or_test(
+            batches, self.val_loss_meter, self.val_metric_manager, LoggingMode.VALIDATION, include_losses_in_metrics)
         if self.test_loader:
             test_loss, test_metrics = self._fully_validate_or_test(
-                self.test_loader, self.test_loss_meter, self.test_metric_manager, LoggingMode.TEST,
-                include_losses_in_metrics=include_losses_in_metrics,
-            )
+                self.test_loader, self.test_loss_meter, self.test_metric_manager, LoggingMode.TEST, include_losses_in_metrics)
             if self.num_test_samples is not None:
                 val_metrics[TEST_NUM_EXAMPLES_KEY] = self.num_test_samples
             val_metrics[TEST_LOSS_KEY] = test_loss
             val_metrics.update(test_metrics)
         return val_loss, val_metrics
 
-    def get_properties(self, config: Config) -> dict[str, Scalar]:
-        if not self.initialized:
-            self.setup_client(config)
-        return {"num_train_samples": self.num_train_samples, "num_val_samples": self.num_val_samples}
+    def _fully_validate_or_test(
+        self, loader: Any, loss_meter: LossMeter, metric_manager: MetricManager,
+        logging_mode: LoggingMode = LoggingMode.VALIDATION, include_losses_in_metrics: bool = False,
+    ) -> tuple[float, dict[str, Scalar]]:
+        """Evaluate every batch of ``loader`` (any iterable of batches); returns (checkpoint loss, metrics)."""
+        assert logging_mode in (LoggingMode.VALIDATION, LoggingMode.TEST, LoggingMode.EARLY_STOP_VALIDATION)
+        run_evaluation(self, loader, loss_meter, metric_manager)
+        loss_dict, metrics = loss_meter.compute().as_dict(), metric_manager.compute()
+        self._log_results(loss_dict, metrics, logging_mode=logging_mode)
+        if include_losses_in_metrics:
+            fold_loss_dict_into_metrics(metrics, loss_dict, logging_mode)
+        return loss_dict["checkpoint"], metrics
 
-    # ==================================================================================================================
-    # setup
-    # ==================================================================================================================
-    def _place_model(self, model: nn.Module, with_grad: bool = True) -> nn.Module:
-        """Move a model to the device and (engine option) re-home its state into a flat arena."""
-        model = model.to(self.device)
-        if self.engine.arena:
-            arena = attach_arena(model, self.device, with_grad=with_grad, channels_last=self.engine.channels_last,
-                                 allocator=self._arena_allocator())
-            if self.engine.master_weights and self.engine.amp_dtype is not None and self.engine.fused_optimizer and with_grad:
-                arena.enable_compute_shadow(self.engine.amp_dtype)
-        elif self.engine.channels_last:
-            model = model.to(memory_format=torch.channels_last)
-        return model
+    # ------------------------------------------------------------------------------------------------------------------
+    # logging / reporting
+    # ------------------------------------------------------------------------------------------------------------------
+    def _log_header_str(self, current_round: int | None = None, current_epoch: int | None = None,
+                        logging_mode: LoggingMode = LoggingMode.TRAIN) -> None:
+        where = [text for text, value in ((f"Current FL Round: {current_round}", current_round),
+                                          (f"Current Epoch: {current_epoch}", current_epoch)) if value is not None]
+        log(INFO, f"{logging_mode.value} | " + "\t".join(where))
 
-    def _arena_allocator(self) -> Any:
-        """Hook for the SPMD runtime: allocate arenas from peer-mapped symmetric memory."""
-        return getattr(self, "arena_allocator", None)
+    def _log_results(self, loss_dict: dict[str, float], metrics_dict: dict[str, Scalar], current_round: int | None = None,
+                     current_epoch: int | None = None, logging_mode: LoggingMode = LoggingMode.TRAIN) -> None:
+        mode = logging_mode.value
+        summary = [f"Client {mode} Losses: " + ", ".join(f"{name}: {value:.6f}" for name, value in loss_dict.items())]
+        if metrics_dict:
+            summary.append(f"Client {mode} Metrics: " + ", ".join(f"{name}: {value}" for name, value in metrics_dict.items()))
+        log(INFO, " | ".join(summary))
+        for level, message in self.get_client_specific_logs(current_round, current_epoch, logging_mode)[1]:
+            log(level.value, message)
 
-    def _maybe_fuse_optimizers(self) -> None:
-        if not self.engine.fused_optimizer:
-            return
-        for key, optimizer in list(self.optimizers.items()):
-            arena = self._arena_for_optimizer(optimizer)
-            if arena is not None:
-                self.optimizers[key] = translate_optimizer(optimizer, arena)
+    def _step_reports_enabled(self) -> bool:
+        if self.engine.step_reports is not None:
+            return self.engine.step_reports
+        return any(getattr(reporter, "wants_step_reports", False) for reporter in self.reports_manager.reporters)
 
-    def _candidate_modules(self) -> list[nn.Module]:
-        """Modules whose arenas an optimizer may be operating on (clients with extra models extend this)."""
-        return [self.model]
+    def get_client_specific_logs(self, current_round: int | None, current_epoch: int | None,
+                                 logging_mode: LoggingMode) -> tuple[str, list[tuple[LogLevel, str]]]:
+        """Hook: extra header text + log lines (e.g. current FedProx mu)."""
+        return "", []
 
-    def _arena_for_optimizer(self, optimizer: Optimizer) -> ParameterArena | None:
-        opt_params = {id(p) for group in optimizer.param_groups for p in group["params"]}
-        for module in self._candidate_modules():
-            arena = arena_of(module)
-            if arena is None:
-                continue
-            if opt_params and opt_params <= {id(p) for p in module.parameters()}:
-                return arena
-        return None
+    def get_client_specific_reports(self) -> dict[str, Any]:
+        """Hook: extra key/values merged into reporter payloads."""
+        return {}
 
-    def setup_client(self, config: Config) -> None:
-        self.model = self._place_model(self.get_model(config))
-        train_loader, val_loader = self.get_data_loaders(config)
-        self.train_loader = train_loader
-        self.val_loader = val_loader
-        self.test_loader = self.get_test_data_loader(config)
-
-        self.num_validation_steps = process_and_check_validation_steps(config, self.val_loader)
-        self.num_train_samples = len(self.train_loader.dataset)  # type: ignore[arg-type]
-        self.num_val_samples = len(self.val_loader.dataset)  # type: ignore[arg-type]
-        if self.num_validation_steps is not None:
-            assert self.val_loader.batch_size is not None, (
-                "Validation batch size must be defined if we want to limit the number of validation steps"
-            )
-            self.num_val_samples = self.num_validation_steps * self.val_loader.batch_size
-        if self.test_loader:
-            self.num_test_samples = len(self.test_loader.dataset)  # type: ignore[arg-type]
-
-        self.set_optimizer(config)
-        self._maybe_fuse_optimizers()
-
-        self.lr_schedulers = {}
-        for optimizer_key in self.optimizers:
-            lr_scheduler = self.get_lr_scheduler(optimizer_key, config)
-            if lr_scheduler is not None:
-                self.lr_schedulers[optimizer_key] = lr_scheduler
-
-        self.criterion = self.get_criterion(config).to(self.device)
-        self.parameter_exchanger = self.get_parameter_exchanger(config)
-
-        self.reports_manager.report({"host_type": "client", "initialized": str(datetime.datetime.now())})
-        self.initialized = True
-
-    def get_parameter_exchanger(self, config: Config) -> ParameterExchanger:
-        return FullParameterExchanger()
-
-    # ==================================================================================================================
-    # model forward + losses (hooks)
-    # ==================================================================================================================
+    # ------------------------------------------------------------------------------------------------------------------
+    # model forward + losses
+    # ------------------------------------------------------------------------------------------------------------------
     def predict(self, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]:
         """Forward pass.  The model may return a tensor, a dict of predictions, or ``(preds_dict, features_dict)``."""
-        if isinstance(input, torch.Tensor):
-            output = self.model(input)
-        elif isinstance(input, dict):
+        if isinstance(input, dict):
             output = self.model(**input)
+        elif isinstance(input, torch.Tensor):
+            output = self.model(input)
         else:
             raise TypeError('"input" must be of type torch.Tensor or dict[str, torch.Tensor].')
-        if isinstance(output, dict):
-            return output, {}
         if isinstance(output, torch.Tensor):
             return {"prediction": output}, {}
-        if isinstance(output, tuple):
-            if len(output) != 2:
-                raise ValueError(f"Output tuple should have length 2 but has length {len(output)}")
-            preds, features = output
-            return preds, features
-        raise ValueError("Model forward did not return a tensor, dictionary of tensors, or tuple of tensors")
+        if isinstance(output, dict):
+            return output, {}
+        if not isinstance(output, tuple):
+            raise ValueError("Model forward did not return a tensor, dictionary of tensors, or tuple of tensors")
+        if len(output) != EXPECTED_OUTPUT_TUPLE_SIZE:
+            raise ValueError(f"Output tuple should have length 2 but has length {len(output)}")
+        return output[0], output[1]
 
     def compute_loss_and_additional_losses(
         self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
     ) -> tuple[torch.Tensor, dict[str, torch.Tensor] | None]:
         return self.criterion(preds["prediction"], target), None
 
-    def compute_training_loss(
-        self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
-    ) -> TrainingLosses:
-        loss, additional_losses = self.compute_loss_and_additional_losses(preds, features, target)
-        return TrainingLosses(backward=loss, additional_losses=additional_losses)
+    def compute_training_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> TrainingLosses:
+        main, extra = self.compute_loss_and_additional_losses(preds, features, target)
+        return TrainingLosses(backward=main, additional_losses=extra)
 
-    def compute_evaluation_loss(
-        self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
-    ) -> EvaluationLosses:
-        loss, additional_losses = self.compute_loss_and_additional_losses(preds, features, target)
-        return EvaluationLosses(checkpoint=loss, additional_losses=additional_losses)
+    def compute_evaluation_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> EvaluationLosses:
+        main, extra = self.compute_loss_and_additional_losses(preds, features, target)
+        return EvaluationLosses(checkpoint=main, additional_losses=extra)
 
-    def set_optimizer(self, config: Config) -> None:
-        optimizer = self.get_optimizer(config)
-        assert not isinstance(optimizer, dict), "get_optimizer returned a dict: override set_optimizer to route it"
-        self.optimizers = {"global": optimizer}
+    def update_lr_schedulers(self, step: int | None = None, epoch: int | None = None) -> None:
+        """Called after every batch in both training modes (exactly one of ``step`` / ``epoch`` is passed): every
+        scheduler advances once per call, as in the reference; override for per-epoch stepping."""
+        assert (step is None) != (epoch is None)
+        for scheduler in self.lr_schedulers.values():
+            scheduler.step()
 
-    # ==================================================================================================================
-    # user-supplied pieces
-    # ==================================================================================================================
+    # ------------------------------------------------------------------------------------------------------------------
+    # user-supplied factories and lifecycle hooks
+    # ------------------------------------------------------------------------------------------------------------------
+    def get_model(self, config: Config) -> nn.Module:
+        raise NotImplementedError
+
     def get_data_loaders(self, config: Config) -> tuple[DataLoader, DataLoader]:
         raise NotImplementedError
 
     def get_test_data_loader(self, config: Config) -> DataLoader | None:
         return None
-
-    def transform_target(self, target: TorchTargetType) -> TorchTargetType:
-        return target
 
     def get_criterion(self, config: Config) -> _Loss:
         raise NotImplementedError
@@ -747,29 +557,15 @@ class BasicClient:
     def get_optimizer(self, config: Config) -> Optimizer | dict[str, Optimizer]:
         raise NotImplementedError
 
-    def get_model(self, config: Config) -> nn.Module:
-        raise NotImplementedError
-
     def get_lr_scheduler(self, optimizer_key: str, config: Config) -> LRScheduler | None:
         return None
 
-    def update_lr_schedulers(self, step: int | None = None, epoch: int | None = None) -> None:
-        """Step-mode training steps schedulers every step; epoch-mode at the last batch of each epoch."""
-        assert (step is None) ^ (epoch is None)
-        if step is not None:
-            for scheduler in self.lr_schedulers.values():
-                scheduler.step()
-        elif self.lr_schedulers:
-            assert epoch is not None
-            seen = getattr(self, "_last_scheduler_epoch", None)
-            if seen != (self.total_epochs, epoch):
-                # advance once per epoch (first batch of a new epoch marks the boundary of the previous one)
-                if seen is not None:
-                    for scheduler in self.lr_schedulers.values():
-                        scheduler.step()
-                self._last_scheduler_epoch = (self.total_epochs, epoch)
+    def transform_target(self, target: TorchTargetType) -> TorchTargetType:
+        return target
 
-    # ------------------------------------------------------------------ lifecycle hooks (no-ops by default)
+    def transform_gradients(self, losses: TrainingLosses) -> None:
+        pass
+
     def update_before_train(self, current_server_round: int) -> None:
         pass
 
@@ -785,16 +581,14 @@ class BasicClient:
     def update_before_epoch(self, epoch: int) -> None:
         pass
 
-    def transform_gradients(self, losses: TrainingLosses) -> None:
-        pass
-
-    # ------------------------------------------------------------------ state
+    # ------------------------------------------------------------------------------------------------------------------
+    # persisted client state, Flower-style conversion shim
+    # ------------------------------------------------------------------------------------------------------------------
     def _save_client_state(self) -> None:
         self.checkpoint_and_state_module.save_state(self)
 
     def _load_client_state(self) -> bool:
         return self.checkpoint_and_state_module.maybe_load_state(self)
 
-    # ------------------------------------------------------------------ Flower-style conversion shim
     def to_client(self) -> BasicClient:
         return self

@@ -106,7 +106,7 @@ class _TcConvFn(torch.autograd.Function):
             else:
                 grad_w = tc_conv.conv2d_wgrad(x, grad_out, weight.shape[2], stride, padding)
         if ctx.needs_input_grad[0]:
-            grad_x = tc_conv.conv2d_dgrad(grad_out, tc_conv.permute_filter_for_dgrad(weight), (x.shape[2], x.shape[3]),
+            grad_x = tc_conv.conv2d_dgrad(grad_out, weight, (x.shape[2], x.shape[3]),
                                           stride, padding)
         return grad_x, grad_w, None, None, None
 

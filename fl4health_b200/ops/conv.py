@@ -81,84 +81,103 @@ def _forward_plan(h: int, w: int, cin: int, r: int, stride: int, pad: int) -> di
 
 
 def _pick_splits(ctas: int, k_blocks: int, limit: int) -> int:
+    """Split-K factor (cluster size along z): fill the machine at two resident CTAs per SM — with a 3-stage ring one CTA
+    keeps ~72 KB in flight, i.e. ~80 GB/s at ~1 us TMA latency, so layers with few tiles are latency-bound until more
+    CTAs share the reduction — while every split still has a few K blocks to pipeline."""
     env = os.environ.get("FL4H_CONV_SPLITS")
     if env:
         return max(1, min(int(env), limit, k_blocks))
-    if ctas >= 96:
-        return 1
-    want = max(1, _SM_COUNT // max(ctas, 1))
-    for cand in (16, 8, 4, 2):
-        if cand <= want and cand <= limit and k_blocks // cand >= 4:
+    want = (2 * _SM_COUNT) // max(ctas, 1)
+    for cand in (8, 4, 2):
+        if cand <= want and cand <= limit and k_blocks // cand >= 3:
             return cand
     return 1
+
+
+_MAX_TAPS = 9
+
+
+def _tap_gemm(inp: torch.Tensor, wmat: torch.Tensor, out: torch.Tensor, stats: torch.Tensor | None, n: int, k_ch: int,
+              out_ch: int, wmat_rows: int, wmat_cols: int, b_mn: bool, lattices: list, in_sn: int, plane: tuple[int, int],
+              classes: list[dict], out_strides: tuple[int, int, int], splits: int, what: str) -> None:
+    """Marshal one launch of ``fl4h_conv_tap_gemm``: ``classes`` = [{"off": out element offset, "dh": [...], "dw": [...],
+    "map": [...], "wcol": [...]}, ...] (one per output sub-lattice)."""
+    lib = _lib.load(True)
+
+    def padded(key: str) -> list[int]:
+        flat: list[int] = []
+        for cls in classes:
+            flat.extend(list(cls[key]) + [0] * (_MAX_TAPS - len(cls[key])))
+        return flat
+
+    err = lib.fl4h_conv_tap_gemm(
+        _lib.ptr(inp), _lib.ptr(wmat), _lib.ptr(out), _lib.ptr(stats), ctypes.c_int(0 if inp.dtype == torch.float32 else 1),
+        ctypes.c_int(n), ctypes.c_int(k_ch), ctypes.c_int(out_ch), ctypes.c_int(wmat_rows), ctypes.c_int(wmat_cols),
+        ctypes.c_int(1 if b_mn else 0), ctypes.c_int(len(lattices)), _arr([l[0] for l in lattices], ctypes.c_longlong),
+        _arr([l[1] for l in lattices]), _arr([l[2] for l in lattices]), _arr([l[3] for l in lattices], ctypes.c_longlong),
+        _arr([l[4] for l in lattices], ctypes.c_longlong), ctypes.c_longlong(in_sn), ctypes.c_int(plane[0]), ctypes.c_int(plane[1]),
+        ctypes.c_int(len(classes)), _arr([cls["off"] for cls in classes], ctypes.c_longlong), ctypes.c_longlong(out_strides[0]),
+        ctypes.c_longlong(out_strides[1]), ctypes.c_longlong(out_strides[2]), _arr([len(cls["dh"]) for cls in classes]),
+        _arr(padded("dh")), _arr(padded("dw")), _arr(padded("map")), _arr(padded("wcol")), ctypes.c_int(splits),
+        _lib.stream_ptr(inp.device),
+    )
+    _lib.check(err, f"fl4h_conv_tap_gemm({what})")
+    _lib.count_launches(1)
 
 
 def conv2d_forward(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int,
                    stats: torch.Tensor | None = None) -> torch.Tensor:
     """``y = conv2d(x, weight)`` (no bias).  ``stats`` ([2, Cout] fp32, zero on entry) receives per-channel sum and
     sum of squares of the stored outputs (BatchNorm's batch statistics, produced by the convolution epilogue)."""
-    lib = _lib.load(True)
     n, cin, h, w = x.shape
     cout, _, r, _ = weight.shape
     ho, wo = h // stride, w // stride
     y = torch.empty((n, cout, ho, wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     plan = _forward_plan(h, w, cin, r, stride, padding)
-    lat = plan["lattices"]
     cpb = _ROW_BYTES // x.element_size()
     m_tiles = (n * ho * wo + 127) // 128
     splits = _pick_splits(m_tiles * (cout // 64), len(plan["dh"]) * (cin // cpb), 8)
-    err = lib.fl4h_conv_tap_gemm(
-        _lib.ptr(x), _lib.ptr(weight), _lib.ptr(y), _lib.ptr(stats), ctypes.c_int(0 if x.dtype == torch.float32 else 1),
-        ctypes.c_int(n), ctypes.c_int(cin), ctypes.c_int(cout), ctypes.c_int(r * r * cin), ctypes.c_int(len(lat)),
-        _arr([l[0] for l in lat], ctypes.c_longlong), _arr([l[1] for l in lat]), _arr([l[2] for l in lat]),
-        _arr([l[3] for l in lat], ctypes.c_longlong), _arr([l[4] for l in lat], ctypes.c_longlong),
-        ctypes.c_longlong(h * w * cin), ctypes.c_int(ho), ctypes.c_int(wo), ctypes.c_longlong(0), ctypes.c_longlong(cout),
-        ctypes.c_longlong(wo * cout), ctypes.c_longlong(ho * wo * cout), ctypes.c_int(len(plan["dh"])), _arr(plan["dh"]),
-        _arr(plan["dw"]), _arr(plan["map"]), _arr(plan["wcol"]), ctypes.c_int(splits), _lib.stream_ptr(x.device),
-    )
-    _lib.check(err, "fl4h_conv_tap_gemm(forward)")
-    _lib.count_launches(1)
+    classes = [{"off": 0, "dh": plan["dh"], "dw": plan["dw"], "map": plan["map"], "wcol": plan["wcol"]}]
+    _tap_gemm(x, weight, y, stats, n, cin, cout, cout, r * r * cin, False, plan["lattices"], h * w * cin, (ho, wo), classes,
+              (cout, wo * cout, ho * wo * cout), splits, "forward")
     return y
 
 
-def permute_filter_for_dgrad(weight: torch.Tensor) -> torch.Tensor:
-    """[Cout, R, S, Cin] (physical) -> [Cin, R, S, Cout] (physical), returned as a channels_last [Cin, Cout, R, S] tensor:
-    the K-major filter matrix of the data-gradient GEMM."""
-    return weight.permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
-
-
-def conv2d_dgrad(dy: torch.Tensor, weight_t: torch.Tensor, in_hw: tuple[int, int], stride: int, padding: int) -> torch.Tensor:
-    """``dx`` of ``conv2d`` given ``weight_t = permute_filter_for_dgrad(weight)``."""
-    lib = _lib.load(True)
-    n, cout, ho, wo = dy.shape
-    cin, _, r, _ = weight_t.shape
-    h, w = in_hw
-    dx = torch.empty((n, cin, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
-    cpb = _ROW_BYTES // dy.element_size()
-    dtype = ctypes.c_int(0 if dy.dtype == torch.float32 else 1)
+@lru_cache(maxsize=256)
+def _dgrad_classes(h: int, w: int, cin: int, r: int, stride: int, pad: int) -> tuple:
+    """Output sub-lattices (one per parity of a strided layer) and their taps for the data gradient
+    ``dx[n, h, w] = sum_{r,s} dy[n, (h + pad - r) / stride, (w + pad - s) / stride] . W[:, r, s, :]`` (exact divisions only)."""
     s = stride
+    classes = []
     for ah in range(s):
         for aw in range(s):
             dh, dw, wcol = [], [], []
             for i in range(r):
                 for j in range(r):
-                    if (ah + padding - i) % s == 0 and (aw + padding - j) % s == 0:
-                        dh.append((ah + padding - i) // s)
-                        dw.append((aw + padding - j) // s)
-                        wcol.append((i * r + j) * cout)
-            hv, wv = h // s, w // s
-            m_tiles = (n * hv * wv + 127) // 128
-            splits = _pick_splits(m_tiles * (cin // 64), max(1, len(dh)) * (cout // cpb), 8) if dh else 1
-            err = lib.fl4h_conv_tap_gemm(
-                _lib.ptr(dy), _lib.ptr(weight_t), _lib.ptr(dx), None, dtype, ctypes.c_int(n), ctypes.c_int(cout), ctypes.c_int(cin),
-                ctypes.c_int(r * r * cout), ctypes.c_int(1), _arr([0], ctypes.c_longlong), _arr([ho]), _arr([wo]),
-                _arr([cout], ctypes.c_longlong), _arr([wo * cout], ctypes.c_longlong), ctypes.c_longlong(ho * wo * cout),
-                ctypes.c_int(hv), ctypes.c_int(wv), ctypes.c_longlong((ah * w + aw) * cin), ctypes.c_longlong(s * cin),
-                ctypes.c_longlong(s * w * cin), ctypes.c_longlong(h * w * cin), ctypes.c_int(len(dh)), _arr(dh), _arr(dw),
-                _arr([0] * len(dh)), _arr(wcol), ctypes.c_int(splits), _lib.stream_ptr(dy.device),
-            )
-            _lib.check(err, "fl4h_conv_tap_gemm(dgrad)")
-            _lib.count_launches(1)
+                    if (ah + pad - i) % s == 0 and (aw + pad - j) % s == 0:
+                        dh.append((ah + pad - i) // s)
+                        dw.append((aw + pad - j) // s)
+                        wcol.append((i * r + j) * cin)  # column of tap (i, j)'s input-channel block in W[Cout, R*S*Cin]
+            classes.append({"off": (ah * w + aw) * cin, "dh": dh, "dw": dw, "map": [0] * len(dh), "wcol": wcol})
+    return tuple(classes)
+
+
+def conv2d_dgrad(dy: torch.Tensor, weight: torch.Tensor, in_hw: tuple[int, int], stride: int, padding: int) -> torch.Tensor:
+    """``dx`` of ``conv2d``: ONE launch (the output parities of a strided layer are grid classes); the filters are read
+    MN-major from the forward layout ``[Cout, R, S, Cin]`` — no flipped / transposed copy is made."""
+    n, cout, ho, wo = dy.shape
+    _, cin, r, _ = weight.shape
+    h, w = in_hw
+    dx = torch.empty((n, cin, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+    cpb = _ROW_BYTES // dy.element_size()
+    s = stride
+    classes = list(_dgrad_classes(h, w, cin, r, stride, padding))
+    hv, wv = h // s, w // s
+    m_tiles = (n * hv * wv + 127) // 128
+    fewest = min((len(c["dh"]) for c in classes if c["dh"]), default=1)
+    splits = _pick_splits(m_tiles * (cin // 64) * len(classes), fewest * (cout // cpb), 8)
+    _tap_gemm(dy, weight, dx, None, n, cout, cin, cout, r * r * cin, True, [(0, ho, wo, cout, wo * cout)], ho * wo * cout,
+              (hv, wv), classes, (s * cin, s * w * cin, h * w * cin), splits, "dgrad")
     return dx
 
 
@@ -172,7 +191,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, r: int, stride: int, padding
     lat = plan["lattices"]
     k_blocks = max(1, n * ho * wo // 64)
     ctas = ((cout + 127) // 128) * (cin // 64) * len(plan["dh"])
-    splits = _pick_splits(ctas, k_blocks, 16)
+    splits = _pick_splits(ctas, k_blocks, 8)
     err = lib.fl4h_conv_wgrad(
         _lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw_out), ctypes.c_int(0 if x.dtype == torch.float32 else 1), ctypes.c_int(n),
         ctypes.c_int(cin), ctypes.c_int(cout), ctypes.c_int(r * r * cin), ctypes.c_int(len(lat)),
@@ -204,7 +223,7 @@ class _TcConv2d(torch.autograd.Function):
             dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = conv2d_dgrad(dy, permute_filter_for_dgrad(weight), (x.shape[2], x.shape[3]), ctx.stride, ctx.padding)
+            dx = conv2d_dgrad(dy, weight, (x.shape[2], x.shape[3]), ctx.stride, ctx.padding)
         if ctx.needs_input_grad[1]:
             dw = conv2d_wgrad(x, dy, weight.shape[2], ctx.stride, ctx.padding)
         return dx, dw, None, None, None

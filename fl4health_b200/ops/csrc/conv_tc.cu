@@ -35,7 +35,6 @@ namespace {
 
 constexpr int BM = 128;            // output pixels per tile (TMEM lanes)
 constexpr int kRowBytes = 128;     // one K block = 128 bytes of channels of one tap (32 fp32 / 64 bf16)
-constexpr int kStages = 4;
 constexpr int kThreads = 256;      // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSplit = 8;       // portable cluster size
@@ -177,28 +176,38 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 struct TapTable {
     int ntaps;
-    int wcol[kMaxTaps];          // first column (elements) of the tap's Cin block in the filter matrix
+    int wcol[kMaxTaps];          // first column (elements) of the tap's block in the filter matrix
     signed char dh[kMaxTaps], dw[kMaxTaps], map[kMaxTaps];
+};
+
+// One launch serves up to four "classes" that share the input and the filter matrix but have their own tap list and
+// output sub-lattice: the four output parities of a stride-2 data gradient (a forward convolution has one class).
+struct ConvClasses {
+    TapTable taps[4];
 };
 
 struct ConvMaps {
     CUtensorMap a[4];            // activation maps (parity sub-lattices for strided layers; a[0] otherwise)
-    CUtensorMap b;               // filter matrix [rows, taps*Cin], K-major
-    CUtensorMap out;             // output (C, W, H, N), box (128 B, bw, bh, bn), SWIZZLE_128B
+    CUtensorMap b;               // filter matrix: K-major [rows, taps*Cin] (forward) or the forward matrix read MN-major (dgrad)
+    CUtensorMap out[4];          // output sub-lattice per class: (C, W, H, N), box (128 B, bw, bh, bn), SWIZZLE_128B
 };
 
 struct ConvGeom {
     int tiles_w, tiles_h;        // tiles per image along w / h (tiles along n = gridDim.x / (tiles_w*tiles_h))
     int bw, bh, bn;              // pixel box of one tile
-    int cin_blocks;              // Cin * sizeof(T) / 128
+    int k_blocks;                // reduction channels * sizeof(T) / 128  (K blocks per tap)
     int cout;                    // output channels (statistics stride)
+    int n_tiles;                 // output-channel tiles per class (blockIdx.y = class * n_tiles + n_blk)
 };
 
-// shared memory carve-up (after 1024-byte alignment):
+// shared memory carve-up (after 1024-byte alignment), sized so that TWO CTAs are resident per SM (one CTA's epilogue
+// overlaps the other's main loop, and 296 slots take the 256 tiles of a 32x32x32 layer in a single wave):
 //   [0, kStages*16K)                 A ring           (reused as the split-K staging tile after the main loop)
 //   [.., + kStages*BN*128)           B ring
-//   [.., + BN*4*128 B... ]           output tile: (BN*sizeof(T)/128) groups of [128 px][128 B], swizzled
-//   barriers, TMEM slot, statistics scratch
+//   [.., + BM*BN*4)                  output tile: (BN*sizeof(T)/128) groups of [128 px][128 B], swizzled
+//   statistics scratch, barriers, TMEM slot
+constexpr int kStages = 3;
+
 template <int BN>
 struct SmemPlan {
     static constexpr int a_bytes = kStages * BM * kRowBytes;
@@ -208,15 +217,20 @@ struct SmemPlan {
     static constexpr int stats_bytes = 4 * BN * 2 * 4;
     static constexpr int total = a_bytes + b_bytes + out_bytes + stats_bytes + 256 + 1024;
     static_assert(BM * stage_pitch <= a_bytes + b_bytes, "split-K staging tile must fit in the operand rings");
+    static_assert(2 * (total + 1024) <= 227 * 1024, "two CTAs must fit in one SM's shared memory");
 };
 
-template <typename T, int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps, const ConvGeom g,
+// kBMn: the B operand is the FORWARD filter matrix [Cout, taps*Cin] consumed MN-major (data gradient: n = input
+// channel is the contiguous dimension, k = output channel the row index) — no permuted copy of the filters exists.
+template <typename T, int BN, bool kBMn>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvClasses classes, const ConvGeom g,
                      float* __restrict__ stats /* [2][cout] or null */) {
     constexpr bool kTf32 = sizeof(T) == 4;
     constexpr int kOutGroups = BN * sizeof(T) / kRowBytes;          // 128-byte channel groups of the output tile
     constexpr int kColsPerGroup = kRowBytes / sizeof(T);            // 32 (fp32) / 64 (bf16)
+    constexpr int kBBoxes = kBMn ? kOutGroups : 1;                  // MN-major B: one box per 128 bytes of n
+    constexpr int kBBoxBytes = BN * kRowBytes / kBBoxes;
     using Plan = SmemPlan<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -234,9 +248,10 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
     const int tile = blockIdx.x;
     const int tw = tile % g.tiles_w, th = (tile / g.tiles_w) % g.tiles_h, tn = tile / (g.tiles_w * g.tiles_h);
     const int w0 = tw * g.bw, h0 = th * g.bh, n0 = tn * g.bn;
-    const int n_blk = blockIdx.y;
+    const int cls = blockIdx.y / g.n_tiles, n_blk = blockIdx.y - cls * g.n_tiles;
+    const TapTable& taps = classes.taps[cls];
 
-    const int total_kb = taps.ntaps * g.cin_blocks;
+    const int total_kb = taps.ntaps * g.k_blocks;
     const int per = (total_kb + splits - 1) / splits;
     const int kb_begin = split * per;
     const int kb_end = min(total_kb, kb_begin + per);
@@ -245,7 +260,7 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[0])) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.out)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.out[cls])) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -268,19 +283,31 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
         if (lane == 0) {  // ===== TMA producer =====
             for (int i = 0; i < num_kb; ++i) {
                 const int kb = kb_begin + i;
-                const int t = kb / g.cin_blocks, cb = kb - t * g.cin_blocks;
+                const int t = kb / g.k_blocks, cb = kb - t * g.k_blocks;
                 const int stage = i % kStages;
                 mbar_wait(empty_bar + stage, ((i / kStages) & 1) ^ 1);
                 mbar_expect_tx(full_bar + stage, (BM + BN) * kRowBytes);
                 const int c0 = cb * kColsPerGroup;
                 tma_load_4d(smem_a + stage * BM * kRowBytes, &maps.a[taps.map[t]], c0, w0 + taps.dw[t], h0 + taps.dh[t], n0,
                             full_bar + stage);
-                tma_load_2d(smem_b + stage * BN * kRowBytes, &maps.b, taps.wcol[t] + c0, n_blk * BN, full_bar + stage);
+                uint8_t* b_dst = smem_b + stage * BN * kRowBytes;
+                if constexpr (kBMn) {
+#pragma unroll
+                    for (int bx = 0; bx < kBBoxes; ++bx)            // (128 B of n) x (K-block rows of k)
+                        tma_load_2d(b_dst + bx * kBBoxBytes, &maps.b, taps.wcol[t] + n_blk * BN + bx * kColsPerGroup, c0,
+                                    full_bar + stage);
+                } else {
+                    tma_load_2d(b_dst, &maps.b, taps.wcol[t] + c0, n_blk * BN, full_bar + stage);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc(kTf32, BM, BN, false, false);
+            constexpr uint32_t idesc = make_idesc(kTf32, BM, BN, false, kBMn);
+            // MN-major B (see make_desc): k rows of 128 B; 32-bit types use the 32-byte-atom layout (4-row atoms)
+            constexpr uint32_t b_layout = (kBMn && kTf32) ? 1u : 2u, b_sbo = (kBMn && kTf32) ? 512u : 1024u;
+            constexpr uint32_t b_lbo = kBMn ? (uint32_t)kBBoxBytes : 16u;
+            constexpr uint32_t b_step = kBMn ? (kTf32 ? 8u : 16u) * kRowBytes : 32u;  // bytes of B consumed per MMA
             for (int i = 0; i < num_kb; ++i) {
                 const int stage = i % kStages;
                 mbar_wait(full_bar + stage, (i / kStages) & 1);
@@ -288,9 +315,9 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
                 const uint32_t a_addr = smem_u32(smem_a + stage * BM * kRowBytes);
                 const uint32_t b_addr = smem_u32(smem_b + stage * BN * kRowBytes);
 #pragma unroll
-                for (int k = 0; k < kRowBytes / 32; ++k) {          // one MMA consumes 32 bytes of K per row
-                    umma<kTf32>(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
-                                (i > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kRowBytes / 32; ++k) {          // one MMA consumes 32 bytes of K per A row
+                    umma<kTf32>(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * b_step, b_lbo, b_sbo, b_layout),
+                                idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(empty_bar + stage);
             }
@@ -298,117 +325,133 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
         }
     }
 
-    // ===== epilogue (warps 4-7); with split-K every CTA first parks its partial tile in its own shared memory =====
+    // ===== epilogue (warps 4-7) =====
     const bool epi = warp >= 4;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                            // pixel of this thread inside the tile
-    float acc[BN];                                                  // this pixel's BN channels (fp32)
-    if (epi) {
-        if (num_kb > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            tc_fence_after();
-#pragma unroll
+    const int et = threadIdx.x - 128;                               // 0..127 within the epilogue group
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t stage_base = smem_u32(smem);                     // operand rings are idle once tmem_full fired
+    const uint32_t out_base = smem_u32(smem_out);
+    if (epi && num_kb > 0) {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+    }
+    int rows_here = BM;                                             // rows of the tile this CTA finalises and stores
+    int slice_w = 0, slice_h = 0, slice_n = 0;                      // their offset inside the tile's pixel box
+    if (splits > 1) {
+        // split-K: reduce-scatter over distributed shared memory.  Every CTA parks its fp32 partial tile in its own
+        // smem; after the cluster barrier CTA r sums rows [r*BM/S, (r+1)*BM/S) of all S tiles (its own locally, the others
+        // through ld.shared::cluster, all loads of an element in flight together), then finishes that slice like a
+        // whole tile: swizzled smem -> statistics -> TMA store of the sub-box.
+        if (epi) {
+#pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), v);
+                if (num_kb > 0) tmem_ld_32x32b_x32(tmem_row + c0, v);
+                else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts128(stage_base + row * Plan::stage_pitch + (c0 + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-        }
-    }
-    if (splits > 1) {
-        const uint32_t stage_base = smem_u32(smem);                 // operand rings are idle once tmem_full fired
-        if (epi && split != 0) {
-#pragma unroll
-            for (int j = 0; j < BN; j += 4)
-                sts128(stage_base + row * Plan::stage_pitch + j * 4, __float_as_uint(acc[j]), __float_as_uint(acc[j + 1]),
-                       __float_as_uint(acc[j + 2]), __float_as_uint(acc[j + 3]));
         }
         __syncwarp();
         cluster_sync_all();                                          // partial tiles visible cluster-wide
-        if (epi && split == 0) {
-            for (int peer = 1; peer < splits; ++peer) {              // fixed order: deterministic sum
-                const uint32_t remote = mapa(stage_base + row * Plan::stage_pitch, peer);
+        rows_here = BM / splits;
+        const int m0 = split * rows_here;
+        slice_n = m0 / (g.bh * g.bw);
+        slice_h = (m0 / g.bw) % g.bh;
+        slice_w = m0 % g.bw;
+        if (epi) {
+            const int items = rows_here * (BN / 4);                  // float4 elements of this CTA's slice
+            for (int it = et; it < items; it += 128) {
+                const int lrow = it / (BN / 4), c4 = it - lrow * (BN / 4);
+                const uint32_t off = (m0 + lrow) * Plan::stage_pitch + c4 * 16;
+                float4 part[kMaxSplit];
 #pragma unroll
-                for (int j = 0; j < BN; j += 4) {
-                    const float4 p = ld_dsmem128f(remote + j * 4);
-                    acc[j] += p.x; acc[j + 1] += p.y; acc[j + 2] += p.z; acc[j + 3] += p.w;
+                for (int p = 0; p < kMaxSplit; ++p)
+                    if (p < splits) part[p] = ld_dsmem128f(mapa(stage_base + off, p));
+                float4 a = part[0];
+#pragma unroll
+                for (int p = 1; p < kMaxSplit; ++p)                 // fixed order: deterministic sum
+                    if (p < splits) { a.x += part[p].x; a.y += part[p].y; a.z += part[p].z; a.w += part[p].w; }
+                const int col = c4 * 4;
+                if constexpr (kTf32) {
+                    const uint32_t addr = out_base + (col / 32) * (rows_here * kRowBytes) + lrow * kRowBytes +
+                                          ((((col % 32) / 4) ^ (lrow & 7)) << 4);
+                    sts128(addr, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+                } else {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+                    const uint32_t addr = out_base + (col / 64) * (rows_here * kRowBytes) + lrow * kRowBytes +
+                                          ((((col % 64) / 8) ^ (lrow & 7)) << 4) + ((col % 8) / 4) * 8;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&lo)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&hi)) : "memory");
+                }
+            }
+        }
+    } else if (epi) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (num_kb > 0) tmem_ld_32x32b_x32(tmem_row + c0, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            // registers -> swizzled output tile: a group holds kColsPerGroup channels of all 128 pixels as
+            // [row][128 B] with the 16-byte chunk index XORed by (row & 7)  (= CU_TENSOR_MAP_SWIZZLE_128B)
+            if constexpr (kTf32) {
+                const uint32_t row_addr = out_base + (c0 / 32) * (BM * kRowBytes) + row * kRowBytes;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    sts128(row_addr + ((ch ^ (row & 7)) << 4), v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+            } else {
+                const uint32_t row_addr = out_base + (c0 / 64) * (BM * kRowBytes) + row * kRowBytes;
+                const int ch0 = (c0 % 64) / 8;                       // 32 bf16 = four 16-byte chunks of the row
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[ch * 8 + 2 * e]), __uint_as_float(v[ch * 8 + 2 * e + 1]));
+                        w[e] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    sts128(row_addr + (((ch0 + ch) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
                 }
             }
         }
     }
-    if (epi && split == 0) {
-        // registers -> swizzled output tile: group gidx holds channels [gidx*kColsPerGroup, +kColsPerGroup) of all 128
-        // pixels as [row][128 B] with the 16-byte chunk index XORed by (row & 7)  (= CU_TENSOR_MAP_SWIZZLE_128B)
-        const uint32_t out_base = smem_u32(smem_out);
-#pragma unroll
-        for (int gidx = 0; gidx < kOutGroups; ++gidx) {
-            const uint32_t row_addr = out_base + gidx * (BM * kRowBytes) + row * kRowBytes;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {                        // eight 16-byte chunks per 128-byte row
-                uint32_t w[4];
-                if constexpr (kTf32) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(acc[gidx * 32 + ch * 4 + e]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(acc[gidx * 64 + ch * 8 + 2 * e], acc[gidx * 64 + ch * 8 + 2 * e + 1]);
-                        w[e] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                }
-                sts128(row_addr + ((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+    if (epi) {
+        epi_bar_sync();                                              // the (slice of the) tile is complete in smem_out
+        if (stats != nullptr && et < BN) {
+            // per-channel sum / sum of squares of the STORED values over this CTA's rows: thread c walks column c
+            // (32-bit word index inside the row; consecutive threads hit consecutive banks)
+            const int grp = kTf32 ? et / 32 : et / 64;
+            const int word = kTf32 ? et % 32 : (et % 64) / 2;
+            const uint32_t base = out_base + grp * (rows_here * kRowBytes);
+            float s0 = 0.f, q0 = 0.f;
+            for (int r = 0; r < rows_here; ++r) {
+                const uint32_t wv = lds32(base + r * kRowBytes + ((((word >> 2) ^ (r & 7)) << 4) | ((word & 3) << 2)));
+                const float x = kTf32 ? __uint_as_float(wv) : __uint_as_float((et & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+                s0 += x;
+                q0 = fmaf(x, x, q0);
             }
-        }
-        __syncwarp();
-        if (stats != nullptr) {
-            // column sums over this warp's 32 pixels: lane j reads 32-bit word j of every row (conflict-free: the
-            // swizzle permutes 16-byte chunks within a row, words of one row always cover all 32 banks)
-#pragma unroll
-            for (int gidx = 0; gidx < kOutGroups; ++gidx) {
-                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-                const uint32_t grp = out_base + gidx * (BM * kRowBytes) + quarter * 32 * kRowBytes;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int rr = quarter * 32 + r;
-                    const uint32_t word = lds32(grp + r * kRowBytes + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
-                    if constexpr (kTf32) {
-                        const float x = __uint_as_float(word);
-                        s0 += x; q0 = fmaf(x, x, q0);
-                    } else {
-                        const float x = __uint_as_float(word << 16), y = __uint_as_float(word & 0xFFFF0000u);
-                        s0 += x; q0 = fmaf(x, x, q0); s1 += y; q1 = fmaf(y, y, q1);
-                    }
-                }
-                float* mine = smem_stats + quarter * 2 * BN;
-                if constexpr (kTf32) {
-                    mine[gidx * 32 + lane] = s0;
-                    mine[BN + gidx * 32 + lane] = q0;
-                } else {
-                    mine[gidx * 64 + 2 * lane] = s0;      mine[gidx * 64 + 2 * lane + 1] = s1;
-                    mine[BN + gidx * 64 + 2 * lane] = q0; mine[BN + gidx * 64 + 2 * lane + 1] = q1;
-                }
-            }
+            atomicAdd(stats + n_blk * BN + et, s0);
+            atomicAdd(stats + g.cout + n_blk * BN + et, q0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
         epi_bar_sync();
-        const int et = threadIdx.x - 128;                            // 0..127 within the epilogue group
         if (et == 0) {
 #pragma unroll
             for (int gidx = 0; gidx < kOutGroups; ++gidx)
-                tma_store_4d(&maps.out, smem_out + gidx * (BM * kRowBytes), n_blk * BN + gidx * kColsPerGroup, w0, h0, n0);
+                tma_store_4d(&maps.out[cls], smem_out + gidx * (rows_here * kRowBytes), n_blk * BN + gidx * kColsPerGroup,
+                             w0 + slice_w, h0 + slice_h, n0 + slice_n);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the store's reads
         }
-        if (stats != nullptr && et < 2 * BN) {                       // [sum | sumsq] x BN channels
-            const int which = et / BN, col = et - which * BN;
-            const float total = smem_stats[0 * 2 * BN + which * BN + col] + smem_stats[1 * 2 * BN + which * BN + col] +
-                                smem_stats[2 * 2 * BN + which * BN + col] + smem_stats[3 * 2 * BN + which * BN + col];
-            atomicAdd(stats + which * g.cout + n_blk * BN + col, total);
-        }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the store's reads
     }
     __syncwarp();
     if (splits > 1) cluster_sync_all();                              // peers' staging tiles stay mapped until consumed
@@ -418,7 +461,6 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const TapTable taps,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient:  dW[co, tap, ci] = sum over output pixels p  dy[p, co] * x[p + shift(tap), ci]
@@ -552,72 +594,99 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const TapTable taps, c
     const bool epi = warp >= 4;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                            // output channel (row of dW) inside the tile
-    float acc[WG_N];
-    if (epi) {
-        if (num_kb > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            tc_fence_after();
-#pragma unroll
+    const int et = threadIdx.x - 128;
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t stage_base = smem_u32(smem);
+    const uint32_t out_base = smem_u32(smem_out);
+    if (epi && num_kb > 0) {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+    }
+    int rows_here = WG_M, row0 = 0;
+    if (splits > 1) {                                               // reduce-scatter over DSMEM (see conv_tap_gemm_kernel)
+        if (epi) {
+#pragma unroll 1
             for (int c0 = 0; c0 < WG_N; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), v);
+                if (num_kb > 0) tmem_ld_32x32b_x32(tmem_row + c0, v);
+                else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts128(stage_base + row * Plan::stage_pitch + (c0 + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < WG_N; ++j) acc[j] = 0.f;
-        }
-    }
-    if (splits > 1) {
-        const uint32_t stage_base = smem_u32(smem);
-        if (epi && split != 0) {
-#pragma unroll
-            for (int j = 0; j < WG_N; j += 4)
-                sts128(stage_base + row * Plan::stage_pitch + j * 4, __float_as_uint(acc[j]), __float_as_uint(acc[j + 1]),
-                       __float_as_uint(acc[j + 2]), __float_as_uint(acc[j + 3]));
         }
         __syncwarp();
         cluster_sync_all();
-        if (epi && split == 0) {
-            for (int peer = 1; peer < splits; ++peer) {
-                const uint32_t remote = mapa(stage_base + row * Plan::stage_pitch, peer);
+        rows_here = WG_M / splits;
+        row0 = split * rows_here;
+        if (epi) {
+            const int items = rows_here * (WG_N / 4);
+            for (int it = et; it < items; it += 128) {
+                const int lrow = it / (WG_N / 4), c4 = it - lrow * (WG_N / 4);
+                const uint32_t off = (row0 + lrow) * Plan::stage_pitch + c4 * 16;
+                float4 part[kMaxSplit];
 #pragma unroll
-                for (int j = 0; j < WG_N; j += 4) {
-                    const float4 p = ld_dsmem128f(remote + j * 4);
-                    acc[j] += p.x; acc[j + 1] += p.y; acc[j + 2] += p.z; acc[j + 3] += p.w;
+                for (int p = 0; p < kMaxSplit; ++p)
+                    if (p < splits) part[p] = ld_dsmem128f(mapa(stage_base + off, p));
+                float4 a = part[0];
+#pragma unroll
+                for (int p = 1; p < kMaxSplit; ++p)
+                    if (p < splits) { a.x += part[p].x; a.y += part[p].y; a.z += part[p].z; a.w += part[p].w; }
+                const int col = c4 * 4;
+                if constexpr (kTf32) {
+                    const uint32_t addr = out_base + (col / 32) * (rows_here * kRowBytes) + lrow * kRowBytes +
+                                          ((((col % 32) / 4) ^ (lrow & 7)) << 4);
+                    sts128(addr, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+                } else {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+                    const uint32_t addr = out_base + (col / 64) * (rows_here * kRowBytes) + lrow * kRowBytes +
+                                          ((((col % 64) / 8) ^ (lrow & 7)) << 4) + ((col % 8) / 4) * 8;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&lo)),
+                                 "r"(*reinterpret_cast<uint32_t*>(&hi)) : "memory");
+                }
+            }
+        }
+    } else if (epi) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < WG_N; c0 += 32) {
+            uint32_t v[32];
+            if (num_kb > 0) tmem_ld_32x32b_x32(tmem_row + c0, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if constexpr (kTf32) {
+                const uint32_t row_addr = out_base + (c0 / 32) * (WG_M * kRowBytes) + row * kRowBytes;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    sts128(row_addr + ((ch ^ (row & 7)) << 4), v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+            } else {
+                const uint32_t row_addr = out_base + (c0 / 64) * (WG_M * kRowBytes) + row * kRowBytes;
+                const int ch0 = (c0 % 64) / 8;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[ch * 8 + 2 * e]), __uint_as_float(v[ch * 8 + 2 * e + 1]));
+                        w[e] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    sts128(row_addr + (((ch0 + ch) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
                 }
             }
         }
     }
-    if (epi && split == 0) {
-        const uint32_t out_base = smem_u32(smem_out);
-#pragma unroll
-        for (int gidx = 0; gidx < kOutGroups; ++gidx) {
-            const uint32_t row_addr = out_base + gidx * (WG_M * kRowBytes) + row * kRowBytes;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                uint32_t w[4];
-                if constexpr (kTf32) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(acc[gidx * 32 + ch * 4 + e]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(acc[gidx * 64 + ch * 8 + 2 * e], acc[gidx * 64 + ch * 8 + 2 * e + 1]);
-                        w[e] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                }
-                sts128(row_addr + ((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
-            }
-        }
+    if (epi) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar_sync();
-        if (threadIdx.x == 128) {
+        if (et == 0) {
 #pragma unroll
             for (int gidx = 0; gidx < kOutGroups; ++gidx)
-                tma_store_2d(&maps.dw, smem_out + gidx * (WG_M * kRowBytes), taps.wcol[tap] + ci_blk * WG_N + gidx * kColsPerGroup,
-                             co_blk * WG_M);
+                tma_store_2d(&maps.dw, smem_out + gidx * (rows_here * kRowBytes), taps.wcol[tap] + ci_blk * WG_N + gidx * kColsPerGroup,
+                             co_blk * WG_M + row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
@@ -664,7 +733,8 @@ CUresult nhwc_map(CUtensorMap* map, const void* base, int esize, int C, int W, i
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-CUresult matrix_map(CUtensorMap* map, const void* base, int esize, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+CUresult matrix_map(CUtensorMap* map, const void* base, int esize, int64_t rows, int64_t cols, int box_rows, int box_cols,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn encode = encode_fn();
     if (encode == nullptr) return CUDA_ERROR_NOT_SUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -672,7 +742,7 @@ CUresult matrix_map(CUtensorMap* map, const void* base, int esize, int64_t rows,
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return encode(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
@@ -689,10 +759,10 @@ bool tile_box(int Ho, int Wo, int* bw, int* bh, int* bn) {
     return true;
 }
 
-template <typename T, int BN>
-cudaError_t launch_tap_gemm(const ConvMaps& maps, const TapTable& taps, const ConvGeom& g, float* stats, int m_tiles, int n_tiles,
-                            int splits, cudaStream_t stream) {
-    auto kernel = conv_tap_gemm_kernel<T, BN>;
+template <typename T, int BN, bool kBMn>
+cudaError_t launch_tap_gemm(const ConvMaps& maps, const ConvClasses& classes, const ConvGeom& g, float* stats, int m_tiles,
+                            int y_tiles, int splits, cudaStream_t stream) {
+    auto kernel = conv_tap_gemm_kernel<T, BN, kBMn>;
     static bool configured = false;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<BN>::total);
@@ -701,7 +771,7 @@ cudaError_t launch_tap_gemm(const ConvMaps& maps, const TapTable& taps, const Co
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(m_tiles, n_tiles, splits);
+    cfg.gridDim = dim3(m_tiles, y_tiles, splits);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = SmemPlan<BN>::total;
     cfg.stream = stream;
@@ -712,9 +782,8 @@ cudaError_t launch_tap_gemm(const ConvMaps& maps, const TapTable& taps, const Co
     attr[0].val.clusterDim.z = splits;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, maps, taps, g, stats);
+    return cudaLaunchKernelEx(&cfg, kernel, maps, classes, g, stats);
 }
-
 
 template <typename T>
 cudaError_t launch_wgrad(const WgradMaps& maps, const TapTable& taps, const WgradGeom& g, int co_tiles, int ci_tiles, int splits,
@@ -723,8 +792,6 @@ cudaError_t launch_wgrad(const WgradMaps& maps, const TapTable& taps, const Wgra
     static bool configured = false;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradPlan<T>::total);
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (err != cudaSuccess) return err;
         configured = true;
     }
@@ -761,56 +828,90 @@ bool pixel_box(int Ho, int Wo, int total, int* bw, int* bh, int* bn) {
 extern "C" {
 
 // Generic entry point.  dtype: 0 = fp32 tensors / TF32 math, 1 = bf16.
-//   in        : NHWC activations [N, Hin, Win, Cin]
-//   wmat      : filter matrix [rows = Cout_total, taps_total * Cin] (K-major); tap t starts at column wcol[t]
-//   out       : NHWC output; the written sub-lattice is out_base + out strides (elements) with logical dims (Ho, Wo)
-//   in_off/in_stride describe up to 4 input sub-lattices (element offsets + (sw, sh) strides); all share (Hv, Wv) dims
-//   stats     : optional [2, cout] fp32 accumulators (sum, sum of squares of the stored outputs), must be zero on entry
-int fl4h_conv_tap_gemm(const void* in, const void* wmat, void* out, float* stats, int dtype, int N, int cin, int cout,
-                       int wmat_cols, int n_maps, const long long* in_off, const int* in_hv, const int* in_wv,
-                       const long long* in_sw, const long long* in_sh, long long in_sn, int Ho, int Wo, long long out_off,
-                       long long out_sw, long long out_sh, long long out_sn, int ntaps, const int* tap_dh, const int* tap_dw,
-                       const int* tap_map, const int* tap_wcol, int splits, cudaStream_t stream) {
+//   in        : NHWC activations; up to 4 sub-lattices (element offset, logical (hv, wv), strides (sw, sh), shared sn)
+//   wmat      : filter matrix [wmat_rows, wmat_cols].  b_mn = 0: K-major, rows = output channels, tap t starts at column
+//               wcol[t].  b_mn = 1 (data gradient): the forward matrix [Cout, taps*Cin] read MN-major: rows = reduction
+//               channels, tap t's output-channel block starts at column wcol[t]
+//   out       : NHWC output; class c writes the sub-lattice at element offset out_off[c] with strides (out_sw, out_sh,
+//               out_sn) and logical plane (Ho, Wo); n_classes <= 4, class c has ntaps[c] taps at tap_*[c*9 ...]
+//   stats     : optional [2, out_ch] fp32 accumulators (sum, sum of squares of the stored outputs), zero on entry
+int fl4h_conv_tap_gemm(const void* in, const void* wmat, void* out, float* stats, int dtype, int N, int k_ch, int out_ch,
+                       int wmat_rows, int wmat_cols, int b_mn, int n_maps, const long long* in_off, const int* in_hv,
+                       const int* in_wv, const long long* in_sw, const long long* in_sh, long long in_sn, int Ho, int Wo,
+                       int n_classes, const long long* out_off, long long out_sw, long long out_sh, long long out_sn,
+                       const int* ntaps, const int* tap_dh, const int* tap_dw, const int* tap_map, const int* tap_wcol, int splits,
+                       cudaStream_t stream) {
     const int esize = dtype == 0 ? 4 : 2;
     const int cpb = kRowBytes / esize;                              // channels per K block
-    if (cin % cpb != 0 || cout % 64 != 0 || ntaps > kMaxTaps || n_maps > 4 || splits < 1 || splits > kMaxSplit)
+    constexpr int BN = 64;
+    if (k_ch % cpb != 0 || out_ch % BN != 0 || n_maps > 4 || n_maps < 1 || n_classes < 1 || n_classes > 4 || splits < 1 ||
+        splits > kMaxSplit)
         return (int)cudaErrorInvalidValue;
     ConvGeom g;
     if (!tile_box(Ho, Wo, &g.bw, &g.bh, &g.bn)) return (int)cudaErrorInvalidValue;
     g.tiles_w = Wo / g.bw;
     g.tiles_h = Ho / g.bh;
-    g.cin_blocks = cin / cpb;
-    g.cout = cout;
+    g.k_blocks = k_ch / cpb;
+    g.cout = out_ch;
+    g.n_tiles = out_ch / BN;
     const int tiles_n = (N + g.bn - 1) / g.bn;
     const int m_tiles = g.tiles_w * g.tiles_h * tiles_n;
-    const int BN = 64;
     ConvMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int i = 0; i < n_maps; ++i) {
         const char* base = reinterpret_cast<const char*>(in) + in_off[i] * esize;
-        if (nhwc_map(&maps.a[i], base, esize, cin, in_wv[i], in_hv[i], N, in_sw[i], in_sh[i], in_sn, cpb, g.bw, g.bh, g.bn) !=
+        if (nhwc_map(&maps.a[i], base, esize, k_ch, in_wv[i], in_hv[i], N, in_sw[i], in_sh[i], in_sn, cpb, g.bw, g.bh, g.bn) !=
             CUDA_SUCCESS)
             return (int)cudaErrorInvalidValue;
     }
     for (int i = n_maps; i < 4; ++i) maps.a[i] = maps.a[0];
-    if (matrix_map(&maps.b, wmat, esize, cout, wmat_cols, BN, cpb) != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
-    char* obase = reinterpret_cast<char*>(out) + out_off * esize;
-    if (nhwc_map(&maps.out, obase, esize, cout, Wo, Ho, N, out_sw, out_sh, out_sn, cpb, g.bw, g.bh, g.bn) != CUDA_SUCCESS)
-        return (int)cudaErrorInvalidValue;
-    TapTable taps;
-    memset(&taps, 0, sizeof(taps));
-    taps.ntaps = ntaps;
-    for (int t = 0; t < ntaps; ++t) {
-        taps.dh[t] = (signed char)tap_dh[t];
-        taps.dw[t] = (signed char)tap_dw[t];
-        taps.map[t] = (signed char)tap_map[t];
-        taps.wcol[t] = tap_wcol[t];
+    CUresult berr;
+    if (b_mn)  // box = (128 B of output channels) x (one K block of reduction-channel rows)
+        berr = matrix_map(&maps.b, wmat, esize, wmat_rows, wmat_cols, cpb, cpb,
+                          dtype == 0 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+    else
+        berr = matrix_map(&maps.b, wmat, esize, wmat_rows, wmat_cols, BN, cpb);
+    if (berr != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    // split-K clusters finish the tile as `splits` row slices (reduce-scatter): the store box is the slice's pixel box
+    int min_kb = 1 << 30;
+    for (int c = 0; c < n_classes; ++c) {
+        const int kb = ntaps[c] * g.k_blocks;
+        if (kb > 0 && kb < min_kb) min_kb = kb;
     }
-    const int total_kb = ntaps * g.cin_blocks;
-    if (splits > total_kb) splits = total_kb > 0 ? total_kb : 1;
+    if (min_kb == (1 << 30)) min_kb = 1;
+    while (splits > min_kb || (splits & (splits - 1)) != 0) --splits;   // power of two, at most the shortest K range
+    int sub_w = g.bw, sub_h = g.bh, sub_n = g.bn;
+    for (int rest = splits; rest > 1; rest >>= 1) {                     // halve the slowest dimension that still can be
+        if (sub_n > 1) sub_n >>= 1;
+        else if (sub_h > 1) sub_h >>= 1;
+        else sub_w >>= 1;
+    }
+    if (sub_w < 1) return (int)cudaErrorInvalidValue;
+    ConvClasses classes;
+    memset(&classes, 0, sizeof(classes));
+    for (int c = 0; c < n_classes; ++c) {
+        char* obase = reinterpret_cast<char*>(out) + out_off[c] * esize;
+        if (nhwc_map(&maps.out[c], obase, esize, out_ch, Wo, Ho, N, out_sw, out_sh, out_sn, cpb, sub_w, sub_h, sub_n) != CUDA_SUCCESS)
+            return (int)cudaErrorInvalidValue;
+        if (ntaps[c] < 0 || ntaps[c] > kMaxTaps) return (int)cudaErrorInvalidValue;
+        TapTable& t = classes.taps[c];
+        t.ntaps = ntaps[c];
+        for (int i = 0; i < ntaps[c]; ++i) {
+            t.dh[i] = (signed char)tap_dh[c * kMaxTaps + i];
+            t.dw[i] = (signed char)tap_dw[c * kMaxTaps + i];
+            t.map[i] = (signed char)tap_map[c * kMaxTaps + i];
+            t.wcol[i] = tap_wcol[c * kMaxTaps + i];
+        }
+    }
+    for (int c = n_classes; c < 4; ++c) maps.out[c] = maps.out[0];
+    const int y_tiles = g.n_tiles * n_classes;
     cudaError_t err;
-    if (dtype == 0) err = launch_tap_gemm<float, 64>(maps, taps, g, stats, m_tiles, cout / BN, splits, stream);
-    else err = launch_tap_gemm<__nv_bfloat16, 64>(maps, taps, g, stats, m_tiles, cout / BN, splits, stream);
+    if (dtype == 0)
+        err = b_mn ? launch_tap_gemm<float, BN, true>(maps, classes, g, stats, m_tiles, y_tiles, splits, stream)
+                   : launch_tap_gemm<float, BN, false>(maps, classes, g, stats, m_tiles, y_tiles, splits, stream);
+    else
+        err = b_mn ? launch_tap_gemm<__nv_bfloat16, BN, true>(maps, classes, g, stats, m_tiles, y_tiles, splits, stream)
+                   : launch_tap_gemm<__nv_bfloat16, BN, false>(maps, classes, g, stats, m_tiles, y_tiles, splits, stream);
     return (int)err;
 }
 
@@ -823,7 +924,7 @@ int fl4h_conv_wgrad(const void* x, const void* dy, void* dw, int dtype, int N, i
                     const int* tap_wcol, int splits, cudaStream_t stream) {
     const int esize = dtype == 0 ? 4 : 2;
     const int cpb = kRowBytes / esize;
-    if (cin % WG_N != 0 || cout % cpb != 0 || ntaps > kMaxTaps || ntaps < 1 || n_maps > 4 || splits < 1 || splits > 16)
+    if (cin % WG_N != 0 || cout % cpb != 0 || ntaps > kMaxTaps || ntaps < 1 || n_maps > 4 || splits < 1 || splits > kMaxSplit)
         return (int)cudaErrorInvalidValue;
     WgradGeom g;
     if (!pixel_box(Ho, Wo, WG_KP, &g.pw, &g.ph, &g.pn)) return (int)cudaErrorInvalidValue;
@@ -845,7 +946,9 @@ int fl4h_conv_wgrad(const void* x, const void* dy, void* dw, int dtype, int N, i
     if (nhwc_map(&maps.dy, dy, esize, cout, Wo, Ho, N, cout, (int64_t)Wo * cout, (int64_t)Ho * Wo * cout, cpb, g.pw, g.ph, g.pn,
                  op_swizzle) != CUDA_SUCCESS)
         return (int)cudaErrorInvalidValue;
-    if (matrix_map(&maps.dw, dw, esize, cout, dw_cols, WG_M, cpb) != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    const int total_kb = g.tiles_w * g.tiles_h * g.tiles_n;
+    while (splits > total_kb || (splits & (splits - 1)) != 0) --splits;     // power of two: row slices of the tile
+    if (matrix_map(&maps.dw, dw, esize, cout, dw_cols, WG_M / splits, cpb) != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
     TapTable taps;
     memset(&taps, 0, sizeof(taps));
     taps.ntaps = ntaps;
@@ -855,8 +958,6 @@ int fl4h_conv_wgrad(const void* x, const void* dy, void* dw, int dtype, int N, i
         taps.map[t] = (signed char)tap_map[t];
         taps.wcol[t] = tap_wcol[t];
     }
-    const int total_kb = g.tiles_w * g.tiles_h * g.tiles_n;
-    if (splits > total_kb) splits = total_kb;
     const int co_tiles = (cout + WG_M - 1) / WG_M, ci_tiles = cin / WG_N;
     cudaError_t err = dtype == 0 ? launch_wgrad<float>(maps, taps, g, co_tiles, ci_tiles, splits, stream)
                                  : launch_wgrad<__nv_bfloat16>(maps, taps, g, co_tiles, ci_tiles, splits, stream);
