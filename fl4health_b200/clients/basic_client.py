@@ -163,6 +163,8 @@ class BasicClient:
                              allocator=self._arena_allocator())
         if with_grad and options.master_weights and options.fused_optimizer and options.amp_dtype is not None:
             arena.enable_compute_shadow(options.amp_dtype)
+        elif with_grad and options.table_grads and options.fused_optimizer:
+            arena.use_table_gradients()
         return model
 
     def _arena_allocator(self) -> Any:

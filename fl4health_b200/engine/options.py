@@ -28,6 +28,9 @@ class EngineOptions:
     * ``master_weights``   with ``amp_dtype``: conv/linear parameters become ``amp_dtype`` views of an arena shadow
                            region (fp32 masters stay in the arena and are what is exchanged); the optimizer becomes one
                            multi-tensor launch that reads per-tensor low-precision gradients and writes master+shadow
+    * ``table_grads``      (any precision) drop the flat gradient region: autograd assigns per-tensor gradients instead
+                           of accumulating into arena views (one elementwise kernel per parameter and step saved), the
+                           fused optimizer consumes them through a pointer table in one launch
     """
 
     arena: bool = True
@@ -36,6 +39,7 @@ class EngineOptions:
     amp_dtype: torch.dtype | None = None
     channels_last: bool = False
     master_weights: bool = False
+    table_grads: bool = False  # fp32 too: no flat gradient region, optimizer reads per-tensor grads (pointer table)
     graph_warmup_steps: int = 3
     step_reports: bool | None = None  # None = only when a reporter asks for per-step data
 
@@ -50,4 +54,5 @@ class EngineOptions:
             amp_dtype=amp_dtype,
             channels_last=_env_flag("FL4H_CHANNELS_LAST", False),
             master_weights=_env_flag("FL4H_MASTER_WEIGHTS", False),
+            table_grads=_env_flag("FL4H_TABLE_GRADS", False),
         )

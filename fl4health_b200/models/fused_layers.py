@@ -111,6 +111,32 @@ class _TcConvFn(torch.autograd.Function):
         return grad_x, grad_w, None, None, None
 
 
+class _StemConvFn(torch.autograd.Function):
+    """First-layer convolution over raw image channels (``ops/csrc/conv_stem.cu``); the input never needs a gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stats):  # noqa: ANN001, ANN205
+        ctx.save_for_backward(x)
+        return tc_conv.stem_forward(x, weight, stats)
+
+    @staticmethod
+    def backward(ctx, grad_out):  # noqa: ANN001, ANN205
+        (x,) = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the stem convolution kernel does not produce input gradients (FL4H_TC_CONV=0 for that)")
+        if grad_out.dtype != x.dtype or not grad_out.is_contiguous(memory_format=torch.channels_last):
+            grad_out = grad_out.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        if not streams.overlap_enabled():
+            return None, tc_conv.stem_wgrad(x, grad_out), None
+        main = torch.cuda.current_stream(x.device)
+        side = streams.fork(x.device)
+        with torch.cuda.stream(side):
+            grad_w = tc_conv.stem_wgrad(x, grad_out)
+        grad_w.record_stream(main)
+        streams.defer_join(x.device, grad_out, x)
+        return None, grad_w, None
+
+
 class _ConvOverlappedWgrad(torch.autograd.Function):
     """``conv2d`` whose backward issues the data gradient on the current stream (critical path) and the weight
     gradient on a side stream (only the optimizer needs it); see ``engine/streams.py``."""
@@ -164,16 +190,27 @@ class TcConv2d(Conv2dOverlapWgrad):
     stride 1 / 2, channels_last fp32 (TF32 math) or bf16 — and ``Conv2dOverlapWgrad`` (cuDNN) for everything else.
     ``FL4H_TC_CONV=0`` forces the library path (A/B runs)."""
 
-    def kernel_applies(self, x: torch.Tensor) -> bool:
+    def _plain(self, x: torch.Tensor) -> bool:
         if os.environ.get("FL4H_TC_CONV", "1") == "0" or self.bias is not None or self.padding_mode != "zeros":
             return False
         if isinstance(self.padding, str) or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
             return False
-        if x.dtype != self.weight.dtype:
+        return x.dtype == self.weight.dtype
+
+    def stem_applies(self, x: torch.Tensor) -> bool:
+        """Raw-image first layer (Cin <= 4): the CUDA-core stem kernels; the input must not require a gradient."""
+        return (self._plain(x) and not x.requires_grad
+                and tc_conv.stem_supported(x, self.weight, self.stride[0], self.padding[0], self.groups, self.dilation[0]))
+
+    def kernel_applies(self, x: torch.Tensor) -> bool:
+        if not self._plain(x):
             return False
-        return tc_conv.supported(x, self.weight, self.stride[0], self.padding[0], self.groups, self.dilation[0])
+        return (tc_conv.supported(x, self.weight, self.stride[0], self.padding[0], self.groups, self.dilation[0])
+                or self.stem_applies(x))
 
     def forward(self, input: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:  # noqa: A002
+        if self.stem_applies(input):
+            return _StemConvFn.apply(input, self.weight, stats)
         if self.kernel_applies(input):
             return _TcConvFn.apply(input, self.weight, self.stride[0], self.padding[0], stats)
         assert stats is None, "epilogue statistics requested for a shape the tcgen05 kernel does not cover"

@@ -60,7 +60,7 @@ class ResNet18(nn.Module):
             self.conv1 = Conv2dOverlapWgrad(in_channels, 64, 7, stride=2, padding=3, bias=False)
             self.maxpool: nn.Module = nn.MaxPool2d(3, stride=2, padding=1)
         else:
-            self.conv1 = Conv2dOverlapWgrad(in_channels, 64, 3, stride=1, padding=1, bias=False)
+            self.conv1 = TcConv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)  # Cin = 3: CUDA-core stem kernels
             self.maxpool = nn.Identity()
         self.bn1 = BatchNormAct2d(64, relu=True)
         widths, strides = (64, 128, 256, 512), (1, 2, 2, 2)
@@ -75,7 +75,7 @@ class ResNet18(nn.Module):
                 nn.init.kaiming_normal_(module.weight, mode="fan_out", nonlinearity="relu")
 
     def forward_features(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.maxpool(bn_act(self.bn1, self.conv1(x)))
+        x = self.maxpool(conv_bn_act(self.conv1, self.bn1, x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return torch.flatten(self.avgpool(x), 1)
 

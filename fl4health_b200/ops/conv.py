@@ -205,6 +205,51 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, r: int, stride: int, padding
     return dw_out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# stem (Cin <= 4): CUDA-core kernels, csrc/conv_stem.cu
+# ------------------------------------------------------------------------------------------------------------------
+_STEM_SCRATCH: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def stem_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int, groups: int = 1, dilation: int = 1) -> bool:
+    """3x3 / stride 1 / pad 1 / 64 filters over 1, 3 or 4 input channels (the first layer of the image models)."""
+    if not x.is_cuda or _lib.load() is None or groups != 1 or dilation != 1 or stride != 1 or padding != 1:
+        return False
+    if x.dtype not in (torch.float32, torch.bfloat16) or weight.dtype != x.dtype or not _is_cl(x) or not _is_cl(weight):
+        return False
+    cout, cin, r, s = weight.shape
+    return cout == 64 and cin in (1, 3, 4) and r == 3 and s == 3 and x.shape[2] % 4 == 0 and x.shape[3] <= 64
+
+
+def stem_forward(x: torch.Tensor, weight: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:
+    lib = _lib.load(True)
+    n, cin, h, w = x.shape
+    y = torch.empty((n, 64, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    err = lib.fl4h_conv_stem_fwd(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(y), _lib.ptr(stats),
+                                 ctypes.c_int(0 if x.dtype == torch.float32 else 1), ctypes.c_int(n), ctypes.c_int(h),
+                                 ctypes.c_int(w), ctypes.c_int(cin), ctypes.c_int(64), _lib.stream_ptr(x.device))
+    _lib.check(err, "fl4h_conv_stem_fwd")
+    _lib.count_launches(1)
+    return y
+
+
+def stem_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load(True)
+    n, cin, h, w = x.shape
+    dw_out = torch.empty((64, cin, 3, 3), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream, cin)
+    scratch = _STEM_SCRATCH.get(key)
+    if scratch is None:  # self-resetting accumulators: one pair per (device, stream, Cin)
+        scratch = (torch.zeros(64 * 9 * cin, dtype=torch.float32, device=x.device), torch.zeros(1, dtype=torch.int32, device=x.device))
+        _STEM_SCRATCH[key] = scratch
+    err = lib.fl4h_conv_stem_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw_out), _lib.ptr(scratch[0]), _lib.ptr(scratch[1]),
+                                   ctypes.c_int(0 if x.dtype == torch.float32 else 1), ctypes.c_int(n), ctypes.c_int(h),
+                                   ctypes.c_int(w), ctypes.c_int(cin), ctypes.c_int(64), _lib.stream_ptr(x.device))
+    _lib.check(err, "fl4h_conv_stem_wgrad")
+    _lib.count_launches(1)
+    return dw_out
+
+
 def conv2d_reference(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int) -> torch.Tensor:
     return F_nn.conv2d(x, weight, None, stride, padding)
 

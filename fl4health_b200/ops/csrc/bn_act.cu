@@ -22,6 +22,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 #include <stdint.h>
 
 #include "bn_common.cuh"
@@ -174,6 +176,10 @@ bn_apply_presum_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __
                        float* sums, const float* __restrict__ gamma, const float* __restrict__ beta, float* rmean,
                        float* rvar, long long* nbt, float momentum, float eps, float* __restrict__ mean_out,
                        float* __restrict__ invstd_out, unsigned* done) {
+    // programmatic dependent launch (see conv_tc.cu): started while the producing convolution drains; its statistics
+    // and output are visible after the wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int LP = C >> 3;
     const float inv_m = 1.f / (float)M;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -745,13 +751,25 @@ int fl4h_bn_fwd_train_presum(const void* x, const void* res, void* y, int64_t M,
     const int64_t nvec = M * C / 8;
     const bool has_res = res != nullptr;
     if ((C & 7) != 0 || kThreads % (C >> 3) != 0) return (int)cudaErrorInvalidValue;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(apply_grid(nvec));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    const char* pdl = getenv("FL4H_PDL");
+    cfg.numAttrs = (pdl != nullptr && pdl[0] == '0') ? 0 : 1;
+    cudaError_t lerr = cudaSuccess;
 #define LAUNCH_PRESUM(T, R, S)                                                                                         \
-    bn_apply_presum_kernel<T, R, S><<<apply_grid(nvec), kThreads, 0, stream>>>((const T*)x, (const T*)res, (T*)y, nvec, C, \
-        M, sums, gamma, beta, running_mean, running_var, nbt, momentum, eps, mean_out, invstd_out, done)
+    lerr = cudaLaunchKernelEx(&cfg, bn_apply_presum_kernel<T, R, S>, (const T*)x, (const T*)res, (T*)y, nvec, C,       \
+        M, sums, gamma, beta, running_mean, running_var, (long long*)nbt, momentum, eps, mean_out, invstd_out, done)
     if (is_bf16) FL4H_BN_DISPATCH(__nv_bfloat16, relu, has_res, LAUNCH_PRESUM);
     else FL4H_BN_DISPATCH(float, relu, has_res, LAUNCH_PRESUM);
 #undef LAUNCH_PRESUM
-    return (int)cudaGetLastError();
+    return (int)lerr;
 }
 
 int fl4h_bn_fwd_eval(const void* x, const void* res, void* y, int64_t M, int C, const float* gamma, const float* beta,

@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -172,6 +173,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// Programmatic dependent launch: the kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so
+// their prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the
+// stream; `pdl_wait` blocks until that kernel's memory is visible, `pdl_trigger` lets the NEXT kernel start its own
+// prologue early.  (In a CUDA graph these become programmatic dependency edges.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // epilogue warps only
 
 struct TapTable {
@@ -278,6 +286,8 @@ conv_tap_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();                                                     // inputs written by the previous kernel are visible
+    pdl_trigger();                                                  // the next kernel may begin its prologue
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -547,6 +557,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const TapTable taps, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();                                                     // inputs written by the previous kernel are visible
+    pdl_trigger();                                                  // the next kernel may begin its prologue
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -759,6 +771,15 @@ bool tile_box(int Ho, int Wo, int* bw, int* bh, int* bn) {
     return true;
 }
 
+bool use_pdl() {
+    static int on = -1;
+    if (on < 0) {
+        const char* v = getenv("FL4H_PDL");
+        on = (v != nullptr && v[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 template <typename T, int BN, bool kBMn>
 cudaError_t launch_tap_gemm(const ConvMaps& maps, const ConvClasses& classes, const ConvGeom& g, float* stats, int m_tiles,
                             int y_tiles, int splits, cudaStream_t stream) {
@@ -775,13 +796,15 @@ cudaError_t launch_tap_gemm(const ConvMaps& maps, const ConvClasses& classes, co
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = SmemPlan<BN>::total;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = use_pdl() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, maps, classes, g, stats);
 }
 
@@ -801,13 +824,15 @@ cudaError_t launch_wgrad(const WgradMaps& maps, const TapTable& taps, const Wgra
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = WgradPlan<T>::total;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = use_pdl() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, maps, taps, g);
 }
 

@@ -227,6 +227,15 @@ class ParameterArena:
         self.refresh_shadow()
         return self.shadow
 
+    def use_table_gradients(self) -> None:
+        """Drop the flat gradient region: ``.grad`` is None before every backward, so autograd ASSIGNS each parameter's
+        gradient (no zero-fill and no accumulate kernel per parameter) and the multi-tensor optimizer reads the
+        per-tensor gradients through a pointer table (``ops/csrc/mt_optim.cu``).  What ``enable_compute_shadow`` does
+        for bf16 master weights, available to plain fp32 training too (``EngineOptions.table_grads``)."""
+        for param in self.module.parameters():
+            param.grad = None
+        self.grad = None
+
     @property
     def params_end(self) -> int:
         ends = [_round_up(e.end, ALIGN) for e in self.entries if e.kind != "buffer"]

@@ -93,3 +93,48 @@ def test_conv_autograd_matches_reference_end_to_end() -> None:
     (y1 * y1).sum().backward()
     (y2 * y2).sum().backward()
     assert _rel_err(y1, y2) < 4e-3 and _rel_err(x1.grad, x2.grad) < 8e-3 and _rel_err(w1.grad, w2.grad) < 8e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_stem_conv_forward_statistics_and_weight_gradient(dtype) -> None:  # noqa: ANN001
+    from fl4health_b200.ops import conv
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(32, 3, 32, 32, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 3, 3, 3, device="cuda", generator=g) / 27 ** 0.5).to(dtype).contiguous(memory_format=torch.channels_last)
+    assert conv.stem_supported(x, w, 1, 1)
+    stats = torch.zeros(2, 64, device="cuda")
+    y = conv.stem_forward(x, w, stats)
+    wr = w.float().requires_grad_(True)
+    ref = F.conv2d(x.float(), wr, None, 1, 1)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert _rel_err(y, ref) < tol
+    assert torch.allclose(stats[0], y.float().sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[1], (y.float() ** 2).sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2)
+    dy = torch.randn_like(ref).to(dtype).contiguous(memory_format=torch.channels_last)
+    ref.backward(dy.float())
+    for _ in range(2):  # twice: the scratch accumulator must have reset itself
+        dw = conv.stem_wgrad(x, dy)
+        assert _rel_err(dw, wr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+def test_resnet18_step_launches_no_library_convolution() -> None:
+    """One training step of the flagship model under the profiler: every convolution is one of ours."""
+    from torch.profiler import ProfilerActivity, profile
+
+    from fl4health_b200.models import resnet18_cifar
+
+    model = resnet18_cifar().cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(32, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    target = torch.randint(0, 10, (32,), device="cuda")
+    for _ in range(2):
+        F.cross_entropy(model(x), target).backward()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        F.cross_entropy(model(x), target).backward()
+        torch.cuda.synchronize()
+    names = [evt.key for evt in prof.key_averages()]
+    ours = [n for n in names if "conv_tap_gemm_kernel" in n or "conv_wgrad_kernel" in n or "stem_" in n]
+    library = [n for n in names if any(tag in n.lower() for tag in ("cudnn", "cutlass", "implicit_gemm", "xmma", "wgrad_alg"))
+               and "sgemm" not in n.lower()]
+    assert ours and not library, library

@@ -7,3 +7,7 @@ for sel in "forward and tf32" "forward and bf16" "backward and tf32" "backward a
   echo "== $sel rc=$?"; tail -6 gpurun_out/conv/$name.log | cut -c1-220
 done
 timeout 300 python benchmarks/conv_bench.py > gpurun_out/conv/bench.txt 2>&1; grep CONV gpurun_out/conv/bench.txt || tail -5 gpurun_out/conv/bench.txt
+for sel in "stem" "resnet18_step"; do
+  timeout 240 python -m pytest tests/test_gpu_conv.py -q --tb=short -k "$sel" > gpurun_out/conv/$sel.log 2>&1
+  echo "== $sel rc=$?"; tail -8 gpurun_out/conv/$sel.log | cut -c1-220
+done
