@@ -168,7 +168,7 @@ def main() -> None:
             arena=not eager_impl, fused_optimizer=not eager_impl, cuda_graphs=not (args.no_graphs or eager_impl),
             amp_dtype=torch.bfloat16 if bf16 else None, channels_last=not eager_impl,
             master_weights=bf16 and not (eager_impl or args.no_master_weights),
-            table_grads=not (bf16 or eager_impl),  # fp32: per-tensor gradients + pointer-table optimizer
+            table_grads=not (bf16 or eager_impl) and os.environ.get("FL4H_TABLE_GRADS", "1") != "0",  # fp32: pointer-table optimizer
         )
 
     def synthetic(n: int, seed: int) -> TensorDataset:

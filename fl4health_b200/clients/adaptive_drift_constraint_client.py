@@ -12,74 +12,88 @@ using a non-translatable optimizer transparently gets the autograd path.
 
 from __future__ import annotations
 
-from collections.abc import Sequence
 from logging import INFO
-from pathlib import Path
+from typing import Any
 
 import torch
 
-from fl4health_b200.checkpointing.client_module import ClientCheckpointAndStateModule
 from fl4health_b200.clients.basic_client import BasicClient
 from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, NDArrays
 from fl4health_b200.engine.fused_optim import _FlatOptimizer
-from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.losses.weight_drift_loss import WeightDriftLoss
-from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.ops import flat as flat_ops
 from fl4health_b200.parallel.arena import arena_of
+from fl4health_b200.parameter_exchange.full_exchanger import FullParameterExchanger
 from fl4health_b200.parameter_exchange.packing_exchanger import FullParameterExchangerWithPacking
 from fl4health_b200.parameter_exchange.parameter_exchanger_base import ParameterExchanger
 from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerAdaptiveConstraint
-from fl4health_b200.reporting.base_reporter import BaseReporter
-from fl4health_b200.utils.losses import LossMeterType, TrainingLosses
+from fl4health_b200.utils.losses import TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchPredType, TorchTargetType
 
 
 class AdaptiveDriftConstraintClient(BasicClient):
-    def __init__(
-        self,
-        data_path: Path,
-        metrics: Sequence[Metric],
-        device: torch.device,
-        loss_meter_type: LossMeterType = LossMeterType.AVERAGE,
-        checkpoint_and_state_module: ClientCheckpointAndStateModule | None = None,
-        reporters: Sequence[BaseReporter] | None = None,
-        progress_bar: bool = False,
-        client_name: str | None = None,
-        engine_options: EngineOptions | None = None,
-    ) -> None:
-        super().__init__(
-            data_path=data_path, metrics=metrics, device=device, loss_meter_type=loss_meter_type,
-            checkpoint_and_state_module=checkpoint_and_state_module, reporters=reporters, progress_bar=progress_bar,
-            client_name=client_name, engine_options=engine_options,
-        )
-        self.drift_penalty_tensors: list[torch.Tensor] | None = None
+    """Constructor arguments are ``BasicClient``'s.  Subclasses describe their variant declaratively:
+
+    * ``exchanged_model``       attribute holding the network that travels to / from the server (Ditto: its global twin);
+    * ``anchor_model``          attribute whose weights are the drift reference ``w_ref`` at the start of local training
+                                (None: no automatic snapshot; "model": the weights just received, FedProx);
+    * ``penalty_optimizer_key`` the optimizer stepping the *constrained* network ``self.model`` (absorbs ``mu (w - w_ref)``);
+    * ``receives_into``         attribute the aggregate is written to outside the very first fit.
+    """
+
+    exchanged_model = "model"
+    receives_into = "model"
+    anchor_model: str | None = None
+    penalty_optimizer_key = "global"
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
         self.parameter_exchanger: FullParameterExchangerWithPacking[float]
+        self.drift_penalty_tensors: list[torch.Tensor] | None = None
         self.drift_penalty_weight: float | None = None
         self.loss_for_adaptation: float = 0.0
         self.penalty_loss_function = WeightDriftLoss(self.device)
-        # which optimizer steps the drift-constrained model (Ditto: the personal model's "local" optimizer)
-        self.penalty_optimizer_key = "global"
 
     # ---------------------------------------------------------------------------------------- wire format
+    def get_parameter_exchanger(self, config: Config) -> ParameterExchanger:
+        return FullParameterExchangerWithPacking(ParameterPackerAdaptiveConstraint())
+
     def get_parameters(self, config: Config) -> NDArrays:
+        """``weights(exchanged model) ++ [vanilla training loss]`` — the loss lets the server adapt the penalty weight."""
         if not self.initialized:
             return self.setup_client_and_return_all_model_parameters(config)
         if self.initial_parameters_requested(config):  # already set up by a properties poll: plain model state, unpacked
             return FullParameterExchanger().push_parameters(self.model, config=config)
-        assert self.model is not None and self.parameter_exchanger is not None and self.loss_for_adaptation is not None
-        model_weights = self.parameter_exchanger.push_parameters(self.model, config=config)
-        return self.parameter_exchanger.pack_parameters(model_weights, self.loss_for_adaptation)
+        outgoing = self.parameter_exchanger.push_parameters(getattr(self, self.exchanged_model), config=config)
+        return self.parameter_exchanger.pack_parameters(outgoing, self.loss_for_adaptation)
 
     def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
-        assert self.model is not None and self.parameter_exchanger is not None
-        server_model_state, self.drift_penalty_weight = self.parameter_exchanger.unpack_parameters(parameters)
+        """``weights ++ [mu]`` from the server: remember ``mu``, route the weights to where this variant keeps them."""
+        aggregate, self.drift_penalty_weight = self.parameter_exchanger.unpack_parameters(parameters)
         log(INFO, f"Penalty weight received from the server: {self.drift_penalty_weight}")
-        super().set_parameters(server_model_state, config, fitting_round)
+        self._install_aggregate(aggregate, config, fitting_round)
 
-    def get_parameter_exchanger(self, config: Config) -> ParameterExchanger:
-        return FullParameterExchangerWithPacking(ParameterPackerAdaptiveConstraint())
+    def _install_aggregate(self, aggregate: NDArrays, config: Config, fitting_round: bool) -> None:
+        if self.receives_into == "model":
+            BasicClient.set_parameters(self, aggregate, config, fitting_round)
+        elif fitting_round and config.get("current_server_round") == 1 and self.exchanged_model != "model" \
+                and self.receives_into == self.exchanged_model:
+            log(INFO, "Initializing the global and local models weights for the first time")
+            self.initialize_all_model_weights(aggregate, config)
+        else:
+            self.parameter_exchanger.pull_parameters(aggregate, getattr(self, self.receives_into), config)
+
+    def update_before_train(self, current_server_round: int) -> None:
+        if self.anchor_model is not None:
+            self.drift_penalty_tensors = self.snapshot_drift_anchor(
+                source_model=getattr(self, self.anchor_model), constrained_model=self.model)
+        super().update_before_train(current_server_round)
+
+    def update_after_train(self, local_steps: int, loss_dict: dict[str, float], config: Config) -> None:
+        assert "loss_for_adaptation" in loss_dict
+        self.loss_for_adaptation = loss_dict["loss_for_adaptation"]
+        super().update_after_train(local_steps, loss_dict, config)
 
     # ---------------------------------------------------------------------------------------- drift anchor
     def snapshot_drift_anchor(self, source_model: torch.nn.Module | None = None, constrained_model: torch.nn.Module | None = None) -> list[torch.Tensor]:
@@ -118,18 +132,11 @@ class AdaptiveDriftConstraintClient(BasicClient):
     def compute_training_loss(
         self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
     ) -> TrainingLosses:
-        loss, additional_losses = self.compute_loss_and_additional_losses(preds, features, target)
-        additional_losses = additional_losses or {}
-        additional_losses["loss"] = loss.clone()
-        additional_losses["loss_for_adaptation"] = loss.clone()
-        penalty_loss = self.compute_penalty_loss()
-        additional_losses["penalty_loss"] = penalty_loss.clone()
-        return TrainingLosses(backward=loss + penalty_loss, additional_losses=additional_losses)
-
-    def update_after_train(self, local_steps: int, loss_dict: dict[str, float], config: Config) -> None:
-        assert "loss_for_adaptation" in loss_dict
-        self.loss_for_adaptation = loss_dict["loss_for_adaptation"]
-        super().update_after_train(local_steps, loss_dict, config)
+        task_loss, extras = self.compute_loss_and_additional_losses(preds, features, target)
+        penalty = self.compute_penalty_loss()
+        recorded = {**(extras or {}), "loss": task_loss.clone(), "loss_for_adaptation": task_loss.clone(),
+                    "penalty_loss": penalty.clone()}
+        return TrainingLosses(backward=task_loss + penalty, additional_losses=recorded)
 
     def compute_penalty_loss(self) -> torch.Tensor:
         assert self.drift_penalty_tensors is not None and self.drift_penalty_weight is not None

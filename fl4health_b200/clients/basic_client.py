@@ -35,6 +35,7 @@ from torch.utils.data import DataLoader
 from fl4health_b200.checkpointing.client_module import CheckpointMode, ClientCheckpointAndStateModule
 from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, NDArrays, Scalar
+from fl4health_b200.engine.companions import Companion, build_companions, companion_modules
 from fl4health_b200.engine.fused_optim import translate_optimizer
 from fl4health_b200.engine.graph_runner import GraphStepRunner
 from fl4health_b200.engine.local_loop import BatchCycler, EpochSchedule, StepSchedule, run_evaluation, run_training
@@ -123,7 +124,10 @@ class BasicClient:
     # ------------------------------------------------------------------------------------------------------------------
     # set-up: user factories -> placed model, loaders, (fused) optimizers, schedulers, criterion, exchanger
     # ------------------------------------------------------------------------------------------------------------------
+    companions: dict[str, Companion] = {}  # extra models kept next to ``self.model`` (engine/companions.py)
+
     def setup_client(self, config: Config) -> None:
+        build_companions(self, config)
         self.model = self._place_model(self.get_model(config))
         self.train_loader, self.val_loader = self.get_data_loaders(config)
         self.test_loader = self.get_test_data_loader(config)
@@ -172,8 +176,8 @@ class BasicClient:
         return getattr(self, "arena_allocator", None)
 
     def _candidate_modules(self) -> list[nn.Module]:
-        """Modules whose arenas an optimizer may be operating on (clients with extra models extend this)."""
-        return [self.model]
+        """Modules whose arenas an optimizer may be operating on: the model and the trainable companions."""
+        return [self.model, *companion_modules(self, trainable_only=True)]
 
     def _arena_for_optimizer(self, optimizer: Optimizer) -> ParameterArena | None:
         """The arena of the candidate module that owns every parameter of ``optimizer`` (None: keep the stock one)."""

@@ -1,5 +1,5 @@
 """FedProx client (parity: ``fl4health/clients/fed_prox_client.py:4-22``): the drift reference is the model received
-at the start of the round."""
+at the start of the round — in the engine the pull kernel writes it (``ParameterArena._fused_pull``)."""
 
 from __future__ import annotations
 
@@ -7,6 +7,4 @@ from fl4health_b200.clients.adaptive_drift_constraint_client import AdaptiveDrif
 
 
 class FedProxClient(AdaptiveDriftConstraintClient):
-    def update_before_train(self, current_server_round: int) -> None:
-        self.drift_penalty_tensors = self.snapshot_drift_anchor()
-        return super().update_before_train(current_server_round)
+    anchor_model = "model"

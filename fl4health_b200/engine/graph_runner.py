@@ -41,6 +41,10 @@ def _signature(obj: Any) -> tuple:
 
 def _alloc_like(obj: Any, device: torch.device) -> Any:
     if isinstance(obj, torch.Tensor):
+        # same physical layout as the live batch (channels-last images stay channels-last: layout-specialised kernels
+        # — the NHWC stem convolution — must see during capture what they saw during the eager warm-up)
+        if obj.dim() == 4 and not obj.is_contiguous() and obj.is_contiguous(memory_format=torch.channels_last):
+            return torch.empty(obj.shape, dtype=obj.dtype, device=device, memory_format=torch.channels_last)
         return torch.empty(obj.shape, dtype=obj.dtype, device=device)
     if isinstance(obj, dict):
         return {k: _alloc_like(v, device) for k, v in obj.items()}

@@ -199,7 +199,7 @@ class TcConv2d(Conv2dOverlapWgrad):
 
     def stem_applies(self, x: torch.Tensor) -> bool:
         """Raw-image first layer (Cin <= 4): the CUDA-core stem kernels; the input must not require a gradient."""
-        return (self._plain(x) and not x.requires_grad
+        return (self._plain(x) and not x.requires_grad and os.environ.get("FL4H_STEM", "1") != "0"
                 and tc_conv.stem_supported(x, self.weight, self.stride[0], self.padding[0], self.groups, self.dilation[0]))
 
     def kernel_applies(self, x: torch.Tensor) -> bool:
