@@ -70,6 +70,9 @@ def conv_bn_act(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: torch
                 relu: bool = True) -> torch.Tensor:
     """``relu(bn(conv(x)) + residual)``.  When ``conv`` runs on the tcgen05 kernel and ``bn`` is a ``BatchNormAct2d`` in
     training mode, the convolution epilogue reduces the batch statistics and BatchNorm becomes a single apply pass."""
+    if isinstance(conv, TcConv2d) and isinstance(bn, BatchNormAct2d):
+        if torch.is_autocast_enabled() and x.is_cuda and x.dtype != conv.weight.dtype == torch.bfloat16:
+            x = x.to(torch.bfloat16)
     if isinstance(conv, TcConv2d) and isinstance(bn, BatchNormAct2d) and conv.kernel_applies(x):
         sums = bn.presum_buffer(x, residual)
         if sums is not None:
@@ -209,6 +212,8 @@ class TcConv2d(Conv2dOverlapWgrad):
                 or self.stem_applies(x))
 
     def forward(self, input: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:  # noqa: A002
+        if torch.is_autocast_enabled() and input.is_cuda and input.dtype != self.weight.dtype == torch.bfloat16:
+            input = input.to(torch.bfloat16)  # master-weight mode: weights already bf16, the image batch follows autocast
         if self.stem_applies(input):
             return _StemConvFn.apply(input, self.weight, stats)
         if self.kernel_applies(input):
