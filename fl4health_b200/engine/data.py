@@ -54,6 +54,12 @@ class BatchedTensorLoader:
         self._epoch_pool: ThreadPoolExecutor | None = None
         self._epoch_done: dict[int, torch.cuda.Event] = {}  # H2D copies out of an epoch buffer have been enqueued
         self.max_epoch_buffer_bytes = 8 << 30
+        # pinned placement + device: copy-stream prefetch (see _iter_device_prefetched)
+        self.prefetch_to_device = True
+        self.prefetch_depth = 2
+        self._copy_stream: torch.cuda.Stream | None = None
+        self._device_ring: list[tuple[torch.Tensor, torch.Tensor]] = []
+        self._device_ring_pos = 0
         if placement == "device":
             assert self.device is not None, "device placement needs a device"
             dataset.data = dataset.data.to(self.device)
@@ -150,11 +156,61 @@ class BatchedTensorLoader:
             yield ds.apply_transforms(ds.data[start:stop], ds.targets[start:stop])
 
     def __iter__(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
+        if self.placement == "pinned" and self.device is not None and self.device.type == "cuda" and self.prefetch_to_device:
+            return self._iter_device_prefetched(self._iter_host())
+        return self._iter_host()
+
+    def _iter_host(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
         if not self.shuffle and self._plain():
             return self._iter_sequential()  # contiguous views: zero-copy for every placement
         if self._epoch_mode():
             return self._iter_epoch_buffered()
         return self._iter_gathered()
+
+    def _iter_device_prefetched(self, host_batches: Iterator) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
+        """Pinned placement with a target device: H2D copies run on a dedicated copy stream ``prefetch_depth`` batches
+        ahead of the consumer, into a small ring of device buffers; the consumer's stream only waits on the copy's event
+        (already complete in steady state), so the host->device transfer never sits on the training critical path."""
+        depth = self.prefetch_depth
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy_stream
+        in_flight: list[tuple[torch.Tensor, torch.Tensor, torch.cuda.Event]] = []
+
+        def enqueue(batch: tuple[torch.Tensor, torch.Tensor]) -> None:
+            data, target = batch
+            slot = self._device_ring_pos % (depth + 2)
+            self._device_ring_pos += 1
+            if len(self._device_ring) <= slot or self._device_ring[slot][0].shape != data.shape:
+                fresh = (torch.empty(data.shape, dtype=data.dtype, device=self.device),
+                         torch.empty(target.shape, dtype=target.dtype, device=self.device))
+                if len(self._device_ring) <= slot:
+                    self._device_ring.append(fresh)
+                else:
+                    self._device_ring[slot] = fresh
+            dst_data, dst_target = self._device_ring[slot]
+            # the slot's previous consumer ran on the current stream: the copy must not overtake it
+            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(copy_stream):
+                dst_data.copy_(data, non_blocking=True)
+                dst_target.copy_(target, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            in_flight.append((dst_data, dst_target, ready))
+
+        for batch in host_batches:
+            if not (isinstance(batch[0], torch.Tensor) and isinstance(batch[1], torch.Tensor)):
+                yield batch  # structured batches (dict inputs) take the plain path
+                continue
+            enqueue(batch)
+            if len(in_flight) > depth:
+                data, target, ready = in_flight.pop(0)
+                torch.cuda.current_stream(self.device).wait_event(ready)
+                yield data, target
+        while in_flight:
+            data, target, ready = in_flight.pop(0)
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            yield data, target
 
     def _iter_gathered(self) -> Iterator[tuple[torch.Tensor, torch.Tensor]]:
         n = len(self.dataset)

@@ -218,7 +218,8 @@ def stem_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: 
     if x.dtype not in (torch.float32, torch.bfloat16) or weight.dtype != x.dtype or not _is_cl(x) or not _is_cl(weight):
         return False
     cout, cin, r, s = weight.shape
-    return cout == 64 and cin in (1, 3, 4) and r == 3 and s == 3 and x.shape[2] % 4 == 0 and x.shape[3] <= 64
+    return (cout == 64 and cin in (1, 3, 4) and r == 3 and s == 3 and x.shape[2] % 8 == 0 and x.shape[3] % 32 == 0
+            and x.shape[3] <= 64)
 
 
 def stem_forward(x: torch.Tensor, weight: torch.Tensor, stats: torch.Tensor | None = None) -> torch.Tensor:

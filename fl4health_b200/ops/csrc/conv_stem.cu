@@ -28,82 +28,82 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
 // x: [N, H, W, CIN]   w: [64, 3, 3, CIN]   y: [N, H, W, 64]   stats: [2][64] (nullable)
+// One CTA = 2 image rows x 32 pixels (64 pixels, 4 threads each).  Thread `g` of a pixel owns channels 16 q + 4 g + e
+// (q, e in 0..3): the four threads of a pixel then read 64 contiguous bytes of a filter row (conflict-free LDS.128) and
+// write 64 contiguous bytes of the output row per store instruction (full sectors).  The 4 x 34 input halo tile is staged
+// in shared memory once (every input value is used by 4 threads x up to 9 taps).
+constexpr int kFwdRows = 2, kFwdCols = 32;
+
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y, float* stats, int N, int H, int W) {
-    __shared__ float ws[kTaps * CIN][kCout];          // [k][co]: lanes of a pixel read 16 consecutive co
+    __shared__ __align__(16) float ws[kTaps * CIN][kCout];     // [k][co]
+    __shared__ float halo[(kFwdRows + 2) * (kFwdCols + 2) * CIN];
     __shared__ float red[2][kCout];
-    for (int i = threadIdx.x; i < kCout * kTaps * CIN; i += blockDim.x) {
-        const int co = i / (kTaps * CIN), k = i - co * (kTaps * CIN);
-        ws[k][co] = to_f(w[i]);
+    const int tiles_w = W / kFwdCols, tiles_h = H / kFwdRows;
+    const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
+    const int w0 = tw * kFwdCols, h0 = th * kFwdRows;
+    for (int i = threadIdx.x; i < kCout * kTaps * CIN; i += blockDim.x) {   // co fastest: conflict-free smem stores
+        const int k = i / kCout, co = i - k * kCout;
+        ws[k][co] = to_f(w[co * (kTaps * CIN) + k]);
+    }
+    constexpr int pitch = (kFwdCols + 2) * CIN;
+    for (int i = threadIdx.x; i < (kFwdRows + 2) * pitch; i += blockDim.x) {
+        const int hh = h0 - 1 + i / pitch, rem = i % pitch, ww = w0 - 1 + rem / CIN, c = rem % CIN;
+        halo[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? to_f(x[(((long long)n * H + hh) * W + ww) * CIN + c]) : 0.f;
     }
     if (threadIdx.x < 2 * kCout) red[threadIdx.x / kCout][threadIdx.x % kCout] = 0.f;
     __syncthreads();
-    const int group = threadIdx.x & 3;                // 16-channel group of this thread
-    const long long pixels = (long long)N * H * W;
-    const long long p = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+    const int group = threadIdx.x & 3, pix = threadIdx.x >> 2;    // pixel of the tile: row pix / 32, column pix % 32
+    const int pr = pix / kFwdCols, pc = pix % kFwdCols;
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    const bool live = p < pixels;
-    if (live) {
-        const int wq = (int)(p % W), hq = (int)((p / W) % H);
-        const long long n = p / ((long long)W * H);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int hh = hq + r - 1;
-            if (hh < 0 || hh >= H) continue;
+    for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int ww = wq + s - 1;
-                if (ww < 0 || ww >= W) continue;
-                const T* px = x + ((n * H + hh) * W + ww) * CIN;
+        for (int s = 0; s < 3; ++s) {
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) {
-                    const float xv = to_f(px[c]);
-                    const float4* wrow = reinterpret_cast<const float4*>(&ws[(r * 3 + s) * CIN + c][group * 16]);
+            for (int c = 0; c < CIN; ++c) {
+                const float xv = halo[(pr + r) * pitch + (pc + s) * CIN + c];
+                const float* wrow = &ws[(r * 3 + s) * CIN + c][4 * group];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 wv = wrow[q];
-                        acc[4 * q] = fmaf(xv, wv.x, acc[4 * q]);
-                        acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wrow + 16 * q);
+                    acc[4 * q] = fmaf(xv, wv.x, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
                 }
             }
         }
-        T* out = y + p * kCout + group * 16;
+    }
+    T* out = y + ((((long long)n * H + h0 + pr) * W + w0 + pc) * kCout) + 4 * group;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
         if constexpr (sizeof(T) == 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                reinterpret_cast<float4*>(out)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            *reinterpret_cast<float4*>(out + 16 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         } else {
-            uint32_t packed[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-                packed[q] = *reinterpret_cast<uint32_t*>(&h);
-                acc[2 * q] = __bfloat162float(h.x);   // statistics of the STORED values
-                acc[2 * q + 1] = __bfloat162float(h.y);
-            }
-            reinterpret_cast<uint4*>(out)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            reinterpret_cast<uint4*>(out)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(acc[4 * q], acc[4 * q + 1]), hi = __floats2bfloat162_rn(acc[4 * q + 2], acc[4 * q + 3]);
+            *reinterpret_cast<uint2*>(out + 16 * q) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            acc[4 * q] = __bfloat162float(lo.x); acc[4 * q + 1] = __bfloat162float(lo.y);   // statistics of the STORED values
+            acc[4 * q + 2] = __bfloat162float(hi.x); acc[4 * q + 3] = __bfloat162float(hi.y);
         }
     }
     if (stats != nullptr) {
-        // lanes l, l^4, l^8, l^16 hold the same channel group for 8 different pixels: butterfly over the pixels
+        // lanes l, l^4, l^8, l^16 hold the same channel set for 8 different pixels: butterfly over the pixels
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float s = live ? acc[j] : 0.f, q = s * s;
+            float s = acc[j], q = s * s;
 #pragma unroll
             for (int m = 4; m < 32; m <<= 1) {
                 s += __shfl_xor_sync(0xffffffffu, s, m);
                 q += __shfl_xor_sync(0xffffffffu, q, m);
             }
             if ((threadIdx.x & 31) < 4) {
-                atomicAdd(&red[0][group * 16 + j], s);
-                atomicAdd(&red[1][group * 16 + j], q);
+                const int ch = 16 * (j >> 2) + 4 * group + (j & 3);
+                atomicAdd(&red[0][ch], s);
+                atomicAdd(&red[1][ch], q);
             }
         }
         __syncthreads();
@@ -113,7 +113,7 @@ stem_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict_
 
 // dW[co][r][s][ci] += sum over this CTA's rows of pixels.  One CTA = `rows` image rows of one image; threads =
 // 64 output channels x 4 tap groups; the input halo strip ((rows + 2) x (W + 2) x CIN, zero padded) sits in smem.
-constexpr int kWgThreads = 256, kWgRows = 4, kWgMaxW = 64;
+constexpr int kWgThreads = 256, kWgRows = 8, kWgMaxW = 64;
 
 template <typename T, int CIN>
 __global__ void __launch_bounds__(kWgThreads)
@@ -132,19 +132,22 @@ stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restri
     constexpr int kPer = (kK + 3) / 4;                 // handled by 4 threads per channel
     const int co = threadIdx.x & 63, part = threadIdx.x >> 6;
     float acc[kPer];
+    int off[kPer];                                     // halo offset of this thread's taps relative to the pixel
 #pragma unroll
-    for (int j = 0; j < kPer; ++j) acc[j] = 0.f;
+    for (int j = 0; j < kPer; ++j) {
+        acc[j] = 0.f;
+        const int k = min(part * kPer + j, kK - 1);    // k = (tap_r * 3 + tap_s) * CIN + c
+        const int tap = k / CIN, c = k - tap * CIN;
+        off[j] = (tap / 3) * pitch + (tap % 3) * CIN + c;
+    }
+    const T* dyp = dy + (((long long)n * H + h0) * W) * kCout + co;
     for (int r = 0; r < kWgRows; ++r) {
+        const float* hrow = halo + r * pitch;
+#pragma unroll 4
         for (int wq = 0; wq < W; ++wq) {
-            const float g = to_f(dy[(((long long)n * H + h0 + r) * W + wq) * kCout + co]);   // coalesced over co
+            const float g = to_f(dyp[((long long)r * W + wq) * kCout]);   // coalesced over co
 #pragma unroll
-            for (int j = 0; j < kPer; ++j) {
-                const int k = part * kPer + j;         // k = (tap_r * 3 + tap_s) * CIN + c
-                if (k < kK) {
-                    const int tap = k / CIN, c = k - tap * CIN;
-                    acc[j] = fmaf(g, halo[(r + tap / 3) * pitch + (wq + tap % 3) * CIN + c], acc[j]);   // warp-wide broadcast
-                }
-            }
+            for (int j = 0; j < kPer; ++j) acc[j] = fmaf(g, hrow[wq * CIN + off[j]], acc[j]);   // warp-wide broadcast
         }
     }
 #pragma unroll
@@ -177,8 +180,8 @@ extern "C" {
 int fl4h_conv_stem_fwd(const void* x, const void* w, void* y, float* stats, int dtype, int N, int H, int W, int cin, int cout,
                        cudaStream_t stream) {
     if (cout != kCout || cin < 1 || cin > kCinMax || cin == 2) return (int)cudaErrorInvalidValue;
-    const long long pixels = (long long)N * H * W;
-    const int grid = (int)((pixels + 63) / 64);
+    if (W % kFwdCols != 0 || H % kFwdRows != 0) return (int)cudaErrorInvalidValue;
+    const int grid = N * (H / kFwdRows) * (W / kFwdCols);
 #define STEM_FWD(T, C) stem_fwd_kernel<T, C><<<grid, 256, 0, stream>>>((const T*)x, (const T*)w, (T*)y, stats, N, H, W)
     if (dtype == 0) { if (cin == 3) STEM_FWD(float, 3); else if (cin == 1) STEM_FWD(float, 1); else STEM_FWD(float, 4); }
     else { if (cin == 3) STEM_FWD(__nv_bfloat16, 3); else if (cin == 1) STEM_FWD(__nv_bfloat16, 1); else STEM_FWD(__nv_bfloat16, 4); }

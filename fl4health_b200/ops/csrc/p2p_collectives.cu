@@ -127,6 +127,22 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& t, int phase, uint
     }
 }
 
+// Entry barrier without a grid-wide join: CTA 0 announces this rank (everything this rank contributes was written before
+// the kernel started, or before the grid.sync preceding this call), EVERY CTA polls this rank's own flag row until all
+// peers have announced.  Saves one grid.sync (~2-3 us of a ~25 us fixed cost) per collective.
+__device__ __forceinline__ void peer_barrier_enter(const PeerTable& t, int phase, uint32_t epoch) {
+    if (threadIdx.x < t.world) {
+        const int peer = threadIdx.x;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(t.flags[peer] + phase * FL4H_MAX_RANKS + t.rank, epoch);
+        }
+        const uint32_t* mine = t.flags[t.rank] + phase * FL4H_MAX_RANKS + peer;
+        while (ld_acquire_sys(mine) < epoch) { __nanosleep(32); }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ float epi_apply(int mode, const EpiArgs& ea, float avg, float wcur, float& m, float& v) {
     switch (mode) {
         case EPI_FEDADAM: {
@@ -186,8 +202,7 @@ agg_fused_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict_
                  EpiArgs ea, int64_t numel, int64_t slice, uint32_t epoch) {
     cg::grid_group grid = cg::this_grid();
     // (0) all ranks finished local training and are inside the kernel: contributions may be read.
-    peer_barrier(t, 0, epoch);
-    grid.sync();
+    peer_barrier_enter(t, 0, epoch);
     reduce_int_buffers(t);
 
     const int64_t begin = (int64_t)t.rank * slice;
@@ -280,8 +295,7 @@ bcast_fused_kernel(PeerTable t, int root, float* __restrict__ w, float* __restri
                    const float* __restrict__ c_local, float* __restrict__ cv_out, int64_t numel, int64_t slice,
                    uint32_t epoch) {
     cg::grid_group grid = cg::this_grid();
-    peer_barrier(t, 0, epoch);  // root's buffer is final; everyone's result buffer may be overwritten
-    grid.sync();
+    peer_barrier_enter(t, 0, epoch);  // root's buffer is final; everyone's result buffer may be overwritten
 
     const int64_t begin = (int64_t)t.rank * slice;
     int64_t end = begin + slice;
@@ -345,9 +359,8 @@ agg_nvls_kernel(PeerTable t, const float* __restrict__ wcur, float* __restrict__
         grid.sync();
     }
     coll_stamp(1);
-    peer_barrier(t, 0, epoch);
+    peer_barrier_enter(t, 0, epoch);
     coll_stamp(2);
-    grid.sync();
     coll_stamp(3);
     reduce_int_buffers(t);
 
@@ -400,8 +413,7 @@ bcast_nvls_kernel(PeerTable t, int root, float* __restrict__ w, float* __restric
                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ c_server,
                   const float* __restrict__ c_local, float* __restrict__ cv_out, int64_t numel, uint32_t epoch) {
     cg::grid_group grid = cg::this_grid();
-    peer_barrier(t, 0, epoch);  // everyone's result buffer may be overwritten
-    grid.sync();
+    peer_barrier_enter(t, 0, epoch);  // everyone's result buffer may be overwritten
     if (t.rank == root) {
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
         const int64_t total4 = numel >> 2;

@@ -19,8 +19,8 @@ segments, so every buffer has the same offset on every rank.
 * ``broadcast``   — root -> every rank (``multimem.st``) + receiver-side unpack (w, FedProx anchor, bf16 shadow,
   SCAFFOLD ``c - c_i``) in ONE kernel (``bcast_nvls`` / ``bcast_fused``).
 
-``FL4H_NVLS=0`` selects the fixed-order P2P kernels (bit-deterministic reduction order); the default is NVLS whenever the
-driver reports multicast support.
+``FL4H_NVLS=0`` selects the fixed-order P2P kernels (bit-deterministic reduction order), ``FL4H_NVLS=1`` the multimem
+kernels; by default the path that moves fewer bytes for the world size is taken (P2P below 4 ranks, NVLS from 4).
 """
 
 from __future__ import annotations
@@ -163,7 +163,11 @@ class FusedCollectives:
         for peer in range(torch.cuda.device_count()):
             if peer != self.device_index and not lib.fl4h_can_access_peer(self.device_index, peer):
                 raise RuntimeError(f"GPU {self.device_index} cannot access peer {peer}")
-        want_nvls = os.environ.get("FL4H_NVLS", "1") != "0"
+        # FL4H_NVLS: 1 = multimem kernels, 0 = fixed-order P2P kernels, unset = by traffic: per direction and GPU the
+        # NVLS aggregate moves payload*(1 + 1/K), the P2P one 2*payload*(K-1)/K  ->  P2P wins at K = 2 (measured 100 vs
+        # 158 us for 44.7 MB), they tie at K = 3, NVLS wins from K = 4 (1.25 vs 1.5, 1.125 vs 1.75 at K = 8)
+        policy = os.environ.get("FL4H_NVLS", "auto")
+        want_nvls = policy == "1" or (policy != "0" and self.world >= 4)
         # every rank must take the same decision: multicast needs all devices to support it
         self.has_multicast = bool(want_nvls and self.world > 1
                                   and ctx.all_reduce_max(0.0 if features & 4 else 1.0) == 0.0)

@@ -138,8 +138,13 @@ class SpmdContext:
         if use_cuda:
             torch.cuda.set_device(self.local_rank % torch.cuda.device_count())
             self.device = torch.device("cuda", torch.cuda.current_device())
+            from fl4health_b200.utils.affinity import bind_to_gpu
+
+            # before any pinned allocation / worker thread: CPU share + first-touch pages on the GPU's NUMA node
+            self.affinity = bind_to_gpu(self.device.index) if self.world_size > 1 else {"bound": False, "reason": "single rank"}
         else:
             self.device = torch.device("cpu")
+            self.affinity = {"bound": False, "reason": "cpu"}
         self.backend = backend or ("nccl" if use_cuda else "gloo")
         if self.world_size > 1 and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
