@@ -587,6 +587,10 @@ class BasicClient:
     def update_before_epoch(self, epoch: int) -> None:
         pass
 
+    def stop_after_epoch(self, epoch: int) -> bool:
+        """Hook (epoch-based training only): return True to end local training after this epoch."""
+        return False
+
     # ------------------------------------------------------------------------------------------------------------------
     # persisted client state, Flower-style conversion shim
     # ------------------------------------------------------------------------------------------------------------------

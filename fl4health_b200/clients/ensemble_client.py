@@ -12,40 +12,42 @@ from fl4health_b200.model_bases.ensemble_base import EnsembleModel
 from fl4health_b200.utils.losses import EvaluationLosses, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 
+_VOTE = "ensemble-pred"  # key of the combined prediction; every other key is one member
+
 
 class EnsembleClient(BasicClient):
     model: EnsembleModel
 
-    def setup_client(self, config: Config) -> None:
-        super().setup_client(config)
-        assert len(self.optimizers) == len(self.model.ensemble_models)
-        assert sorted(self.optimizers.keys()) == sorted(self.model.ensemble_models.keys())
+    def get_optimizer(self, config: Config) -> dict[str, Optimizer]:
+        raise NotImplementedError("Return one optimizer per ensemble member, keyed like EnsembleModel.ensemble_models")
 
     def set_optimizer(self, config: Config) -> None:
-        optimizers = self.get_optimizer(config)
-        assert isinstance(optimizers, dict)
-        self.optimizers = optimizers
+        per_member = self.get_optimizer(config)
+        assert isinstance(per_member, dict)
+        self.optimizers = per_member
+
+    def setup_client(self, config: Config) -> None:
+        super().setup_client(config)
+        assert set(self.optimizers) == set(self.model.ensemble_models) and len(self.optimizers) == len(self.model.ensemble_models)
+
+    def compute_training_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> TrainingLosses:
+        """Members are trained independently: one backward loss per member, nothing on the vote."""
+        return TrainingLosses(backward={member: self.criterion(logits.float(), target)
+                                        for member, logits in preds.items() if member != _VOTE})
+
+    def compute_evaluation_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> EvaluationLosses:
+        return EvaluationLosses(checkpoint=self.criterion(preds[_VOTE].float(), target))
 
     def train_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
         assert isinstance(input, torch.Tensor)
-        for optimizer in self.optimizers.values():
+        members = list(self.optimizers.values())
+        for optimizer in members:
             optimizer.zero_grad()
         with self._amp():
             preds, features = self.predict(input)
-            target = self.transform_target(target)
-            losses = self.compute_training_loss(preds, features, target)
-        for loss in losses.backward.values():
-            loss.backward()
-        for optimizer in self.optimizers.values():
+            losses = self.compute_training_loss(preds, features, self.transform_target(target))
+        for member_loss in losses.backward.values():  # the members share no parameters: order is irrelevant
+            member_loss.backward()
+        for optimizer in members:
             optimizer.step()
         return losses, preds
-
-    def compute_training_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> TrainingLosses:
-        losses = {key: self.criterion(pred.float(), target) for key, pred in preds.items() if key != "ensemble-pred"}
-        return TrainingLosses(backward=losses)
-
-    def compute_evaluation_loss(self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType) -> EvaluationLosses:
-        return EvaluationLosses(checkpoint=self.criterion(preds["ensemble-pred"].float(), target))
-
-    def get_optimizer(self, config: Config) -> dict[str, Optimizer]:
-        raise NotImplementedError("Return one optimizer per ensemble member, keyed like EnsembleModel.ensemble_models")

@@ -1,5 +1,8 @@
 """FLASH client (parity: ``fl4health/clients/flash_client.py:18-176``): epoch-level early stop — training ends once the
-validation-loss improvement drops below ``gamma / (epoch + 1)``.  ``gamma`` comes from the server config."""
+validation-loss improvement drops below ``gamma / (epoch + 1)``.  ``gamma`` comes from the server config.
+
+The reference re-implements the whole epoch loop to slot the rule in; here the shared loop driver
+(``engine/local_loop.run_training``) asks ``stop_after_epoch`` at every epoch boundary, so the client is only the rule."""
 
 from __future__ import annotations
 
@@ -9,7 +12,6 @@ from typing import Any
 from fl4health_b200.clients.basic_client import BasicClient
 from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, Scalar
-from fl4health_b200.utils.client import check_if_batch_is_empty_and_verify_input
 from fl4health_b200.utils.config import narrow_dict_type
 
 
@@ -17,55 +19,32 @@ class FlashClient(BasicClient):
     def __init__(self, *args: Any, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
         self.gamma: float | None = None
-
-    def process_config(self, config: Config) -> tuple[int | None, int | None, int, bool, bool]:
-        local_epochs, local_steps, server_round, evaluate_after_fit, pack = super().process_config(config)
-        if local_steps is not None and self.gamma is not None:
-            raise ValueError("Training by steps is not applicable for FLASH clients with gamma defined (epochs only).")
-        return local_epochs, local_steps, server_round, evaluate_after_fit, pack
-
-    def train_by_epochs(self, epochs: int, current_round: int | None = None) -> tuple[dict[str, float], dict[str, Scalar]]:
-        if self.gamma is None:
-            return super().train_by_epochs(epochs, current_round)
-        self.model.train()
-        local_step = 0
-        previous_loss = float("inf")
-        report_data: dict = {"round": current_round}
-        step_reports = self._step_reports_enabled()
-        loss_dict: dict[str, float] = {}
-        metrics: dict[str, Scalar] = {}
-        for local_epoch in range(epochs):
-            self.train_metric_manager.clear()
-            self.train_loss_meter.clear()
-            self._log_header_str(current_round, local_epoch)
-            report_data.update({"fit_epoch": local_epoch})
-            for input, target in self.train_loader:
-                if check_if_batch_is_empty_and_verify_input(input):
-                    log(INFO, "Empty batch generated by data loader. Skipping step.")
-                    continue
-                input, target = self._prepare_batch(input, target)
-                losses, _ = self._run_train_unit(input, target)
-                self.update_after_step(local_step, current_round)
-                if step_reports:
-                    report_data.update({"fit_losses": losses.as_dict(), "fit_step": self.total_steps})
-                    report_data.update(self.get_client_specific_reports())
-                    self.reports_manager.report(report_data, current_round, local_epoch, self.total_steps)
-                self.total_steps += 1
-                local_step += 1
-            metrics = self.train_metric_manager.compute()
-            loss_dict = self.train_loss_meter.compute().as_dict()
-            current_loss, _ = self.validate()
-            self.model.train()
-            self._log_results(loss_dict, metrics, current_round=current_round, current_epoch=local_epoch)
-            if previous_loss - current_loss < self.gamma / (local_epoch + 1):
-                log(INFO, f"Early stopping at epoch {local_epoch} with loss change {abs(previous_loss - current_loss)} and gamma {self.gamma}")
-                break
-            previous_loss = current_loss
-        return loss_dict, metrics
+        self._previous_validation_loss = float("inf")
 
     def setup_client(self, config: Config) -> None:
         super().setup_client(config)
-        if "gamma" in config:
-            self.gamma = narrow_dict_type(config, "gamma", float)
-        else:
+        if "gamma" not in config:
             log(INFO, "Gamma not present in config. Early stopping is disabled.")
+            return
+        self.gamma = narrow_dict_type(config, "gamma", float)
+
+    def process_config(self, config: Config) -> tuple[int | None, int | None, int, bool, bool]:
+        plan = super().process_config(config)
+        if plan[1] is not None and self.gamma is not None:
+            raise ValueError("Training by steps is not applicable for FLASH clients with gamma defined (epochs only).")
+        return plan
+
+    def train_by_epochs(self, epochs: int, current_round: int | None = None) -> tuple[dict[str, float], dict[str, Scalar]]:
+        self._previous_validation_loss = float("inf")  # the rule compares epochs of ONE round
+        return super().train_by_epochs(epochs, current_round)
+
+    def stop_after_epoch(self, epoch: int) -> bool:
+        if self.gamma is None:
+            return False
+        current, _ = self.validate()
+        improvement = self._previous_validation_loss - current
+        if improvement < self.gamma / (epoch + 1):
+            log(INFO, f"Early stopping at epoch {epoch} with loss change {abs(improvement)} and gamma {self.gamma}")
+            return True
+        self._previous_validation_loss = current
+        return False
