@@ -35,6 +35,7 @@ from torch.utils.data import DataLoader
 from fl4health_b200.checkpointing.client_module import CheckpointMode, ClientCheckpointAndStateModule
 from fl4health_b200.common.logger import log
 from fl4health_b200.common.typing import Config, NDArrays, Scalar
+from fl4health_b200.engine import outputs as model_outputs
 from fl4health_b200.engine.companions import Companion, build_companions, companion_modules
 from fl4health_b200.engine.fused_optim import translate_optimizer
 from fl4health_b200.engine.graph_runner import GraphStepRunner
@@ -509,21 +510,7 @@ class BasicClient:
     # ------------------------------------------------------------------------------------------------------------------
     def predict(self, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]:
         """Forward pass.  The model may return a tensor, a dict of predictions, or ``(preds_dict, features_dict)``."""
-        if isinstance(input, dict):
-            output = self.model(**input)
-        elif isinstance(input, torch.Tensor):
-            output = self.model(input)
-        else:
-            raise TypeError('"input" must be of type torch.Tensor or dict[str, torch.Tensor].')
-        if isinstance(output, torch.Tensor):
-            return {"prediction": output}, {}
-        if isinstance(output, dict):
-            return output, {}
-        if not isinstance(output, tuple):
-            raise ValueError("Model forward did not return a tensor, dictionary of tensors, or tuple of tensors")
-        if len(output) != EXPECTED_OUTPUT_TUPLE_SIZE:
-            raise ValueError(f"Output tuple should have length 2 but has length {len(output)}")
-        return output[0], output[1]
+        return model_outputs.forward(self.model, input)
 
     def compute_loss_and_additional_losses(
         self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType

@@ -18,10 +18,11 @@ from torch.optim import Optimizer
 
 from fl4health_b200.clients.basic_client import BasicClient
 from fl4health_b200.common.logger import log
+from fl4health_b200.engine import outputs as model_outputs
 from fl4health_b200.utils.losses import EvaluationLosses, TrainingLosses
 from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
 
-EXPECTED_OUTPUT_TUPLE_SIZE = 2
+EXPECTED_OUTPUT_TUPLE_SIZE = model_outputs.PAIR
 _LEGACY_HOOKS = {
     "predict": "predict_with_model()",
     "val_step": "_val_step_with_model()",
@@ -32,27 +33,28 @@ _LEGACY_HOOKS = {
 class FlexibleClient(BasicClient):
     def __init_subclass__(cls, **kwargs: Any) -> None:
         super().__init_subclass__(**kwargs)
-        if cls.__dict__.get("_dynamically_created", False) or any(
-            getattr(base, "_is_flexible_mixin", False) for base in cls.__mro__[1:] if base is not FlexibleClient
-        ):
-            return  # mixins legitimately re-define the legacy entry points on top of the helpers
-        for name, replacement in _LEGACY_HOOKS.items():
-            if name in cls.__dict__:
-                msg = (f"`{cls.__name__}` overrides `{name}()`, but this method should no longer be overridden. "
-                       f"Please use `{replacement}` instead.")
-                log(WARNING, msg)
-                warnings.warn(msg, RuntimeWarning, stacklevel=2)
+        exempt = cls.__dict__.get("_dynamically_created", False) or any(
+            getattr(ancestor, "_is_flexible_mixin", False) for ancestor in cls.__mro__[1:] if ancestor is not FlexibleClient
+        )
+        if exempt:  # mixins legitimately re-define the legacy entry points on top of the helpers
+            return
+        for legacy in sorted(set(_LEGACY_HOOKS) & set(cls.__dict__)):
+            message = (f"`{cls.__name__}` overrides `{legacy}()`, but this method should no longer be overridden. "
+                       f"Please use `{_LEGACY_HOOKS[legacy]}` instead.")
+            log(WARNING, message)
+            warnings.warn(message, RuntimeWarning, stacklevel=2)
 
-    # ------------------------------------------------------------------------------------------ train
+    # ---- the model-parameterised helpers (what subclasses and mixins customise) -------------------------------
+    def predict_with_model(self, model: nn.Module, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]:
+        return model_outputs.forward(model, input)
+
     def _compute_preds_and_losses(
         self, model: nn.Module, optimizer: Optimizer, input: TorchInputType, target: TorchTargetType
     ) -> tuple[TrainingLosses, TorchPredType]:
         optimizer.zero_grad()
         with self._amp():
             preds, features = self.predict_with_model(model, input)
-            target = self.transform_target(target)
-            losses = self.compute_training_loss(preds, features, target)
-        return losses, preds
+            return self.compute_training_loss(preds, features, self.transform_target(target)), preds
 
     def _apply_backwards_on_losses_and_take_step(
         self, model: nn.Module, optimizer: Optimizer, losses: TrainingLosses
@@ -68,47 +70,25 @@ class FlexibleClient(BasicClient):
         losses, preds = self._compute_preds_and_losses(model, optimizer, input, target)
         return self._apply_backwards_on_losses_and_take_step(model, optimizer, losses), preds
 
-    def train_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
-        return self._train_step_with_model_and_optimizer(self.model, self.optimizers["global"], input, target)
-
-    # ------------------------------------------------------------------------------------------ eval
     def _val_step_with_model(
         self, model: nn.Module, input: TorchInputType, target: TorchTargetType
     ) -> tuple[EvaluationLosses, TorchPredType]:
         with torch.no_grad(), self._amp():
             preds, features = self.predict_with_model(model, input)
-            target = self.transform_target(target)
-            losses = self.compute_evaluation_loss(preds, features, target)
-        return losses, preds
+            return self.compute_evaluation_loss(preds, features, self.transform_target(target)), preds
 
-    def val_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[EvaluationLosses, TorchPredType]:
-        return self._val_step_with_model(self.model, input, target)
+    def _transform_gradients_with_model(self, model: nn.Module, losses: TrainingLosses) -> None:
+        pass
 
-    # ------------------------------------------------------------------------------------------ predict
-    def predict_with_model(self, model: nn.Module, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]:
-        if isinstance(input, torch.Tensor):
-            output = model(input)
-        elif isinstance(input, dict):
-            output = model(**input)
-        else:
-            raise TypeError('"input" must be of type torch.Tensor or dict[str, torch.Tensor].')
-        if isinstance(output, dict):
-            return output, {}
-        if isinstance(output, torch.Tensor):
-            return {"prediction": output}, {}
-        if isinstance(output, tuple):
-            if len(output) != EXPECTED_OUTPUT_TUPLE_SIZE:
-                raise ValueError(f"Output tuple should have length 2 but has length {len(output)}")
-            preds, features = output
-            return preds, features
-        raise ValueError("Model forward did not return a tensor, dictionary of tensors, or tuple of tensors")
-
+    # ---- the classic entry points: the helpers applied to (self.model, optimizers["global"]) -----------------
     def predict(self, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]:
         return self.predict_with_model(self.model, input)
 
-    # ------------------------------------------------------------------------------------------ gradients
-    def _transform_gradients_with_model(self, model: nn.Module, losses: TrainingLosses) -> None:
-        pass
+    def train_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
+        return self._train_step_with_model_and_optimizer(self.model, self.optimizers["global"], input, target)
+
+    def val_step(self, input: TorchInputType, target: TorchTargetType) -> tuple[EvaluationLosses, TorchPredType]:
+        return self._val_step_with_model(self.model, input, target)
 
     def transform_gradients(self, losses: TrainingLosses) -> None:
         self._transform_gradients_with_model(self.model, losses)
