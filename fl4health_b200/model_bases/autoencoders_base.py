@@ -2,6 +2,8 @@
 
 The variational models return ONE packed tensor ``[logvar | mu | flattened reconstruction]`` so they fit the
 single-tensor prediction contract of the clients; ``preprocessing/autoencoders/loss.py::VaeLoss`` unpacks it.
+Both variational flavours share ``_Variational``: encode (with optional conditioning tensors) -> reparameterised sample
+-> decode -> pack.
 """
 
 from __future__ import annotations
@@ -16,8 +18,7 @@ from torch import nn
 class AbstractAe(nn.Module, ABC):
     def __init__(self, encoder: nn.Module, decoder: nn.Module) -> None:
         super().__init__()
-        self.encoder = encoder
-        self.decoder = decoder
+        self.encoder, self.decoder = encoder, decoder
 
     @abstractmethod
     def forward(self, input: torch.Tensor) -> torch.Tensor:
@@ -32,18 +33,24 @@ class BasicAe(AbstractAe):
         return self.decoder(latent_vector)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        return self.decode(self.encode(input))
+        return self.decoder(self.encoder(input))
 
 
-def _reparameterize(mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
-    return torch.addcmul(mu, torch.randn_like(mu), torch.exp(0.5 * logvar))
+class _Variational(AbstractAe):
+    """Shared body of the (conditional) variational auto-encoders; ``context`` = the conditioning tensors (possibly none)
+    handed to both halves of the network."""
+
+    def sampling(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
+        """z = mu + eps * sigma with eps ~ N(0, I) (one fused addcmul)."""
+        return torch.addcmul(mu, torch.randn_like(mu), torch.exp(0.5 * logvar))
+
+    def _packed_forward(self, sample: torch.Tensor, *context: torch.Tensor) -> torch.Tensor:
+        mu, logvar = self.encoder(sample, *context)
+        reconstruction = self.decoder(self.sampling(mu, logvar), *context)
+        return torch.cat((logvar, mu, reconstruction.flatten(start_dim=1)), dim=1)
 
 
-def _pack(logvar: torch.Tensor, mu: torch.Tensor, output: torch.Tensor) -> torch.Tensor:
-    return torch.cat((logvar, mu, output.reshape(output.shape[0], -1)), dim=1)
-
-
-class VariationalAe(AbstractAe):
+class VariationalAe(_Variational):
     """``encoder(x) -> (mu, logvar)``; forward returns the packed ``[logvar | mu | recon]`` tensor."""
 
     def encode(self, input: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
@@ -53,15 +60,11 @@ class VariationalAe(AbstractAe):
     def decode(self, latent_vector: torch.Tensor) -> torch.Tensor:
         return self.decoder(latent_vector)
 
-    def sampling(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
-        return _reparameterize(mu, logvar)
-
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        mu, logvar = self.encode(input)
-        return _pack(logvar, mu, self.decode(self.sampling(mu, logvar)))
+        return self._packed_forward(input)
 
 
-class ConditionalVae(AbstractAe):
+class ConditionalVae(_Variational):
     """CVAE: encoder and decoder both receive the condition; ``unpack_input_condition`` splits the single input tensor
     the data loader provides into (input, condition)."""
 
@@ -79,11 +82,6 @@ class ConditionalVae(AbstractAe):
     def decode(self, latent_vector: torch.Tensor, condition: torch.Tensor | None = None) -> torch.Tensor:
         return self.decoder(latent_vector, condition)
 
-    def sampling(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
-        return _reparameterize(mu, logvar)
-
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         assert self.unpack_input_condition is not None
-        input, condition = self.unpack_input_condition(input)
-        mu, logvar = self.encode(input, condition)
-        return _pack(logvar, mu, self.decode(self.sampling(mu, logvar), condition))
+        return self._packed_forward(*self.unpack_input_condition(input))

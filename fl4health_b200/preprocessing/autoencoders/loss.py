@@ -14,18 +14,19 @@ REQUIRED_PREDS_DIMENSIONS = 2
 class VaeLoss(_Loss):
     def __init__(self, latent_dim: int, base_loss: _Loss) -> None:
         super().__init__()
-        self.base_loss = base_loss
-        self.latent_dim = latent_dim
-
-    def standard_normal_kl_divergence_loss(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
-        return -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
+        self.latent_dim, self.base_loss = latent_dim, base_loss
 
     def unpack_model_output(self, preds: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        assert preds.dim() == REQUIRED_PREDS_DIMENSIONS, (
-            f"Expected a 2D tensor for VaeLoss, but got {preds.dim()}D tensor with shape {preds.shape}.")
-        logvar, mu, recon = torch.split(preds, [self.latent_dim, self.latent_dim, preds.shape[1] - 2 * self.latent_dim], dim=1)
-        return recon, mu, logvar
+        """(reconstruction, mu, logvar) views of the packed prediction."""
+        if preds.dim() != REQUIRED_PREDS_DIMENSIONS:
+            raise AssertionError(f"Expected a 2D tensor for VaeLoss, but got {preds.dim()}D tensor with shape {preds.shape}.")
+        d = self.latent_dim
+        return preds[:, 2 * d:], preds[:, d : 2 * d], preds[:, :d]
+
+    def standard_normal_kl_divergence_loss(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
+        return 0.5 * (mu.square() + logvar.exp() - logvar - 1).sum()
 
     def forward(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        recon, mu, logvar = self.unpack_model_output(preds)
-        return self.base_loss(recon.reshape(target.shape), target) + self.standard_normal_kl_divergence_loss(mu, logvar)
+        reconstruction, mu, logvar = self.unpack_model_output(preds)
+        fidelity = self.base_loss(reconstruction.reshape(target.shape), target)
+        return fidelity + self.standard_normal_kl_divergence_loss(mu, logvar)
