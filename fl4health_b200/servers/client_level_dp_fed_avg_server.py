@@ -4,7 +4,6 @@ matches the client manager, logs (epsilon, delta)."""
 
 from __future__ import annotations
 
-from collections.abc import Callable, Sequence
 from logging import INFO
 from math import ceil
 from typing import Any
@@ -14,13 +13,12 @@ from fl4health_b200.client_managers.fixed_without_replacement_manager import Fix
 from fl4health_b200.client_managers.poisson_sampling_manager import PoissonSamplingClientManager
 from fl4health_b200.common.history import History
 from fl4health_b200.common.logger import log
-from fl4health_b200.common.typing import Config, Scalar
+from fl4health_b200.common.typing import Config
 from fl4health_b200.privacy.fl_accountants import (
     ClientLevelAccountant,
     FlClientLevelAccountantFixedSamplingNoReplacement,
     FlClientLevelAccountantPoissonSampling,
 )
-from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.servers.base_server import FlServer
 from fl4health_b200.servers.client_manager import ClientManager
 from fl4health_b200.strategies.client_dp_fedavgm import ClientLevelDPFedAvgM
@@ -35,40 +33,37 @@ class ClientLevelDPFedAvgServer(FlServer):
         server_noise_multiplier: float,
         num_server_rounds: int,
         checkpoint_and_state_module: ClippingBitServerCheckpointAndStateModule | None = None,
-        reporters: Sequence[BaseReporter] | None = None,
         delta: int | None = None,
-        on_init_parameters_config_fn: Callable[[int], dict[str, Scalar]] | None = None,
-        server_name: str | None = None,
-        accept_failures: bool = True,
-        transport: Any = None,
+        **server_options: Any,
     ) -> None:
-        if checkpoint_and_state_module is not None:
-            assert isinstance(checkpoint_and_state_module, ClippingBitServerCheckpointAndStateModule)
-        super().__init__(client_manager=client_manager, fl_config=fl_config, strategy=strategy, reporters=reporters,
-                         checkpoint_and_state_module=checkpoint_and_state_module,
-                         on_init_parameters_config_fn=on_init_parameters_config_fn, server_name=server_name,
-                         accept_failures=accept_failures, transport=transport)
+        """``server_options``: the remaining ``FlServer`` keywords (``reporters``, ``on_init_parameters_config_fn``,
+        ``server_name``, ``accept_failures``, ``transport``)."""
+        assert checkpoint_and_state_module is None or isinstance(checkpoint_and_state_module, ClippingBitServerCheckpointAndStateModule)
+        super().__init__(client_manager, fl_config, strategy, checkpoint_and_state_module=checkpoint_and_state_module,
+                         **server_options)
+        self.server_noise_multiplier, self.num_server_rounds, self.delta = server_noise_multiplier, num_server_rounds, delta
         self.accountant: ClientLevelAccountant
-        self.server_noise_multiplier = server_noise_multiplier
-        self.num_server_rounds = num_server_rounds
-        self.delta = delta
 
     def fit(self, num_rounds: int, timeout: float | None = None) -> tuple[History, float]:
         assert isinstance(self.strategy, ClientLevelDPFedAvgM)
-        sample_counts = self.poll_clients_for_sample_counts(timeout)
-        self.strategy.sample_counts = sample_counts  # weighted aggregation needs the per-client weights
-        self.setup_privacy_accountant(sample_counts)
+        self.strategy.sample_counts = self.poll_clients_for_sample_counts(timeout)  # weights of the noisy aggregate
+        self.setup_privacy_accountant(self.strategy.sample_counts)
         return super().fit(num_rounds=num_rounds, timeout=timeout)
+
+    def _accountant_for(self, population: int, sampling_rate: float) -> ClientLevelAccountant:
+        """The accountant matching how the client manager samples: Poisson (independent coin flips) or a fixed-size draw
+        without replacement."""
+        manager = self._client_manager
+        if isinstance(manager, PoissonSamplingClientManager):
+            return FlClientLevelAccountantPoissonSampling(sampling_rate, self.server_noise_multiplier)
+        assert isinstance(manager, FixedSamplingByFractionClientManager)
+        return FlClientLevelAccountantFixedSamplingNoReplacement(population, ceil(population * sampling_rate),
+                                                                 self.server_noise_multiplier)
 
     def setup_privacy_accountant(self, sample_counts: list[int]) -> None:
         assert isinstance(self.strategy, ClientLevelDPFedAvgM)
-        num_clients = len(sample_counts)
-        target_delta = 1.0 / num_clients if self.delta is None else self.delta
-        if isinstance(self._client_manager, PoissonSamplingClientManager):
-            self.accountant = FlClientLevelAccountantPoissonSampling(self.strategy.fraction_fit, self.server_noise_multiplier)
-        else:
-            assert isinstance(self._client_manager, FixedSamplingByFractionClientManager)
-            sampled = ceil(num_clients * self.strategy.fraction_fit)
-            self.accountant = FlClientLevelAccountantFixedSamplingNoReplacement(num_clients, sampled, self.server_noise_multiplier)
+        population = len(sample_counts)
+        target_delta = self.delta if self.delta is not None else 1.0 / population
+        self.accountant = self._accountant_for(population, self.strategy.fraction_fit)
         epsilon = self.accountant.get_epsilon(self.num_server_rounds, target_delta)
         log(INFO, f"Model privacy after full training will be ({epsilon}, {target_delta})")

@@ -8,6 +8,7 @@ from typing import TYPE_CHECKING
 
 from fl4health_b200.checkpointing.state_checkpointer import ClientStateCheckpointer
 from fl4health_b200.common.logger import log
+from fl4health_b200.engine.companions import set_phase
 from fl4health_b200.utils.logging import LoggingMode
 
 if TYPE_CHECKING:
@@ -15,6 +16,10 @@ if TYPE_CHECKING:
 
 
 class EarlyStopper:
+    """Every ``interval_steps`` steps: score the model on the client's validation loader; a new best is snapshotted (whole
+    client training state, through ``ClientStateCheckpointer``); ``patience`` non-improving checks end local training
+    (``patience=None``: never stop, only keep the best snapshot for ``load_snapshot``)."""
+
     def __init__(
         self,
         client: BasicClient,
@@ -24,45 +29,41 @@ class EarlyStopper:
         train_loop_checkpoint_dir: Path | None = None,
     ) -> None:
         """``train_loop_checkpoint_dir`` is the reference's name for ``snapshot_dir`` (``early_stopper.py:14-60``)."""
-        if snapshot_dir is None:
-            snapshot_dir = train_loop_checkpoint_dir
-        self.client = client
-        self.patience = patience
+        directory = snapshot_dir if snapshot_dir is not None else train_loop_checkpoint_dir
+        if directory is None:
+            log(WARNING, "EarlyStopper snapshots go to the current directory because snapshot_dir is None")
+            directory = Path(".")
+        self.client, self.patience, self.interval_steps = client, patience, interval_steps
         self.count_down = patience
-        self.interval_steps = interval_steps
         self.best_score: float | None = None
         self.snapshot_ckpt: dict = {}
-        checkpoint_name = f"temp_{client.client_name}.pt"
-        self.state_checkpointer = ClientStateCheckpointer(
-            checkpoint_dir=snapshot_dir if snapshot_dir is not None else Path("."), checkpoint_name=checkpoint_name
-        )
-        if snapshot_dir is None:
-            log(WARNING, "EarlyStopper snapshots go to the current directory because snapshot_dir is None")
+        self.state_checkpointer = ClientStateCheckpointer(checkpoint_dir=directory, checkpoint_name=f"temp_{client.client_name}.pt")
 
     def load_snapshot(self, attributes: list[str] | None = None) -> None:
         self.state_checkpointer.maybe_load_client_state(self.client, attributes)
 
+    def _score(self) -> float | None:
+        client = self.client
+        loss, _ = client._fully_validate_or_test(client.val_loader, client.val_loss_meter, client.val_metric_manager,
+                                                 LoggingMode.EARLY_STOP_VALIDATION, include_losses_in_metrics=False)
+        set_phase(client, training=True)  # scoring flipped every network to eval
+        return loss
+
     def should_stop(self, steps: int) -> bool:
-        if steps % self.interval_steps != 0:
+        if steps % self.interval_steps:
             return False
-        val_loss, _ = self.client._fully_validate_or_test(
-            loader=self.client.val_loader,
-            loss_meter=self.client.val_loss_meter,
-            metric_manager=self.client.val_metric_manager,
-            logging_mode=LoggingMode.EARLY_STOP_VALIDATION,
-            include_losses_in_metrics=False,
-        )
-        self.client.model.train()
-        if val_loss is None:
+        score = self._score()
+        if score is None:
             return False
-        if self.best_score is None or val_loss < self.best_score:
-            self.best_score = val_loss
-            self.count_down = self.patience
+        improved = self.best_score is None or score < self.best_score
+        if improved:
+            self.best_score, self.count_down = score, self.patience
             self.state_checkpointer.save_client_state(self.client)
             return False
-        if self.count_down is not None:
-            self.count_down -= 1
-            if self.count_down <= 0:
-                log(INFO, "Early stopping patience exhausted.")
-                return True
-        return False
+        if self.count_down is None:
+            return False
+        self.count_down -= 1
+        exhausted = self.count_down <= 0
+        if exhausted:
+            log(INFO, "Early stopping patience exhausted.")
+        return exhausted
