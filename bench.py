@@ -308,7 +308,8 @@ def main() -> None:
             "local_steps": args.local_steps, "val_batches_per_client": args.val_batches, "strategy": "BasicFedAvg (weighted)",
             "optimizer": "SGD lr=0.01 momentum=0.9", "seq_len": None,
             "l2": "explicit 256 MiB write between rounds (inside the timed region)",
-            "collectives": "fused-p2p" if ctx.fused is not None else ("nccl" if world > 1 else "local"),
+            "collectives": (("fused-nvls (multimem)" if ctx.fused.has_multicast else "fused-p2p") if ctx.fused is not None
+                            else ("nccl" if world > 1 else "local")),
             "cuda_graphs": engine.cuda_graphs, "channels_last": engine.channels_last,
         },
         "gpu_launches": main_run["launches"],  # this rank's launches of fl4h kernels in the timed region (each rank: same)
