@@ -58,7 +58,9 @@ class ParameterPackerWithControlVariates(ParameterPacker[NDArrays]):
 
 class _TrailingScalarPacker(ParameterPacker[float]):
     def pack_parameters(self, model_weights: NDArrays, additional_parameters: float) -> NDArrays:
-        packed = NDArrays(list(model_weights) + [np.array(additional_parameters)])
+        # a device-resident scalar (e.g. the clipping bit written by the clip kernel) travels as is: no host read-back
+        trailing = additional_parameters if isinstance(additional_parameters, torch.Tensor) else np.array(additional_parameters)
+        packed = NDArrays(list(model_weights) + [trailing])
         # keep arena metadata of the weight part so fused aggregation still applies
         packed.flat, packed.layout = getattr(model_weights, "flat", None), getattr(model_weights, "layout", None)
         return packed
