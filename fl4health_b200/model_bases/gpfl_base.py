@@ -16,42 +16,52 @@ from fl4health_b200.model_bases.partial_layer_exchange_model import PartialLayer
 from fl4health_b200.model_bases.sequential_split_models import SequentiallySplitExchangeBaseModel
 
 
+def _class_indices_or_distribution(label: torch.Tensor, num_classes: int, dtype: torch.dtype) -> torch.Tensor:
+    """Hard labels stay indices, ``[B, num_classes]`` rows are taken as target distributions (one-hot included)."""
+    if label.dim() == 1:
+        return label.long()
+    assert label.shape[1] == num_classes, "One-hot labels must have shape (batch_size, num_classes)."
+    return label.to(dtype)
+
+
 class Gce(nn.Module):
+    """Global category embedding: one learnable prototype per class, trained with a softmax over cosine similarities
+    between the (normalised) features and the (normalised) prototypes."""
+
     def __init__(self, feature_dim: int, num_classes: int) -> None:
         super().__init__()
-        self.feature_dim = feature_dim
-        self.num_classes = num_classes
+        self.feature_dim, self.num_classes = feature_dim, num_classes
         self.embedding = nn.Embedding(num_classes, feature_dim)
 
     def forward(self, feature_tensor: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
-        cosine = F.linear(F.normalize(feature_tensor), F.normalize(self.embedding.weight))
-        if label.dim() == 1:
-            one_hot = F.one_hot(label.long(), self.num_classes).to(cosine.dtype)
-        else:
-            assert label.shape[1] == self.num_classes, "One-hot labels must have shape (batch_size, num_classes)."
-            one_hot = label.to(cosine.dtype)
-        return -(one_hot * F.log_softmax(cosine, dim=1)).sum(dim=1).mean()
+        similarities = F.normalize(feature_tensor) @ F.normalize(self.embedding.weight).T
+        return F.cross_entropy(similarities, _class_indices_or_distribution(label, self.num_classes, similarities.dtype))
 
     def lookup(self, target: torch.Tensor) -> torch.Tensor:
         if self.training:
             log(WARNING, "Lookup is an embedding read-out (no forward pass) and is not meant for training mode.")
-        if target.dim() == 2:
-            assert target.shape[1] == self.num_classes, "One-hot labels must have shape (batch_size, num_classes)."
-            target = torch.argmax(target, dim=1)
-        assert target.dim() == 1, "lookup requires 1D tensor of class indices."
-        return self.embedding.weight.data[target.long()]
+        indices = _class_indices_or_distribution(target, self.num_classes, torch.float32)
+        if indices.dim() == 2:
+            indices = indices.argmax(dim=1)
+        assert indices.dim() == 1, "lookup requires 1D tensor of class indices."
+        return self.embedding.weight.data[indices.long()]
+
+
+def _conditioner(width: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(width, width), nn.ReLU(), nn.LayerNorm([width]))
 
 
 class CoV(nn.Module):
+    """Conditional valve: ``relu(f * (gamma(context) + 1) + beta(context))``."""
+
     def __init__(self, feature_dim: int) -> None:
         super().__init__()
-        self.conditional_gamma = nn.Sequential(nn.Linear(feature_dim, feature_dim), nn.ReLU(), nn.LayerNorm([feature_dim]))
-        self.conditional_beta = nn.Sequential(nn.Linear(feature_dim, feature_dim), nn.ReLU(), nn.LayerNorm([feature_dim]))
+        self.conditional_gamma, self.conditional_beta = _conditioner(feature_dim), _conditioner(feature_dim)
         self.activation = nn.ReLU()
 
     def forward(self, feature_tensor: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
-        gamma, beta = self.conditional_gamma(context), self.conditional_beta(context)
-        return self.activation(feature_tensor * (gamma + 1) + beta)
+        scale = self.conditional_gamma(context) + 1
+        return self.activation(torch.addcmul(self.conditional_beta(context), feature_tensor, scale))
 
 
 class GpflBaseAndHeadModules(SequentiallySplitExchangeBaseModel):
@@ -60,11 +70,12 @@ class GpflBaseAndHeadModules(SequentiallySplitExchangeBaseModel):
 
 
 class GpflModel(PartialLayerExchangeModel):
+    _SHARED_PREFIXES = ("cov.", "gce.")  # exchanged next to the base feature extractor
+
     def __init__(self, base_module: nn.Module, head_module: nn.Module, feature_dim: int, num_classes: int,
                  flatten_features: bool = False) -> None:
         super().__init__()
-        self.feature_dim = feature_dim
-        self.num_classes = num_classes
+        self.feature_dim, self.num_classes = feature_dim, num_classes
         self.gpfl_main_module = GpflBaseAndHeadModules(base_module, head_module, flatten_features)
         self.cov = CoV(feature_dim)
         self.gce = Gce(feature_dim, num_classes)
@@ -74,14 +85,13 @@ class GpflModel(PartialLayerExchangeModel):
     ) -> tuple[dict[str, torch.Tensor], dict[str, torch.Tensor]]:
         features = self.gpfl_main_module.features_forward(input)
         assert features.shape[1] == self.feature_dim, "Base-module output width must equal feature_dim."
-        local_features = self.cov(features, personalized_conditional_input)
-        predictions = self.gpfl_main_module.head_module(local_features)
+        personalised = self.cov(features, personalized_conditional_input)
+        preds = {"prediction": self.gpfl_main_module.head_module(personalised)}
         if not self.training:
-            return {"prediction": predictions}, {}
+            return preds, {}
         assert len(global_conditional_input) == self.feature_dim
-        global_features = self.cov(features, global_conditional_input)
-        return {"prediction": predictions}, {"local_features": local_features, "global_features": global_features}
+        return preds, {"local_features": personalised, "global_features": self.cov(features, global_conditional_input)}
 
     def layers_to_exchange(self) -> list[str]:
-        base = [f"gpfl_main_module.{name}" for name in self.gpfl_main_module.layers_to_exchange()]
-        return base + [name for name in self.state_dict() if name.startswith(("cov.", "gce."))]
+        shared = [key for key in self.state_dict() if key.startswith(self._SHARED_PREFIXES)]
+        return [f"gpfl_main_module.{key}" for key in self.gpfl_main_module.layers_to_exchange()] + shared
