@@ -16,18 +16,23 @@ import torch
 from torch.utils.data import Dataset
 
 
+def _then(first: Callable | None, second: Callable) -> Callable:
+    """``second`` applied after ``first`` (or alone when there is no ``first``)."""
+    if first is None:
+        return second
+    return lambda *args: second(first(*args))
+
+
 class BaseDataset(ABC, Dataset):
     def __init__(self, transform: Callable | None, target_transform: Callable | None) -> None:
-        self.transform = transform
-        self.target_transform = target_transform
+        self.transform, self.target_transform = transform, target_transform
 
     def update_transform(self, f: Callable) -> None:
-        previous = self.transform
-        self.transform = (lambda *x: f(previous(*x))) if previous else f
+        """Append ``f`` to the input transform chain."""
+        self.transform = _then(self.transform, f)
 
     def update_target_transform(self, g: Callable) -> None:
-        previous = self.target_transform
-        self.target_transform = (lambda *x: g(previous(*x))) if previous else g
+        self.target_transform = _then(self.target_transform, g)
 
     @abstractmethod
     def __getitem__(self, index: int) -> tuple[torch.Tensor, torch.Tensor]:
@@ -48,35 +53,33 @@ class TensorDataset(BaseDataset):
         batch_transform: Callable | None = None,
     ) -> None:
         super().__init__(transform, target_transform)
-        self.data = data
-        self.targets = targets
+        self.data, self.targets = data, targets
         self.batch_transform = batch_transform  # applied to a whole [B, ...] batch (vectorised path)
+
+    def __len__(self) -> int:
+        return len(self.data)
 
     def __getitem__(self, index: int) -> tuple[torch.Tensor, torch.Tensor]:
         assert self.targets is not None
-        data, target = self.data[index], self.targets[index]
-        if self.transform is not None:
-            data = self.transform(data)
+        sample, label = self.data[index], self.targets[index]
+        sample = sample if self.transform is None else self.transform(sample)
+        label = label if self.target_transform is None else self.target_transform(label)
+        return sample, label
+
+    def apply_transforms(self, data: torch.Tensor, target: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Transforms of an already gathered ``[B, ...]`` batch (the loader gathers whole epochs at once): the batched
+        transform if one was given, else the per-sample transform row by row."""
+        if self.batch_transform is not None:
+            data = self.batch_transform(data)
+        elif self.transform is not None:
+            data = torch.stack([self.transform(row) for row in data])
         if self.target_transform is not None:
-            target = self.target_transform(target)
+            target = torch.stack([torch.as_tensor(self.target_transform(label)) for label in target])
         return data, target
 
     def get_batch(self, indices: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         assert self.targets is not None
         return self.apply_transforms(self.data.index_select(0, indices), self.targets.index_select(0, indices))
-
-    def apply_transforms(self, data: torch.Tensor, target: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        """Transforms of an already gathered ``[B, ...]`` batch (the loader gathers whole epochs at once)."""
-        if self.batch_transform is not None:
-            data = self.batch_transform(data)
-        elif self.transform is not None:
-            data = torch.stack([self.transform(sample) for sample in data])
-        if self.target_transform is not None:
-            target = torch.stack([torch.as_tensor(self.target_transform(t)) for t in target])
-        return data, target
-
-    def __len__(self) -> int:
-        return len(self.data)
 
 
 class SslTensorDataset(TensorDataset):
@@ -93,27 +96,24 @@ class SslTensorDataset(TensorDataset):
         super().__init__(data, targets, transform, target_transform)
 
     def __getitem__(self, index: int) -> tuple[torch.Tensor, torch.Tensor]:
-        data = self.data[index]
         assert self.target_transform is not None, "Target transform cannot be None."
-        if self.transform is not None:
-            data = self.transform(data)
-        return data, self.target_transform(data)
+        view = self.data[index] if self.transform is None else self.transform(self.data[index])
+        return view, self.target_transform(view)
 
     def get_batch(self, indices: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        pairs = [self[int(i)] for i in indices]
-        return torch.stack([p[0] for p in pairs]), torch.stack([p[1] for p in pairs])
+        views, targets = zip(*(self[int(i)] for i in indices))
+        return torch.stack(views), torch.stack(targets)
 
 
 class DictionaryDataset(Dataset):
     def __init__(self, data: dict[str, list[torch.Tensor]], targets: torch.Tensor) -> None:
-        self.data = data
-        self.targets = targets
-
-    def __getitem__(self, index: int) -> tuple[dict[str, torch.Tensor], torch.Tensor]:
-        return {key: val[index] for key, val in self.data.items()}, self.targets[index]
+        self.data, self.targets = data, targets
 
     def __len__(self) -> int:
         return len(next(iter(self.data.values())))
+
+    def __getitem__(self, index: int) -> tuple[dict[str, torch.Tensor], torch.Tensor]:
+        return {field: column[index] for field, column in self.data.items()}, self.targets[index]
 
 
 class SyntheticDataset(TensorDataset):
@@ -126,13 +126,14 @@ D = TypeVar("D", TensorDataset, DictionaryDataset)
 
 
 def select_by_indices(dataset: D, selected_indices: torch.Tensor) -> D:
-    if isinstance(dataset, TensorDataset):
-        subset = copy.copy(dataset)
-        subset.data = dataset.data[selected_indices]
-        if dataset.targets is not None:
-            subset.targets = dataset.targets[selected_indices]
-        return cast(D, subset)
+    """A dataset of the same kind restricted to ``selected_indices`` (transforms are shared, tensors are gathered)."""
     if isinstance(dataset, DictionaryDataset):
-        new_data = {key: [val[int(i)] for i in selected_indices] for key, val in dataset.data.items()}
-        return cast(D, DictionaryDataset(new_data, dataset.targets[selected_indices]))
-    raise TypeError("Dataset type is not supported by this function.")
+        rows = [int(i) for i in selected_indices]
+        picked = {field: [column[i] for i in rows] for field, column in dataset.data.items()}
+        return cast(D, DictionaryDataset(picked, dataset.targets[selected_indices]))
+    if not isinstance(dataset, TensorDataset):
+        raise TypeError("Dataset type is not supported by this function.")
+    subset = copy.copy(dataset)
+    subset.data = dataset.data[selected_indices]
+    subset.targets = None if dataset.targets is None else dataset.targets[selected_indices]
+    return cast(D, subset)
