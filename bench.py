@@ -63,6 +63,8 @@ def parse_args() -> argparse.Namespace:
     p.add_argument("--no-master-weights", action="store_true", help="bf16 autocast over fp32 params instead of bf16 shadow params")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--device", default="cuda", help="reference arm only: cpu runs its plumbing test without a GPU")
+    p.add_argument("--config", default="cifar_fedavg", choices=["cifar_fedavg", "scaffold_fedprox", "fedper_ditto_dp", "bert_fedadam"],
+                   help="BASELINE.json configuration (default: the headline CIFAR-10 ResNet-18 FedAvg)")
     return p.parse_args()
 
 
@@ -130,25 +132,31 @@ class ClockSampler:
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
+        if args.config != "cifar_fedavg":
+            print(json.dumps({"impl": "reference", "config": args.config,
+                              "unavailable": "the reference arm drives the headline configuration (cifar_fedavg) only"}))
+            return
         reference_arm()
+        return
+    if args.config == "bert_fedadam":  # BASELINE config #4 has its own harness (token batches, FedAdam server, bf16)
+        import runpy
+
+        sys.argv = [sys.argv[0], "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        runpy.run_path(str(Path(__file__).resolve().parent / "benchmarks" / "bert_fedopt_round.py"), run_name="__main__")
         return
 
     import torch
     from torch import nn
 
     from fl4health_b200 import ops
-    from fl4health_b200.clients.basic_client import BasicClient
     from fl4health_b200.engine.data import BatchedTensorLoader
     from fl4health_b200.engine.options import EngineOptions
-    from fl4health_b200.metrics import Accuracy
-    from fl4health_b200.metrics.metric_aggregation import evaluate_metrics_aggregation_fn, fit_metrics_aggregation_fn
-    from fl4health_b200.models import resnet18_cifar
     from fl4health_b200.parallel.spmd import SpmdContext, build_spmd_federation
-    from fl4health_b200.servers.base_server import FlServer
-    from fl4health_b200.servers.client_manager import SimpleClientManager
-    from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
     from fl4health_b200.utils.dataset import TensorDataset
     from fl4health_b200.utils import tracing
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "benchmarks"))
+    import fl_variants
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     os.environ["FL4H_COLLECTIVES"] = args.collectives
@@ -177,18 +185,17 @@ def main() -> None:
         data = torch.randn(n, 3, 32, 32, generator=gen) * 0.5 + (targets.float().view(-1, 1, 1, 1) - 4.5) * 0.1
         return TensorDataset(data, targets)
 
-    class CifarResNetClient(BasicClient):
-        placement = "device"
+    class BenchHooks:
+        """Data / criterion / optimizer factories shared by every variant's client class (mixed in before the
+        algorithm's client, see benchmarks/fl_variants.py)."""
 
-        def get_model(self, config):  # noqa: ANN001, ANN202
-            torch.manual_seed(1234)
-            return resnet18_cifar()
+        placement = "device"
 
         def get_data_loaders(self, config):  # noqa: ANN001, ANN202
             bs = int(config["batch_size"])
             train = BatchedTensorLoader(synthetic(args.train_samples, 100 + ctx.rank), bs, shuffle=True, drop_last=True,
-                                        placement=self.placement, device=self.device)
-            val = BatchedTensorLoader(synthetic(args.val_batches * bs, 900 + ctx.rank), bs, placement=self.placement,
+                                        placement=BenchHooks.placement, device=self.device)
+            val = BatchedTensorLoader(synthetic(args.val_batches * bs, 900 + ctx.rank), bs, placement=BenchHooks.placement,
                                       device=self.device)
             return train, val
 
@@ -203,18 +210,10 @@ def main() -> None:
 
     l2_flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
 
-    def run_federation(dtype: str, with_e2e: bool) -> tuple[dict, dict | None, EngineOptions]:
+    def run_federation(dtype: str, with_e2e: bool, variant: str = "fedavg") -> tuple[dict, dict | None, EngineOptions]:
         """Build one federation at `dtype` and time it (e2e staging first, then device-resident datasets)."""
         engine = engine_for(dtype)
-        client = CifarResNetClient(Path("."), [Accuracy()], device, client_name=f"rank{ctx.rank}", engine_options=engine)
-        strategy = BasicFedAvg(
-            min_fit_clients=world, min_evaluate_clients=world, min_available_clients=world,
-            on_fit_config_fn=config_fn, on_evaluate_config_fn=config_fn,
-            fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
-            evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
-        )
-        server = FlServer(SimpleClientManager(), {"n_server_rounds": args.steps + args.warmup, "local_steps": args.local_steps},
-                          strategy, on_init_parameters_config_fn=config_fn, accept_failures=False)
+        client, server = fl_variants.build(variant, BenchHooks, ctx, engine, args.steps + args.warmup, args.local_steps, args.batch_size)
         build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
 
         def timed_fit(label: str) -> dict:
@@ -258,10 +257,10 @@ def main() -> None:
         # ---- e2e first (pinned host datasets -> H2D every batch), then device-resident ------------------------
         e2e_run = None
         if with_e2e:
-            CifarResNetClient.placement = "pinned"
+            BenchHooks.placement = "pinned"
             e2e_run = timed_fit("e2e")
             # re-create loaders for the device-resident run (graphs and model state are reused)
-            CifarResNetClient.placement = "device"
+            BenchHooks.placement = "device"
             client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
             client.train_iterator = None
         device_run = timed_fit("device")
@@ -271,9 +270,15 @@ def main() -> None:
             print(json.dumps({"dtype": dtype, **{k: round(v["mean_ms"], 4) for k, v in report.items()}}), file=sys.stderr)
         return device_run, e2e_run, engine
 
-    main_run, e2e, engine = run_federation(headline_dtype, with_e2e=not args.skip_e2e)
+    variants = fl_variants.GROUPS[args.config]
+    main_run, e2e, engine = run_federation(headline_dtype, with_e2e=not args.skip_e2e, variant=variants[0])
+    others = {}
+    for name in variants[1:]:  # further algorithms of this BASELINE configuration: device-resident timing each
+        run, _, _ = run_federation(headline_dtype, with_e2e=False, variant=name)
+        others[name] = {"value": world * 1000.0 / run["ms_per_round"], "ms_per_step": run["ms_per_round"],
+                        "final_val_loss": run["final_loss"], "gpu_launches": run["launches"]}
     extra = None
-    if not (args.skip_extra_dtype or eager_impl):
+    if not (args.skip_extra_dtype or eager_impl or args.config != "cifar_fedavg"):
         other = "bf16" if headline_dtype == "fp32" else "fp32"
         extra_run, extra_e2e, _ = run_federation(other, with_e2e=not args.skip_e2e)
         extra = {"dtype": other, "value": world * 1000.0 / extra_run["ms_per_round"], "ms_per_step": extra_run["ms_per_round"],
@@ -284,7 +289,8 @@ def main() -> None:
     rounds_per_s = 1000.0 / main_run["ms_per_round"]
     bytes_in = args.local_steps * args.batch_size * (3 * 32 * 32 * 4 + 8) + args.val_batches * args.batch_size * (3 * 32 * 32 * 4 + 8)
     result = {
-        "metric": "fl_rounds_per_sec_cifar10_resnet18_fedavg",
+        "metric": ("fl_rounds_per_sec_cifar10_resnet18_fedavg" if args.config == "cifar_fedavg"
+                   else f"fl_rounds_per_sec_cifar10_{args.config}[{variants[0]}]"),
         # whole-job aggregate: client rounds completed per second summed over the N client-GPUs.  The federation as a
         # whole advances `federation_rounds_per_s` rounds per second, each round doing N clients' worth of work (weak
         # scaling: per-GPU work fixed), so the aggregate is N x that; at N=1 both are the reference's "FL rounds/sec".
@@ -305,7 +311,7 @@ def main() -> None:
         "config": {
             "model": "resnet18_cifar (11.17M params)", "clients": world, "parallelism": f"fl_dp{world} (one client per GPU)",
             "global_batch": args.batch_size * world, "batch_per_client": args.batch_size,
-            "local_steps": args.local_steps, "val_batches_per_client": args.val_batches, "strategy": "BasicFedAvg (weighted)",
+            "local_steps": args.local_steps, "val_batches_per_client": args.val_batches, "strategy": "BasicFedAvg (weighted)" if args.config == "cifar_fedavg" else variants[0],
             "optimizer": "SGD lr=0.01 momentum=0.9", "seq_len": None,
             "l2": "explicit 256 MiB write between rounds (inside the timed region)",
             "collectives": (("fused-nvls (multimem)" if ctx.fused.has_multicast else "fused-p2p") if ctx.fused is not None
@@ -325,6 +331,8 @@ def main() -> None:
             "note": "per federation round, summed over ranks: every train/val batch copied from pinned host memory; "
                     "loss+accuracy scalars read back on every rank",
         }
+    if others:
+        result["variants"] = {variants[0]: {"value": result["value"], "ms_per_step": result["ms_per_step"]}, **others}
     if extra is not None:
         result[extra["dtype"]] = extra  # the other precision, same federation code, measured after the headline
     if ctx.rank == 0:
