@@ -81,6 +81,13 @@ def conv_bn_act(conv: nn.Module, bn: nn.Module, x: torch.Tensor, residual: torch
     return bn_act(bn, conv(x), residual, relu)
 
 
+def _wgrad_may_overlap(weight: torch.Tensor) -> bool:
+    """The weight gradient may be produced on the side stream only when autograd will ASSIGN it (``.grad`` is None:
+    table-gradient / bf16-shadow engines).  With a live ``.grad`` (flat gradient region, gradient accumulation)
+    AccumulateGrad adds it in place on the main stream right after this node returns, before the deferred join."""
+    return streams.overlap_enabled() and weight.grad is None
+
+
 class _TcConvFn(torch.autograd.Function):
     """tcgen05 implicit-GEMM convolution (``ops/conv.py``); the weight gradient runs on a side stream like the stock
     path's (only the optimizer needs it), the data gradient stays on the critical path."""
@@ -99,7 +106,7 @@ class _TcConvFn(torch.autograd.Function):
             grad_out = grad_out.to(x.dtype).contiguous(memory_format=torch.channels_last)
         grad_x = grad_w = None
         if ctx.needs_input_grad[1]:
-            if streams.overlap_enabled():
+            if _wgrad_may_overlap(weight):
                 main = torch.cuda.current_stream(x.device)
                 side = streams.fork(x.device)
                 with torch.cuda.stream(side):
@@ -119,17 +126,17 @@ class _StemConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, stats):  # noqa: ANN001, ANN205
-        ctx.save_for_backward(x)
+        ctx.save_for_backward(x, weight)
         return tc_conv.stem_forward(x, weight, stats)
 
     @staticmethod
     def backward(ctx, grad_out):  # noqa: ANN001, ANN205
-        (x,) = ctx.saved_tensors
+        x, weight = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
             raise RuntimeError("the stem convolution kernel does not produce input gradients (FL4H_TC_CONV=0 for that)")
         if grad_out.dtype != x.dtype or not grad_out.is_contiguous(memory_format=torch.channels_last):
             grad_out = grad_out.to(x.dtype).contiguous(memory_format=torch.channels_last)
-        if not streams.overlap_enabled():
+        if not _wgrad_may_overlap(weight):
             return None, tc_conv.stem_wgrad(x, grad_out), None
         main = torch.cuda.current_stream(x.device)
         side = streams.fork(x.device)
@@ -157,7 +164,10 @@ class _ConvOverlappedWgrad(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], bias_sizes is not None and ctx.needs_input_grad[2]
         zeros = [0] * len(stride)
         grad_w = grad_b = grad_x = None
-        if need_w or need_b:
+        if (need_w or need_b) and not _wgrad_may_overlap(weight):
+            _, grad_w, grad_b = torch.ops.aten.convolution_backward(
+                grad_out, x, weight, bias_sizes, stride, padding, dilation, False, zeros, groups, [False, need_w, need_b])
+        elif need_w or need_b:
             main = torch.cuda.current_stream(x.device)
             side = streams.fork(x.device)
             with torch.cuda.stream(side):

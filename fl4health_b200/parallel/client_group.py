@@ -7,9 +7,9 @@ the library itself is unaware.  Here the notion is part of the SPMD runtime:
 * the world of ``W`` ranks is cut into consecutive groups of ``G`` ranks; every group is ONE federated client
   (``ClientGroup``), every rank of the group holds a full replica of the client's model and a disjoint shard of its
   data (``shard_dataset``);
-* ``ReplicatedClientMixin`` averages the gradients over the group between backward and the optimizer step (one
+* ``ReplicatedClientMixin`` averages the gradients over the group in a pre-hook of every ``optimizer.step()`` (one
   collective on the flat arena gradient — the arena makes the "bucket" the whole model), so all replicas take the
-  same step on the union batch;
+  same step on the union batch, whichever ``train_step`` the client algorithm brings;
 * the federation layer needs no change: each replica reports its shard's sample count, and because the replicas of a
   client are identical, the sample-weighted aggregate over all ``W`` ranks equals the client-weighted aggregate over
   the ``W / G`` clients (``Σ_r n_r w_r = Σ_k (Σ_{r∈k} n_r) w_k``).  Metrics aggregate the same way.
@@ -75,10 +75,13 @@ def shard_dataset(dataset: TensorDataset, group: ClientGroup, seed: int = 0) -> 
 class ReplicatedClientMixin:
     """Combine as ``class C(ReplicatedClientMixin, SomeClient)`` and set ``client.client_group``.
 
-    ``transform_gradients`` is the hook every client calls between ``backward()`` and ``optimizer.step()``
-    (``basic_client.py`` ``train_step``); clients that already use it (SCAFFOLD's control-variate correction, DP
-    clipping) compose through ``super()``: their correction is applied to the local gradient first, then the
-    replicas are averaged.
+    The group all-reduce hangs on the one point every training step reaches whatever ``train_step`` looks like:
+    ``optimizer.step()``.  Each optimizer of the client gets a step pre-hook (``torch.optim.Optimizer.
+    register_step_pre_hook``; the one-launch flat optimizers are ``Optimizer`` subclasses too) that averages the
+    gradients of the parameters that optimizer owns over the group.  Clients with several optimizers and their own
+    ``train_step`` (Ditto: global twin + personal model, APFL, FedRep's head / representation phases, ensembles) are
+    covered without knowing about replication, and gradient corrections applied in ``transform_gradients`` (SCAFFOLD's
+    control variates, DP clipping) still act on the local gradient first.
     """
 
     client_group: ClientGroup | None = None
@@ -97,43 +100,71 @@ class ReplicatedClientMixin:
             log(WARNING, "client spans several ranks: CUDA-graph capture of the training step is disabled for it")
             self.engine = replace(engine, cuda_graphs=False)
         super().setup_client(config)  # type: ignore[misc]
+        self._hook_group_averaging()
 
-    def transform_gradients(self, losses: Any) -> None:
-        super().transform_gradients(losses)  # type: ignore[misc]
+    def train_step(self, input: Any, target: Any) -> Any:
+        self._hook_group_averaging()  # optimizers re-created since set-up (new round, new phase) are picked up here
+        return super().train_step(input, target)  # type: ignore[misc]
+
+    def _hook_group_averaging(self) -> None:
         group = self.client_group
         if group is None or group.process_group is None:
             return
-        for model in self._replicated_models():
-            average_gradients(model, group)
+        for optimizer in getattr(self, "optimizers", {}).values():
+            if getattr(optimizer, "_fl4h_group_hook", None) is None:
+                if not hasattr(optimizer, "register_step_pre_hook"):
+                    raise TypeError(f"{type(optimizer).__name__} is not a torch.optim.Optimizer: a client spanning several "
+                                    "ranks needs step pre-hooks to average its gradients over the group")
+                optimizer._fl4h_group_hook = optimizer.register_step_pre_hook(self._average_before_step)
 
-    def _replicated_models(self) -> list[torch.nn.Module]:
-        models = [self.model]  # type: ignore[attr-defined]
-        twin = getattr(self, "global_model", None)  # Ditto-style clients train a second model in the same step
-        if isinstance(twin, torch.nn.Module):
-            models.append(twin)
-        return models
+    def _average_before_step(self, optimizer: Any, args: Any, kwargs: Any) -> None:
+        group = self.client_group
+        if group is None or group.process_group is None:
+            return
+        params = self._parameters_reduced_for(optimizer)
+        average_parameter_gradients(params, group, self._flat_gradient_of(params))
+
+    def _parameters_reduced_for(self, optimizer: Any) -> list[torch.nn.Parameter]:
+        """Whose gradients are averaged before ``optimizer`` steps: by default exactly what it updates."""
+        return [p for param_group in optimizer.param_groups for p in param_group["params"] if p.requires_grad]
+
+    def _flat_gradient_of(self, params: list[torch.nn.Parameter]) -> torch.Tensor | None:
+        """The arena's flat gradient region when ``params`` are exactly one arena-backed module's trainable parameters
+        (then one collective on the flat buffer does it)."""
+        wanted = {id(p) for p in params}
+        modules = [getattr(self, "model", None), getattr(self, "global_model", None)]
+        candidates = getattr(self, "_candidate_modules", None)
+        if callable(candidates):
+            modules = list(candidates())
+        for module in modules:
+            if isinstance(module, torch.nn.Module):
+                arena = arena_of(module)
+                flat = getattr(arena, "grad", None) if arena is not None else None
+                if flat is not None and wanted == {id(p) for p in module.parameters() if p.requires_grad}:
+                    return flat
+        return None
 
 
 def average_gradients(model: torch.nn.Module, group: ClientGroup) -> None:
-    """Mean of the gradients over the group.  One collective when the gradients live in the arena's flat buffer;
-    otherwise the per-parameter gradients are coalesced into one temporary."""
+    """Mean of a model's gradients over the group.  One collective when the gradients live in the arena's flat buffer;
+    otherwise the per-parameter gradients are coalesced into one temporary per dtype."""
     arena = arena_of(model)
-    flat = getattr(arena, "grad", None) if arena is not None else None
-    params = [p for p in model.parameters() if p.requires_grad]
-    if flat is not None and params and all(p.grad is not None and _is_view_of(p.grad, flat) for p in params):
+    average_parameter_gradients([p for p in model.parameters() if p.requires_grad], group,
+                                getattr(arena, "grad", None) if arena is not None else None)
+
+
+def average_parameter_gradients(params: list[torch.nn.Parameter], group: ClientGroup, flat: torch.Tensor | None = None) -> None:
+    if group.process_group is None or not params:
+        return
+    if flat is not None and all(p.grad is not None and _is_view_of(p.grad, flat) for p in params):
         group.all_reduce_mean(flat)
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if len(grads) != len(params):  # a parameter unused on this replica must still take part: the collective is by position
-        for p in params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-        grads = [p.grad for p in params]
-    if not grads:
-        return
+    for p in params:  # a parameter unused on this replica must still take part: the collective is by position
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
     by_dtype: dict[torch.dtype, list[torch.Tensor]] = {}
-    for g in grads:
-        by_dtype.setdefault(g.dtype, []).append(g)
+    for p in params:
+        by_dtype.setdefault(p.grad.dtype, []).append(p.grad)  # type: ignore[union-attr]
     for bucket in by_dtype.values():
         coalesced = torch.cat([g.reshape(-1) for g in bucket])
         group.all_reduce_mean(coalesced)
@@ -199,6 +230,10 @@ class Zero1ClientMixin(ReplicatedClientMixin):
         # what actually divides the state memory by G.  (A compact companion layout for the fused kernels is future work.)
         sharded.fl4h_keep_stock = True  # type: ignore[attr-defined]
         return sharded
+
+    def _parameters_reduced_for(self, optimizer: Any) -> list[torch.nn.Parameter]:
+        # the optimizer only holds this replica's share, but the collective is by position over the whole model
+        return [p for p in self.model.parameters() if p.requires_grad]  # type: ignore[attr-defined]
 
     def update_after_step(self, step: int, current_round: int | None = None) -> None:
         group = self.client_group

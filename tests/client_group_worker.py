@@ -66,9 +66,44 @@ class Zero1Client(Zero1ClientMixin, _Hooks, BasicClient):
     """Same hooks, optimizer state sharded over the replicas."""
 
 
+def _twin_optimizers(self, config):  # noqa: ANN001, ANN202
+    return {"global": torch.optim.SGD(self.global_model.parameters(), lr=0.05, momentum=0.9),
+            "local": torch.optim.SGD(self.model.parameters(), lr=0.05, momentum=0.9)}
+
+
+def _client_class() -> type:
+    if os.environ.get("FL4H_TEST_ZERO1") == "1":
+        return Zero1Client
+    variant = os.environ.get("FL4H_TEST_VARIANT", "basic")
+    if variant == "ditto":  # own train_step, two models, two optimizers
+        from fl4health_b200.clients.ditto_client import DittoClient
+
+        return type("ShardedDitto", (ReplicatedClientMixin, _Hooks, DittoClient), {"get_optimizer": _twin_optimizers})
+    if variant == "apfl":
+        from fl4health_b200.clients.apfl_client import ApflClient
+        from fl4health_b200.model_bases.apfl_base import ApflModule
+
+        def apfl_model(self, config):  # noqa: ANN001, ANN202
+            torch.manual_seed(99)
+            return ApflModule(GroupNormNet())
+
+        def apfl_optimizers(self, config):  # noqa: ANN001, ANN202
+            return {"global": torch.optim.SGD(self.model.global_model.parameters(), lr=0.05),
+                    "local": torch.optim.SGD(self.model.local_model.parameters(), lr=0.05)}
+
+        return type("ShardedApfl", (ReplicatedClientMixin, _Hooks, ApflClient), {"get_model": apfl_model, "get_optimizer": apfl_optimizers})
+    return ShardedClient
+
+
+def _all_parameters(client) -> torch.Tensor:  # noqa: ANN001
+    """Every trainable tensor the client owns: the exchanged model and any personal / twin model."""
+    modules = [client.model] + ([client.global_model] if isinstance(getattr(client, "global_model", None), torch.nn.Module) else [])
+    return torch.cat([p.detach().double().flatten() for m in modules for p in m.parameters()])
+
+
 def main() -> None:
     out_path, group_size = sys.argv[1], int(sys.argv[2])
-    client_cls = Zero1Client if os.environ.get("FL4H_TEST_ZERO1") == "1" else ShardedClient
+    client_cls = _client_class()
     ctx = SpmdContext()
     group = ClientGroup.from_world(ctx.rank, ctx.world_size, group_size)
 
@@ -76,7 +111,12 @@ def main() -> None:
         return {"current_server_round": server_round, "local_steps": 4, "batch_size": 16}
 
     n = ctx.world_size
-    strategy = BasicFedAvg(min_fit_clients=n, min_evaluate_clients=n, min_available_clients=n, on_fit_config_fn=fn, on_evaluate_config_fn=fn,
+    strategy_cls, extra = BasicFedAvg, {}
+    if os.environ.get("FL4H_TEST_VARIANT") == "ditto":
+        from fl4health_b200.strategies.fedavg_with_adaptive_constraint import FedAvgWithAdaptiveConstraint
+
+        strategy_cls, extra = FedAvgWithAdaptiveConstraint, {"initial_parameters": None, "initial_loss_weight": 0.5}
+    strategy = strategy_cls(**extra, min_fit_clients=n, min_evaluate_clients=n, min_available_clients=n, on_fit_config_fn=fn, on_evaluate_config_fn=fn,
                            fit_metrics_aggregation_fn=fit_metrics_aggregation_fn, evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn)
     server = FlServer(SimpleClientManager(), {"n_server_rounds": 2}, strategy, on_init_parameters_config_fn=fn)
     client = client_cls(Path("."), [Accuracy()], ctx.device, client_name=f"client{group.client_index}.replica{group.group_rank}")
@@ -89,7 +129,7 @@ def main() -> None:
 
     def spying_fit(parameters, config):  # noqa: ANN001, ANN202
         result = original_fit(parameters, config)
-        seen[int(config["current_server_round"])] = torch.cat([p.detach().double().flatten() for p in client.model.parameters()]).clone()
+        seen[int(config["current_server_round"])] = _all_parameters(client).clone()
         return result
 
     client.fit = spying_fit

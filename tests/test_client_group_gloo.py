@@ -88,6 +88,19 @@ def test_four_ranks_two_clients_of_two_replicas(tmp_path: Path) -> None:
     assert all(r["losses"] == results[0]["losses"] for r in results)
 
 
+@pytest.mark.parametrize("variant", ["ditto", "apfl"])
+def test_replicas_of_multi_optimizer_clients_stay_identical(tmp_path: Path, variant: str) -> None:
+    """Clients that write their own ``train_step`` around several optimizers (Ditto: exchanged twin + personal model;
+    APFL: global + local sub-models) never go through ``transform_gradients``: the group average hangs on
+    ``optimizer.step()`` instead, and every model of the client -- including the ones that are never exchanged, which
+    only the averaging keeps in sync -- is the same on both replicas before each aggregate."""
+    replicas = _launch(tmp_path, world=2, group_size=2, port=29750 + (os.getpid() + len(variant)) % 40, FL4H_TEST_VARIANT=variant)
+    for key in ("1", "2"):
+        assert replicas[0]["pre_aggregate"][key] == pytest.approx(replicas[1]["pre_aggregate"][key], rel=1e-9)
+    assert replicas[0]["pre_aggregate"]["1"] != pytest.approx(replicas[0]["pre_aggregate"]["2"], rel=1e-6)  # and they do train
+    assert replicas[0]["losses"] == replicas[1]["losses"]
+
+
 def test_partition_is_balanced_and_deterministic() -> None:
     from fl4health_b200.parallel.client_group import partition_parameters
 
