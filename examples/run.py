@@ -68,6 +68,9 @@ def main(argv: list[str] | None = None) -> dict:
         server, clients = SCENARIOS[args.scenario](config, ctx.device)
         if args.ranks_per_client > 1:
             assert per_rank == 1, "--ranks-per-client and --clients-per-rank are mutually exclusive"
+            from fl4health_b200.parallel.client_group import require_replica_safe_strategy
+
+            require_replica_safe_strategy(server.strategy, args.ranks_per_client)
             build_spmd_federation(ctx, server, _replicated(clients, ctx, args.ranks_per_client))
         elif per_rank == 1:
             build_spmd_federation(ctx, server, clients[ctx.rank])

@@ -3,12 +3,11 @@
 from __future__ import annotations
 
 import math
-import random
 from logging import INFO
 
 from fl4health_b200.client_managers.base_sampling_manager import BaseFractionSamplingManager
 from fl4health_b200.common.logger import log
-from fl4health_b200.servers.client_manager import Criterion
+from fl4health_b200.servers.client_manager import Criterion, sampling_streams
 from fl4health_b200.servers.client_proxy import ClientProxy
 
 
@@ -23,4 +22,4 @@ class FixedSamplingByFractionClientManager(BaseFractionSamplingManager):
         if n_clients == 0:
             log(INFO, f"Sample fraction {sample_fraction} of {len(available_cids)} clients selects no one.")
             return []
-        return [self.clients[cid] for cid in random.sample(available_cids, n_clients)]
+        return [self.clients[cid] for cid in sampling_streams.python.sample(available_cids, n_clients)]

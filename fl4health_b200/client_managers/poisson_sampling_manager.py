@@ -4,17 +4,15 @@ from __future__ import annotations
 
 from logging import INFO
 
-import numpy as np
-
 from fl4health_b200.client_managers.base_sampling_manager import BaseFractionSamplingManager
 from fl4health_b200.common.logger import log
-from fl4health_b200.servers.client_manager import Criterion
+from fl4health_b200.servers.client_manager import Criterion, sampling_streams
 from fl4health_b200.servers.client_proxy import ClientProxy
 
 
 class PoissonSamplingClientManager(BaseFractionSamplingManager):
     def _poisson_sample(self, sampling_probability: float, available_cids: list[str]) -> list[str]:
-        draws = np.random.binomial(1, sampling_probability, len(available_cids)).astype(bool)
+        draws = sampling_streams.numpy.binomial(1, sampling_probability, len(available_cids)).astype(bool)
         return [cid for cid, keep in zip(available_cids, draws) if keep]
 
     def sample_fraction(

@@ -212,9 +212,10 @@ class FlatSGD(_FlatOptimizer):
                            anchor, cv, self.shadow)
             return loss
         for idx, ranges in enumerate(self._ranges):
-            for start, end in ranges:
+            for r, (start, end) in enumerate(ranges):
                 s = self._slices(start, end)
-                F.sgd_step(s["w"], s["g"], self.momentum_buffer[start:end], self._hp[idx], s["anchor"], s["cv"], s["shadow"])
+                F.sgd_step(s["w"], s["g"], self.momentum_buffer[start:end], self._hp[idx], s["anchor"], s["cv"], s["shadow"],
+                           more_ranges=r + 1 < len(ranges))
         return loss
 
     def state_dict(self) -> dict[str, Any]:  # type: ignore[override]

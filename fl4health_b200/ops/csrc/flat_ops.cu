@@ -456,9 +456,13 @@ extern "C" {
 
 int fl4h_num_sms() { return num_sms(); }
 
+// `flags`: bit 0 = gradient is bf16; bit 1 = more ranges of the same parameter group follow, so the "first step" marker
+// in the shared hyper-parameter block stays armed (a group over non-contiguous arena ranges is stepped range by range
+// and every range must initialise its momentum as g, not (1 - dampening) g).
 int fl4h_sgd_step(float* w, const void* grad, float* mbuf, const float* anchor, const float* cv, void* shadow,
-                  float* hp, int64_t n, int grad_is_bf16, cudaStream_t stream) {
+                  float* hp, int64_t n, int flags, cudaStream_t stream) {
     if (n & 3) return (int)cudaErrorInvalidValue;
+    const int grad_is_bf16 = flags & 1;
     const int grid = stream_grid(n, 4);
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
 #define LAUNCH_SGD(A, C, S, G) \
@@ -483,7 +487,7 @@ int fl4h_sgd_step(float* w, const void* grad, float* mbuf, const float* anchor, 
         default: LAUNCH_SGD(true, true, true, true); break;
     }
 #undef LAUNCH_SGD
-    clear_first_kernel<<<1, 1, 0, stream>>>(hp);
+    if (!(flags & 2)) clear_first_kernel<<<1, 1, 0, stream>>>(hp);
     return (int)cudaGetLastError();
 }
 

@@ -56,23 +56,26 @@ def sgd_step(
     anchor: torch.Tensor | None = None,
     cv: torch.Tensor | None = None,
     shadow: torch.Tensor | None = None,
+    more_ranges: bool = False,
 ) -> None:
-    """w <- SGD(w, g + cv + mu (w - anchor) + wd w); also refreshes the bf16 compute shadow if given."""
+    """w <- SGD(w, g + cv + mu (w - anchor) + wd w); also refreshes the bf16 compute shadow if given.  ``more_ranges``:
+    further ranges of the same parameter group follow with the same ``hp`` block, whose first-step marker is then
+    left armed for them."""
     n = _check_flat(w)
     if _use_kernel(w):
         lib = _lib.load(True)
         err = lib.fl4h_sgd_step(
             _lib.ptr(w), _lib.ptr(grad), _lib.ptr(momentum_buf), _lib.ptr(anchor), _lib.ptr(cv), _lib.ptr(shadow),
-            _lib.ptr(hp), ctypes.c_int64(n), ctypes.c_int(1 if grad.dtype == torch.bfloat16 else 0),
+            _lib.ptr(hp), ctypes.c_int64(n), ctypes.c_int((1 if grad.dtype == torch.bfloat16 else 0) | (2 if more_ranges else 0)),
             _lib.stream_ptr(w.device),
         )
         _lib.check(err, "fl4h_sgd_step")
-        _lib.count_launches(2)
+        _lib.count_launches(1 if more_ranges else 2)
         return
-    sgd_step_reference(w, grad, momentum_buf, hp, anchor, cv, shadow)
+    sgd_step_reference(w, grad, momentum_buf, hp, anchor, cv, shadow, more_ranges)
 
 
-def sgd_step_reference(w, grad, momentum_buf, hp, anchor=None, cv=None, shadow=None) -> None:  # noqa: ANN001
+def sgd_step_reference(w, grad, momentum_buf, hp, anchor=None, cv=None, shadow=None, more_ranges=False) -> None:  # noqa: ANN001
     h = hp.tolist()
     lr, mom, damp, wd, mu = h[HP_LR], h[HP_MOM], h[HP_DAMP], h[HP_WD], h[HP_MU]
     nesterov, first = h[HP_NESTEROV] != 0.0, h[HP_FIRST] != 0.0
@@ -95,7 +98,8 @@ def sgd_step_reference(w, grad, momentum_buf, hp, anchor=None, cv=None, shadow=N
     else:
         upd = g
     w.sub_(lr * upd)
-    hp[HP_FIRST] = 0.0
+    if not more_ranges:
+        hp[HP_FIRST] = 0.0
     if shadow is not None:
         shadow[:n].copy_(w)
 

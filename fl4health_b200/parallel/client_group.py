@@ -61,6 +61,30 @@ class ClientGroup:
         return tensor
 
 
+def require_replica_safe_strategy(strategy: Any, group_size: int) -> None:
+    """Every replica registers as a federated client, which is exact only for aggregates that are (sample-weighted or
+    uniform) MEANS of what the replicas report: identical replicas then count as one client with the summed weight.
+    Strategies whose math depends on the number or identity of the participants are wrong under that bookkeeping:
+    client-level DP clips every registered client separately (a real client would contribute ``G`` clipped updates,
+    ``G`` times the sensitivity the accountant assumes), SCAFFOLD / FedDG-GA keep per-participant state and divide by
+    the participant count, FedPM's Bayesian vote and FedPCA's subspace merge count participants.  Refuse those."""
+    if group_size <= 1:
+        return
+    from fl4health_b200.strategies.client_dp_fedavgm import ClientLevelDPFedAvgM
+    from fl4health_b200.strategies.feddg_ga import FedDgGa
+    from fl4health_b200.strategies.fedpca import FedPCA
+    from fl4health_b200.strategies.fedpm import FedPm
+    from fl4health_b200.strategies.scaffold import Scaffold
+
+    for family, why in ((ClientLevelDPFedAvgM, "per-client clipping and noise calibrated to the number of clients"),
+                        (Scaffold, "per-client control variates averaged over the client count"),
+                        (FedDgGa, "per-client generalisation-gap weights"), (FedPm, "a per-client Bayesian mask vote"),
+                        (FedPCA, "a merge of per-client subspaces")):
+        if isinstance(strategy, family):
+            raise ValueError(f"{type(strategy).__name__} uses {why}; with {group_size} ranks per client every replica "
+                             "would be counted as a client of its own. Run this strategy with one rank per client.")
+
+
 def shard_dataset(dataset: TensorDataset, group: ClientGroup, seed: int = 0) -> TensorDataset:
     """Replica ``r`` of ``G`` keeps samples ``perm[r::G]`` of a seeded permutation: disjoint, equal-sized up to one."""
     assert dataset.targets is not None

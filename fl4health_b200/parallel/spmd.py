@@ -610,9 +610,10 @@ def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any, fuse
     # replicated server logic must draw identical client samples on every rank: align the sampling RNGs
     import random
 
+    from fl4health_b200.servers.client_manager import sampling_streams
+
     seed = ctx.broadcast_object(random.getrandbits(31), src=0)
-    random.seed(seed)
-    np.random.seed(seed)
+    sampling_streams.seed(seed)  # the managers' own streams: rank-local use of the global RNGs cannot desynchronise them
     proxies = []
     for rank in range(ctx.world_size):
         proxy = SpmdClientProxy(ctx, rank, local_client if rank == ctx.rank else None)

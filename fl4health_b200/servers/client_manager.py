@@ -7,8 +7,50 @@ import threading
 from abc import ABC, abstractmethod
 from logging import INFO
 
+import numpy as np
+
 from fl4health_b200.common.logger import log
 from fl4health_b200.servers.client_proxy import ClientProxy
+
+
+class _SamplingStreams:
+    """The random streams client sampling draws from -- its own, not the process-global ``random`` / ``np.random``.
+
+    With the server logic replicated on every rank (``parallel/spmd.py``) all ranks must draw the same cohort each
+    round.  Global generators cannot promise that: anything rank-local that consumes them between rounds (a client's
+    data loaders, a Dirichlet partitioner, user augmentation) desynchronises the ranks, which then disagree on who
+    trains and mismatch collectives.  ``seed()`` is called with the broadcast seed when a federation is built and by
+    ``set_all_random_seeds``; unseeded, the streams start from one draw of the global ``random`` (so a plain
+    ``random.seed(...)`` before building the server still fixes the cohorts)."""
+
+    def __init__(self) -> None:
+        self._python: random.Random | None = None
+        self._numpy: np.random.Generator | None = None
+
+    def seed(self, seed: int | None) -> None:
+        if seed is None:
+            self._python = self._numpy = None
+        else:
+            self._python, self._numpy = random.Random(seed), np.random.default_rng(seed)
+
+    def _ensure(self) -> None:
+        if self._python is None or self._numpy is None:
+            self.seed(random.getrandbits(63))
+
+    @property
+    def python(self) -> random.Random:
+        self._ensure()
+        assert self._python is not None
+        return self._python
+
+    @property
+    def numpy(self) -> np.random.Generator:
+        self._ensure()
+        assert self._numpy is not None
+        return self._numpy
+
+
+sampling_streams = _SamplingStreams()
 
 
 class Criterion(ABC):
@@ -81,4 +123,4 @@ class SimpleClientManager(ClientManager):
         if num_clients > len(available):
             log(INFO, f"Sampling failed: available clients ({len(available)}) < requested clients ({num_clients}).")
             return []
-        return [self.clients[cid] for cid in random.sample(available, num_clients)]
+        return [self.clients[cid] for cid in sampling_streams.python.sample(available, num_clients)]

@@ -9,7 +9,6 @@ global model's initial parameters.
 
 from __future__ import annotations
 
-import random
 from collections.abc import Callable, Sequence
 from functools import partial
 from logging import DEBUG, INFO, WARNING
@@ -28,7 +27,7 @@ from fl4health_b200.feature_alignment.constants import (
 from fl4health_b200.feature_alignment.tab_features_info_encoder import TabularFeaturesInfoEncoder
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.servers.base_server import FlServer
-from fl4health_b200.servers.client_manager import ClientManager
+from fl4health_b200.servers.client_manager import ClientManager, sampling_streams
 from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
 
 
@@ -104,7 +103,7 @@ class TabularFeatureAlignmentServer(FlServer):
     def poll_clients_for_feature_info(self, timeout: float | None) -> str:
         log(INFO, "Feature information source unspecified. Polling clients for feature information.")
         instructions = self.strategy.configure_poll(server_round=1, client_manager=self._client_manager)
-        chosen = random.sample(population=instructions, k=1)  # one client's schema becomes the source of truth
+        chosen = sampling_streams.python.sample(population=instructions, k=1)  # one client's schema becomes the source of truth
         results, _ = self.transport.poll_clients(chosen, max_workers=self.max_workers, timeout=timeout)
         assert len(results) == 1
         return str(results[0][1].properties[FEATURE_INFO])

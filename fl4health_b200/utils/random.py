@@ -37,9 +37,17 @@ _SOURCES: tuple[_Source, ...] = (
 )
 
 
+def _seed_client_sampling(seed: int | None) -> None:
+    """Client sampling draws from its own streams (``servers/client_manager.py``), which follow the global seed."""
+    from fl4health_b200.servers.client_manager import sampling_streams
+
+    sampling_streams.seed(seed)
+
+
 def set_all_random_seeds(
     seed: int | None = 42, use_deterministic_torch_algos: bool = False, disable_torch_benchmarking: bool = False
 ) -> None:
+    _seed_client_sampling(seed)
     if seed is not None:
         log(INFO, f"Setting seed to {seed}")
         for source in _SOURCES:
@@ -58,6 +66,7 @@ def unset_all_random_seeds() -> None:
     log(INFO, "Setting all random seeds to None. Reverting torch determinism settings")
     for source in _SOURCES:
         source.unseed()
+    _seed_client_sampling(None)
     torch.use_deterministic_algorithms(False)
 
 

@@ -55,6 +55,22 @@ def test_single_rank_group_leaves_gradients_alone() -> None:
     assert Base.calls == 1
 
 
+def test_strategies_that_count_participants_refuse_replicated_clients() -> None:
+    from fl4health_b200.parallel.client_group import require_replica_safe_strategy
+    from fl4health_b200.strategies.basic_fedavg import BasicFedAvg
+    from fl4health_b200.strategies.client_dp_fedavgm import ClientLevelDPFedAvgM
+    from fl4health_b200.strategies.scaffold import Scaffold
+    from fl4health_b200.common.typing import ndarrays_to_parameters
+
+    require_replica_safe_strategy(BasicFedAvg(), 2)
+    dp = ClientLevelDPFedAvgM(initial_parameters=ndarrays_to_parameters([torch.zeros(2)]))
+    require_replica_safe_strategy(dp, 1)  # one rank per client: anything goes
+    scaffold = Scaffold(initial_parameters=ndarrays_to_parameters([torch.zeros(2)]), model=torch.nn.Linear(1, 1, bias=False))
+    for strategy in (dp, scaffold):
+        with pytest.raises(ValueError, match="one rank per client"):
+            require_replica_safe_strategy(strategy, 2)
+
+
 def _launch(tmp_path: Path, world: int, group_size: int, port: int, **extra_env: str) -> list[dict]:
     out = tmp_path / f"w{world}g{group_size}{'z' if extra_env else ''}"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",

@@ -84,3 +84,26 @@ def test_bf16_master_weight_federation_cpu() -> None:
     assert clients[0].optimizers["global"].table_mode
     losses = [v for _, v in history.losses_distributed]
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0] * 1.5
+
+
+def test_flat_sgd_over_non_contiguous_ranges_matches_torch_with_dampening() -> None:
+    """A parameter group that covers several separate arena ranges (FedRep head / base optimizers, sub-module
+    optimizers) is stepped range by range with one hyper-parameter block: every range must take the first-step branch
+    (momentum <- g), which only shows when dampening != 0."""
+    torch.manual_seed(0)
+    ours = nn.Sequential(nn.Linear(6, 8), nn.Linear(8, 8), nn.Linear(8, 8), nn.Linear(8, 3))
+    stock = copy.deepcopy(ours)
+    arena = attach_arena(ours)
+    picked = lambda net: [*net[0].parameters(), *net[2].parameters()]  # noqa: E731 - layers 0 and 2: two separate ranges
+    flat = FlatSGD(arena, picked(ours), lr=0.1, momentum=0.9, dampening=0.5)
+    assert not flat.table_mode and len(flat._ranges[0]) >= 2
+    reference = torch.optim.SGD(picked(stock), lr=0.1, momentum=0.9, dampening=0.5)
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        x, y = torch.randn(5, 6, generator=gen), torch.randint(0, 3, (5,), generator=gen)
+        for net, opt in ((ours, flat), (stock, reference)):
+            opt.zero_grad()
+            nn.functional.cross_entropy(net(x), y).backward()
+            opt.step()
+        for mine, theirs in zip(ours.parameters(), stock.parameters()):
+            assert torch.allclose(mine, theirs, atol=1e-6)
