@@ -47,8 +47,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 def parse_args() -> argparse.Namespace:
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20, help="timed FL rounds")
-    p.add_argument("--warmup", type=int, default=3, help="untimed warm-up FL rounds")
+    p.add_argument("--steps", type=int, default=200, help="timed FL rounds")
+    p.add_argument("--warmup", type=int, default=5, help="untimed warm-up FL rounds")
     p.add_argument("--impl", default="native", choices=["native", "reference", "eager"])
     p.add_argument("--local-steps", type=int, default=8)
     p.add_argument("--batch-size", type=int, default=32)

@@ -122,3 +122,53 @@ def test_tabular_alignment_federation(server_has_schema: bool) -> None:
     assert dims["out"] == 2 and dims["in"] == clients[0].input_dimension == clients[1].input_dimension
     assert len(history.losses_distributed) == 3
     assert history.losses_distributed[-1][1] < history.losses_distributed[0][1]
+
+
+def test_type_conversion_helpers_cover_every_feature_type() -> None:
+    """The conversion table behind ``infer_types`` / ``to_types`` (reference handle_types.py: 20 helpers): ranking for
+    binary / ordinal columns with the inverse map in the metadata, one-hot for categorical indicators, bounds on the
+    number of categories, and floats never being categorical."""
+    import numpy as np
+    import pandas as pd
+    import pytest
+
+    from fl4health_b200.feature_alignment import handle_types as ht
+    from fl4health_b200.feature_alignment.constants import FEATURE_INDICATOR_ATTR, FEATURE_MAPPING_ATTR, FEATURE_TYPE_ATTR, FeatureType
+
+    frame = pd.DataFrame({"flag": [True, False, True, True], "yn": ["y", "n", "y", "n"], "grade": [3, 1, 2, 3],
+                          "dose": [0.5, 1.5, 2.5, 0.5], "colour": ["r", "g", "b", "r"]})
+    assert ht.infer_types(frame, list(frame.columns)) == {
+        "flag": FeatureType.BINARY, "yn": FeatureType.BINARY, "grade": FeatureType.ORDINAL, "dose": FeatureType.NUMERIC,
+        "colour": FeatureType.ORDINAL}
+    wide = pd.DataFrame({"name": [f"p{i}" for i in range(30)], "digits": [str(i) for i in range(30)]})
+    assert ht.infer_types(wide, ["name", "digits"]) == {"name": FeatureType.STRING, "digits": FeatureType.NUMERIC}
+
+    converted, meta = ht.to_types(frame.copy(), {"flag": FeatureType.BINARY, "yn": FeatureType.BINARY, "grade": FeatureType.ORDINAL,
+                                                 "dose": FeatureType.NUMERIC, "colour": FeatureType.CATEGORICAL_INDICATOR})
+    assert converted["yn"].tolist() == [1, 0, 1, 0] and meta["yn"][FEATURE_MAPPING_ATTR] == {0: "n", 1: "y"}
+    assert converted["grade"].tolist() == [2, 0, 1, 2] and meta["grade"][FEATURE_MAPPING_ATTR] == {0: 1, 1: 2, 2: 3}
+    assert meta["flag"][FEATURE_MAPPING_ATTR] == {False: False, True: True} and str(converted["flag"].dtype) == "category"
+    assert "colour" not in converted and {"colour_r", "colour_g", "colour_b"} <= set(converted.columns)
+    assert converted["colour_r"].tolist() == [True, False, False, True]
+    assert meta["colour_g"] == {FEATURE_TYPE_ATTR: FeatureType.CATEGORICAL_INDICATOR, FEATURE_INDICATOR_ATTR: "colour"}
+    assert meta["dose"] == {FEATURE_TYPE_ATTR: FeatureType.NUMERIC}
+
+    # bounds and errors
+    assert not ht.convertible_to_type(frame["dose"], FeatureType.ORDINAL)  # floats are never categorical
+    assert not ht._convertible_to_ordinal(wide["name"]) and ht._convertible_to_ordinal(wide["name"], category_max=30)
+    with pytest.raises(ValueError, match="at most 20"):
+        ht._convertible_to_ordinal(wide["name"], raise_error_over_max=True)
+    with pytest.raises(ValueError, match="at least 2"):
+        ht._convertible_to_categorical(pd.Series([1, 1, 1]), category_min=2, raise_error_under_min=True)
+    with pytest.raises(ValueError, match="Cannot convert series dose"):
+        ht.to_types(frame.copy(), {"dose": FeatureType.BINARY})
+    with pytest.raises(ValueError, match="Cannot duplicate columns"):
+        ht._to_categorical_indicators(pd.DataFrame({"c": ["a", "b"], "c_a": [0, 1]}), "c")
+    assert ht._convertible_to_numeric(pd.Series(["1", "2"])) and not ht._convertible_to_numeric(pd.Series(["1", "x"]))
+    with pytest.raises(ValueError):
+        ht._convertible_to_numeric(pd.Series(["1", "x"]), raise_error=True)
+    # caller-supplied distinct values are honoured, missing values are not a category
+    assert ht._convertible_to_binary(pd.Series(["a", None, "b", "a"]))
+    ranked, ranked_meta = ht._to_ordinal(pd.Series(["lo", "hi", "mid"], name="level"), unique=np.array(["hi", "lo", "mid"], dtype=object))
+    assert ranked.tolist() == [1, 0, 2] and ranked_meta[FEATURE_TYPE_ATTR] == FeatureType.ORDINAL
+    assert ht.to_dtype(pd.Series([0, 1]), FeatureType.NUMERIC).dtype == np.int64 and ht._type_to_dtype(FeatureType.STRING) is None
