@@ -213,8 +213,14 @@ def main() -> None:
     def run_federation(dtype: str, with_e2e: bool, variant: str = "fedavg") -> tuple[dict, dict | None, EngineOptions]:
         """Build one federation at `dtype` and time it (e2e staging first, then device-resident datasets)."""
         engine = engine_for(dtype)
-        client, server = fl_variants.build(variant, BenchHooks, ctx, engine, args.steps + args.warmup, args.local_steps, args.batch_size)
-        build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
+
+        def federation(placement: str):  # noqa: ANN202
+            BenchHooks.placement = placement
+            client, server = fl_variants.build(variant, BenchHooks, ctx, engine, args.steps + args.warmup, args.local_steps, args.batch_size)
+            build_spmd_federation(ctx, server, client, fused=False if args.collectives == "nccl" else None)
+            return client, server
+
+        client, server = federation("pinned" if with_e2e else "device")
 
         def timed_fit(label: str) -> dict:
             """Run warmup+steps rounds through FlServer.fit; time the last `steps` rounds on the device."""
@@ -257,12 +263,15 @@ def main() -> None:
         # ---- e2e first (pinned host datasets -> H2D every batch), then device-resident ------------------------
         e2e_run = None
         if with_e2e:
-            BenchHooks.placement = "pinned"
             e2e_run = timed_fit("e2e")
-            # re-create loaders for the device-resident run (graphs and model state are reused)
-            BenchHooks.placement = "device"
-            client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
-            client.train_iterator = None
+            if variant == "fedavg":  # re-create loaders for the device-resident run (graphs and model state are reused)
+                BenchHooks.placement = "device"
+                client.train_loader, client.val_loader = client.get_data_loaders(config_fn(1))
+                client.train_iterator = None
+            else:
+                # algorithms with server-held initial state (SCAFFOLD's variates) or partial exchange (FedPer) define
+                # one fit() per federation: the device-resident pass gets a fresh client and server
+                client, server = federation("device")
         device_run = timed_fit("device")
         if tracing.tracing_enabled() and ctx.rank == 0:  # FL4H_TRACE=1: device ms per round phase (diagnostic, stderr)
             torch.cuda.synchronize()

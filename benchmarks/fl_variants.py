@@ -85,8 +85,9 @@ def build(variant: str, hooks: type, ctx: Any, engine: Any, rounds: int, local_s
 
     def seeded(factory: Any) -> Any:
         def make() -> nn.Module:
-            torch.manual_seed(1234)
-            return factory()
+            with torch.random.fork_rng(devices=[]):  # same initialisation everywhere, ambient random stream untouched
+                torch.manual_seed(1234)
+                return factory()
         return make
 
     if variant == "fedavg":

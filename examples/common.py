@@ -79,8 +79,11 @@ class ExampleClientMixin:
     model_factory: Callable[[], nn.Module]
 
     def get_model(self, config: Config) -> nn.Module:
-        torch.manual_seed(self.example_config["seed"])
-        return self.model_factory()
+        # every client starts from the same initialisation, without rewinding the process' random stream (which the
+        # client keeps using for mask sampling, dropout, DP noise ...)
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(self.example_config["seed"])
+            return self.model_factory()
 
     def get_data_loaders(self, config: Config) -> tuple[BatchedTensorLoader, BatchedTensorLoader]:
         train, val = client_datasets(self.example_config, self.client_index)

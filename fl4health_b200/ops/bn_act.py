@@ -67,9 +67,14 @@ def _is_channels_last_dense(t: torch.Tensor) -> bool:
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
 
 
+def _kernels_enabled() -> bool:
+    """``FL4H_BN_KERNEL=0`` sends every BatchNorm through the stock-op reference path (A/B runs, numerics tests)."""
+    return os.environ.get("FL4H_BN_KERNEL", "1") != "0"
+
+
 def kernel_eligible(x: torch.Tensor, residual: torch.Tensor | None, momentum: float | None, training: bool,
                     running_mean: torch.Tensor | None) -> bool:
-    if not x.is_cuda or _lib.load() is None:
+    if not x.is_cuda or not _kernels_enabled() or _lib.load() is None:
         return False
     if x.dtype not in (torch.bfloat16, torch.float32) or not _is_channels_last_dense(x):
         return False
@@ -95,7 +100,9 @@ def presums_eligible(x_like: torch.Tensor, channels: int, residual: torch.Tensor
                      training: bool, running_mean: torch.Tensor | None) -> bool:
     """True when ``batch_norm_act(..., presums=...)`` will take the kernel path for a tensor shaped like ``x_like``
     with ``channels`` channels (decided BEFORE the convolution runs, so its epilogue knows whether to reduce)."""
-    if not training or not x_like.is_cuda or _lib.load() is None or x_like.dtype not in (torch.bfloat16, torch.float32):
+    if not training or not x_like.is_cuda or not _kernels_enabled() or _lib.load() is None:
+        return False
+    if x_like.dtype not in (torch.bfloat16, torch.float32):
         return False
     if channels % 8 != 0 or channels // 8 > 256 or 256 % (channels // 8) != 0:
         return False

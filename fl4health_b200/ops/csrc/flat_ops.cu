@@ -447,6 +447,47 @@ fedpm_vote_kernel(MaskPack pack, float* __restrict__ alpha, float* __restrict__ 
     }
 }
 
+// FedPM vote over BIT-PACKED masks (the cross-GPU form: every client ships n/32 words instead of n bytes and the K
+// contributions are one all-gather).  pack: one ballot per 32 scores.  vote: a warp owns 32 consecutive words = 1024
+// scores; in step t every lane reads word (base + t) of each client (one broadcast transaction) and lane l counts bit
+// l, so the alpha / beta / theta accesses of a step are 32 consecutive floats.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pack_mask_bits_kernel(const T* __restrict__ mask, uint32_t* __restrict__ words, int64_t n) {
+    const int64_t padded = (n + 31) & ~int64_t(31);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += stride) {
+        const bool set = i < n && mask[i] != T(0);
+        const uint32_t word = __ballot_sync(0xffffffffu, set);
+        if ((threadIdx.x & 31) == 0) words[i >> 5] = word;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fedpm_vote_packed_kernel(const uint32_t* __restrict__ words, int k, int64_t n_words, float* __restrict__ alpha,
+                         float* __restrict__ beta, float* __restrict__ theta, int bayesian, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t groups = (n_words + 31) >> 5;
+    for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+        const int64_t base = g << 5;
+        for (int t = 0; t < 32 && base + t < n_words; ++t) {
+            const int64_t i = ((base + t) << 5) + lane;
+            int votes = 0;
+            for (int c = 0; c < k; ++c) votes += (int)((words[(int64_t)c * n_words + base + t] >> lane) & 1u);
+            if (i >= n) continue;
+            const float s = (float)votes;
+            if (bayesian) {
+                const float a = alpha[i] + s, b = beta[i] + ((float)k - s);
+                alpha[i] = a; beta[i] = b;
+                theta[i] = (a - 1.f) / (a + b - 2.f);
+            } else {
+                theta[i] = s / (float)k;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ===================================================================================================================
@@ -594,6 +635,27 @@ int fl4h_fedpm_vote(const uint8_t* const* masks, int k, float* alpha, float* bet
     pack.k = k;
     for (int i = 0; i < FL4H_MAX_SRC; ++i) pack.src[i] = i < k ? masks[i] : nullptr;
     fedpm_vote_kernel<<<stream_grid(n, 1), kThreads, 0, stream>>>(pack, alpha, beta, theta, bayesian, n);
+    return (int)cudaGetLastError();
+}
+
+// `kind`: 0 = uint8 masks, 1 = fp32 masks.  `words` holds ceil(n / 32) uint32.
+int fl4h_pack_mask_bits(const void* mask, int kind, uint32_t* words, int64_t n, cudaStream_t stream) {
+    const int64_t padded = (n + 31) & ~int64_t(31);
+    if (kind == 0)
+        pack_mask_bits_kernel<uint8_t><<<stream_grid(padded, 1), kThreads, 0, stream>>>((const uint8_t*)mask, words, n);
+    else if (kind == 1)
+        pack_mask_bits_kernel<float><<<stream_grid(padded, 1), kThreads, 0, stream>>>((const float*)mask, words, n);
+    else
+        return (int)cudaErrorInvalidValue;
+    return (int)cudaGetLastError();
+}
+
+// `words`: k rows of n_words (row c = client c's packed masks, as an all-gather leaves them).
+int fl4h_fedpm_vote_packed(const uint32_t* words, int k, int64_t n_words, float* alpha, float* beta, float* theta,
+                           int bayesian, int64_t n, cudaStream_t stream) {
+    if (k < 1 || n_words * 32 < n) return (int)cudaErrorInvalidValue;
+    fedpm_vote_packed_kernel<<<stream_grid(n_words * 32, 4), kThreads, 0, stream>>>(words, k, n_words, alpha, beta, theta,
+                                                                                 bayesian, n);
     return (int)cudaGetLastError();
 }
 

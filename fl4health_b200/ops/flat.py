@@ -402,3 +402,61 @@ def fedpm_vote(
     else:
         theta.copy_(s / k)
     return theta
+
+
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """Flat {0,1} mask (uint8 / bool / float) -> ``ceil(n / 32)`` int32 words, score ``i`` at bit ``i % 32`` of word
+    ``i // 32``.  What a FedPM client ships across GPUs: 1 bit per score."""
+    flat = mask.reshape(-1)
+    if flat.dtype == torch.bool:
+        flat = flat.view(torch.uint8)
+    elif flat.dtype not in (torch.uint8, torch.float32):
+        flat = flat.to(torch.uint8)
+    flat = flat.contiguous()
+    n = flat.numel()
+    n_words = (n + 31) // 32
+    if _use_kernel(flat):
+        words = torch.empty(n_words, dtype=torch.int32, device=flat.device)
+        lib = _lib.load(True)
+        err = lib.fl4h_pack_mask_bits(_lib.ptr(flat), ctypes.c_int(0 if flat.dtype == torch.uint8 else 1), _lib.ptr(words),
+                                      ctypes.c_int64(n), _lib.stream_ptr(flat.device))
+        _lib.check(err, "fl4h_pack_mask_bits")
+        _lib.count_launches(1)
+        return words
+    bits = torch.zeros(n_words * 32, dtype=torch.int64, device=flat.device)
+    bits[:n] = (flat != 0).to(torch.int64)
+    packed = (bits.view(n_words, 32) << torch.arange(32, device=flat.device)).sum(dim=1)  # < 2**32, exact in int64
+    return torch.where(packed >= 2**31, packed - 2**32, packed).to(torch.int32)
+
+
+def unpack_mask_bits(words: torch.Tensor, n: int) -> torch.Tensor:
+    """Inverse of ``pack_mask_bits`` (uint8, length ``n``); ``words`` may carry leading batch dimensions."""
+    lanes = torch.arange(32, device=words.device)
+    bits = (words.to(torch.int64).unsqueeze(-1) >> lanes) & 1
+    return bits.reshape(*words.shape[:-1], -1)[..., :n].to(torch.uint8)
+
+
+def fedpm_vote_packed(words: torch.Tensor, n: int, alpha: torch.Tensor | None, beta: torch.Tensor | None, bayesian: bool) -> torch.Tensor:
+    """FedPM vote over ``K`` rows of bit-packed masks (``words``: ``[K, ceil(n/32)]`` int32, e.g. straight out of an
+    all-gather).  Same update as ``fedpm_vote``: ``alpha += votes``, ``beta += K - votes``, posterior mode out."""
+    assert words.dim() == 2 and words.dtype == torch.int32 and words.shape[1] * 32 >= n
+    words = words.contiguous()
+    k, n_words = words.shape
+    theta = torch.empty(n, dtype=torch.float32, device=words.device)
+    if _use_kernel(words):
+        lib = _lib.load(True)
+        err = lib.fl4h_fedpm_vote_packed(_lib.ptr(words), ctypes.c_int(k), ctypes.c_int64(n_words), _lib.ptr(alpha), _lib.ptr(beta),
+                                         _lib.ptr(theta), ctypes.c_int(1 if bayesian else 0), ctypes.c_int64(n),
+                                         _lib.stream_ptr(words.device))
+        _lib.check(err, "fl4h_fedpm_vote_packed")
+        _lib.count_launches(1)
+        return theta
+    votes = unpack_mask_bits(words, n).sum(dim=0).to(torch.float32)
+    if bayesian:
+        assert alpha is not None and beta is not None
+        alpha.add_(votes)
+        beta.add_(k - votes)
+        theta.copy_((alpha - 1.0) / (alpha + beta - 2.0))
+    else:
+        theta.copy_(votes / k)
+    return theta

@@ -333,6 +333,16 @@ class SpmdContext:
             return result
         return target
 
+    def all_gather_rows(self, row: torch.Tensor) -> torch.Tensor:
+        """``[world, numel]``: row ``r`` is rank ``r``'s (equal-length) flat tensor.  One collective."""
+        row = row.reshape(-1).contiguous()
+        table = torch.empty((self.world_size, row.numel()), dtype=row.dtype, device=row.device)
+        if self.world_size == 1:
+            table[0].copy_(row)
+        else:
+            dist.all_gather_into_tensor(table.view(-1), row)
+        return table
+
     def broadcast_flat(self, tensor: torch.Tensor, src: int) -> torch.Tensor:
         if self.world_size > 1:
             dist.broadcast(tensor, src=src)
@@ -598,6 +608,15 @@ class SpmdTransport:
         return GetParametersRes(Status(Code.OK), ndarrays_to_parameters(full))
 
 
+def decorrelate_client_randomness(rank: int) -> None:
+    """Give the clients hosted by rank ``r > 0`` their own torch random stream.  Launch scripts seed every rank alike
+    (so that models initialise identically); without this, clients on different ranks would also draw identical
+    Bernoulli masks (FedPM), dropout patterns and DP noise -- unlike a simulation, where the clients consume one
+    generator in turn.  Server-side randomness does not use the global generators (``sampling_streams``)."""
+    if rank > 0:
+        torch.manual_seed((torch.initial_seed() + 7919 * rank) % (2**63 - 1))
+
+
 def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any, fused: bool | None = None) -> list[SpmdClientProxy]:
     """Register one proxy per rank with the server's client manager; only this rank's proxy holds a client.
 
@@ -612,8 +631,9 @@ def build_spmd_federation(ctx: SpmdContext, server: Any, local_client: Any, fuse
 
     from fl4health_b200.servers.client_manager import sampling_streams
 
-    seed = ctx.broadcast_object(random.getrandbits(31), src=0)
-    sampling_streams.seed(seed)  # the managers' own streams: rank-local use of the global RNGs cannot desynchronise them
+    seed = ctx.broadcast_object(sampling_streams.base_seed, src=0)
+    sampling_streams.seed(seed)  # server-side streams: rank-local use of the global RNGs cannot desynchronise them
+    decorrelate_client_randomness(ctx.rank)
     proxies = []
     for rank in range(ctx.world_size):
         proxy = SpmdClientProxy(ctx, rank, local_client if rank == ctx.rank else None)

@@ -168,11 +168,13 @@ def build_spmd_federation_multi(ctx: SpmdContext, server: Any, local_clients: li
     for the clients hosted elsewhere.  Ranks may host different numbers of clients."""
     import random
 
+    from fl4health_b200.parallel.spmd import decorrelate_client_randomness
     from fl4health_b200.servers.client_manager import sampling_streams
 
     counts = ctx.all_gather_object(len(local_clients))
-    seed = ctx.broadcast_object(random.getrandbits(31), src=0)  # replicated server logic: identical client sampling
-    sampling_streams.seed(seed)  # the managers' own streams: rank-local use of the global RNGs cannot desynchronise them
+    seed = ctx.broadcast_object(sampling_streams.base_seed, src=0)  # replicated server logic: identical client sampling
+    sampling_streams.seed(seed)  # server-side streams: rank-local use of the global RNGs cannot desynchronise them
+    decorrelate_client_randomness(ctx.rank)
     proxies = []
     for rank, count in enumerate(counts):
         for index in range(count):

@@ -5,6 +5,7 @@ from __future__ import annotations
 import random
 import threading
 from abc import ABC, abstractmethod
+from typing import Any
 from logging import INFO
 
 import numpy as np
@@ -14,7 +15,8 @@ from fl4health_b200.servers.client_proxy import ClientProxy
 
 
 class _SamplingStreams:
-    """The random streams client sampling draws from -- its own, not the process-global ``random`` / ``np.random``.
+    """The random streams SERVER-side logic draws from (client sampling, DP noise on aggregates) -- its own, not the
+    process-global ``random`` / ``np.random`` / torch generators.
 
     With the server logic replicated on every rank (``parallel/spmd.py``) all ranks must draw the same cohort each
     round.  Global generators cannot promise that: anything rank-local that consumes them between rounds (a client's
@@ -26,16 +28,29 @@ class _SamplingStreams:
     def __init__(self) -> None:
         self._python: random.Random | None = None
         self._numpy: np.random.Generator | None = None
+        self._torch: Any = None
+        self._seed = 0
+        self._draws = 0
 
     def seed(self, seed: int | None) -> None:
         if seed is None:
-            self._python = self._numpy = None
+            self._python = self._numpy = self._torch = None
         else:
+            import torch
+
             self._python, self._numpy = random.Random(seed), np.random.default_rng(seed)
+            self._torch = torch.Generator().manual_seed(seed)
+            self._seed, self._draws = int(seed), 0
 
     def _ensure(self) -> None:
         if self._python is None or self._numpy is None:
             self.seed(random.getrandbits(63))
+
+    @property
+    def base_seed(self) -> int:
+        """The seed the streams were (or, unseeded, are now) started from: what rank 0 shares with the other ranks."""
+        self._ensure()
+        return self._seed
 
     @property
     def python(self) -> random.Random:
@@ -48,6 +63,18 @@ class _SamplingStreams:
         self._ensure()
         assert self._numpy is not None
         return self._numpy
+
+    @property
+    def torch(self) -> Any:
+        """CPU ``torch.Generator`` for small server-side draws (identical on every rank of a replicated server)."""
+        self._ensure()
+        return self._torch
+
+    def next_kernel_seed(self) -> int:
+        """A fresh 63-bit seed for a counter-based (Philox) kernel: same sequence on every rank, new value per call."""
+        self._ensure()
+        self._draws += 1
+        return (self._seed * 1_000_003 + self._draws) & (2**63 - 1)
 
 
 sampling_streams = _SamplingStreams()

@@ -4,7 +4,9 @@
 the CPU (SURVEY hot-op C7).  Here the K client updates are folded into ONE flat fp32 vector (one ``weighted_sum`` launch
 per call when the layers are CUDA tensors), the noise is added by the counter-based Philox kernel
 (``fl4h_add_gaussian``: no noise tensor is ever materialised) and the result is handed back as per-layer views of that
-vector.  Seeds come from ``torch.initial_seed()`` + a call counter, so a seeded run is reproducible.
+vector.  Seeds (and the scalar noise on the clipping bits) come from the server-side random streams
+(``servers/client_manager.py``): seeded with everything else by ``set_all_random_seeds``, identical on every rank of a
+replicated SPMD server, and untouched by what clients do with the global generators.
 """
 
 from __future__ import annotations
@@ -13,14 +15,12 @@ import torch
 
 from fl4health_b200.common.typing import NDArray, NDArrays, to_tensor
 from fl4health_b200.ops import flat as flat_ops
+from fl4health_b200.servers.client_manager import sampling_streams
 
-_NOISE_DRAWS = 0  # distinct Philox streams for successive aggregations of one process
 
 
 def _next_seed() -> int:
-    global _NOISE_DRAWS
-    _NOISE_DRAWS += 1
-    return (torch.initial_seed() * 1_000_003 + _NOISE_DRAWS) & (2**63 - 1)
+    return sampling_streams.next_kernel_seed()
 
 
 def _flatten(update: NDArrays, device: torch.device) -> torch.Tensor:
@@ -72,5 +72,5 @@ def gaussian_noisy_weighted_aggregate(
 def gaussian_noisy_aggregate_clipping_bits(bits: NDArrays, noise_std_dev: float) -> float:
     count = len(bits)
     clipped = sum(float(to_tensor(bit).reshape(()).item()) for bit in bits)
-    noise = float(torch.randn(()).item()) * noise_std_dev if noise_std_dev > 0 else 0.0
+    noise = float(torch.randn((), generator=sampling_streams.torch).item()) * noise_std_dev if noise_std_dev > 0 else 0.0
     return (clipped + noise) / count

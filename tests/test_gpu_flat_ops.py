@@ -311,7 +311,8 @@ def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape, fus
 @pytest.mark.gpu
 def test_resnet_fused_bn_matches_stock_bn() -> None:
     """Whole-model check: ResNet-18 with the fused BN path vs the same weights through the stock-op fallback."""
-    import fl4health_b200.ops.bn_act as bn_mod
+    import os
+
     from fl4health_b200.models import resnet18_cifar
 
     torch.manual_seed(0)
@@ -327,14 +328,12 @@ def test_resnet_fused_bn_matches_stock_bn() -> None:
     def run(fused: bool):
         model.zero_grad()
         state = {k: v.clone() for k, v in model.state_dict().items()}
-        original = bn_mod.kernel_eligible
-        if not fused:
-            bn_mod.kernel_eligible = lambda *a, **k: False
+        os.environ["FL4H_BN_KERNEL"] = "1" if fused else "0"  # 0: stock-op BatchNorm (and no statistics in the conv epilogue)
         try:
             loss = torch.nn.functional.cross_entropy(model(x), target)
             loss.backward()
         finally:
-            bn_mod.kernel_eligible = original
+            os.environ.pop("FL4H_BN_KERNEL", None)
         grads = {n: p.grad.clone() for n, p in model.named_parameters()}
         stats = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "tracked" in k}
         model.load_state_dict(state)

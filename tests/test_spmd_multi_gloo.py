@@ -99,6 +99,14 @@ def test_strategies_that_need_whole_payloads_run_in_spmd_and_match_simulation(sc
             assert r1 == r2 and abs(l1 - l2) < 1e-5, (summary["losses"], local["losses"])
 
 
+def test_fedpm_votes_on_bit_packed_masks_across_ranks() -> None:
+    """FedPM with one client per rank: the masks cross ranks as packed words in one all-gather (``strategies/fedpm.py``);
+    two real processes over gloo, and the posterior keeps producing finite, changing losses."""
+    (summary,) = _run_scenario_spmd("fedpm_example", 29681)
+    losses = [loss for _, loss in summary["losses"]]
+    assert len(losses) == 2 and all(loss == loss for loss in losses) and losses[0] != losses[1]
+
+
 def test_partial_participation_with_idle_ranks(tmp_path: Path) -> None:
     """Half of six clients (hosted 1 + 5) are sampled each round for five rounds: rounds in which a rank has no selected
     client — including before it has ever seen a payload — must neither deadlock nor change the collective sequence."""

@@ -94,3 +94,75 @@ def test_flash_server_step() -> None:
     new = [0.1 * m / (np.sqrt(v) - d + 1e-9) for m, v, d in zip(exp_m, exp_v, exp_d)]
     for got, exp in zip(parameters_to_ndarrays(params), new):
         assert np.allclose(to_numpy(got), exp, rtol=1e-5)
+
+
+def test_fedpm_bit_packed_cross_rank_vote_matches_per_tensor_vote() -> None:
+    """One client per rank: masks are packed to 1 bit / score, all-gathered as words and voted in one launch for every
+    layer.  Same posterior as the per-tensor uint8 vote over materialised payloads, over two rounds (evidence carries)."""
+    import numpy as np
+    import torch
+
+    from fl4health_b200.common.typing import Code, FitRes, NDArrays, Status
+    from fl4health_b200.ops import flat as flat_ops
+    from fl4health_b200.parallel.spmd import PayloadSpec, RemoteNDArrays, _TaggedParameters, _tag_local
+    from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerWithLayerNames
+    from fl4health_b200.servers.client_proxy import ClientProxy
+    from fl4health_b200.strategies.fedpm import FedPm
+
+    # pack / unpack round trip on an awkward length
+    gen = torch.Generator().manual_seed(0)
+    bits = (torch.rand(1000 + 13, generator=gen) < 0.4).to(torch.uint8)
+    words = flat_ops.pack_mask_bits(bits)
+    assert words.dtype == torch.int32 and words.numel() == 32 and torch.equal(flat_ops.unpack_mask_bits(words, bits.numel()), bits)
+    assert torch.equal(flat_ops.pack_mask_bits(bits.float()), words) and torch.equal(flat_ops.pack_mask_bits(bits.bool()), words)
+
+    names, shapes = ["conv.weight_scores", "conv.bias_scores", "fc.weight_scores"], [(4, 3, 3, 3), (4,), (10, 37)]
+    packer = ParameterPackerWithLayerNames()
+
+    class Proxy(ClientProxy):
+        get_properties = get_parameters = fit = evaluate = reconnect = None  # type: ignore[assignment]
+
+    def masks_of(round_index: int, client: int) -> NDArrays:
+        g = torch.Generator().manual_seed(100 * round_index + client)
+        return NDArrays([(torch.rand(shape, generator=g) < 0.3 + 0.2 * client).to(torch.uint8) for shape in shapes])
+
+    class TwoRankWorld:  # what rank 0 of a two-rank federation sees
+        world_size, rank, device = 2, 0, torch.device("cpu")
+
+        def __init__(self) -> None:
+            self.other: torch.Tensor | None = None
+            self.gathers = 0
+
+        def all_gather_rows(self, row: torch.Tensor) -> torch.Tensor:
+            self.gathers += 1
+            return torch.stack([row, self.other])
+
+    world = TwoRankWorld()
+    packed_strategy, plain_strategy = FedPm(), FedPm()
+    for round_index in (1, 2):
+        payloads = [packer.pack_parameters(masks_of(round_index, c), names) for c in range(2)]
+        world.other = flat_ops.pack_mask_bits(torch.cat([m.reshape(-1) for m in masks_of(round_index, 1)]))
+        mine = _tag_local(payloads[0], world)
+        theirs = RemoteNDArrays(world, 1, PayloadSpec.of(payloads[1]))  # tensors never arrive: only the spec is known
+        assert all(entry is None for entry in list(theirs)[:-1])
+        spmd_results = [(Proxy(cid=f"rank{r:03d}"), FitRes(Status(Code.OK, ""), _TaggedParameters(p), 10, {})) for r, p in enumerate((mine, theirs))]
+        plain_results = [(Proxy(cid=f"rank{r:03d}"), FitRes(Status(Code.OK, ""), _TaggedParameters(NDArrays(p)), 10, {})) for r, p in enumerate(payloads)]
+        voted, _ = packed_strategy.aggregate_fit(round_index, spmd_results, [])
+        expected, _ = plain_strategy.aggregate_fit(round_index, plain_results, [])
+        assert packed_strategy.last_vote_path == "packed-bits" and plain_strategy.last_vote_path == "per-tensor"
+        got_layers, got_names = packer.unpack_parameters(NDArrays(voted.tensors))
+        want_layers, want_names = packer.unpack_parameters(NDArrays(expected.tensors))
+        assert list(got_names) == list(want_names) == names
+        for got, want in zip(got_layers, want_layers):
+            assert got.shape == want.shape and torch.allclose(torch.as_tensor(got), torch.as_tensor(want), atol=1e-7)
+    assert world.gathers == 2  # one collective per round, whatever the number of layers
+    for name in names:
+        for flat_prior, plain_prior in zip(packed_strategy.beta_parameters[name], plain_strategy.beta_parameters[name]):
+            assert torch.equal(flat_prior, plain_prior)
+    packed_strategy.reset_beta_priors()
+    assert float(packed_strategy._flat_priors[1].min()) == float(packed_strategy._flat_priors[2].max()) == 1.0
+    # the uniform-mean variant takes the same route
+    mean_strategy = FedPm(bayesian_aggregation=False)
+    voted, _ = mean_strategy.aggregate_fit(3, spmd_results, [])
+    layers, _ = packer.unpack_parameters(NDArrays(voted.tensors))
+    assert mean_strategy.last_vote_path == "packed-bits" and set(np.unique(torch.as_tensor(layers[2]).numpy())) <= {0.0, 0.5, 1.0}
