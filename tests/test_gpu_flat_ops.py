@@ -168,6 +168,25 @@ def test_fedpm_vote():
     assert torch.allclose(theta, (alpha - 1) / (alpha + beta - 2))
 
 
+@pytest.mark.parametrize("n", [32, 1000 + 13, 1 << 20])
+@pytest.mark.parametrize("k", [2, 8, 11])
+def test_fedpm_packed_vote_matches_byte_vote(n: int, k: int):
+    """Ballot-packed masks + popcount vote vs the plain PyTorch fp32 computation, incl. lengths that are not a multiple
+    of 32 / of a warp's 1024 scores, fp32 and uint8 mask inputs, and the uniform-mean variant."""
+    gen = torch.Generator(device="cuda").manual_seed(n + k)
+    masks = [(torch.rand(n, device="cuda", generator=gen) < 0.2 + 0.05 * c).to(torch.uint8) for c in range(k)]
+    words = torch.stack([F.pack_mask_bits(m if c % 2 else m.float()) for c, m in enumerate(masks)])
+    assert words.shape == (k, (n + 31) // 32) and words.dtype == torch.int32
+    for c, m in enumerate(masks):  # bit i % 32 of word i // 32
+        assert torch.equal(F.unpack_mask_bits(words[c], n), m)
+    votes = torch.stack(masks).float().sum(0)
+    alpha, beta = torch.full((n,), 1.5, device="cuda"), torch.full((n,), 2.0, device="cuda")
+    theta = F.fedpm_vote_packed(words, n, alpha, beta, bayesian=True)
+    assert torch.equal(alpha, 1.5 + votes) and torch.equal(beta, 2.0 + k - votes)
+    assert torch.allclose(theta, (alpha - 1) / (alpha + beta - 2), rtol=1e-6, atol=0)
+    assert torch.allclose(F.fedpm_vote_packed(words, n, None, None, bayesian=False), votes / k, rtol=1e-6, atol=0)
+
+
 def test_fused_moon_contrastive_matches_reference():
     from fl4health_b200.ops.contrastive import moon_contrastive, moon_contrastive_reference
 
