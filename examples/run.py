@@ -40,6 +40,15 @@ def _replicated(clients: list, ctx, ranks_per_client: int):  # noqa: ANN001, ANN
     return client
 
 
+def _attach_json_reporters(server, clients: list, folder: str) -> None:  # noqa: ANN001
+    """The reporting path of the reference's smoke tests: per-round server / client payloads as JSON files."""
+    from fl4health_b200.reporting.json_reporter import JsonReporter
+
+    server.reports_manager.reporters.append(JsonReporter(run_id="server", output_folder=folder))
+    for index, client in enumerate(clients):
+        client.reports_manager.reporters.append(JsonReporter(run_id=f"client_{index}", output_folder=folder))
+
+
 def main(argv: list[str] | None = None) -> dict:
     parser = argparse.ArgumentParser(description=__doc__)
     parser.add_argument("scenario", choices=sorted(SCENARIOS), nargs="?")
@@ -52,6 +61,8 @@ def main(argv: list[str] | None = None) -> dict:
     parser.add_argument("--clients-per-rank", type=int, default=1, help="with --spmd: host this many clients on every rank")
     parser.add_argument("--ranks-per-client", type=int, default=1,
                         help="with --spmd: every client spans this many GPUs (replicas on disjoint data shards, gradients averaged per step)")
+    parser.add_argument("--metrics-dir", default=None,
+                        help="attach a JsonReporter to the server and every client; writes server.json / client_<i>.json there")
     args = parser.parse_args(argv)
     if args.list or args.scenario is None:
         print("\n".join(sorted(SCENARIOS)))
@@ -83,7 +94,12 @@ def main(argv: list[str] | None = None) -> dict:
         ctx.shutdown()
     else:
         server, clients = SCENARIOS[args.scenario](config, torch.device(args.device))
+        if args.metrics_dir is not None:
+            _attach_json_reporters(server, clients, args.metrics_dir)
         history = run_simulation(server, clients, config["n_server_rounds"])
+        if args.metrics_dir is not None:
+            for host in (server, *clients):
+                host.reports_manager.shutdown()
     summary = {"scenario": args.scenario, "rounds": config["n_server_rounds"], "losses": history.losses_distributed,
                "metrics": {k: v[-1][1] for k, v in history.metrics_distributed.items()}}
     if not args.spmd or is_reporting_rank:
