@@ -118,6 +118,51 @@ def test_stem_conv_forward_statistics_and_weight_gradient(dtype) -> None:  # noq
         assert _rel_err(dw, wr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("with_residual", [False, True])
+def test_conv_epilogue_statistics_feed_batchnorm(dtype, with_residual: bool, monkeypatch) -> None:  # noqa: ANN001
+    """``conv_bn_act``: convolution whose epilogue reduces the batch statistics + apply-only BatchNorm kernel, against
+    the SAME convolution followed by the stock BatchNorm composition (``FL4H_BN_KERNEL=0``).  Both see bit-identical
+    convolution outputs, so this isolates the statistics hand-off: outputs, input / weight / affine gradients and the
+    running statistics."""
+    from fl4health_b200.models.fused_layers import BatchNormAct2d, TcConv2d, conv_bn_act
+
+    torch.manual_seed(3)
+    conv = TcConv2d(64, 128, 3, stride=2, padding=1, bias=False).cuda().to(memory_format=torch.channels_last)
+    bn = BatchNormAct2d(128, relu=True).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.2, 0.2)
+    x0 = (torch.randn(32, 64, 16, 16, device="cuda") + 0.3).contiguous(memory_format=torch.channels_last)
+    res0 = torch.randn(32, 128, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last) if with_residual else None
+    if dtype == torch.bfloat16:
+        conv = conv.to(torch.bfloat16)
+        x0, res0 = x0.to(dtype), (res0.to(dtype) if res0 is not None else None)
+    state = {k: v.clone() for k, v in bn.state_dict().items()}
+
+    def run(kernel: bool):  # noqa: ANN202
+        monkeypatch.setenv("FL4H_BN_KERNEL", "1" if kernel else "0")
+        bn.load_state_dict(state)
+        for p in (*conv.parameters(), *bn.parameters()):
+            p.grad = None
+        x = x0.clone().requires_grad_()
+        res = res0.clone().requires_grad_() if res0 is not None else None
+        y = conv_bn_act(conv, bn, x, res)
+        (y.float() * torch.linspace(-1, 1, y.numel(), device="cuda").view_as(y)).sum().backward()
+        grads = [x.grad, conv.weight.grad, bn.weight.grad, bn.bias.grad] + ([res.grad] if res is not None else [])
+        return y.detach().clone(), [g.detach().clone() for g in grads], {k: v.clone() for k, v in bn.state_dict().items()}
+
+    y_ref, g_ref, s_ref = run(False)
+    y_ker, g_ker, s_ker = run(True)
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-4  # bf16: the statistics come from the fp32 accumulators, the stock path re-reads the rounded output
+    assert _rel_err(y_ker, y_ref) < tol
+    for got, ref in zip(g_ker, g_ref):
+        assert _rel_err(got, ref) < 5 * tol
+    assert int(s_ker["num_batches_tracked"]) == int(s_ref["num_batches_tracked"]) == int(state["num_batches_tracked"]) + 1
+    for key in ("running_mean", "running_var"):
+        assert torch.allclose(s_ker[key], s_ref[key], rtol=tol, atol=tol * 0.1), key
+
+
 def test_resnet18_step_launches_no_library_convolution() -> None:
     """One training step of the flagship model under the profiler: every convolution is one of ours."""
     from torch.profiler import ProfilerActivity, profile

@@ -328,8 +328,16 @@ def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape, fus
 
 
 @pytest.mark.gpu
-def test_resnet_fused_bn_matches_stock_bn() -> None:
-    """Whole-model check: ResNet-18 with the fused BN path vs the same weights through the stock-op fallback."""
+@pytest.mark.parametrize("own_convs", [False, True])
+def test_resnet_fused_bn_matches_stock_bn(own_convs: bool, monkeypatch) -> None:
+    """Whole-model check: ResNet-18 with the fused BN path vs the same weights through the stock-op fallback.
+
+    ``own_convs=False``: cuDNN convolutions in true fp32, so the two BatchNorm implementations are compared in
+    isolation at tight tolerance.  ``own_convs=True``: the tcgen05 convolutions (TF32 products) whose epilogue feeds
+    the batch statistics to the apply-only BatchNorm kernel -- the product path; the rounding of every convolution's
+    inputs to 10 mantissa bits amplifies the last-bit differences of the statistics, so only direction, loss and
+    running statistics are held to a tolerance there."""
+    monkeypatch.setenv("FL4H_TC_CONV", "1" if own_convs else "0")
     import os
 
     from fl4health_b200.models import resnet18_cifar
@@ -363,7 +371,7 @@ def test_resnet_fused_bn_matches_stock_bn() -> None:
         l1, g1, s1 = run(True)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
-    assert abs(l0 - l1) < 1e-4
+    assert abs(l0 - l1) < (1e-3 if own_convs else 1e-4)
     # A pre-activation within rounding distance of 0 can land on different sides of a ReLU in the two implementations
     # (different summation order of the batch statistics); one such flip perturbs every upstream gradient at the
     # 1e-3 level and the nearest small layers by a few percent.  Direction and typical size must agree regardless.
@@ -371,9 +379,9 @@ def test_resnet_fused_bn_matches_stock_bn() -> None:
     worst = sorted(cosines.items(), key=lambda kv: kv[1])[:5]
     assert worst[0][1] > 0.99, worst
     errors = sorted(float((g0[n] - g1[n]).abs().max() / g0[n].abs().max().clamp_min(1e-6)) for n in g0)
-    assert errors[len(errors) // 2] < 1e-2, errors
+    assert errors[len(errors) // 2] < (0.15 if own_convs else 1e-2), errors
     for name in s0:
-        assert torch.allclose(s0[name].float(), s1[name].float(), rtol=1e-4, atol=1e-5), name
+        assert torch.allclose(s0[name].float(), s1[name].float(), rtol=1e-3 if own_convs else 1e-4, atol=1e-4 if own_convs else 1e-5), name
 
 
 @pytest.mark.gpu
