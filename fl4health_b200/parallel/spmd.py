@@ -60,28 +60,50 @@ def current_context() -> SpmdContext | None:
 
 @dataclass
 class PayloadSpec:
-    """Shapes/dtypes of one client's array list; tiny or non-numeric arrays ride along by value."""
+    """Shapes/dtypes of one client's array list; tiny or non-numeric arrays ride along by value.
+
+    An arena-backed payload is described by its flat buffer(s) rather than entry by entry: ``flat_numel`` covers the
+    first ``main_len`` entries (the model state), ``aux_numel`` the ``aux_len`` entries right after it (a second
+    arena-shaped block, SCAFFOLD's control variates).  Whatever follows (a packed scalar, layer names) is ordinary side
+    information.  Slices that coincide with a block keep its flat description, so ``weights ++ [mu]`` or
+    ``weights ++ variates`` still reduce with one collective per block."""
 
     entries: list[tuple[tuple[int, ...], str, Any]]  # (shape, dtype-string, inline value or None)
-    flat_numel: int | None = None  # set when the list is a whole-arena view
+    flat_numel: int | None = None  # set when the leading ``main_len`` entries are one whole-arena view
+    main_len: int = 0
+    aux_numel: int | None = None
+    aux_len: int = 0
+
+    @property
+    def is_arena(self) -> bool:
+        """The payload is exactly one arena block (nothing packed behind it): reducible as a single flat buffer."""
+        return self.flat_numel is not None and len(self.entries) == self.main_len
 
     @staticmethod
     def of(arrays: NDArrays) -> PayloadSpec:
         entries: list[tuple[tuple[int, ...], str, Any]] = []
         flat = getattr(arrays, "flat", None)
         layout = getattr(arrays, "layout", None)
-        whole = flat is not None and layout is not None and len(arrays) == len(layout.state_keys)
-        for arr in arrays:
+        main_len = len(layout.state_keys) if (flat is not None and layout is not None) else 0
+        if main_len == 0 or len(arrays) < main_len:
+            main_len = 0
+        aux_flat, aux_layout = getattr(arrays, "aux_flat", None), getattr(arrays, "aux_layout", None)
+        aux_len = len(aux_layout.state_keys) if (main_len and aux_flat is not None and aux_layout is not None) else 0
+        if aux_len and len(arrays) < main_len + aux_len:
+            aux_len = 0
+        in_blocks = main_len + aux_len
+        for index, arr in enumerate(arrays):
             if isinstance(arr, torch.Tensor):
-                # whole-arena payloads reduce their scalar entries on the device (int_flat): no by-value copies, which
-                # would cost a D2H sync per entry per round and make the spec differ from round to round
-                inline = arr.detach().cpu().numpy() if (not whole and arr.numel() <= 8 and arr.dim() == 0) else None
-                entries.append((tuple(arr.shape), str(arr.dtype), inline))
+                # entries of an arena block reduce on the device with the block (scalars included: no by-value copies,
+                # which would cost a D2H sync per entry per round and make the spec differ from round to round)
+                by_value = index >= in_blocks and arr.numel() <= 8 and arr.dim() == 0
+                entries.append((tuple(arr.shape), str(arr.dtype), arr.detach().cpu().numpy() if by_value else None))
             else:
                 np_arr = np.asarray(arr)
                 small = np_arr.dtype.kind in ("U", "S", "O") or np_arr.size <= 64
                 entries.append((tuple(np_arr.shape), f"numpy.{np_arr.dtype}", np_arr if small else None))
-        return PayloadSpec(entries, int(flat.numel()) if whole else None)
+        return PayloadSpec(entries, int(flat.numel()) if main_len else None, main_len,
+                           int(aux_flat.numel()) if aux_len else None, aux_len)
 
 
 class RemoteNDArrays(NDArrays):
@@ -99,11 +121,15 @@ class RemoteNDArrays(NDArrays):
 
 
 def _slice_spec(spec: PayloadSpec, start: int | None, stop: int | None, total: int) -> PayloadSpec:
-    entries = spec.entries[slice(start, stop)]
-    keeps_arena = spec.flat_numel is not None and start in (None, 0) and len(entries) >= 1 and all(
-        e[2] is not None for e in spec.entries[len(entries):]
-    )
-    return PayloadSpec(entries, spec.flat_numel if keeps_arena else None)
+    first, last, _ = slice(start, stop).indices(total)
+    entries = spec.entries[first:last]
+    if spec.flat_numel is not None and first == 0 and last >= spec.main_len:
+        keeps_aux = spec.aux_numel is not None and last >= spec.main_len + spec.aux_len
+        return PayloadSpec(entries, spec.flat_numel, spec.main_len, spec.aux_numel if keeps_aux else None,
+                           spec.aux_len if keeps_aux else 0)
+    if spec.aux_numel is not None and first == spec.main_len and last - first == spec.aux_len:
+        return PayloadSpec(entries, spec.aux_numel, spec.aux_len)  # the second block on its own: it is the main one now
+    return PayloadSpec(entries, None)
 
 
 def _sliced_with_tags(source: Any, start: int | None, stop: int | None) -> NDArrays:

@@ -47,6 +47,7 @@ class ParameterPackerWithControlVariates(ParameterPacker[NDArrays]):
     def pack_parameters(self, model_weights: NDArrays, additional_parameters: NDArrays) -> NDArrays:
         packed = NDArrays(list(model_weights) + list(additional_parameters))
         packed.flat, packed.layout = getattr(model_weights, "flat", None), getattr(model_weights, "layout", None)
+        packed.int_flat = getattr(model_weights, "int_flat", None)
         packed.aux_flat = getattr(additional_parameters, "flat", None)
         packed.aux_layout = getattr(additional_parameters, "layout", None)
         return packed
@@ -63,6 +64,7 @@ class _TrailingScalarPacker(ParameterPacker[float]):
         packed = NDArrays(list(model_weights) + [trailing])
         # keep arena metadata of the weight part so fused aggregation still applies
         packed.flat, packed.layout = getattr(model_weights, "flat", None), getattr(model_weights, "layout", None)
+        packed.int_flat = getattr(model_weights, "int_flat", None)
         return packed
 
     def unpack_parameters(self, packed_parameters: NDArrays) -> tuple[NDArrays, float]:

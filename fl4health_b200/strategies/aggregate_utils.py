@@ -128,7 +128,7 @@ def _spmd_weighted_combine(
         if nds.rank == ctx.rank:
             local = nds
     assert spec is not None
-    arena_route = spec.flat_numel is not None
+    arena_route = spec.is_arena
     if arena_route:
         layout = local.layout if local is not None else None
         local_flat = local.flat if local is not None else None
@@ -140,6 +140,8 @@ def _spmd_weighted_combine(
             # peer-memory kernel's launch decision identical on every rank.  If some rank has never seen the layout,
             # everybody takes the packed route below (one agreement collective, only in this mode).
             hint = layout if layout is not None else _LAYOUT_HINTS.get(spec.flat_numel)
+            if hint is not None and not hasattr(hint, "flat"):
+                hint = None  # a companion-region layout has no buffer of its own to stand in with
             if ctx.all_reduce_max(0.0 if hint is not None else 1.0) > 0.0:
                 arena_route = False
             elif layout is None:
@@ -208,7 +210,7 @@ def _spmd_weighted_combine_multi(
     spec = arrays[0].spec
     local = [(nds, float(c)) for nds, c in zip(arrays, coefficients) if nds.rank == ctx.rank and not getattr(nds, "remote", False)]
     layout = next((nds.layout for nds, _ in local if getattr(nds, "layout", None) is not None), None)
-    arena_shaped = spec.flat_numel is not None and all(nds.spec.flat_numel == spec.flat_numel for nds in arrays)
+    arena_shaped = spec.is_arena and all(nds.spec.is_arena and nds.spec.flat_numel == spec.flat_numel for nds in arrays)
     if arena_shaped and layout is not None:
         _LAYOUT_HINTS[spec.flat_numel] = layout
     elif arena_shaped:

@@ -68,7 +68,7 @@ class FedOpt(FedAvg):
         current_flat = getattr(self.current_weights, "flat", None)
         spmd = any(getattr(a, "ctx", None) is not None for a in client_arrays)
         if spmd and current_flat is not None and self._mode != flat_ops.EPI_NONE and all(
-            a.spec.flat_numel == current_flat.numel() for a in client_arrays
+            a.spec.is_arena and a.spec.flat_numel == current_flat.numel() for a in client_arrays
         ):
             if self._flat_m is None:
                 self._flat_m = torch.zeros_like(current_flat)

@@ -133,12 +133,55 @@ class Scaffold(BasicFedAvg):
 
     def compute_updated_weights(self, weights: NDArrays) -> NDArrays:
         """x <- x + lr_s * (ybar - x)"""
+        stepped = self._flat_server_step("x", self.server_model_weights, weights, self.learning_rate, towards=True)
+        if stepped is not None:
+            return stepped
         delta = self.compute_parameter_delta(weights, self.server_model_weights)
         return self.compute_updated_parameters(self.learning_rate, self.server_model_weights, delta)
 
     def compute_updated_control_variates(self, control_variates_update: NDArrays) -> NDArrays:
         """c <- c + (|S| / N) * mean(delta_c)"""
+        stepped = self._flat_server_step("c", self.server_control_variates, control_variates_update, self.fraction_fit, towards=False)
+        if stepped is not None:
+            return stepped
         return self.compute_updated_parameters(self.fraction_fit, self.server_control_variates, control_variates_update)
+
+    def _flat_server_step(self, which: str, current: NDArrays, incoming: NDArrays, scale: float, towards: bool) -> NDArrays | None:
+        """The server update of one block as ONE launch over flat storage when the aggregate is arena-shaped:
+        ``state.lerp_(incoming, scale)`` (``towards``: x <- x + scale (ybar - x)) or ``state.add_(incoming, alpha=scale)``
+        (c <- c + scale * mean(delta_c)) instead of three element-wise kernels per tensor.  The strategy keeps the
+        block in a flat buffer of its own (``state``); the returned list are per-tensor views of it."""
+        flat, layout = getattr(incoming, "flat", None), getattr(incoming, "layout", None)
+        if flat is None or layout is None or not flat.is_floating_point() or len(incoming) != len(current):
+            return None
+        store: dict[str, Any] = self.__dict__.setdefault("_flat_server_state", {})
+        held = store.get(which)
+        if held is None or held[0] is not layout or held[1].shape != flat.shape or held[1].device != flat.device:
+            state = torch.zeros_like(flat)  # first arena-shaped aggregate: adopt the current values, tensor by tensor, once
+            views = _views_of(layout, state)
+            for view, value in zip(views, current):
+                if view.is_floating_point():
+                    view.copy_(_t(value, view))
+            store[which] = held = (layout, state)
+        state = held[1]
+        if towards:
+            state.lerp_(flat, float(scale))
+        else:
+            state.add_(flat, alpha=float(scale))
+        out = _views_of(layout, state)
+        integer_positions = [i for i, value in enumerate(incoming) if isinstance(value, torch.Tensor) and not value.is_floating_point()]
+        for i in integer_positions:  # integer buffers (num_batches_tracked) are not in the float block: reference formula, per entry
+            if towards and scale == 1.0:
+                out[i] = incoming[i]  # x + 1 * (ybar - x)
+                continue
+            old, new = _t(current[i], incoming[i]).double(), incoming[i].double()
+            out[i] = (old + scale * ((new - old) if towards else new)).to(incoming[i].dtype)
+        return out
+
+
+def _views_of(layout: Any, region: torch.Tensor) -> NDArrays:
+    """A fresh list of per-tensor views of ``region`` (the layout's own list may be cached and shared)."""
+    return NDArrays(layout.ndarrays(region=region), flat=region, layout=layout)
 
 
 def _t(value: Any, like: torch.Tensor | None = None) -> torch.Tensor:

@@ -117,3 +117,36 @@ def test_scaffold_end_to_end_with_bn_and_frozen_layer() -> None:
     n_trainable = len([p for p in template.parameters() if p.requires_grad])
     assert len(strategy.server_control_variates) == n_trainable
     assert any(float(torch.as_tensor(v).abs().sum()) > 0 for v in strategy.server_control_variates)
+
+
+def test_server_flat_step_matches_per_tensor_update() -> None:
+    """Arena-shaped aggregates update the server's x and c with one op per block; same numbers as the per-tensor rule,
+    including the integer BatchNorm counter, over consecutive rounds (the flat state persists between them)."""
+    import copy
+
+    from fl4health_b200.parallel.arena import TrainableRegionLayout, attach_arena
+
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Flatten(), torch.nn.Linear(4, 2))
+    initial = [v.detach().clone() for v in net.state_dict().values()]
+    make = lambda: Scaffold(initial_parameters=ndarrays_to_parameters([v.clone() for v in initial]), model=copy.deepcopy(net),  # noqa: E731
+                            learning_rate=0.7, fraction_fit=0.5)
+    flat_strategy, list_strategy = make(), make()
+    arena = attach_arena(net)
+    variates_layout = TrainableRegionLayout(arena)
+    gen = torch.Generator().manual_seed(9)
+    for round_index in range(3):
+        aggregate_flat = torch.randn(arena.flat.shape, generator=gen)
+        weights = NDArrays(arena.ndarrays(region=aggregate_flat), flat=aggregate_flat, layout=arena)
+        counter_position = list(net.state_dict()).index("1.num_batches_tracked")
+        weights[counter_position] = torch.tensor(10 * (round_index + 1))
+        deltas_flat = torch.randn(arena.trainable_padded, generator=gen)
+        deltas = variates_layout.ndarrays(region=deltas_flat)
+        plain_weights, plain_deltas = NDArrays([w.clone() for w in weights]), NDArrays([d.clone() for d in deltas])
+        new_x, new_c = flat_strategy.compute_updated_weights(weights), flat_strategy.compute_updated_control_variates(deltas)
+        ref_x, ref_c = list_strategy.compute_updated_weights(plain_weights), list_strategy.compute_updated_control_variates(plain_deltas)
+        assert getattr(new_x, "flat", None) is not None and getattr(ref_x, "flat", None) is None  # the two routes were taken
+        for got, want in zip([*new_x, *new_c], [*ref_x, *ref_c]):
+            assert got.dtype == want.dtype and torch.allclose(got.double(), want.double(), atol=1e-6)
+        flat_strategy.server_model_weights, flat_strategy.server_control_variates = new_x, new_c
+        list_strategy.server_model_weights, list_strategy.server_control_variates = ref_x, ref_c
