@@ -13,10 +13,21 @@ torch.backends.cudnn.benchmark = True
 from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics import Accuracy
 BF16 = os.environ.get("KINETO_DTYPE", "bf16") == "bf16"
-engine = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16 if BF16 else None, channels_last=True, master_weights=BF16)
-client = ps.Client(Path("."), [Accuracy()], device, client_name="prof", engine_options=engine)
+engine = EngineOptions(cuda_graphs=True, amp_dtype=torch.bfloat16 if BF16 else None, channels_last=True, master_weights=BF16,
+                       table_grads=not BF16)
+KIND = os.environ.get("KINETO_CLIENT", "basic")  # basic | fedprox : which client algorithm's step is profiled
+if KIND == "fedprox":
+    from fl4health_b200.clients.fed_prox_client import FedProxClient
+
+    client_cls = type("ProfFedProx", (ps.Client, FedProxClient), {"get_model": ps.Client.get_model})
+else:
+    client_cls = ps.Client
+client = client_cls(Path("."), [Accuracy()], device, client_name="prof", engine_options=engine)
 cfg = {"current_server_round": 1, "local_steps": 8, "batch_size": ps.BS}
 client.setup_client(cfg)
+if KIND == "fedprox":
+    client.drift_penalty_weight = 0.1
+    client.drift_penalty_tensors = client.snapshot_drift_anchor()
 client.model.train()
 x, y = next(iter(client.train_loader))
 x, y = client._prepare_batch(x, y)

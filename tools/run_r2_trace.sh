@@ -6,3 +6,6 @@ for cfg in cifar_fedavg scaffold_fedprox fedper_ditto_dp; do
   FL4H_TRACE=1 timeout 420 python bench.py --config $cfg --steps 10 --warmup 3 --skip-e2e --skip-extra-dtype > $out/trace_$cfg.json 2> $out/trace_$cfg.err; echo "== $cfg rc=$?"
   grep '^{"dtype"' $out/trace_$cfg.err | cut -c1-1200
 done
+for kind in basic fedprox; do
+  KINETO_DTYPE=fp32 KINETO_CLIENT=$kind timeout 300 python benchmarks/kineto_step.py > $out/kineto_$kind.txt 2>&1; echo "== kineto $kind rc=$?"; head -3 $out/kineto_$kind.txt | cut -c1-250
+done
