@@ -59,6 +59,38 @@ def _copy_into(dst: Any, src: Any) -> None:
             _copy_into(value, src[key])
 
 
+_STEP_STREAMS: dict[int, torch.cuda.Stream] = {}
+
+
+def step_stream(device: torch.device) -> torch.cuda.Stream:
+    """The ONE stream per device on which steps are warmed up and captured.  Autograd's gradient accumulators remember
+    the stream they were created on; if the eager warm-up ran on the default stream and the capture on torch's private
+    capture stream, every accumulator kept alive across iterations (a client holding on to a loss tensor is enough)
+    makes the captured backward copy each parameter gradient instead of adopting it -- one extra elementwise kernel per
+    parameter per step.  Same stream for both, shared by every runner of the device: no mismatch."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    if index not in _STEP_STREAMS:
+        _STEP_STREAMS[index] = torch.cuda.Stream(device=device)
+    return _STEP_STREAMS[index]
+
+
+def _record_on(obj: Any, stream: torch.cuda.Stream) -> None:
+    """Tell the caching allocator that tensors produced on the step stream are consumed on ``stream``."""
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for value in obj.values():
+            _record_on(value, stream)
+    elif isinstance(obj, (list, tuple)):
+        for value in obj:
+            _record_on(value, stream)
+    elif hasattr(obj, "__dict__") and not isinstance(obj, torch.nn.Module):
+        for value in vars(obj).values():
+            if isinstance(value, (torch.Tensor, dict, list, tuple)):
+                _record_on(value, stream)
+
+
 @dataclass
 class _Captured:
     graph: torch.cuda.CUDAGraph
@@ -105,8 +137,17 @@ class GraphStepRunner:
         if sig in self._disabled or count < self.warmup:
             self._seen[sig] = count + 1
             self.eager_steps += 1
-            return self.fn(input, target)
+            return self._eager_on_step_stream(input, target)
         return self._capture_and_run(sig, input, target)
+
+    def _eager_on_step_stream(self, input: Any, target: Any) -> Any:
+        caller, stream = torch.cuda.current_stream(self.device), step_stream(self.device)
+        stream.wait_stream(caller)
+        with torch.cuda.stream(stream):
+            outputs = self.fn(input, target)
+        caller.wait_stream(stream)
+        _record_on(outputs, caller)
+        return outputs
 
     def _capture_and_run(self, sig: tuple, input: Any, target: Any) -> Any:
         from fl4health_b200.ops import _lib
@@ -121,14 +162,14 @@ class GraphStepRunner:
         torch.cuda.synchronize(self.device)
         launches_before = _lib.launch_count()
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=step_stream(self.device)):
                 outputs = self.fn(static_input, static_target)
         except Exception as exc:  # noqa: BLE001 - any capture failure means "run eagerly"
             torch.cuda.synchronize(self.device)
             self._disabled.add(sig)
             log(WARNING, f"[{self.name}] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly.")
             self.eager_steps += 1
-            return self.fn(input, target)
+            return self._eager_on_step_stream(input, target)
         launched = _lib.launch_count() - launches_before  # our kernels recorded into the graph (not executed yet)
         _lib.count_launches(-launched)
         captured = _Captured(graph, static_input, static_target, outputs, launched)

@@ -401,13 +401,20 @@ class TrainableRegionLayout:
         ]
         self.int_state: dict[str, torch.Tensor] = {}
         self.total = arena.trainable_padded
+        self._views_cache: dict[tuple[int, int], NDArrays] = {}
 
     def ndarrays(self, names: Iterable[str] | None = None, region: torch.Tensor | None = None) -> NDArrays:
         assert region is not None
-        out = NDArrays([self.arena.view(name, region) for name in (names or self.state_keys)])
-        if names is None:
-            out.flat, out.layout = region[: self.total], self
-        return out
+        if names is not None:
+            return NDArrays([self.arena.view(name, region) for name in names])
+        key = (region.data_ptr(), region.numel())
+        cached = self._views_cache.get(key)
+        if cached is None:  # the per-tensor views of a region are built once (a model's worth of slicing per call otherwise)
+            if len(self._views_cache) > 8:
+                self._views_cache.pop(next(iter(self._views_cache)))
+            cached = self._views_cache[key] = NDArrays([self.arena.view(name, region) for name in self.state_keys])
+            cached.flat, cached.layout = region[: self.total], self
+        return NDArrays(cached, flat=cached.flat, layout=self)
 
     def same_layout(self, other: object) -> bool:
         return isinstance(other, TrainableRegionLayout) and self.arena.same_layout(other.arena)

@@ -170,6 +170,8 @@ class Scaffold(BasicFedAvg):
             state.add_(flat, alpha=float(scale))
         out = _views_of(layout, state)
         integer_positions = [i for i, value in enumerate(incoming) if isinstance(value, torch.Tensor) and not value.is_floating_point()]
+        if towards and scale == 1.0:
+            out.int_flat = getattr(incoming, "int_flat", None)  # every counter is adopted as aggregated: so is their packed form
         for i in integer_positions:  # integer buffers (num_batches_tracked) are not in the float block: reference formula, per entry
             if towards and scale == 1.0:
                 out[i] = incoming[i]  # x + 1 * (ybar - x)
