@@ -85,8 +85,7 @@ class BasicClient:
         self.device = torch.device(device)
         self.client_name = client_name or generate_hash()
         log(INFO, f"Client Name: {self.client_name}")
-        self.engine = engine_options or EngineOptions.from_env()
-        self._executor = StepExecutor(self.engine, self.device, self.client_name)
+        self._executor = StepExecutor(engine_options or EngineOptions.from_env(), self.device, self.client_name)
 
         self.checkpoint_and_state_module = checkpoint_and_state_module or ClientCheckpointAndStateModule(
             pre_aggregation=None, post_aggregation=None, state_checkpointer=None
@@ -126,6 +125,16 @@ class BasicClient:
     # set-up: user factories -> placed model, loaders, (fused) optimizers, schedulers, criterion, exchanger
     # ------------------------------------------------------------------------------------------------------------------
     companions: dict[str, Companion] = {}  # extra models kept next to ``self.model`` (engine/companions.py)
+
+    @property
+    def engine(self) -> EngineOptions:
+        """How the hooks are executed.  One object, shared with the step executor: replacing it (a client variant
+        turning graphs or table gradients off) is seen by both."""
+        return self._executor.engine
+
+    @engine.setter
+    def engine(self, options: EngineOptions) -> None:
+        self._executor.engine = options
 
     def setup_client(self, config: Config) -> None:
         build_companions(self, config)

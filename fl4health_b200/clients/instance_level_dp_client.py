@@ -18,8 +18,13 @@ class InstanceLevelDpClient(BasicClient):
         super().__init__(*args, **kwargs)
         self.clipping_bound: float
         self.noise_multiplier: float
-        # per-sample gradients are produced by hooks with data-dependent shapes: keep the step eager
-        self.engine.cuda_graphs = False
+        # The DP step is capturable: the engine book-keeps per-sample norms instead of materialising per-sample
+        # gradients and draws its noise from a device-resident stream (privacy/dp_engine.py).  Poisson sampling makes
+        # the batch size vary, so one graph is kept per size seen (engine/graph_runner.py).  A flat gradient region is
+        # kept (no pointer-table gradients): clipped sums are written into it and noised by ONE kernel.
+        from dataclasses import replace
+
+        self.engine = replace(self.engine, table_grads=False)
 
     def _place_model(self, model, with_grad: bool = True):  # noqa: ANN001, ANN201
         # fix DP-incompatible layers BEFORE the arena is laid out so optimizer/arena see the final parameters

@@ -109,6 +109,7 @@ class GraphStepRunner:
     warmup: int = 3
     name: str = "step"
     before_replay: Callable[[], None] | None = None  # e.g. push changed LR into the device hyper-parameter block
+    max_signatures: int = 64  # captured graphs pin memory: past this many input signatures, new ones run eagerly
     _seen: dict[tuple, int] = field(default_factory=dict)
     _graphs: dict[tuple, _Captured] = field(default_factory=dict)
     _disabled: set = field(default_factory=set)
@@ -134,7 +135,12 @@ class GraphStepRunner:
                 _lib.count_launches(captured.kernel_launches)
             return captured.outputs
         count = self._seen.get(sig, 0)
-        if sig in self._disabled or count < self.warmup:
+        # lazily created state (optimizer moments, meters) exists once ANY signature has been captured: a further
+        # signature (Poisson-sampled batch sizes, a ragged last batch) needs one eager pass, for library autotuning
+        needed = self.warmup if not self._graphs else min(self.warmup, 1)
+        if sig not in self._disabled and count >= needed and len(self._graphs) >= self.max_signatures:
+            self._disabled.add(sig)
+        if sig in self._disabled or count < needed:
             self._seen[sig] = count + 1
             self.eager_steps += 1
             return self._eager_on_step_stream(input, target)

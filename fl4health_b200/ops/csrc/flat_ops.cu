@@ -411,6 +411,24 @@ add_gaussian_kernel(float* __restrict__ y, float stddev, uint64_t seed, int64_t 
     }
 }
 
+// y = (y + std * N(0,1)) * scale with the stream taken from DEVICE memory: state[0] = seed, state[1] = draws so far.
+// A captured CUDA graph replays the same launch arguments; reading the stream position from memory (and bumping it in
+// a follow-up launch) gives every replay fresh noise -- DP-SGD's clip/noise/step inside one graph.
+__global__ void __launch_bounds__(kThreads)
+add_gaussian_state_kernel(float* __restrict__ y, float stddev, float scale, const uint64_t* __restrict__ state, int64_t n) {
+    const uint64_t seed = mix64(state[0] ^ mix64(state[1] * 0xD1342543DE82EF95ull + 1ull));
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t e = i << 2;
+        float4 v = ld4(y + e);
+        float2 a = gauss2(seed, (uint64_t)i * 2), b = gauss2(seed, (uint64_t)i * 2 + 1);
+        st4(y + e, make_float4((v.x + stddev * a.x) * scale, (v.y + stddev * a.y) * scale, (v.z + stddev * b.x) * scale,
+                               (v.w + stddev * b.y) * scale));
+    }
+}
+__global__ void bump_draws_kernel(uint64_t* state) { state[1] += 1ull; }
+
 // fp32 -> bf16 shadow refresh
 __global__ void __launch_bounds__(kThreads)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -619,6 +637,13 @@ int fl4h_clip_scale(float* x, const float* sq_norm, float clip, float* bit, int6
 int fl4h_add_gaussian(float* y, float stddev, uint64_t seed, int64_t n, cudaStream_t stream) {
     if (n & 3) return (int)cudaErrorInvalidValue;
     add_gaussian_kernel<<<stream_grid(n, 4), kThreads, 0, stream>>>(y, stddev, seed, n);
+    return (int)cudaGetLastError();
+}
+
+int fl4h_add_gaussian_state(float* y, float stddev, float scale, uint64_t* state, int64_t n, cudaStream_t stream) {
+    if (n & 3) return (int)cudaErrorInvalidValue;
+    add_gaussian_state_kernel<<<stream_grid(n, 4), kThreads, 0, stream>>>(y, stddev, scale, state, n);
+    bump_draws_kernel<<<1, 1, 0, stream>>>(state);
     return (int)cudaGetLastError();
 }
 

@@ -365,6 +365,30 @@ def add_gaussian_(y: torch.Tensor, stddev: float, seed: int) -> None:
     y.add_(torch.randn(y.shape, generator=gen, device=y.device, dtype=y.dtype), alpha=stddev)
 
 
+def make_noise_state(device: torch.device | str, seed: int) -> torch.Tensor:
+    """``[seed, draws]`` (int64) on the device: the position of a counter-based noise stream that kernels advance."""
+    return torch.tensor([seed & (2**63 - 1), 0], dtype=torch.int64, device=device)
+
+
+def add_gaussian_state_(y: torch.Tensor, stddev: float, state: torch.Tensor, scale: float = 1.0) -> None:
+    """``y = (y + stddev * N(0, 1)) * scale`` drawing from the device-resident stream ``state`` (``make_noise_state``),
+    which is advanced on the device: safe inside a captured CUDA graph (every replay draws new noise)."""
+    n = _check_flat(y)
+    if _use_kernel(y):
+        lib = _lib.load(True)
+        err = lib.fl4h_add_gaussian_state(_lib.ptr(y), ctypes.c_float(stddev), ctypes.c_float(scale), _lib.ptr(state),
+                                          ctypes.c_int64(n), _lib.stream_ptr(y.device))
+        _lib.check(err, "fl4h_add_gaussian_state")
+        _lib.count_launches(2)
+        return
+    seed, draws = (int(v) for v in state.tolist())
+    gen = torch.Generator(device=y.device).manual_seed((seed * 1_000_003 + draws) & (2**63 - 1))
+    if stddev != 0.0:
+        y.add_(torch.randn(y.shape, generator=gen, device=y.device, dtype=y.dtype), alpha=stddev)
+    y.mul_(scale)
+    state[1] += 1
+
+
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     n = _check_flat(src)
     if _use_kernel(src):

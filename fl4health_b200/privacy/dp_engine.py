@@ -5,6 +5,13 @@ Pieces, with the names users of the reference already know:
 * ``GradSampleModule``  — wraps a model and computes *per-sample gradients* during the ordinary ``loss.backward()``
   with forward/backward hooks (Linear, Conv1d/2d, LayerNorm, GroupNorm, Embedding; anything else must be replaced by
   ``ModuleValidator.fix``, e.g. BatchNorm -> GroupNorm).  State-dict keys carry the ``_module.`` prefix, like Opacus.
+  Two modes: ``"hooks"`` materialises ``p.grad_sample`` ([B, *p.shape], Opacus' contract); ``"ghost"`` (what
+  ``PrivacyEngine.make_private`` uses) only *book-keeps*: per layer it adds the per-sample squared gradient norm to a
+  [B] accumulator -- for Linear / Conv weights through the Gram identity ``||sum_t g_t a_t^T||^2 = sum_{t,s} (a_t.a_s)
+  (g_t.g_s)`` whenever that is cheaper than forming the per-sample gradient -- and keeps the layer's (activation,
+  back-propagated signal) pair; after the backward pass the optimizer turns the norms into clip factors and forms the
+  CLIPPED SUM directly with one GEMM per layer (``(f . g)^T a``).  No [B, *p.shape] tensor for the large layers, every
+  shape static: the whole clip / noise / step is CUDA-graph capturable.
 * ``DPOptimizer``       — flat clipping: per-sample global L2 norm over all parameters, clip to ``max_grad_norm``, sum,
   add ``N(0, (noise_multiplier * max_grad_norm)^2)``, divide by the expected batch size, then the wrapped optimizer
   steps.  When the parameters' gradients are views of a flat arena the noise is ONE counter-RNG kernel over the flat
@@ -114,6 +121,70 @@ def _rule_for(module: nn.Module) -> Any:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# book-keeping ("ghost") rules:  per-sample squared norms now, the clipped sum later
+# ---------------------------------------------------------------------------------------------------------------
+class _Deferred:
+    """What a layer leaves behind in ghost mode: either per-sample gradients that were cheap to form (``samples``:
+    parameter -> [B, *shape]) or the token-major factors of a weight gradient (``a``: [B, T, in], ``g``: [B, T, out])."""
+
+    __slots__ = ("samples", "weight", "a", "g")
+
+    def __init__(self) -> None:
+        self.samples: dict[nn.Parameter, torch.Tensor] = {}
+        self.weight: nn.Parameter | None = None
+        self.a: torch.Tensor | None = None
+        self.g: torch.Tensor | None = None
+
+    def clipped_sums(self, factor: torch.Tensor) -> dict[nn.Parameter, torch.Tensor]:
+        out = {p: torch.einsum("n,n...->...", factor.to(sample.dtype), sample) for p, sample in self.samples.items()}
+        if self.weight is not None:
+            assert self.a is not None and self.g is not None
+            scaled = self.g * factor.to(self.g.dtype).view(-1, 1, 1)
+            grad = scaled.reshape(-1, scaled.shape[-1]).t() @ self.a.reshape(-1, self.a.shape[-1])  # [out, in]: ONE GEMM
+            out[self.weight] = grad.reshape(self.weight.shape)
+        return out
+
+
+def _factored_sq_norm(a: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """``||sum_t g[n,t] a[n,t]^T||_F^2`` per sample without forming the [out, in] products."""
+    if a.shape[1] == 1:
+        return a.pow(2).sum(dim=(1, 2)) * g.pow(2).sum(dim=(1, 2))
+    return (torch.bmm(a, a.transpose(1, 2)) * torch.bmm(g, g.transpose(1, 2))).sum(dim=(1, 2))
+
+
+def _gram_is_cheaper(tokens: int, fan_in: int, fan_out: int) -> bool:
+    # Gram: B T^2 (in + out) multiply-adds and T^2 floats;  direct: B T in out and in*out floats per sample
+    return tokens * (fan_in + fan_out) < fan_in * fan_out
+
+
+def _ghost_rule(layer: nn.Module, a: torch.Tensor, g: torch.Tensor) -> tuple[torch.Tensor, _Deferred]:
+    """(per-sample squared gradient norm of this layer's parameters [B], what to keep for the clipped sum)."""
+    kept = _Deferred()
+    factored: tuple[torch.Tensor, torch.Tensor] | None = None
+    if isinstance(layer, nn.Linear) and layer.weight.requires_grad:
+        a3, g3 = a.reshape(a.shape[0], -1, a.shape[-1]), g.reshape(g.shape[0], -1, g.shape[-1])
+        if a3.shape[1] == 1 or _gram_is_cheaper(a3.shape[1], a3.shape[2], g3.shape[2]):
+            factored = (a3, g3)
+    elif isinstance(layer, nn.Conv2d) and layer.weight.requires_grad and layer.groups == 1 and not isinstance(layer.padding, str):
+        tokens = g.shape[2] * g.shape[3]
+        fan_in = layer.in_channels * layer.kernel_size[0] * layer.kernel_size[1]
+        if _gram_is_cheaper(tokens, fan_in, layer.out_channels):
+            cols = F.unfold(a, layer.kernel_size, dilation=layer.dilation, padding=layer.padding, stride=layer.stride)
+            factored = (cols.transpose(1, 2), g.reshape(g.shape[0], layer.out_channels, -1).transpose(1, 2))
+    if factored is None:
+        kept.samples = _rule_for(layer)(layer, a, g)
+    else:
+        kept.weight, (kept.a, kept.g) = layer.weight, factored  # type: ignore[union-attr]
+        bias = getattr(layer, "bias", None)
+        if bias is not None and bias.requires_grad:
+            kept.samples[bias] = factored[1].sum(dim=1)
+    squared = sum(sample.reshape(sample.shape[0], -1).pow(2).sum(dim=1) for sample in kept.samples.values())
+    if factored is not None:
+        squared = squared + _factored_sq_norm(*factored)
+    return squared, kept  # type: ignore[return-value]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # module validation / fixing
 # ---------------------------------------------------------------------------------------------------------------
 class ModuleValidator:
@@ -153,12 +224,17 @@ class ModuleValidator:
 # GradSampleModule
 # ---------------------------------------------------------------------------------------------------------------
 class GradSampleModule(nn.Module):
-    def __init__(self, module: nn.Module, batch_first: bool = True, loss_reduction: str = "mean") -> None:
+    def __init__(self, module: nn.Module, batch_first: bool = True, loss_reduction: str = "mean",
+                 grad_sample_mode: str = "hooks") -> None:
         super().__init__()
         errors = [e for e in ModuleValidator.validate(module) if "BatchNorm" in e or "no per-sample" in e]
         if errors:
             raise ValueError("Model is not DP-compatible:\n" + "\n".join(errors))
+        assert grad_sample_mode in ("hooks", "ghost"), "grad_sample_mode must be 'hooks' (materialise) or 'ghost' (book-keep)"
         self._module = module
+        self.grad_sample_mode = grad_sample_mode
+        self.sq_norms: torch.Tensor | None = None  # ghost mode: per-sample squared gradient norm over all layers so far
+        self.deferred: list[_Deferred] = []
         self.loss_reduction = loss_reduction
         self.hooks_enabled = True
         self._handles: list[Any] = []
@@ -193,6 +269,11 @@ class GradSampleModule(nn.Module):
         backprop = grad_output[0].detach()
         if self.loss_reduction == "mean":
             backprop = backprop * backprop.shape[0]  # undo the 1/B of the mean loss: per-sample grads are unscaled
+        if self.grad_sample_mode == "ghost":
+            squared, kept = _ghost_rule(module, activation, backprop)
+            self.sq_norms = squared if self.sq_norms is None else self.sq_norms + squared
+            self.deferred.append(kept)
+            return
         for param, grad_sample in _rule_for(module)(module, activation, backprop).items():
             existing = getattr(param, "grad_sample", None)
             param.grad_sample = grad_sample if existing is None else existing + grad_sample  # type: ignore[attr-defined]
@@ -201,6 +282,7 @@ class GradSampleModule(nn.Module):
         for param in self._module.parameters():
             param.grad_sample = None  # type: ignore[attr-defined]
         self._activations = {}
+        self.sq_norms, self.deferred = None, []
         super().zero_grad(set_to_none)
 
     def to_standard_module(self) -> nn.Module:
@@ -209,8 +291,7 @@ class GradSampleModule(nn.Module):
 
 
 def wrap_model(model: nn.Module, grad_sample_mode: str = "hooks", *args: Any, **kwargs: Any) -> GradSampleModule:
-    assert grad_sample_mode == "hooks", "only hook-based per-sample gradients are implemented"
-    return GradSampleModule(model, *args, **kwargs)
+    return GradSampleModule(model, *args, grad_sample_mode=grad_sample_mode, **kwargs)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -231,12 +312,37 @@ class DPOptimizer(Optimizer):
         self.state = optimizer.state
         self._step_count = 0
         self._module = module
+        self._noise_state: torch.Tensor | None = None
 
     @property
     def params(self) -> list[nn.Parameter]:
         return [p for group in self.param_groups for p in group["params"] if p.requires_grad]
 
+    def _assign(self, param: nn.Parameter, summed: torch.Tensor, first: bool) -> None:
+        if param.grad is not None and first:
+            param.grad.copy_(summed.to(param.grad.dtype))  # keeps arena gradient views alive
+        elif param.grad is not None:
+            param.grad.add_(summed.to(param.grad.dtype))
+        else:
+            param.grad = summed
+
+    def _clip_and_accumulate_from_book(self, book: GradSampleModule) -> bool:
+        """Ghost mode: norms were accumulated layer by layer; the clipped sum of every layer is formed now."""
+        if book.sq_norms is None:
+            return False
+        clip_factor = (self.max_grad_norm / (book.sq_norms.sqrt() + 1e-6)).clamp(max=1.0)
+        mine, seen = {id(p) for p in self.params}, set()
+        for kept in book.deferred:
+            for param, summed in kept.clipped_sums(clip_factor).items():
+                if id(param) in mine:
+                    self._assign(param, summed, first=id(param) not in seen)  # a shared layer contributes once per use
+                    seen.add(id(param))
+        book.sq_norms, book.deferred = None, []
+        return True
+
     def clip_and_accumulate(self) -> bool:
+        if isinstance(self._module, GradSampleModule) and self._module.grad_sample_mode == "ghost":
+            return self._clip_and_accumulate_from_book(self._module)
         params = [p for p in self.params if getattr(p, "grad_sample", None) is not None]
         if not params:
             return False
@@ -262,17 +368,20 @@ class DPOptimizer(Optimizer):
         if arena is None and inner is not None:
             arena = arena_of(inner)
         params = self.params
-        if (arena is not None and arena.grad is not None and std > 0
+        if (arena is not None and arena.grad is not None
                 and all(p.grad is not None and p.grad.untyped_storage().data_ptr() == arena.grad.untyped_storage().data_ptr() for p in params)):
-            seed = int(torch.randint(0, 2**62, (1,), generator=self.generator).item())
-            flat_ops.add_gaussian_(arena.grad, std, seed)  # one kernel over the whole flat gradient
-            arena.grad.mul_(scale)
+            # one kernel over the whole flat gradient: (g + std z) / B, the noise stream position lives on the device and
+            # is advanced there, so a captured graph draws fresh noise on every replay
+            if self._noise_state is None or self._noise_state.device != arena.grad.device:
+                seed = int(torch.randint(0, 2**62, (1,), generator=self.generator).item())
+                self._noise_state = flat_ops.make_noise_state(arena.grad.device, seed)
+            flat_ops.add_gaussian_state_(arena.grad, std, self._noise_state, scale)
             return
         for p in params:
             if p.grad is None:
                 continue
-            if std > 0:
-                p.grad.add_(torch.normal(0.0, std, p.grad.shape, device=p.grad.device, dtype=p.grad.dtype, generator=None))
+            if std > 0:  # default generator of the gradient's device: CUDA-graph safe (torch registers its offset)
+                p.grad.add_(torch.randn(p.grad.shape, device=p.grad.device, dtype=p.grad.dtype), alpha=std)
             p.grad.mul_(scale)
 
     def pre_step(self) -> bool:
@@ -362,10 +471,12 @@ class PrivacyEngine:
     def make_private(
         self, *, module: nn.Module, optimizer: Optimizer, data_loader: Any, noise_multiplier: float,
         max_grad_norm: float, batch_first: bool = True, loss_reduction: str = "mean", poisson_sampling: bool = True,
-        clipping: str = "flat", noise_generator: torch.Generator | None = None, **kwargs: Any,
+        clipping: str = "flat", noise_generator: torch.Generator | None = None, grad_sample_mode: str = "ghost",
+        **kwargs: Any,
     ) -> tuple[GradSampleModule, DPOptimizer, Any]:
         assert clipping == "flat", "only flat clipping is implemented"
-        wrapped = module if isinstance(module, GradSampleModule) else GradSampleModule(module, batch_first, loss_reduction)
+        wrapped = module if isinstance(module, GradSampleModule) else GradSampleModule(
+            module, batch_first, loss_reduction, grad_sample_mode=grad_sample_mode)
         expected_batch_size = int(data_loader.batch_size) if getattr(data_loader, "batch_size", None) else None
         dp_loader = DPDataLoader.from_data_loader(data_loader, noise_generator) if poisson_sampling else data_loader
         dp_optimizer = DPOptimizer(optimizer, noise_multiplier=noise_multiplier, max_grad_norm=max_grad_norm,

@@ -166,3 +166,65 @@ def test_client_level_dp_end_to_end(manager_cls) -> None:
     assert strategy.clipping_bound != 0.5  # adapted
     s0, s1 = clients[0].model.state_dict(), clients[1].model.state_dict()
     assert all(torch.allclose(s0[k].float(), s1[k].float()) for k in s0)
+
+
+class _GramNet(nn.Module):
+    """Layers on both sides of the ghost-norm decision: a convolution with few output positions and a per-token Linear
+    with few tokens take the Gram identity, the first convolution (many positions, tiny filter) forms its per-sample
+    gradients, the classifier sees one token per sample."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.stem = nn.Conv2d(3, 8, 3, padding=1)            # 64 positions, 27 x 8 filter: direct
+        self.deep = nn.Conv2d(8, 32, 3, stride=2, padding=1)   # 4 positions, 72 x 32 filter: Gram
+        self.token_mlp = nn.Linear(32, 48)                      # 4 tokens, 32 x 48: Gram
+        self.head = nn.Linear(48, 5)                            # 1 token: norm product
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h = torch.relu(self.stem(x))
+        h = torch.relu(self.deep(nn.functional.avg_pool2d(h, 2)))  # [B, 32, 2, 2]
+        tokens = torch.relu(self.token_mlp(h.flatten(2).transpose(1, 2)))  # [B, 4, 48]
+        return self.head(tokens.mean(dim=1))
+
+
+@pytest.mark.parametrize("net", [DpNet, _GramNet])
+def test_ghost_book_keeping_matches_materialised_per_sample_gradients(net) -> None:  # noqa: ANN001
+    """``grad_sample_mode="ghost"`` (norms via Gram identities, clipped sum as one GEMM per layer, no [B, *shape]
+    tensors for the factored layers) takes the same DP-SGD step as the Opacus-style materialising hooks."""
+    import copy
+
+    from fl4health_b200.privacy import dp_engine
+
+    torch.manual_seed(5)
+    reference_model = net()
+    ghost_model = copy.deepcopy(reference_model)
+    batch = 6
+    if net is DpNet:
+        inputs = (torch.randn(batch, 3, 8, 8), torch.randint(0, 7, (batch, 3)))
+    else:
+        inputs = (torch.randn(batch, 3, 8, 8) * 3,)
+    labels = torch.randint(0, 5, (batch,))
+    taken: dict[str, list] = {}
+    for mode, model in (("hooks", reference_model), ("ghost", ghost_model)):
+        wrapped = GradSampleModule(model, grad_sample_mode=mode)
+        optimizer = DPOptimizer(torch.optim.SGD(model.parameters(), lr=0.5), noise_multiplier=0.0, max_grad_norm=0.7,
+                                expected_batch_size=batch, module=wrapped)
+        for _ in range(2):  # two steps: the book is emptied and refilled
+            optimizer.zero_grad()
+            nn.functional.cross_entropy(wrapped(*inputs), labels).backward()
+            if mode == "ghost":
+                assert all(getattr(p, "grad_sample", None) is None for p in model.parameters())
+                factored = [kept.weight is not None for kept in wrapped.deferred]
+                assert any(factored) and (net is DpNet or not all(factored))
+                norms = wrapped.sq_norms.sqrt()
+            else:
+                norms = torch.stack([p.grad_sample.reshape(batch, -1).norm(dim=1) for p in model.parameters()], 1).norm(dim=1)
+            taken.setdefault(mode + "_norms", []).append(norms.clone())
+            optimizer.step()
+        taken[mode] = [p.detach().clone() for p in model.parameters()]
+    for got, want in zip(taken["ghost_norms"], taken["hooks_norms"]):
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-6)
+    assert float(taken["hooks_norms"][0].max()) > 0.7  # clipping was active
+    for got, want in zip(taken["ghost"], taken["hooks"]):
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-6)
+    assert dp_engine._gram_is_cheaper(4, 72, 32) and not dp_engine._gram_is_cheaper(64, 27, 8)
