@@ -34,6 +34,15 @@ x, y = client._prepare_batch(x, y)
 for _ in range(8):
     client._run_train_unit(x, y)
 torch.cuda.synchronize()
+if os.environ.get("KINETO_GC") == "1":  # what keeps autograd history alive between steps (it should be nothing)
+    import gc
+
+    gc.collect()
+    alive = [o for o in gc.get_objects() if isinstance(o, torch.Tensor) and o.grad_fn is not None]
+    print(f"tensors with autograd history alive after a step: {len(alive)}")
+    for t in alive[:12]:
+        holders = [type(r).__name__ + (":" + ",".join(k for k, v in r.items() if v is t)[:60] if isinstance(r, dict) else "") for r in gc.get_referrers(t)][:4]
+        print("  ", tuple(t.shape), t.dtype, type(t.grad_fn).__name__, holders)
 N = 5
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(N):

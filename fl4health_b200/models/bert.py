@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
-from fl4health_b200.models.fused_layers import LinearAct
+from fl4health_b200.models.fused_layers import LinearAct, ResidualLayerNorm
 
 
 @dataclass
@@ -50,7 +50,10 @@ class BertEmbeddings(nn.Module):
         positions = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0)
         types = token_type_ids if token_type_ids is not None else torch.zeros_like(input_ids)
         x = self.word_embeddings(input_ids) + self.position_embeddings(positions) + self.token_type_embeddings(types)
-        return self.dropout(self.LayerNorm(x))
+        x = self.dropout(self.LayerNorm(x))
+        if torch.is_autocast_enabled() and x.is_cuda:  # the encoder's activations travel in the compute dtype
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        return x
 
 
 class BertLayer(nn.Module):
@@ -59,20 +62,19 @@ class BertLayer(nn.Module):
         self.num_heads = cfg.num_attention_heads
         self.qkv = LinearAct(cfg.hidden_size, 3 * cfg.hidden_size)
         self.attn_out = LinearAct(cfg.hidden_size, cfg.hidden_size)
-        self.attn_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.attn_norm = ResidualLayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps, dropout=cfg.hidden_dropout_prob)
         assert cfg.activation in ("gelu", "relu")
         self.ffn_in = LinearAct(cfg.hidden_size, cfg.intermediate_size, activation=cfg.activation)  # activation in the epilogue
         self.act = nn.Identity()
         self.ffn_out = LinearAct(cfg.intermediate_size, cfg.hidden_size)
-        self.ffn_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
+        self.ffn_norm = ResidualLayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps, dropout=cfg.hidden_dropout_prob)
 
     def forward(self, x: torch.Tensor, mask: torch.Tensor | None) -> torch.Tensor:
         b, t, h = x.shape
         q, k, v = self.qkv(x).view(b, t, 3, self.num_heads, h // self.num_heads).permute(2, 0, 3, 1, 4)
         attn = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)
-        x = self.attn_norm(x + self.dropout(self.attn_out(attn.transpose(1, 2).reshape(b, t, h))))
-        return self.ffn_norm(x + self.dropout(self.ffn_out(self.act(self.ffn_in(x)))))
+        x = self.attn_norm(self.attn_out(attn.transpose(1, 2).reshape(b, t, h)), residual=x)  # LN(x + dropout(.)): one kernel
+        return self.ffn_norm(self.ffn_out(self.act(self.ffn_in(x))), residual=x)
 
 
 class BertEncoder(nn.Module):

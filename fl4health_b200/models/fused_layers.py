@@ -10,8 +10,25 @@ from torch import nn
 
 from fl4health_b200.engine import streams
 from fl4health_b200.ops import conv as tc_conv
+from fl4health_b200.ops.layer_norm import add_dropout_layer_norm
 from fl4health_b200.ops.bn_act import batch_norm_act, presums_eligible
 from fl4health_b200.ops.tc_gemm import linear_bias_act
+
+
+class ResidualLayerNorm(nn.LayerNorm):
+    """``LayerNorm(residual + dropout(y))`` -- a transformer sub-layer's epilogue -- as one kernel per direction on CUDA
+    (``ops/layer_norm.py``); exactly ``nn.LayerNorm`` (same parameters / state-dict) applied to the stock composition
+    everywhere else.  ``dropout`` is the probability applied to ``y`` in training mode."""
+
+    def __init__(self, normalized_shape: int, eps: float = 1e-5, dropout: float = 0.0) -> None:
+        super().__init__(normalized_shape, eps=eps)
+        self.dropout = dropout
+
+    def forward(self, y: torch.Tensor, residual: torch.Tensor | None = None) -> torch.Tensor:  # type: ignore[override]
+        return add_dropout_layer_norm(y, residual, self.weight, self.bias, self.eps, self.dropout, self.training)
+
+    def extra_repr(self) -> str:
+        return super().extra_repr() + f", dropout={self.dropout}"
 
 
 class BatchNormAct2d(nn.BatchNorm2d):
