@@ -82,6 +82,8 @@ class Parameters:
     flat: Any = None
     layout: Any = None
     int_flat: Any = None  # all integer entries as one int64 tensor (see ``NDArrays.int_flat``)
+    aux_flat: Any = None  # second arena-shaped block packed behind the model state (see ``NDArrays.aux_flat``)
+    aux_layout: Any = None
 
 
 def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
@@ -91,6 +93,8 @@ def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
         flat=getattr(ndarrays, "flat", None),
         layout=getattr(ndarrays, "layout", None),
         int_flat=getattr(ndarrays, "int_flat", None),
+        aux_flat=getattr(ndarrays, "aux_flat", None),
+        aux_layout=getattr(ndarrays, "aux_layout", None),
     )
 
 
@@ -100,6 +104,7 @@ def parameters_to_ndarrays(parameters: Parameters) -> NDArrays:
         return tagged
     arrays = NDArrays(parameters.tensors, flat=parameters.flat, layout=parameters.layout)
     arrays.int_flat = getattr(parameters, "int_flat", None)
+    arrays.aux_flat, arrays.aux_layout = getattr(parameters, "aux_flat", None), getattr(parameters, "aux_layout", None)
     return arrays
 
 

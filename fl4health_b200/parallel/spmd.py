@@ -427,6 +427,7 @@ class _LocalPayload(NDArrays):
 def _tag_local(arrays: NDArrays, ctx: SpmdContext) -> NDArrays:
     tagged = _LocalPayload(arrays, flat=getattr(arrays, "flat", None), layout=getattr(arrays, "layout", None))
     tagged.int_flat = getattr(arrays, "int_flat", None)
+    tagged.aux_flat, tagged.aux_layout = getattr(arrays, "aux_flat", None), getattr(arrays, "aux_layout", None)
     tagged.ctx, tagged.rank, tagged.spec = ctx, ctx.rank, PayloadSpec.of(arrays)  # type: ignore[attr-defined]
     return tagged
 
