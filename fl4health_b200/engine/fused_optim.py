@@ -314,8 +314,9 @@ def translate_optimizer(optimizer: Optimizer, arena: ParameterArena) -> Optimize
     if isinstance(optimizer, _FlatOptimizer) or getattr(optimizer, "fl4h_keep_stock", False):
         return optimizer  # (ZeRO-1 shards keep the stock optimizer: the flat companions are arena-length by construction)
     kind = type(optimizer)
-    if kind not in (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW) or (arena.grad is None and arena.shadow is None):
-        return optimizer
+    trainable_arena = arena.grad is not None or arena.shadow is not None or getattr(arena, "table_gradients", False)
+    if kind not in (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW) or not trainable_arena:
+        return optimizer  # (an arena attached without gradients holds an evaluation-only / frozen model)
     module_params = {id(p) for p in arena.module.parameters()}
     groups = []
     for group in optimizer.param_groups:

@@ -91,6 +91,7 @@ class ParameterArena:
         self._views_cache: dict[tuple[int, int], NDArrays] = {}
         self._rehome()
         self.grad: torch.Tensor | None = None
+        self.table_gradients = False  # True: trainable, but gradients are per-tensor (no flat region); see use_table_gradients
         self.shadow: torch.Tensor | None = None  # bf16 compute copy (see enable_compute_shadow)
         self.shadow_names: set[str] = set()
         if with_grad and self.trainable_numel > 0:
@@ -235,6 +236,7 @@ class ParameterArena:
         for param in self.module.parameters():
             param.grad = None
         self.grad = None
+        self.table_gradients = True
 
     @property
     def params_end(self) -> int:

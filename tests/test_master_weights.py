@@ -107,3 +107,37 @@ def test_flat_sgd_over_non_contiguous_ranges_matches_torch_with_dampening() -> N
             opt.step()
         for mine, theirs in zip(ours.parameters(), stock.parameters()):
             assert torch.allclose(mine, theirs, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adamw"])
+def test_fp32_table_gradients_get_the_fused_optimizer(kind: str) -> None:
+    """``EngineOptions.table_grads`` (fp32, no flat gradient region, no shadow): the stock optimizer must still be
+    translated to the one-launch pointer-table optimizer, and take the same steps as torch.optim -- with the FedProx
+    anchor folded in (a stock optimizer would silently send drift-penalised clients down the autograd path)."""
+    def net() -> nn.Module:  # (no convolution bias in front of BatchNorm: its true gradient is zero, Adam would amplify rounding noise)
+        torch.manual_seed(3)
+        return nn.Sequential(nn.Conv2d(3, 5, 3, padding=1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), nn.Flatten(), nn.Linear(5 * 16, 7))
+
+    ours, stock = net(), net()
+    arena = attach_arena(ours)
+    arena.use_table_gradients()
+    assert arena.grad is None and arena.shadow is None and all(p.grad is None for p in ours.parameters())
+    make = (lambda params: torch.optim.SGD(params, lr=0.1, momentum=0.9, weight_decay=1e-3)) if kind == "sgd" else \
+        (lambda params: torch.optim.AdamW(params, lr=1e-2, weight_decay=1e-2))
+    fused = translate_optimizer(make(ours.parameters()), arena)
+    assert isinstance(fused, FlatSGD if kind == "sgd" else FlatAdamW) and fused.table_mode
+    reference = make(stock.parameters())
+    gen = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        x, y = torch.randn(6, 3, 4, 4, generator=gen), torch.randint(0, 7, (6,), generator=gen)
+        for net, opt in ((ours, fused), (stock, reference)):
+            opt.zero_grad()
+            nn.functional.cross_entropy(net(x), y).backward()
+            opt.step()
+        for mine, theirs in zip(ours.parameters(), stock.parameters()):
+            assert torch.allclose(mine, theirs, atol=1e-5)
+    assert all(p.grad is None for p in ours.parameters()) is False
+    fused.zero_grad()
+    assert all(p.grad is None for p in ours.parameters())
+    frozen = attach_arena(_model(), with_grad=False)  # evaluation-only arenas keep whatever optimizer they are handed
+    assert isinstance(translate_optimizer(torch.optim.SGD(frozen.module.parameters(), lr=0.1), frozen), torch.optim.SGD)
