@@ -3,9 +3,11 @@
 randomly initialised or loaded from a local state dict with HF-compatible shapes).
 
 Inputs follow the HF convention and arrive as a dict (``input_ids``, ``attention_mask``[, ``token_type_ids``]), which
-exercises the clients' dict-input path.  Attention uses ``scaled_dot_product_attention`` (flash kernels on CUDA); the
-attention, feed-forward and classifier projections are ``LinearAct`` modules, i.e. the tcgen05 GEMM with fused
-bias(+GELU / ReLU) epilogue when running in bf16 on a B200.
+exercises the clients' dict-input path.  On a B200 in bf16 every block is in-house: attention (sequence <= 128, head
+dimension 64) is one tcgen05 kernel per direction reading the packed QKV projection in place (``ops/attention.py``),
+the sub-layer epilogues ``LayerNorm(x + dropout(.))`` are one kernel each (``ops/layer_norm.py``), and the projections
+are ``LinearAct`` modules (tcgen05 GEMM with fused bias(+GELU / ReLU) epilogue).  Elsewhere the same modules run the
+stock PyTorch composition.
 """
 
 from __future__ import annotations
@@ -16,6 +18,7 @@ import torch
 from torch import nn
 
 from fl4health_b200.models.fused_layers import LinearAct, ResidualLayerNorm
+from fl4health_b200.ops.attention import packed_self_attention
 
 
 @dataclass
@@ -70,10 +73,9 @@ class BertLayer(nn.Module):
         self.ffn_norm = ResidualLayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps, dropout=cfg.hidden_dropout_prob)
 
     def forward(self, x: torch.Tensor, mask: torch.Tensor | None) -> torch.Tensor:
-        b, t, h = x.shape
-        q, k, v = self.qkv(x).view(b, t, 3, self.num_heads, h // self.num_heads).permute(2, 0, 3, 1, 4)
-        attn = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)
-        x = self.attn_norm(self.attn_out(attn.transpose(1, 2).reshape(b, t, h)), residual=x)  # LN(x + dropout(.)): one kernel
+        # the packed projection goes to the attention kernel as is ([B, T, 3H]: Q, K, V are addressed inside it by TMA)
+        context = packed_self_attention(self.qkv(x), mask, self.num_heads)
+        x = self.attn_norm(self.attn_out(context), residual=x)  # LN(x + dropout(.)): one kernel
         return self.ffn_norm(self.ffn_out(self.act(self.ffn_in(x))), residual=x)
 
 
@@ -87,8 +89,8 @@ class BertEncoder(nn.Module):
     def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor | None = None,
                 token_type_ids: torch.Tensor | None = None) -> torch.Tensor:
         mask = None
-        if attention_mask is not None:  # [B, T] of {0,1} -> boolean key mask broadcast over heads and queries
-            mask = attention_mask[:, None, None, :].to(torch.bool)
+        if attention_mask is not None:  # [B, T] of {0,1}: key padding mask, one byte per token
+            mask = attention_mask.to(torch.uint8).contiguous()
         x = self.embeddings(input_ids, token_type_ids)
         for layer in self.layers:
             x = layer(x, mask)
