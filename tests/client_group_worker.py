@@ -138,7 +138,7 @@ def main() -> None:
     from fl4health_b200.parallel.client_group import average_gradients
 
     torch.manual_seed(7)
-    probe, x, y = GroupNormNet(), torch.randn(16, 3, 32, 32), torch.randint(0, 10, (16,))
+    probe, x, y = GroupNormNet().to(ctx.device), torch.randn(16, 3, 32, 32).to(ctx.device), torch.randint(0, 10, (16,)).to(ctx.device)
     reference = torch.autograd.grad(torch.nn.functional.cross_entropy(probe(x), y), list(probe.parameters()))
     mine = slice(group.group_rank, None, group.group_size)
     torch.nn.functional.cross_entropy(probe(x[mine]), y[mine]).backward()
