@@ -81,7 +81,7 @@ def main() -> None:
     weight, bias = torch.ones(hidden, device="cuda"), torch.zeros(hidden, device="cuda")
     for p in (0.0, 0.1):
         bench_pair(f"add_dropout_layernorm_p{p}", lambda a, b, w, c: add_dropout_layer_norm(a, b, w, c, 1e-12, p, True),
-                   lambda a, b, w, c: add_dropout_layer_norm_reference(a, b, w, c, 1e-12, p, True).to(torch.bfloat16),
+                   lambda a, b, w, c: add_dropout_layer_norm_reference(a.float(), b.float(), w, c, 1e-12, p, True).to(torch.bfloat16),  # = autocast
                    [y, res, weight, bias], bytes_moved=4.0 * rows * hidden * 2)
 
 

@@ -171,7 +171,7 @@ ln_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ pre, const float
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, float p_drop,
               const uint64_t* __restrict__ rng_state, const uint64_t* __restrict__ used_draw) {
     constexpr int H = CHUNKS * 256;
-    __shared__ float acc_g[kWarpsPerCta - 1][H], acc_b[kWarpsPerCta - 1][H];
+    __shared__ float acc_g[kWarpsPerCta][H], acc_b[kWarpsPerCta][H];
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + warp_in_cta;
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
@@ -227,32 +227,25 @@ ln_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ pre, const float
             }
         }
     }
-    // CTA reduction of the parameter gradients: warps 1..3 park theirs in shared memory, warp 0 adds and publishes
-    if (warp_in_cta > 0) {
+    // CTA reduction of the parameter gradients: every warp parks its partials in shared memory, then all 128 threads
+    // add the four copies of "their" columns and publish them (2 * H / 128 atomics per thread, spread over the CTA)
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
+    for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc_g[warp_in_cta - 1][c * 256 + lane * 8 + i] = dg[c][i];
-                acc_b[warp_in_cta - 1][c * 256 + lane * 8 + i] = db[c][i];
-            }
-    }
+        for (int i = 0; i < 8; ++i) {
+            acc_g[warp_in_cta][c * 256 + lane * 8 + i] = dg[c][i];
+            acc_b[warp_in_cta][c * 256 + lane * 8 + i] = db[c][i];
+        }
     __syncthreads();
-    if (warp_in_cta == 0) {
+    for (int col = threadIdx.x; col < H; col += kThreads) {
+        float tg = 0.f, tb = 0.f;
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int col = c * 256 + lane * 8 + i;
-                float tg = dg[c][i], tb = db[c][i];
-#pragma unroll
-                for (int w = 0; w < kWarpsPerCta - 1; ++w) {
-                    tg += acc_g[w][col];
-                    tb += acc_b[w][col];
-                }
-                atomicAdd(dgamma + col, tg);
-                atomicAdd(dbeta + col, tb);
-            }
+        for (int w = 0; w < kWarpsPerCta; ++w) {
+            tg += acc_g[w][col];
+            tb += acc_b[w][col];
+        }
+        atomicAdd(dgamma + col, tg);
+        atomicAdd(dbeta + col, tb);
     }
 }
 
@@ -308,7 +301,7 @@ int fl4h_ln_bwd(const void* dout, const void* pre, const float* mean, const floa
                 const uint64_t* used_draw, int is_bf16, cudaStream_t stream) {
     if (hidden % 256 != 0 || hidden < 256 || hidden > 1024) return (int)cudaErrorInvalidValue;
     int grid = grid_for(rows);
-    if (grid > 296) grid = 296;  // fewer, longer CTAs: each ends with 2 * H atomics
+    if (grid > 148) grid = 148;  // fewer, longer CTAs: each ends with 2 * H atomics
 #define LN_BWD(T, C)                                                                                                   \
     ln_bwd_kernel<T, C><<<grid, kThreads, 0, stream>>>((const T*)dout, (const T*)pre, mean, rstd, gamma, (T*)dpre, (T*)dy, \
                                                        dgamma, dbeta, rows, p_drop, rng_state, used_draw)

@@ -3,6 +3,9 @@
 out=gpurun_out/n2; mkdir -p $out
 NP=${NP:-2}
 tr() { timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) "$@"; }
+timeout 300 python benchmarks/bert_block_bench.py > $out/bert_block_bench.txt 2>&1; grep BLOCK $out/bert_block_bench.txt | cut -c1-400
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:ln_bwd_kernel -c 2 -o $out/ncu_ln_bwd_kernel -f python benchmarks/bert_block_bench.py > $out/ncu_ln_bwd.log 2>&1
+ncu -i $out/ncu_ln_bwd_kernel.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > $out/ncu_ln_bwd_kernel.summary.csv 2>/dev/null
 timeout 600 python -m pytest tests/test_multigpu_fused.py -m gpu -q --tb=short > $out/pytest_multigpu.log 2>&1; echo "== multigpu tests rc=$?"; tail -3 $out/pytest_multigpu.log | cut -c1-200
 tr bench.py --gpus $NP --steps 50 --warmup 5 > $out/bench_fused.json 2> $out/bench_fused.err; echo "== headline fused rc=$?"; tail -1 $out/bench_fused.json | cut -c1-500
 tr bench.py --gpus $NP --steps 50 --warmup 5 --collectives nccl --skip-extra-dtype > $out/bench_nccl.json 2> $out/bench_nccl.err; echo "== headline nccl rc=$?"; tail -1 $out/bench_nccl.json | cut -c1-300
