@@ -21,29 +21,6 @@ _WORKSPACES: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
 _ACC_STRIDE = 4096  # floats; must match kAccStride in bn_act.cu (supports C <= 2048)
 
 
-_CLUSTER = {"size": int(os.environ.get("FL4H_BN_CLUSTER_SIZE", "16"))}
-
-
-def _cluster_bytes() -> int:
-    """Activations up to this size take the single-cluster kernels (``csrc/bn_cluster.cu``); 0 disables them."""
-    # default 0: measured on B200 the 16-CTA cluster kernels (16-29 us) lose to the grid-wide cooperative kernels
-    # (11-15 us) at every ResNet-18/CIFAR layer size -- cluster scheduling plus the serial DSMEM partial reads cost more
-    # than the global-memory barrier they replace.  Kept for experiments (FL4H_BN_CLUSTER_MAX_BYTES=<bytes>).
-    return int(os.environ.get("FL4H_BN_CLUSTER_MAX_BYTES", "0"))
-
-
-def _try_cluster(launch) -> bool:  # noqa: ANN001
-    """Run ``launch(cluster_size)``; on a launch failure retry once with the portable cluster size, then give up."""
-    for size in dict.fromkeys((_CLUSTER["size"], 8)):
-        if size < 1:
-            return False
-        if launch(size) == 0:
-            _CLUSTER["size"] = size
-            return True
-    _CLUSTER["size"] = 0  # this device / driver cannot launch the cluster kernels: stop trying
-    return False
-
-
 def _allow_fused() -> int:
     """One cooperative kernel per direction (default) vs the two-kernel chain (``FL4H_BN_FUSED=0``, for A/B runs)."""
     return 0 if os.environ.get("FL4H_BN_FUSED", "1") == "0" else 1
@@ -150,21 +127,6 @@ class _BatchNormAct(torch.autograd.Function):
             ctx.relu, ctx.has_res, ctx.has_bias = relu, residual is not None, bias is not None
             ctx.training = True
             return y
-        use_cluster = training and lib.fl4h_bn_cluster_supported(ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int64(_cluster_bytes()),
-                                                                 ctypes.c_int(x.element_size())) == 1 and _CLUSTER["size"] > 0
-        if use_cluster:
-            stats = torch.empty(4, c, dtype=torch.float32, device=x.device)
-            done = _try_cluster(lambda size: lib.fl4h_bn_fwd_train_cluster(
-                _lib.ptr(x), _lib.ptr(residual), _lib.ptr(y), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(weight), _lib.ptr(bias),
-                _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(nbt), ctypes.c_float(momentum if momentum is not None else 0.0),
-                ctypes.c_float(eps), _lib.ptr(stats[0]), _lib.ptr(stats[1]), ctypes.c_int(is_bf16), ctypes.c_int(1 if relu else 0),
-                ctypes.c_int(size), stream))
-            if done:
-                _lib.count_launches(1)
-                ctx.save_for_backward(x, y, weight, stats)
-                ctx.relu, ctx.has_res, ctx.has_bias = relu, residual is not None, bias is not None
-                ctx.training = True
-                return y
         if training:
             acc, counter = _workspace(x.device, c)
             stats = torch.empty(4, c, dtype=torch.float32, device=x.device)  # mean, invstd, scale, shift
@@ -214,16 +176,6 @@ class _BatchNormAct(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         grads = torch.empty(2, c, dtype=torch.float32, device=x.device)
-        if _CLUSTER["size"] > 0 and lib.fl4h_bn_cluster_supported(ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int64(_cluster_bytes()),
-                                                                  ctypes.c_int(x.element_size())) == 1:
-            done = _try_cluster(lambda size: lib.fl4h_bn_bwd_cluster(
-                _lib.ptr(dy), _lib.ptr(y), _lib.ptr(x), ctypes.c_int64(m), ctypes.c_int(c), _lib.ptr(weight), _lib.ptr(stats[0]),
-                _lib.ptr(stats[1]), _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(grads[0]), _lib.ptr(grads[1]),
-                ctypes.c_int(1 if x.dtype == torch.bfloat16 else 0), ctypes.c_int(1 if ctx.relu else 0), ctypes.c_int(size),
-                _lib.stream_ptr(x.device)))
-            if done:
-                _lib.count_launches(1)
-                return dx, dres, (grads[0] if weight is not None else None), (grads[1] if ctx.has_bias else None), None, None, None, None, None, None, None, None, None
         coef = torch.empty(3, c, dtype=torch.float32, device=x.device)
         acc, counter = _workspace(x.device, c)
         err = lib.fl4h_bn_bwd(

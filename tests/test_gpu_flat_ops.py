@@ -267,15 +267,13 @@ def test_multi_tensor_step_matches_reference(adam: bool) -> None:
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False), (False, True)])
 @pytest.mark.parametrize("shape", [(32, 64, 32, 32), (8, 512, 4, 4), (5, 24, 7, 3), (64, 64, 32, 32)])
-@pytest.mark.parametrize("fused", ["cluster", "1", "0"])
+@pytest.mark.parametrize("fused", ["1", "0"])
 def test_fused_batchnorm_act_matches_reference(dtype, relu, with_res, shape, fused, monkeypatch) -> None:
-    """bn_act.cu / bn_cluster.cu (training fwd/bwd + eval fwd) vs F.batch_norm + add + relu in fp32; ``fused`` selects
-    the single-cluster DSMEM kernels, the grid-wide cooperative kernel or the two-kernel chain; the last shape exceeds
-    the register-cached tile sizes."""
+    """bn_act.cu (training fwd/bwd + eval fwd) vs F.batch_norm + add + relu in fp32; ``fused`` selects the grid-wide
+    cooperative kernel or the two-kernel chain; the last shape exceeds the register-cached tile sizes."""
     from fl4health_b200.ops.bn_act import batch_norm_act, batch_norm_act_reference, kernel_eligible
 
     monkeypatch.setenv("FL4H_BN_FUSED", "0" if fused == "0" else "1")
-    monkeypatch.setenv("FL4H_BN_CLUSTER_MAX_BYTES", str(1 << 30) if fused == "cluster" else "0")
 
     torch.manual_seed(1)
     dev = torch.device("cuda")
