@@ -1,8 +1,10 @@
 """Per-split metric bookkeeping (parity: ``fl4health/metrics/metric_managers.py:11-86``).
 
-Result keys keep the reference's schema ``"{manager} - {prediction_key} - {metric}"``.  Unlike the reference,
-``clear`` resets the metric objects *in place* when possible (``Metric.clear``) so device-side counters referenced
-by a captured CUDA graph keep their addresses; ``reset`` drops them entirely.
+A manager is handed prototype metrics once and a dictionary of predictions per batch.  On the first batch it *binds* a
+private copy of every prototype to every prediction key; from then on an update is a walk over that flat binding list.
+Result keys keep the reference's schema ``"{manager} - {prediction_key} - {metric}"``.  ``clear`` resets the bound
+metric objects *in place* (device-side counters referenced by a captured CUDA graph keep their addresses); ``reset``
+drops the bindings, so the next batch may bring different prediction keys.
 """
 
 from __future__ import annotations
@@ -16,46 +18,56 @@ from fl4health_b200.common.typing import Metrics
 from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.utils.typing import TorchPredType, TorchTargetType
 
+_KEY_MISMATCH = (
+    "Received a dict with multiple targets, but the keys of the targets do not match the keys of the "
+    "predictions. Please pass a single target or ensure the keys between preds and target are the same"
+)
+
 
 class MetricManager:
     def __init__(self, metrics: Sequence[Metric], metric_manager_name: str) -> None:
         self.original_metrics = metrics
         self.metric_manager_name = metric_manager_name
-        self.metrics_per_prediction_type: dict[str, Sequence[Metric]] = {}
+        self._bound: list[tuple[str, Metric]] = []  # (prediction key, this key's own copy of a prototype), update order
+
+    @property
+    def metrics_per_prediction_type(self) -> dict[str, Sequence[Metric]]:
+        """The bindings grouped by prediction key (the reference's attribute)."""
+        grouped: dict[str, list[Metric]] = {}
+        for key, metric in self._bound:
+            grouped.setdefault(key, []).append(metric)
+        return grouped  # type: ignore[return-value]
+
+    def _bind(self, prediction_keys: Sequence[str]) -> None:
+        self._bound = [(key, copy.deepcopy(prototype)) for key in prediction_keys for prototype in self.original_metrics]
+
+    @staticmethod
+    def _target_for(key: str, target: TorchTargetType) -> torch.Tensor:
+        if isinstance(target, torch.Tensor):
+            return target
+        return next(iter(target.values())) if len(target) == 1 else target[key]
 
     def update(self, preds: TorchPredType, target: TorchTargetType) -> None:
-        if not self.metrics_per_prediction_type:
-            self.metrics_per_prediction_type = {key: copy.deepcopy(self.original_metrics) for key in preds}
-        if isinstance(target, dict):
-            if len(target) > 1:
-                self.check_target_prediction_keys_equal(preds, target)
-            else:
-                target = next(iter(target.values()))
-        assert len(preds) == len(self.metrics_per_prediction_type)
-        for prediction_key, pred in preds.items():
-            tgt = target if isinstance(target, torch.Tensor) else target[prediction_key]
-            for metric in self.metrics_per_prediction_type[prediction_key]:
-                metric.update(pred, tgt)
+        if not self._bound:
+            self._bind(list(preds))
+        if isinstance(target, dict) and len(target) > 1:
+            self.check_target_prediction_keys_equal(preds, target)
+        assert {key for key, _ in self._bound} == set(preds), "prediction keys changed between batches: call reset() first"
+        for key, metric in self._bound:
+            metric.update(preds[key], self._target_for(key, target))
 
     def compute(self) -> Metrics:
         results: Metrics = {}
-        for prediction_key, metrics in self.metrics_per_prediction_type.items():
-            for metric in metrics:
-                results.update(metric.compute(f"{self.metric_manager_name} - {prediction_key}"))
+        for key, metric in self._bound:
+            results.update(metric.compute(f"{self.metric_manager_name} - {key}"))
         return results
 
     def clear(self) -> None:
-        for metrics in self.metrics_per_prediction_type.values():
-            for metric in metrics:
-                metric.clear()
+        for _, metric in self._bound:
+            metric.clear()
 
     def reset(self) -> None:
-        self.metrics_per_prediction_type = {}
+        self._bound = []
 
-    def check_target_prediction_keys_equal(
-        self, preds: dict[str, torch.Tensor], target: dict[str, torch.Tensor]
-    ) -> None:
-        assert target.keys() == preds.keys(), (
-            "Received a dict with multiple targets, but the keys of the targets do not match the keys of the "
-            "predictions. Please pass a single target or ensure the keys between preds and target are the same"
-        )
+    def check_target_prediction_keys_equal(self, preds: dict[str, torch.Tensor], target: dict[str, torch.Tensor]) -> None:
+        assert target.keys() == preds.keys(), _KEY_MISMATCH
