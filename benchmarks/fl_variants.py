@@ -27,6 +27,12 @@ from fl4health_b200.servers.client_manager import SimpleClientManager
 GROUPS = {"cifar_fedavg": ["fedavg"], "scaffold_fedprox": ["scaffold", "fedprox"], "fedper_ditto_dp": ["fedper", "ditto", "dp_sgd"]}
 
 
+def _rng_devices() -> list[int]:
+    """Devices whose generators ``torch.manual_seed`` would rewind: forked together with the CPU generator so that a
+    seeded model construction leaves the client's random streams (mask sampling, dropout, DP noise) where they were."""
+    return [torch.cuda.current_device()] if torch.cuda.is_available() and torch.cuda.is_initialized() else []
+
+
 class _ResNetFeatures(nn.Module):
     def __init__(self) -> None:
         super().__init__()
@@ -85,7 +91,7 @@ def build(variant: str, hooks: type, ctx: Any, engine: Any, rounds: int, local_s
 
     def seeded(factory: Any) -> Any:
         def make() -> nn.Module:
-            with torch.random.fork_rng(devices=[]):  # same initialisation everywhere, ambient random stream untouched
+            with torch.random.fork_rng(devices=_rng_devices()):  # same initialisation everywhere, ambient random stream untouched
                 torch.manual_seed(1234)
                 return factory()
         return make

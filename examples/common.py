@@ -70,6 +70,12 @@ def client_datasets(config: dict[str, Any], client_index: int) -> tuple[TensorDa
     return train, val
 
 
+def _rng_devices() -> list[int]:
+    """Devices whose generators ``torch.manual_seed`` would rewind: forked together with the CPU generator so that a
+    seeded model construction leaves the client's random streams (mask sampling, dropout, DP noise) where they were."""
+    return [torch.cuda.current_device()] if torch.cuda.is_available() and torch.cuda.is_initialized() else []
+
+
 class ExampleClientMixin:
     """Hooks shared by every example client (combine as ``class C(ExampleClientMixin, SomeClient)``).  The scenario
     sets ``example_config``, ``client_index`` and ``model_factory`` on the instance."""
@@ -81,7 +87,7 @@ class ExampleClientMixin:
     def get_model(self, config: Config) -> nn.Module:
         # every client starts from the same initialisation, without rewinding the process' random stream (which the
         # client keeps using for mask sampling, dropout, DP noise ...)
-        with torch.random.fork_rng(devices=[]):
+        with torch.random.fork_rng(devices=_rng_devices()):
             torch.manual_seed(self.example_config["seed"])
             return self.model_factory()
 
