@@ -27,6 +27,28 @@ def aggregate(self, params):
 
 
 S.Scaffold.aggregate = aggregate
+
+from fl4health_b200.parallel import spmd as P
+import torch.distributed as dist
+
+orig_ws = P.SpmdContext.weighted_sum_flat
+
+
+def checked(self, local, coef_by_rank, numel, out=None, epilogue=None, int_local=None):
+    expect = None
+    if local is not None and self.world_size > 1 and not epilogue:
+        expect = local[:numel].detach().clone() * coef_by_rank[self.rank]
+        dist.all_reduce(expect)
+    got = orig_ws(self, local, coef_by_rank, numel, out=out, epilogue=epilogue, int_local=int_local)
+    if expect is not None:
+        torch.cuda.synchronize()
+        print(f"DBG r{self.rank} weighted_sum_flat numel={numel} fused={self.fused is not None and self.fused.owns(local)} "
+              f"max|fused-nccl|={float((got[:numel] - expect).abs().max()):.3e} |expect|={float(expect.norm()):.4f} |got|={float(got[:numel].norm()):.4f} "
+              f"local_ptr_off={local.data_ptr() % (1 << 28)}", flush=True)
+    return got
+
+
+P.SpmdContext.weighted_sum_flat = checked
 from examples.run import main
 
 main(["scaffold_example", "--spmd", "--rounds", "3"])
