@@ -159,7 +159,7 @@ class ParameterArena:
                     src.data = view
                 else:
                     owner, leaf = self._find_owner(entry.name)
-                    owner._buffers[leaf] = view
+                    owner._buffers[leaf] = _own_version_alias(view)
             # integer buffers (num_batches_tracked ...) live in ONE int64 buffer so they aggregate with one op
             int_sizes = [(name, t.numel()) for name, t in self.int_state.items() if t.dtype == torch.int64]
             if int_sizes:
@@ -420,6 +420,16 @@ class TrainableRegionLayout:
 
     def same_layout(self, other: object) -> bool:
         return isinstance(other, TrainableRegionLayout) and self.arena.same_layout(other.arena)
+
+
+def _own_version_alias(view: torch.Tensor) -> torch.Tensor:
+    """The same memory as ``view`` behind a tensor with its OWN autograd version counter.  Views of one base share the
+    base's counter: BatchNorm's in-place running-statistics update of one layer would then invalidate what another
+    layer saved for its backward ("modified by an inplace operation") -- always the case when the arena is carved out
+    of a single symmetric-memory segment, where every region of every arena is a view of the same base tensor."""
+    alias = torch.empty(0, dtype=view.dtype, device=view.device)
+    alias.data = view
+    return alias
 
 
 def _as_tensor(arr: object, device: torch.device) -> torch.Tensor:
