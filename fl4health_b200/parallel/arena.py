@@ -327,16 +327,20 @@ class ParameterArena:
                     self.refresh_shadow()
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
+            destinations, sources = [], []
             for key, arr in zip(keys, arrays):
                 key = self.aliases.get(key, key)
                 t = _as_tensor(arr, self.device)
                 if key in self.by_name:
                     dst = self.view(key)
                     assert dst.shape == t.shape, f"shape mismatch for {key}: {tuple(dst.shape)} vs {tuple(t.shape)}"
-                    dst.copy_(t, non_blocking=True)
+                    destinations.append(dst)
+                    sources.append(t if t.dtype == dst.dtype else t.to(dst.dtype))
                 else:
                     dst_int = self.int_state[key]
                     dst_int.copy_(t.to(dst_int.dtype).reshape(dst_int.shape))
+            if destinations:  # partial payloads (FedPer, FedRep, layer exchange): a couple of batched launches, not one per tensor
+                torch._foreach_copy_(destinations, sources, non_blocking=True)
             self.refresh_shadow()
 
     def _fused_pull(self, src_flat: torch.Tensor) -> bool:
