@@ -39,6 +39,11 @@ class NDArrays(list):
     aux_layout: Any = None
     # all integer entries (``num_batches_tracked`` ...) as one int64 tensor, in list order, when available
     int_flat: torch.Tensor | None = None
+    # a NAMED SUBSET of an arena (partial exchange: FedPer, FedRep, FedBN ...): the arena-shaped buffer the entries are
+    # views of, the arena (layout) and the state keys, so subsets can ride the whole-arena kernels
+    subset_flat: torch.Tensor | None = None
+    subset_layout: Any = None
+    subset_names: tuple[str, ...] | None = None
 
     def __init__(self, iterable: Any = (), flat: torch.Tensor | None = None, layout: Any = None) -> None:
         super().__init__(iterable)
@@ -84,6 +89,9 @@ class Parameters:
     int_flat: Any = None  # all integer entries as one int64 tensor (see ``NDArrays.int_flat``)
     aux_flat: Any = None  # second arena-shaped block packed behind the model state (see ``NDArrays.aux_flat``)
     aux_layout: Any = None
+    subset_flat: Any = None  # named arena subset (see ``NDArrays.subset_flat``)
+    subset_layout: Any = None
+    subset_names: Any = None
 
 
 def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
@@ -95,6 +103,9 @@ def ndarrays_to_parameters(ndarrays: list[NDArray] | NDArrays) -> Parameters:
         int_flat=getattr(ndarrays, "int_flat", None),
         aux_flat=getattr(ndarrays, "aux_flat", None),
         aux_layout=getattr(ndarrays, "aux_layout", None),
+        subset_flat=getattr(ndarrays, "subset_flat", None),
+        subset_layout=getattr(ndarrays, "subset_layout", None),
+        subset_names=getattr(ndarrays, "subset_names", None),
     )
 
 
@@ -105,6 +116,8 @@ def parameters_to_ndarrays(parameters: Parameters) -> NDArrays:
     arrays = NDArrays(parameters.tensors, flat=parameters.flat, layout=parameters.layout)
     arrays.int_flat = getattr(parameters, "int_flat", None)
     arrays.aux_flat, arrays.aux_layout = getattr(parameters, "aux_flat", None), getattr(parameters, "aux_layout", None)
+    for tag in ("subset_flat", "subset_layout", "subset_names"):
+        setattr(arrays, tag, getattr(parameters, tag, None))
     return arrays
 
 

@@ -29,16 +29,18 @@ class MetricManager:
         self.original_metrics = metrics
         self.metric_manager_name = metric_manager_name
         self._bound: list[tuple[str, Metric]] = []  # (prediction key, this key's own copy of a prototype), update order
+        self._bound_keys: tuple[str, ...] | None = None  # None: nothing bound yet (a manager may have no metrics at all)
 
     @property
     def metrics_per_prediction_type(self) -> dict[str, Sequence[Metric]]:
         """The bindings grouped by prediction key (the reference's attribute)."""
-        grouped: dict[str, list[Metric]] = {}
+        grouped: dict[str, list[Metric]] = {key: [] for key in self._bound_keys or ()}
         for key, metric in self._bound:
             grouped.setdefault(key, []).append(metric)
         return grouped  # type: ignore[return-value]
 
     def _bind(self, prediction_keys: Sequence[str]) -> None:
+        self._bound_keys = tuple(prediction_keys)
         self._bound = [(key, copy.deepcopy(prototype)) for key in prediction_keys for prototype in self.original_metrics]
 
     @staticmethod
@@ -48,11 +50,11 @@ class MetricManager:
         return next(iter(target.values())) if len(target) == 1 else target[key]
 
     def update(self, preds: TorchPredType, target: TorchTargetType) -> None:
-        if not self._bound:
+        if self._bound_keys is None:
             self._bind(list(preds))
         if isinstance(target, dict) and len(target) > 1:
             self.check_target_prediction_keys_equal(preds, target)
-        assert {key for key, _ in self._bound} == set(preds), "prediction keys changed between batches: call reset() first"
+        assert set(self._bound_keys or ()) == set(preds), "prediction keys changed between batches: call reset() first"
         for key, metric in self._bound:
             metric.update(preds[key], self._target_for(key, target))
 
@@ -67,7 +69,7 @@ class MetricManager:
             metric.clear()
 
     def reset(self) -> None:
-        self._bound = []
+        self._bound, self._bound_keys = [], None
 
     def check_target_prediction_keys_equal(self, preds: dict[str, torch.Tensor], target: dict[str, torch.Tensor]) -> None:
         assert target.keys() == preds.keys(), _KEY_MISMATCH

@@ -301,7 +301,33 @@ class ParameterArena:
             if len(self._views_cache) > 8:
                 self._views_cache.pop(next(iter(self._views_cache)))
             self._views_cache[(base.data_ptr(), base.numel())] = NDArrays(out, flat=base, layout=self)
+        else:  # a named subset of the arena: tagged so that it can ride the whole-arena collectives / copies
+            out.subset_flat, out.subset_layout, out.subset_names = base, self, tuple(keys)
         return out
+
+    def subset_plan(self, names: tuple[str, ...]) -> tuple[list[tuple[int, int]], list[int]]:
+        """For a named subset: the arena element ranges its float entries cover (adjacent entries merged -- a FedPer
+        feature extractor is two ranges: its parameters and its BatchNorm buffers) and the list positions of its
+        integer entries.  Cached per subset."""
+        cache = self.__dict__.setdefault("_subset_plans", {})
+        plan = cache.get(names)
+        if plan is None:
+            spans, int_positions = [], []
+            for position, name in enumerate(names):
+                key = self.aliases.get(name, name)
+                if key in self.by_name:
+                    entry = self.by_name[key]
+                    spans.append((entry.offset, _round_up(entry.end, ALIGN)))
+                else:
+                    int_positions.append(position)
+            merged: list[tuple[int, int]] = []
+            for start, end in sorted(set(spans)):
+                if merged and start <= merged[-1][1]:
+                    merged[-1] = (merged[-1][0], max(merged[-1][1], end))
+                else:
+                    merged.append((start, end))
+            plan = cache[names] = ([(a, min(b, self.flat.numel())) for a, b in merged], int_positions)
+        return plan
 
     def load_ndarrays(self, arrays: list, names: Iterable[str] | None = None) -> None:
         """Copy a list of arrays into the arena.  A single flat copy when the source is arena-shaped."""
@@ -327,6 +353,21 @@ class ParameterArena:
                     self.refresh_shadow()
                 return
             assert len(keys) == len(arrays), f"expected {len(keys)} arrays, received {len(arrays)}"
+            subset_flat = getattr(arrays, "subset_flat", None)
+            subset_layout = getattr(arrays, "subset_layout", None)
+            if (subset_flat is not None and isinstance(subset_layout, ParameterArena) and subset_layout.same_layout(self)
+                    and getattr(arrays, "subset_names", None) == tuple(keys) and subset_flat.numel() == self.flat.numel()
+                    and subset_flat.dtype == self.flat.dtype and subset_flat.device == self.flat.device):
+                # the payload is an arena-shaped buffer + the names that matter in it: copy the few ranges they cover
+                ranges, int_positions = self.subset_plan(tuple(keys))
+                for start, end in ranges:
+                    self.flat[start:end].copy_(subset_flat[start:end], non_blocking=True)
+                if int_positions:
+                    targets = [self.int_state[self.aliases.get(keys[i], keys[i])] for i in int_positions]
+                    torch._foreach_copy_(targets, [_as_tensor(arrays[i], self.device).to(t.dtype).reshape(t.shape)
+                                                   for i, t in zip(int_positions, targets)], non_blocking=True)
+                self.refresh_shadow()
+                return
             destinations, sources = [], []
             for key, arr in zip(keys, arrays):
                 key = self.aliases.get(key, key)

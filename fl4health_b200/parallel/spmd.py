@@ -73,6 +73,8 @@ class PayloadSpec:
     main_len: int = 0
     aux_numel: int | None = None
     aux_len: int = 0
+    subset_numel: int | None = None  # the whole list is a named subset of an arena of this many elements ...
+    subset_names: tuple[str, ...] | None = None  # ... namely these state keys (list order)
 
     @property
     def is_arena(self) -> bool:
@@ -102,8 +104,13 @@ class PayloadSpec:
                 np_arr = np.asarray(arr)
                 small = np_arr.dtype.kind in ("U", "S", "O") or np_arr.size <= 64
                 entries.append((tuple(np_arr.shape), f"numpy.{np_arr.dtype}", np_arr if small else None))
-        return PayloadSpec(entries, int(flat.numel()) if main_len else None, main_len,
+        spec = PayloadSpec(entries, int(flat.numel()) if main_len else None, main_len,
                            int(aux_flat.numel()) if aux_len else None, aux_len)
+        subset_flat, subset_names = getattr(arrays, "subset_flat", None), getattr(arrays, "subset_names", None)
+        if subset_flat is not None and subset_names is not None and len(subset_names) == len(arrays) and not main_len:
+            spec.subset_numel, spec.subset_names = int(subset_flat.numel()), tuple(subset_names)
+            spec.entries = [(shape, dtype, None) if dtype.startswith("torch.") else (shape, dtype, inline) for shape, dtype, inline in entries]
+        return spec
 
 
 class RemoteNDArrays(NDArrays):
@@ -122,6 +129,8 @@ class RemoteNDArrays(NDArrays):
 
 def _slice_spec(spec: PayloadSpec, start: int | None, stop: int | None, total: int) -> PayloadSpec:
     first, last, _ = slice(start, stop).indices(total)
+    if first == 0 and last == total:
+        return spec
     entries = spec.entries[first:last]
     if spec.flat_numel is not None and first == 0 and last >= spec.main_len:
         keeps_aux = spec.aux_numel is not None and last >= spec.main_len + spec.aux_len
@@ -428,6 +437,8 @@ def _tag_local(arrays: NDArrays, ctx: SpmdContext) -> NDArrays:
     tagged = _LocalPayload(arrays, flat=getattr(arrays, "flat", None), layout=getattr(arrays, "layout", None))
     tagged.int_flat = getattr(arrays, "int_flat", None)
     tagged.aux_flat, tagged.aux_layout = getattr(arrays, "aux_flat", None), getattr(arrays, "aux_layout", None)
+    for tag in ("subset_flat", "subset_layout", "subset_names"):
+        setattr(tagged, tag, getattr(arrays, tag, None))
     tagged.ctx, tagged.rank, tagged.spec = ctx, ctx.rank, PayloadSpec.of(arrays)  # type: ignore[attr-defined]
     return tagged
 

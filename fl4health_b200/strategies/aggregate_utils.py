@@ -128,6 +128,9 @@ def _spmd_weighted_combine(
         if nds.rank == ctx.rank:
             local = nds
     assert spec is not None
+    subset = _subset_combine(ctx, arrays, coef_by_rank, local, spec) if epilogue is None else None
+    if subset is not None:
+        return subset
     arena_route = spec.is_arena
     if arena_route:
         layout = local.layout if local is not None else None
@@ -192,6 +195,53 @@ def _spmd_weighted_combine(
     for i, shape, size in zip(tensor_idx, shapes, sizes):
         out[i] = reduced[cursor : cursor + size].view(shape)
         cursor += size
+    return out
+
+
+def _subset_combine(ctx: Any, arrays: Sequence[NDArrays], coef_by_rank: list[float], local: NDArrays | None, spec: Any) -> NDArrays | None:
+    """Partial exchange (FedPer, FedRep, FedBN ...): every payload is the same NAMED SUBSET of its rank's arena.  The
+    whole arenas are reduced with the one fused launch of a full exchange (a fraction of a millisecond; what is not
+    exchanged is averaged too and simply never read) and the result is handed out as views of the result buffer at the
+    subset's offsets -- instead of concatenating, reducing and re-slicing a hundred tensors in Python every round."""
+    if spec.subset_numel is None or local is None or len(arrays) < ctx.world_size:
+        return None
+    if any(nds.spec.subset_numel != spec.subset_numel or nds.spec.subset_names != spec.subset_names for nds in arrays):
+        return None
+    layout, local_flat = getattr(local, "subset_layout", None), getattr(local, "subset_flat", None)
+    if layout is None or local_flat is None or not hasattr(layout, "subset_plan"):
+        return None
+    names = spec.subset_names
+    int_flat = getattr(layout, "int_flat", None)
+    out_flat = _result_buffer(layout, local_flat) if ctx.fused is None else None
+    result_flat = ctx.weighted_sum_flat(local_flat, coef_by_rank, spec.subset_numel, out=out_flat, int_local=int_flat)
+    cache = layout.__dict__.setdefault("_subset_result_views", {})
+    key = (result_flat.data_ptr(), names)
+    views = cache.get(key)
+    if views is None:
+        if len(cache) > 8:
+            cache.pop(next(iter(cache)))
+        views = cache[key] = [layout.view(name, result_flat) if layout.aliases.get(name, name) in layout.by_name else None for name in names]
+    out = NDArrays(views)
+    _, int_positions = layout.subset_plan(names)
+    if int_positions:
+        reduced = getattr(ctx, "last_int_reduced", None)
+        all_ints = [key for key in layout.state_keys if key in layout.int_state]
+        if reduced is None or reduced.numel() != sum(layout.int_state[k].numel() for k in all_ints):
+            reduced = int_flat.to(torch.float64) * coef_by_rank[ctx.rank]
+            if ctx.world_size > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(reduced)
+            reduced = reduced.to(torch.int64)
+        offsets, cursor = {}, 0
+        for key in all_ints:
+            offsets[key] = cursor
+            cursor += layout.int_state[key].numel()
+        for position in int_positions:
+            key = layout.aliases.get(names[position], names[position])
+            state = layout.int_state[key]
+            out[position] = reduced[offsets[key]:offsets[key] + state.numel()].view(state.shape).to(state.dtype)
+    out.subset_flat, out.subset_layout, out.subset_names = result_flat, layout, names
     return out
 
 

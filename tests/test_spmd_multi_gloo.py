@@ -85,10 +85,12 @@ def _run_scenario_spmd(scenario: str, port: int, *extra: str) -> list[dict]:
 
 
 @pytest.mark.parametrize("scenario,port", [("scaffold_example", 29661), ("dynamic_layer_exchange_example", 29662),
-                                           ("client_level_dp_example", 29663)])
+                                           ("client_level_dp_example", 29663), ("fedper_example", 29664), ("fedbn_example", 29665)])
 def test_strategies_that_need_whole_payloads_run_in_spmd_and_match_simulation(scenario: str, port: int) -> None:
     """SCAFFOLD (packed variates), dynamic layer exchange and client-level DP either reduce packed side payloads or
-    materialise every client's payload on every rank.  The owner of a payload used to skip that broadcast (deadlock)."""
+    materialise every client's payload on every rank (the owner of a payload used to skip that broadcast: deadlock);
+    FedPer / FedBN exchange a named SUBSET of the arena, which rides the whole-arena reduction and is pulled as a few
+    range copies."""
     from examples.run import main
 
     spmd = _run_scenario_spmd(scenario, port)
