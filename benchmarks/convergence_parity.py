@@ -57,6 +57,7 @@ def main() -> None:
     parser.add_argument("--rounds", type=int, default=30)
     parser.add_argument("--modes", nargs="+", default=["fp32-eager", "fp32", "bf16"])
     parser.add_argument("--collectives", nargs="+", default=["auto"])
+    parser.add_argument("--lr", type=float, default=0.003)
     args = parser.parse_args()
     ctx = SpmdContext()
 
@@ -71,7 +72,7 @@ def main() -> None:
             return nn.CrossEntropyLoss()
 
         def get_optimizer(self, config):  # noqa: ANN001, ANN202
-            return torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9)
+            return torch.optim.SGD(self.model.parameters(), lr=args.lr, momentum=0.9)
 
     for mode in args.modes:
         for collectives in args.collectives:
@@ -89,7 +90,7 @@ def main() -> None:
             accuracy = [round(float(v), 4) for _, v in history.metrics_distributed.get("val - prediction - accuracy", [])]
             if ctx.rank == 0:
                 print("PARITY " + json.dumps({"mode": mode, "collectives": "fused" if (ctx.fused is not None and collectives != "nccl") else
-                                              ("nccl" if ctx.world_size > 1 else "local"), "world": ctx.world_size, "rounds": args.rounds,
+                                              ("nccl" if ctx.world_size > 1 else "local"), "world": ctx.world_size, "rounds": args.rounds, "lr": args.lr,
                                               "final_val_loss": losses[-1], "final_val_accuracy": accuracy[-1] if accuracy else None,
                                               "val_loss_every_5": losses[4::5], "val_accuracy_every_5": accuracy[4::5]}), flush=True)
     ctx.shutdown()
