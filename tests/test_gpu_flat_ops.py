@@ -518,12 +518,14 @@ def test_bert_layer_fused_matches_stock_modules(monkeypatch) -> None:
     model = model.to(torch.bfloat16)
     before = ops.launch_count()
     logits = model(ids, mask)
-    assert ops.launch_count() - before == 2 * 4 + 2  # qkv, attn_out, ffn_in, ffn_out per layer + pooler + classifier
+    # per layer: qkv, attention (tcgen05, one launch), attn_out, ffn_in, ffn_out; + pooler + classifier.  (The model was cast
+    # wholesale to bf16, LayerNorm parameters included, so the fused LayerNorm kernel -- fp32 affine parameters -- stands aside.)
+    assert ops.launch_count() - before == 2 * 5 + 2
     monkeypatch.setenv("FL4H_TC_LINEAR", "auto")
     before = ops.launch_count()
     with torch.no_grad():
         auto_logits = model(ids, mask)
-    assert ops.launch_count() - before == 0  # auto: problems this small stay on the library GEMMs
+    assert ops.launch_count() - before == 2  # auto: GEMMs this small stay on the library; the two attention launches remain
     assert torch.allclose(auto_logits.float(), logits.float(), rtol=5e-2, atol=5e-2)
     monkeypatch.setenv("FL4H_TC_LINEAR", "always")
     torch.nn.functional.cross_entropy(logits.float(), labels).backward()
