@@ -145,16 +145,13 @@ __device__ __forceinline__ void load_key_bias(float* bias, const uint8_t* mask, 
     bias[k] = on ? 0.f : -CUDART_INF_F;
 }
 
-// Resources are recycled along the dependency chain so that four CTAs fit on an SM (384 CTAs = one wave): P is written
-// over the Q | K tiles (dead once S = Q K^T has completed) and O accumulates in S's first TMEM columns (every row of S
-// has been read when the second MMA is issued): 48 KB of shared memory and 128 TMEM columns per CTA.
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads)
 attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, const uint8_t* __restrict__ mask,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t *q_s = smem, *k_s = smem + kTile, *v_s = smem + 2 * kTile, *p_s = smem;   // P (32 KB) recycles Q | K
-    float* bias = reinterpret_cast<float*>(v_s + kTile);
+    uint8_t *q_s = smem, *k_s = smem + kTile, *v_s = smem + 2 * kTile, *p_s = smem + 3 * kTile;
+    float* bias = reinterpret_cast<float*>(p_s + kProb);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias + kT);        // [0] Q,K landed  [1] V landed  [2] S ready  [3] O ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
@@ -166,7 +163,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     load_key_bias(bias, mask, b, g.seq);
@@ -229,8 +226,8 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
         constexpr uint32_t idesc_o = make_idesc(kT, kD, false, true);
 #pragma unroll
         for (int k = 0; k < kT / 16; ++k)                           // contraction over the 128 keys
-            umma(tmem, desc_kmajor(smem_u32(p_s) + (k >> 2) * kTile, k & 3), desc_mnmajor(smem_u32(v_s), k, kTile), idesc_o,
-                 k > 0 ? 1u : 0u);                                   // O lands on S's first 64 columns
+            umma(tmem + kT, desc_kmajor(smem_u32(p_s) + (k >> 2) * kTile, k & 3), desc_mnmajor(smem_u32(v_s), k, kTile), idesc_o,
+                 k > 0 ? 1u : 0u);
         umma_commit(bars + 3);
     }
     mbar_wait(bars + 3, 0);
@@ -240,7 +237,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
 #pragma unroll 1
     for (int c0 = 0; c0 < kD; c0 += 32) {                           // (warp-collective TMEM loads: rows past the sequence take part)
         float o[32];
-        tmem_ld32(lane_base + c0, o);
+        tmem_ld32(lane_base + kT + c0, o);
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[j] *= inv;
         if (tid < g.seq) store_row_bf16(dst, o, c0);
@@ -249,23 +246,21 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
     if (tid < g.seq) lse[((int64_t)b * g.heads + h) * g.seq + tid] = (m + log2f(row_sum)) * 0.6931471805599453f;
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
 }
 
-// TMEM columns of the backward accumulators.  dQ is accumulated last and reuses the first columns of S / dP (all rows of dP
-// have been read by then); dS is written IN PLACE over P (each thread rewrites the chunks of its own row, after the dV
-// MMA that reads P has completed): 96 KB of shared memory and 256 TMEM columns per CTA, two CTAs per SM.
-constexpr int kColS = 0, kColDV = 128, kColDK = 192, kColDQ = 0;
+// TMEM columns of the backward accumulators
+constexpr int kColS = 0, kColDV = 128, kColDK = 192, kColDQ = 256;
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads)
 attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, const uint8_t* __restrict__ mask,
                      const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *q_s = smem, *k_s = smem + kTile, *v_s = smem + 2 * kTile, *do_s = smem + 3 * kTile;
-    uint8_t *p_s = smem + 4 * kTile, *ds_s = p_s;
-    float* bias = reinterpret_cast<float*>(p_s + kProb);
+    uint8_t *p_s = smem + 4 * kTile, *ds_s = p_s + kProb;
+    float* bias = reinterpret_cast<float*>(ds_s + kProb);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias + kT);        // [0] Q,K  [1] V,dO  [2] S  [3] dP,dV  [4] dK,dQ
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
@@ -277,7 +272,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     load_key_bias(bias, mask, b, g.seq);
@@ -404,7 +399,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const AttnGeom g, co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -436,8 +431,8 @@ int token_map(CUtensorMap* map, const void* base, int cols, int seq, int batch) 
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-constexpr int kFwdSmem = 3 * kTile + kT * 4 + 4 * 8 + 16 + 1024;
-constexpr int kBwdSmem = 4 * kTile + kProb + kT * 4 + 5 * 8 + 16 + 1024;
+constexpr int kFwdSmem = 3 * kTile + kProb + kT * 4 + 4 * 8 + 16 + 1024;
+constexpr int kBwdSmem = 4 * kTile + 2 * kProb + kT * 4 + 5 * 8 + 16 + 1024;
 
 }  // namespace
 
