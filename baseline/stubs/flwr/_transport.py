@@ -12,6 +12,7 @@ import threading
 import time
 import uuid
 from multiprocessing.connection import Client as _Connect
+from multiprocessing import AuthenticationError
 from multiprocessing.connection import Connection, Listener
 
 from .common.typing import (
@@ -83,7 +84,9 @@ class Acceptor:
     """Accept loop of the server process."""
 
     def __init__(self, address: str, client_manager) -> None:  # noqa: ANN001
-        self.listener = Listener(_split(address), family="AF_INET", authkey=_AUTH)
+        # a real backlog: every client of the federation connects within the same few milliseconds (the default of 1
+        # makes the kernel drop SYNs; clients then retry while their abandoned half-open attempts are still queued)
+        self.listener = Listener(_split(address), family="AF_INET", backlog=256, authkey=_AUTH)
         self.client_manager = client_manager
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.stopping = False
@@ -94,10 +97,14 @@ class Acceptor:
     def _loop(self) -> None:
         while not self.stopping:
             try:
-                conn = self.listener.accept()
+                conn = self.listener.accept()  # includes the authentication handshake
+                hello = conn.recv()
+            except (EOFError, AuthenticationError, ConnectionError):
+                continue  # an attempt its client gave up on (it retries on a new connection): not a reason to stop accepting
             except OSError:
-                return
-            hello = conn.recv()
+                if self.stopping:
+                    return
+                continue
             cid = str(hello.get("cid") or uuid.uuid4().hex)
             self.client_manager.register(SocketClientProxy(cid, conn))
 
@@ -118,7 +125,7 @@ def start_client(*, server_address: str, client, cid: str | None = None, connect
         try:
             conn = _Connect(_split(server_address), family="AF_INET", authkey=_AUTH)
             break
-        except (ConnectionRefusedError, OSError):
+        except (ConnectionRefusedError, OSError, EOFError, AuthenticationError):
             time.sleep(0.1)
     if conn is None:
         raise ConnectionError(f"could not reach flwr-shim server at {server_address}")

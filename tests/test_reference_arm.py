@@ -79,3 +79,34 @@ def test_reference_arm_runs_the_unmodified_reference_on_cpu() -> None:
         diff = subprocess.run(["diff", "-r", "-q", "-x", "__pycache__", "/root/reference/fl4health",
                                str(ROOT / "baseline" / "_ref" / "fl4health")], capture_output=True, text=True)
         assert diff.returncode == 0, diff.stdout[:500]
+
+
+def test_shim_accept_loop_survives_abandoned_connections_and_a_connect_storm() -> None:
+    """Eight clients connect within the same instant (one rank per GPU does) and some connection attempts are dropped
+    half-way through the authentication handshake: the accept loop has to keep accepting.  (It used to die with the
+    first EOFError, after which the remaining clients were never registered and an 8-GPU reference run hung.)"""
+    out = _run(
+        "import threading, socket, time, numpy as np, flwr\n"
+        "from flwr.client import NumPyClient, start_client\n"
+        "from flwr.server import start_server, ServerConfig\n"
+        "from flwr.server.strategy import FedAvg\n"
+        "from flwr.common import ndarrays_to_parameters\n"
+        "class C(NumPyClient):\n"
+        "    def fit(s,p,c): return [p[0]+1.0], 1, {}\n"
+        "    def evaluate(s,p,c): return float(p[0].sum()), 1, {}\n"
+        "sock=socket.socket(); sock.bind(('127.0.0.1',0)); port=sock.getsockname()[1]; sock.close()\n"
+        "def rude():\n"
+        "    for _ in range(200):\n"
+        "        try:\n"
+        "            s=socket.create_connection(('127.0.0.1',port),timeout=1); s.close(); return\n"
+        "        except OSError: time.sleep(0.05)\n"
+        "K=8\n"
+        "ts=[threading.Thread(target=rude) for _ in range(4)]\n"
+        "ts+=[threading.Thread(target=start_client,kwargs=dict(server_address=f'127.0.0.1:{port}',client=C().to_client(),cid=str(i))) for i in range(K)]\n"
+        "[t.start() for t in ts]\n"
+        "h=start_server(server_address=f'127.0.0.1:{port}',config=ServerConfig(num_rounds=2),"
+        "strategy=FedAvg(min_fit_clients=K,min_evaluate_clients=K,min_available_clients=K,initial_parameters=ndarrays_to_parameters([np.zeros(2)])))\n"
+        "[t.join(30) for t in ts]\n"
+        "print(h.losses_distributed)\n"
+    )
+    assert out.strip() == "[(1, 2.0), (2, 4.0)]"
