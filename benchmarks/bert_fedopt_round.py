@@ -150,7 +150,8 @@ def main() -> None:
                        "batch_per_client": args.batch_size, "local_steps": args.local_steps, "val_batches": args.val_batches,
                        "local_optimizer": "AdamW lr=5e-5", "strategy": "FedAdam eta=1e-3",
                        "linear": "nn.Linear (cuBLAS)" if args.stock_linear else "tcgen05 LinearAct (fused bias/GELU epilogue)",
-                       "collectives": "fused-p2p" if ctx.fused is not None else ("nccl" if world > 1 else "local"),
+                       "collectives": (("fused-nvls (multimem)" if ctx.fused.has_multicast else "fused-p2p") if ctx.fused is not None
+                                       else ("nccl" if world > 1 else "local")),
                        "cuda_graphs": engine.cuda_graphs, "l2": "256 MiB write between rounds"},
             "gpu_launches": marks["launches"], "final_val_loss": history.losses_distributed[-1][1],
         }))
