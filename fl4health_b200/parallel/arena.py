@@ -91,6 +91,7 @@ class ParameterArena:
         self._views_cache: dict[tuple[int, int], NDArrays] = {}
         self._rehome()
         self.grad: torch.Tensor | None = None
+        self._subset_views_cache: dict[tuple, NDArrays] = {}
         self.table_gradients = False  # True: trainable, but gradients are per-tensor (no flat region); see use_table_gradients
         self.shadow: torch.Tensor | None = None  # bf16 compute copy (see enable_compute_shadow)
         self.shadow_names: set[str] = set()
@@ -287,6 +288,14 @@ class ParameterArena:
                 fresh.int_flat = self.int_flat if region is None else None
                 return fresh
         keys = list(names) if names is not None else self.state_keys
+        if names is not None:
+            # a fixed subset (FedPer / FedRep / FedBN exchange the same names every round): the views are built once
+            subset_key = (base.data_ptr(), base.numel(), tuple(keys))
+            cached = self._subset_views_cache.get(subset_key)
+            if cached is not None and cached.subset_flat.dtype == base.dtype and cached.subset_flat.device == base.device:
+                fresh = NDArrays(cached)
+                fresh.subset_flat, fresh.subset_layout, fresh.subset_names = base, self, cached.subset_names
+                return fresh
         out = NDArrays()
         for key in keys:
             key = self.aliases.get(key, key)
@@ -303,6 +312,11 @@ class ParameterArena:
             self._views_cache[(base.data_ptr(), base.numel())] = NDArrays(out, flat=base, layout=self)
         else:  # a named subset of the arena: tagged so that it can ride the whole-arena collectives / copies
             out.subset_flat, out.subset_layout, out.subset_names = base, self, tuple(keys)
+            if len(self._subset_views_cache) > 8:
+                self._subset_views_cache.pop(next(iter(self._subset_views_cache)))
+            keep = NDArrays(out)
+            keep.subset_flat, keep.subset_layout, keep.subset_names = base, self, tuple(keys)
+            self._subset_views_cache[(base.data_ptr(), base.numel(), tuple(keys))] = keep
         return out
 
     def subset_plan(self, names: tuple[str, ...]) -> tuple[list[tuple[int, int]], list[int]]:
