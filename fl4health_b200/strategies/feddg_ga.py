@@ -69,6 +69,47 @@ class FairnessMetric:
         return f"Metric Type: {self.metric_type}, Metric Name: '{self.metric_name}', Signal: {self.signal}"
 
 
+class GeneralizationAdjustment:
+    """The per-client aggregation weights of FedDG-GA and their update rule, separate from the strategy plumbing.
+
+    ``weights`` maps the stable client id to ``a_i``.  ``step(round)`` is the linearly decaying step size
+    ``d (1 - (r - 1) / R)``; ``update`` moves every weight by ``signal * step * (gap_i - mean gap) / max |gap - mean gap|``,
+    clips to [0, 1] and renormalises over the clients that took part."""
+
+    def __init__(self, step_size: float, signal: float) -> None:
+        self.step_size, self.signal = step_size, signal
+        self.weights: dict[str, float] = {}
+        self.total_rounds: int | None = None
+
+    def step(self, server_round: int) -> float:
+        assert self.total_rounds is not None
+        return self.step_size * (1.0 - (server_round - 1) / self.total_rounds)
+
+    def weight_of(self, cid: str, default: float) -> float:
+        return self.weights.setdefault(cid, default)
+
+    def update(self, server_round: int, gaps: dict[str, float]) -> None:
+        cids = list(gaps)
+        centred = np.array([gaps[cid] for cid in cids], dtype=float)
+        centred -= centred.mean()
+        spread = float(np.abs(centred).max())
+        if spread == 0:
+            log(WARNING, "Max variance in generalization gap is 0. Adjustment weights will remain the same. "
+                         f"Gaps: {[gaps[cid] for cid in cids]}")
+            moves = np.zeros_like(centred)
+        else:
+            moves = centred * (self.signal * self.step(server_round) / spread)
+        moved = np.clip(np.array([self.weights[cid] for cid in cids]) + moves, 0.0, 1.0)
+        moved /= moved.sum()
+        self.weights.update({cid: float(value) for cid, value in zip(cids, moved)})
+
+
+_REQUIRED_FIT_FLAGS = {
+    "evaluate_after_fit": "evaluate_after_fit must be present and set to True",
+    "pack_losses_with_val_metrics": "pack_losses_with_val_metrics must be present and True",
+}
+
+
 class FedDgGa(FedAvg):
     def __init__(
         self,
@@ -86,6 +127,7 @@ class FedDgGa(FedAvg):
         fairness_metric: FairnessMetric | None = None,
         adjustment_weight_step_size: float = 0.2,
     ) -> None:
+        assert 0 < adjustment_weight_step_size < 1, f"adjustment_weight_step_size has to be between 0 and 1 ({adjustment_weight_step_size})"
         super().__init__(
             fraction_fit=1.0, fraction_evaluate=1.0, min_fit_clients=min_fit_clients,
             min_evaluate_clients=min_evaluate_clients, min_available_clients=min_available_clients,
@@ -94,94 +136,88 @@ class FedDgGa(FedAvg):
             fit_metrics_aggregation_fn=fit_metrics_aggregation_fn,
             evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
         )
-        self.fairness_metric = fairness_metric if fairness_metric is not None else FairnessMetric(FairnessMetricType.LOSS)
+        self.fairness_metric = fairness_metric or FairnessMetric(FairnessMetricType.LOSS)
         self.adjustment_weight_step_size = adjustment_weight_step_size
-        assert 0 < adjustment_weight_step_size < 1, f"adjustment_weight_step_size has to be between 0 and 1 ({adjustment_weight_step_size})"
+        self._adjustment = GeneralizationAdjustment(adjustment_weight_step_size, self.fairness_metric.signal)
         log(INFO, f"FedDG-GA Strategy initialized with weight_step_size of {adjustment_weight_step_size} and {self.fairness_metric}")
         self.train_metrics: dict[str, dict[str, Scalar]] = {}
         self.evaluation_metrics: dict[str, dict[str, Scalar]] = {}
-        self.num_rounds: int | None = None
         self.initial_adjustment_weight: float | None = None
-        self.adjustment_weights: dict[str, float] = {}
 
+    # the reference's attribute names, as views on the adjustment state
+    @property
+    def adjustment_weights(self) -> dict[str, float]:
+        return self._adjustment.weights
+
+    @adjustment_weights.setter
+    def adjustment_weights(self, weights: dict[str, float]) -> None:
+        self._adjustment.weights = weights
+
+    @property
+    def num_rounds(self) -> int | None:
+        return self._adjustment.total_rounds
+
+    @num_rounds.setter
+    def num_rounds(self, value: int | None) -> None:
+        self._adjustment.total_rounds = value
+
+    # ---- round configuration: fit and evaluate must hit the SAME cohort, and clients must report what GA needs ----
     def configure_fit(self, server_round: int, parameters: Parameters, client_manager: ClientManager) -> list[tuple[ClientProxy, FitIns]]:
         assert isinstance(client_manager, FixedSamplingClientManager), f"Client manager is not of type FixedSamplingClientManager: {type(client_manager)}"
-        client_manager.reset_sample()
-        client_fit_ins = super().configure_fit(server_round, parameters, client_manager)
-        self.initial_adjustment_weight = 1.0 / len(client_fit_ins)
         assert self.on_fit_config_fn is not None, "on_fit_config_fn must be specified"
         config = self.on_fit_config_fn(server_round)
-        assert config.get("evaluate_after_fit") is True, "evaluate_after_fit must be present and set to True"
-        assert config.get("pack_losses_with_val_metrics") is True, "pack_losses_with_val_metrics must be present and True"
-        assert isinstance(config.get("n_server_rounds"), int), "n_server_rounds must be specified as an integer"
-        n_server_rounds = config["n_server_rounds"]
-        if self.num_rounds is None:
-            self.num_rounds = n_server_rounds  # type: ignore[assignment]
-        else:
-            assert n_server_rounds == self.num_rounds, f"n_server_rounds changed from {self.num_rounds} to {n_server_rounds}"
-        return client_fit_ins
+        for flag, complaint in _REQUIRED_FIT_FLAGS.items():
+            assert config.get(flag) is True, complaint
+        declared_rounds = config.get("n_server_rounds")
+        assert isinstance(declared_rounds, int), "n_server_rounds must be specified as an integer"
+        assert self.num_rounds in (None, declared_rounds), f"n_server_rounds changed from {self.num_rounds} to {declared_rounds}"
+        self.num_rounds = declared_rounds
+        client_manager.reset_sample()  # a fresh cohort for this round; evaluate re-uses it
+        instructions = super().configure_fit(server_round, parameters, client_manager)
+        self.initial_adjustment_weight = 1.0 / len(instructions)
+        return instructions
 
     def configure_evaluate(self, server_round: int, parameters: Parameters, client_manager: ClientManager) -> list[tuple[ClientProxy, EvaluateIns]]:
         assert isinstance(client_manager, FixedSamplingClientManager)
-        client_evaluate_ins = super().configure_evaluate(server_round, parameters, client_manager)
         assert self.on_evaluate_config_fn is not None, "on_evaluate_config_fn must be specified"
         assert self.on_evaluate_config_fn(server_round).get("pack_losses_with_val_metrics") is True
-        return client_evaluate_ins
+        return super().configure_evaluate(server_round, parameters, client_manager)
 
+    # ---- aggregation ----------------------------------------------------------------------------------------------
     def aggregate_fit(self, server_round: int, results: list[tuple[ClientProxy, FitRes]], failures: list[Any]) -> tuple[Parameters | None, dict[str, Scalar]]:
         if not results or (not self.accept_failures and failures):
             return None, {}
-        metrics = self._aggregate_fit_metrics(server_round, results)
         self.train_metrics = {proxy.cid: res.metrics for proxy, res in results}
-        return ndarrays_to_parameters(self.weight_and_aggregate_results(results)), metrics
-
-    def aggregate_evaluate(self, server_round: int, results: list[tuple[ClientProxy, EvaluateRes]], failures: list[Any]) -> tuple[float | None, dict[str, Scalar]]:
-        loss_aggregated, metrics_aggregated = super().aggregate_evaluate(server_round, results, failures)
-        self.evaluation_metrics = {}
-        for proxy, res in results:
-            assert FairnessMetricType.LOSS.value in res.metrics
-            self.evaluation_metrics[proxy.cid] = res.metrics
-        log(INFO, "Updating the Generalization Adjustment Weights")
-        self.update_weights_by_ga(server_round, [proxy.cid for proxy, _ in results])
-        return loss_aggregated, metrics_aggregated
+        fit_metrics = self._aggregate_fit_metrics(server_round, results)
+        return ndarrays_to_parameters(self.weight_and_aggregate_results(results)), fit_metrics
 
     def weight_and_aggregate_results(self, results: list[tuple[ClientProxy, FitRes]]) -> NDArrays:
-        decoded = decode_and_pseudo_sort_results(results, materialize=False)
-        arrays, coefficients = [], []
-        for proxy, weights, _ in decoded:
-            if proxy.cid not in self.adjustment_weights:
-                assert self.initial_adjustment_weight is not None
-                self.adjustment_weights[proxy.cid] = self.initial_adjustment_weight
-            arrays.append(weights)
-            coefficients.append(self.adjustment_weights[proxy.cid])
+        assert self.initial_adjustment_weight is not None
+        ordered = decode_and_pseudo_sort_results(results, materialize=False)
+        coefficients = [self._adjustment.weight_of(proxy.cid, self.initial_adjustment_weight) for proxy, _, _ in ordered]
         log(INFO, f"Current adjustment weights by Client ID (CID) are {self.adjustment_weights}")
-        return weighted_combine(arrays, coefficients)
+        return weighted_combine([weights for _, weights, _ in ordered], coefficients)
+
+    def aggregate_evaluate(self, server_round: int, results: list[tuple[ClientProxy, EvaluateRes]], failures: list[Any]) -> tuple[float | None, dict[str, Scalar]]:
+        aggregated = super().aggregate_evaluate(server_round, results, failures)
+        assert all(FairnessMetricType.LOSS.value in res.metrics for _, res in results)
+        self.evaluation_metrics = {proxy.cid: res.metrics for proxy, res in results}
+        log(INFO, "Updating the Generalization Adjustment Weights")
+        self.update_weights_by_ga(server_round, [proxy.cid for proxy, _ in results])
+        return aggregated
 
     def update_weights_by_ga(self, server_round: int, cids: list[str]) -> None:
+        """Generalisation gap per client = metric of the GLOBAL model on the client's validation data (evaluate round)
+        minus the metric of its LOCAL model right after fitting (packed into the fit metrics)."""
         name = self.fairness_metric.metric_name
-        gaps = []
+        gaps: dict[str, float] = {}
         for cid in cids:
             assert cid in self.train_metrics and cid in self.evaluation_metrics, f"{cid} missing from fit or evaluate metrics"
-            global_value, local_value = self.evaluation_metrics[cid][name], self.train_metrics[cid][name]
-            assert isinstance(global_value, float) and isinstance(local_value, float)
-            gaps.append(global_value - local_value)
-        gaps_arr = np.array(gaps)
-        centered = gaps_arr - gaps_arr.mean()
-        max_dev = np.max(np.abs(centered))
-        if max_dev == 0:
-            log(WARNING, f"Max variance in generalization gap is 0. Adjustment weights will remain the same. Gaps: {gaps}")
-            normalized = np.zeros_like(gaps_arr)
-        else:
-            normalized = centered * self.get_current_weight_step_size(server_round) / max_dev
-        total = 0.0
-        for cid, delta in zip(cids, normalized):
-            self.adjustment_weights[cid] = float(np.clip(self.adjustment_weights[cid] + self.fairness_metric.signal * delta, 0.0, 1.0))
-            total += self.adjustment_weights[cid]
-        for cid in cids:
-            self.adjustment_weights[cid] /= total
+            after_aggregation, after_local_fit = self.evaluation_metrics[cid][name], self.train_metrics[cid][name]
+            assert isinstance(after_aggregation, float) and isinstance(after_local_fit, float)
+            gaps[cid] = after_aggregation - after_local_fit
+        self._adjustment.update(server_round, gaps)
         log(INFO, f"New Generalization Adjustment Weights by Client ID (CID) are {self.adjustment_weights}")
 
     def get_current_weight_step_size(self, server_round: int) -> float:
-        assert self.num_rounds is not None
-        decay = self.adjustment_weight_step_size / self.num_rounds
-        return self.adjustment_weight_step_size - (server_round - 1) * decay
+        return self._adjustment.step(server_round)
