@@ -1,131 +1,107 @@
-"""Structural types the mixins rely on (parity: ``fl4health/mixins/core_protocols.py:15-107``)."""
+"""What the mixins expect of the client they are combined with (parity: ``fl4health/mixins/core_protocols.py:15-107``,
+there a ladder of ``typing.Protocol`` classes used for static typing only).
+
+Here the same ladder is *checkable data*: every contract lists the attributes and methods it adds to its parents, and
+``Contract.missing(obj)`` / ``Contract.require(obj)`` / ``isinstance(obj, SomeContract)`` verify an object (or a class)
+against the accumulated list -- so a mixin stacked on the wrong base fails with the names that are absent instead of an
+``AttributeError`` in the middle of a round.  The class names are the reference's, and the inheritance between them
+(Ditto / MR-MTL extend the adaptive-drift contract, which extends the flexible client's) is preserved.
+"""
 
 from __future__ import annotations
 
-from typing import Any, Protocol, runtime_checkable
-
-import torch
-from torch import nn
-from torch.optim import Optimizer
-
-from fl4health_b200.common.typing import Config, NDArrays, Scalar
-from fl4health_b200.utils.losses import EvaluationLosses, TrainingLosses
-from fl4health_b200.utils.typing import TorchFeatureType, TorchInputType, TorchPredType, TorchTargetType
+from typing import Any
 
 
-@runtime_checkable
-class NumPyClientMinimalProtocol(Protocol):
-    def get_parameters(self, config: dict[str, Scalar]) -> NDArrays: ...
+class _ContractType(type):
+    def __instancecheck__(cls, candidate: Any) -> bool:
+        return not cls.missing(candidate)
 
-    def fit(self, parameters: NDArrays, config: dict[str, Scalar]) -> tuple[NDArrays, int, dict[str, Scalar]]: ...
-
-    def evaluate(self, parameters: NDArrays, config: dict[str, Scalar]) -> tuple[float, int, dict[str, Scalar]]: ...
-
-    def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None: ...
-
-    def update_after_train(self, local_steps: int, loss_dict: dict[str, float], config: Config) -> None: ...
+    def __subclasscheck__(cls, candidate: type) -> bool:
+        return type.__subclasscheck__(cls, candidate) or (isinstance(candidate, type) and not cls.missing_methods(candidate))
 
 
-@runtime_checkable
-class FlexibleClientProtocolPreSetup(NumPyClientMinimalProtocol, Protocol):
-    device: torch.device
-    initialized: bool
+class Contract(metaclass=_ContractType):
+    """``attributes`` exist on set-up instances only; ``methods`` exist on the class already."""
 
-    def setup_client(self, config: Config) -> None: ...
+    attributes: tuple[str, ...] = ()
+    methods: tuple[str, ...] = ()
 
-    def get_model(self, config: Config) -> nn.Module: ...
+    @classmethod
+    def _collected(cls, kind: str) -> tuple[str, ...]:
+        names: dict[str, None] = {}
+        for level in reversed(cls.__mro__):
+            names.update(dict.fromkeys(level.__dict__.get(kind, ())))
+        return tuple(names)
 
-    def get_data_loaders(self, config: Config) -> tuple[Any, ...]: ...
+    @classmethod
+    def all_methods(cls) -> tuple[str, ...]:
+        return cls._collected("methods")
 
-    def get_optimizer(self, config: Config) -> Optimizer | dict[str, Optimizer]: ...
+    @classmethod
+    def all_attributes(cls) -> tuple[str, ...]:
+        return cls._collected("attributes")
 
-    def get_criterion(self, config: Config) -> Any: ...
+    @classmethod
+    def missing_methods(cls, candidate: Any) -> list[str]:
+        return [name for name in cls.all_methods() if not callable(getattr(candidate, name, None))]
 
-    def compute_loss_and_additional_losses(
-        self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
-    ) -> tuple[torch.Tensor, dict[str, torch.Tensor] | None]: ...
+    @classmethod
+    def missing(cls, candidate: Any) -> list[str]:
+        absent = cls.missing_methods(candidate)
+        if not isinstance(candidate, type):
+            absent += [name for name in cls.all_attributes() if not hasattr(candidate, name)]
+        return absent
 
-
-@runtime_checkable
-class FlexibleClientProtocol(FlexibleClientProtocolPreSetup, Protocol):
-    model: nn.Module
-    optimizers: dict[str, Optimizer]
-
-    def initialize_all_model_weights(self, parameters: NDArrays, config: Config) -> None: ...
-
-    def update_before_train(self, current_server_round: int) -> None: ...
-
-    def _compute_preds_and_losses(
-        self, model: nn.Module, optimizer: Optimizer, input: TorchInputType, target: TorchTargetType
-    ) -> tuple[TrainingLosses, TorchPredType]: ...
-
-    def _apply_backwards_on_losses_and_take_step(
-        self, model: nn.Module, optimizer: Optimizer, losses: TrainingLosses
-    ) -> TrainingLosses: ...
-
-    def _train_step_with_model_and_optimizer(
-        self, model: nn.Module, optimizer: Optimizer, input: TorchInputType, target: TorchTargetType
-    ) -> tuple[TrainingLosses, TorchPredType]: ...
-
-    def _val_step_with_model(
-        self, model: nn.Module, input: TorchInputType, target: TorchTargetType
-    ) -> tuple[EvaluationLosses, TorchPredType]: ...
-
-    def predict_with_model(self, model: nn.Module, input: TorchInputType) -> tuple[TorchPredType, TorchFeatureType]: ...
-
-    def transform_target(self, target: TorchTargetType) -> TorchTargetType: ...
-
-    def _transform_gradients_with_model(self, model: nn.Module, losses: TrainingLosses) -> None: ...
-
-    def transform_gradients(self, losses: TrainingLosses) -> None: ...
-
-    def compute_training_loss(
-        self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
-    ) -> TrainingLosses: ...
-
-    def validate(self, include_losses_in_metrics: bool = False) -> tuple[float, dict[str, Scalar]]: ...
-
-    def compute_evaluation_loss(
-        self, preds: TorchPredType, features: TorchFeatureType, target: TorchTargetType
-    ) -> EvaluationLosses: ...
+    @classmethod
+    def require(cls, candidate: Any) -> None:
+        absent = cls.missing(candidate)
+        if absent:
+            owner = candidate.__name__ if isinstance(candidate, type) else type(candidate).__name__
+            raise TypeError(f"Protocol requirements not met. {owner} lacks {', '.join(absent)} ({cls.__name__}).")
 
 
-@runtime_checkable
-class AdaptiveDriftConstrainedProtocol(FlexibleClientProtocol, Protocol):
-    """What ``AdaptiveDriftConstrainedMixin`` adds to / expects from the client (adaptive_drift_constrained.py:23-32)."""
-
-    loss_for_adaptation: float
-    drift_penalty_tensors: list[torch.Tensor] | None
-    drift_penalty_weight: float | None
-    penalty_loss_function: Any
-    parameter_exchanger: Any
-
-    def compute_penalty_loss(self) -> torch.Tensor: ...
-
-    def setup_client_and_return_all_model_parameters(self, config: Config) -> NDArrays: ...
+class NumPyClientMinimalProtocol(Contract):
+    methods = ("get_parameters", "fit", "evaluate", "set_parameters", "update_after_train")
 
 
-@runtime_checkable
-class DittoPersonalizedProtocol(AdaptiveDriftConstrainedProtocol, Protocol):
-    """(personalized/ditto.py:30-44)"""
-
-    global_model: nn.Module | None
-    optimizer_keys: list[str]
-
-    def get_global_model(self, config: Config) -> nn.Module: ...
-
-    def _copy_optimizer_with_new_params(self, original_optimizer: Optimizer) -> Optimizer: ...
-
-    def set_initial_global_tensors(self) -> None: ...
-
-    def safe_global_model(self) -> nn.Module: ...
+class FlexibleClientProtocolPreSetup(NumPyClientMinimalProtocol):
+    attributes = ("device", "initialized")
+    methods = (
+        "setup_client", "get_model", "get_data_loaders", "get_optimizer", "get_criterion",
+        "compute_loss_and_additional_losses",
+    )
 
 
-@runtime_checkable
-class MrMtlPersonalizedProtocol(AdaptiveDriftConstrainedProtocol, Protocol):
-    """(personalized/mr_mtl.py:27-32)"""
+class FlexibleClientProtocol(FlexibleClientProtocolPreSetup):
+    attributes = ("model", "optimizers")
+    methods = (
+        "initialize_all_model_weights", "update_before_train", "validate",
+        # the per-model step family a personalised mixin drives once per model it owns
+        "_compute_preds_and_losses", "_apply_backwards_on_losses_and_take_step", "_train_step_with_model_and_optimizer",
+        "_val_step_with_model", "predict_with_model", "_transform_gradients_with_model",
+        "transform_target", "transform_gradients", "compute_training_loss", "compute_evaluation_loss",
+    )
 
-    initial_global_model: nn.Module | None
-    initial_global_tensors: list[torch.Tensor]
 
-    def get_global_model(self, config: Config) -> nn.Module: ...
+class AdaptiveDriftConstrainedProtocol(FlexibleClientProtocol):
+    """(``adaptive_drift_constrained.py:23-32``)"""
+
+    attributes = (
+        "loss_for_adaptation", "drift_penalty_tensors", "drift_penalty_weight", "penalty_loss_function", "parameter_exchanger",
+    )
+    methods = ("compute_penalty_loss", "setup_client_and_return_all_model_parameters")
+
+
+class DittoPersonalizedProtocol(AdaptiveDriftConstrainedProtocol):
+    """(``personalized/ditto.py:30-44``)"""
+
+    attributes = ("global_model", "optimizer_keys")
+    methods = ("get_global_model", "_copy_optimizer_with_new_params", "set_initial_global_tensors", "safe_global_model")
+
+
+class MrMtlPersonalizedProtocol(AdaptiveDriftConstrainedProtocol):
+    """(``personalized/mr_mtl.py:27-32``)"""
+
+    attributes = ("initial_global_model", "initial_global_tensors")
+    methods = ("get_global_model",)

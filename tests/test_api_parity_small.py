@@ -66,6 +66,38 @@ def test_protocol_compliance_decorator_and_protocol_names() -> None:
     assert Flex.method(Flex.__new__(Flex)) == 2
 
 
+def test_contracts_are_checkable_and_name_what_is_missing() -> None:
+    from fl4health_b200.clients.basic_client import BasicClient
+    from fl4health_b200.clients.flexible.base import FlexibleClient
+    from fl4health_b200.mixins.adaptive_drift_constrained import AdaptiveDriftConstrainedMixin
+    from fl4health_b200.mixins.core_protocols import (
+        AdaptiveDriftConstrainedProtocol,
+        DittoPersonalizedProtocol,
+        FlexibleClientProtocol,
+        MrMtlPersonalizedProtocol,
+        NumPyClientMinimalProtocol,
+    )
+    from fl4health_b200.mixins.personalized import PersonalizedMode, make_it_personal
+
+    assert issubclass(FlexibleClient, FlexibleClientProtocol) and not issubclass(FlexibleClient, DittoPersonalizedProtocol)
+    assert issubclass(make_it_personal(FlexibleClient, PersonalizedMode.DITTO), DittoPersonalizedProtocol)
+    assert issubclass(make_it_personal(FlexibleClient, PersonalizedMode.MR_MTL), MrMtlPersonalizedProtocol)
+
+    class Constrained(AdaptiveDriftConstrainedMixin, FlexibleClient):
+        pass
+
+    assert AdaptiveDriftConstrainedProtocol.missing(Constrained) == []
+    # the non-flexible client speaks the NumPy-client part but not the per-model step family
+    assert NumPyClientMinimalProtocol.missing(BasicClient) == []
+    assert "_train_step_with_model_and_optimizer" in FlexibleClientProtocol.missing(BasicClient)
+    assert not isinstance(object(), NumPyClientMinimalProtocol)
+    # instances are also held to the attributes; inherited requirements accumulate, each name once
+    assert {"device", "model", "global_model"} <= set(DittoPersonalizedProtocol.all_attributes())
+    assert len(set(DittoPersonalizedProtocol.all_methods())) == len(DittoPersonalizedProtocol.all_methods())
+    with pytest.raises(TypeError, match="lacks .*fit.*NumPyClientMinimalProtocol"):
+        NumPyClientMinimalProtocol.require(object())
+
+
 def test_constants_exist() -> None:
     from fl4health_b200.clients.basic_client import EXPECTED_OUTPUT_TUPLE_SIZE
     from fl4health_b200.model_bases.ensemble_base import EXPECTED_MAX_PRED_N_DIMS
