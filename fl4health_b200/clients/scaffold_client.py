@@ -31,6 +31,8 @@ from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerWi
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.utils.losses import LossMeterType, TrainingLosses
 
+ScaffoldTrainStepOutput = tuple[torch.Tensor, torch.Tensor]  # (loss, predictions) alias kept from the reference
+
 
 class ScaffoldClient(BasicClient):
     def __init__(

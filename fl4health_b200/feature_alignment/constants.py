@@ -4,6 +4,11 @@ from __future__ import annotations
 
 from enum import Enum
 
+from sklearn.feature_extraction.text import CountVectorizer, HashingVectorizer, TfidfTransformer, TfidfVectorizer
+
+# what a text column may be vectorised with (type alias used by the text column transformers)
+TextFeatureTransformer = CountVectorizer | TfidfTransformer | TfidfVectorizer | HashingVectorizer
+
 # server -> client config keys
 SOURCE_SPECIFIED = "source_specified"  # has the server fixed the "source of truth" schema yet?
 FEATURE_INFO = "feature_info"  # the JSON-encoded schema

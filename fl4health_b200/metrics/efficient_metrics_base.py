@@ -32,6 +32,9 @@ class ClassificationOutcome(Enum):
     FALSE_NEGATIVE = "false_negative"
 
 
+MetricOutcome = ClassificationOutcome  # the reference's older name for the same enum
+
+
 _ORDER = (
     ClassificationOutcome.TRUE_POSITIVE, ClassificationOutcome.FALSE_POSITIVE,
     ClassificationOutcome.TRUE_NEGATIVE, ClassificationOutcome.FALSE_NEGATIVE,

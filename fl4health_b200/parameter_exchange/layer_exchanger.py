@@ -8,6 +8,7 @@ list of state-dict keys is produced, so they share ``_NamedSubsetExchanger``.
 from __future__ import annotations
 
 from collections.abc import Set
+from typing import TypeVar
 
 from torch import nn
 
@@ -17,6 +18,8 @@ from fl4health_b200.parameter_exchange.parameter_exchanger_base import Parameter
 from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerWithLayerNames
 from fl4health_b200.parameter_exchange.partial_parameter_exchanger import PartialParameterExchanger
 from fl4health_b200.utils.typing import LayerSelectionFunction
+
+TorchModule = TypeVar("TorchModule", bound=nn.Module)  # element type of ``module_exclusions``
 
 
 class _NamedSubsetExchanger(ParameterExchanger):

@@ -6,6 +6,8 @@ from abc import ABC, abstractmethod
 
 from torch import nn
 
+from typing import TypeVar
+
 from fl4health_b200.common.typing import Config, NDArrays
 
 
@@ -21,3 +23,6 @@ class ParameterExchanger(ABC):
     def pull_parameters(self, parameters: NDArrays, model: nn.Module, config: Config | None = None) -> None:
         """Server arrays -> model."""
         raise NotImplementedError
+
+
+ExchangerType = TypeVar("ExchangerType", bound=ParameterExchanger)  # for code generic over the exchanger a client uses

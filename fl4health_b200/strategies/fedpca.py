@@ -19,6 +19,7 @@ from fl4health_b200.utils.functions import decode_and_pseudo_sort_results
 EVALUATE_FN_TYPE = Callable[[int, NDArrays, dict[str, Scalar]], tuple[float, dict[str, Scalar]] | None] | None
 
 MINIMUM_PCA_CLIENTS = 2
+MINIMUM_PCA_ClIENTS = MINIMUM_PCA_CLIENTS  # the reference spells the constant with a lower-case "l"; both import
 
 
 class FedPCA(BasicFedAvg):
