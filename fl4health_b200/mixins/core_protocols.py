@@ -13,7 +13,23 @@ from __future__ import annotations
 from typing import Any
 
 
+def _requirement(contract: str, name: str) -> Any:
+    def required(self: Any, *args: Any, **kwargs: Any) -> Any:
+        raise NotImplementedError(f"{contract} requires the client to provide {name}()")
+
+    required.__name__ = required.__qualname__ = name
+    required.__doc__ = f"Required by {contract}; provided by the client class the mixin is combined with."
+    return required
+
+
 class _ContractType(type):
+    def __new__(mcs, name: str, bases: tuple[type, ...], namespace: dict[str, Any]) -> _ContractType:
+        # every required method is also an attribute of the contract class (introspection, ``help()``): a placeholder
+        # that says who has to provide it.  Contracts are never base classes of clients, so nothing inherits these.
+        for method in namespace.get("methods", ()):
+            namespace.setdefault(method, _requirement(name, method))
+        return super().__new__(mcs, name, bases, namespace)
+
     def __instancecheck__(cls, candidate: Any) -> bool:
         return not cls.missing(candidate)
 
