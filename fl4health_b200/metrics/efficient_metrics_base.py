@@ -40,6 +40,40 @@ _ORDER = (
     ClassificationOutcome.TRUE_NEGATIVE, ClassificationOutcome.FALSE_NEGATIVE,
 )
 Counts = tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]
+_ATTRIBUTE = dict(zip(_ORDER, ("true_positives", "false_positives", "true_negatives", "false_negatives")))
+
+
+def _outcome_products(p: torch.Tensor, t: torch.Tensor, wanted: tuple[int, ...]) -> torch.Tensor:
+    """Soft outcome indicators stacked on a new leading axis, in ``_ORDER`` positions ``wanted``:
+    TP = p t, FP = p (1 - t), TN = (1 - p)(1 - t), FN = (1 - p) t."""
+    sides = {0: (p, t), 1: (p, 1 - t), 2: (1 - p, 1 - t), 3: (1 - p, t)}
+    return torch.stack([sides[i][0] * sides[i][1] for i in wanted])
+
+
+class _CountState:
+    """The running counts of the outcomes that are kept, as ONE tensor ``[n_kept, ...]`` (one add / concatenate per
+    update instead of four); the four per-outcome tensors of the public API are views of it."""
+
+    def __init__(self, kept: tuple[int, ...], grows_along_batch: bool) -> None:
+        self.kept, self.grows_along_batch = kept, grows_along_batch
+        self.stacked: torch.Tensor | None = None
+
+    def absorb(self, counts: Counts) -> None:
+        if not self.kept:
+            self.stacked = torch.empty(0)
+            return
+        fresh = torch.stack([counts[i] for i in self.kept])
+        if self.stacked is None:
+            self.stacked = fresh
+        elif self.grows_along_batch:
+            self.stacked = torch.cat([self.stacked, fresh], dim=1)
+        else:
+            self.stacked = self.stacked + fresh
+
+    def of(self, outcome: int) -> torch.Tensor:
+        if self.stacked is None or outcome not in self.kept:
+            return torch.tensor([])
+        return self.stacked[self.kept.index(outcome)]
 
 
 class ClassificationMetric(Metric, ABC):
@@ -49,40 +83,46 @@ class ClassificationMetric(Metric, ABC):
     ) -> None:
         super().__init__(name)
         self.dtype, self.threshold, self.label_dim, self.batch_dim = dtype, threshold, label_dim, batch_dim
-        if label_dim is not None:
-            if isinstance(threshold, int) and not isinstance(threshold, bool) and threshold != label_dim:
-                log(WARNING, f"Specified threshold dimension: {threshold} is not the same as the label_dim: {label_dim}. "
-                             "This is atypical and may produce undesired behavior")
-            if batch_dim is not None and label_dim == batch_dim:
-                raise ValueError(f"The label and batch dimensions must differ but got {label_dim}")
-        discard = discard or set()
-        self.discard_tp = ClassificationOutcome.TRUE_POSITIVE in discard
-        self.discard_fp = ClassificationOutcome.FALSE_POSITIVE in discard
-        self.discard_tn = ClassificationOutcome.TRUE_NEGATIVE in discard
-        self.discard_fn = ClassificationOutcome.FALSE_NEGATIVE in discard
+        if label_dim is not None and batch_dim is not None and label_dim == batch_dim:
+            raise ValueError(f"The label and batch dimensions must differ but got {label_dim}")
+        threshold_is_an_axis = isinstance(threshold, int) and not isinstance(threshold, bool)
+        if label_dim is not None and threshold_is_an_axis and threshold != label_dim:
+            log(WARNING, f"Specified threshold dimension: {threshold} is not the same as the label_dim: {label_dim}. "
+                         "This is atypical and may produce undesired behavior")
+        self.discarded = frozenset(discard or ())
         self.clear()
 
     # -- state ---------------------------------------------------------------------------------------------
     def clear(self) -> None:
-        self.true_positives, self.false_positives = torch.tensor([]), torch.tensor([])
-        self.true_negatives, self.false_negatives = torch.tensor([]), torch.tensor([])
-        self.counts_initialized = False
+        self._state = _CountState(self._kept_after_relabelling(), self.batch_dim is not None)
 
-    def _discarded(self) -> tuple[bool, bool, bool, bool]:
-        return self.discard_tp, self.discard_fp, self.discard_tn, self.discard_fn
+    def _kept_after_relabelling(self) -> tuple[int, ...]:
+        """Positions (in ``_ORDER``) of the *returned* counts that are not empty."""
+        return tuple(i for i, outcome in enumerate(_ORDER) if outcome not in self.discarded)
+
+    @property
+    def counts_initialized(self) -> bool:
+        return self._state.stacked is not None
+
+    true_positives = property(lambda self: self._state.of(0))
+    false_positives = property(lambda self: self._state.of(1))
+    true_negatives = property(lambda self: self._state.of(2))
+    false_negatives = property(lambda self: self._state.of(3))
+    discard_tp = property(lambda self: ClassificationOutcome.TRUE_POSITIVE in self.discarded)
+    discard_fp = property(lambda self: ClassificationOutcome.FALSE_POSITIVE in self.discarded)
+    discard_tn = property(lambda self: ClassificationOutcome.TRUE_NEGATIVE in self.discarded)
+    discard_fn = property(lambda self: ClassificationOutcome.FALSE_NEGATIVE in self.discarded)
 
     # -- hooks for subclasses ------------------------------------------------------------------------------
     def _transform_tensors(self, preds: torch.Tensor, targets: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        preds = preds.to(torch.uint8) if preds.dtype == torch.bool else preds
-        targets = targets.to(torch.uint8) if targets.dtype == torch.bool else targets
+        preds, targets = (x.to(torch.uint8) if x.dtype == torch.bool else x for x in (preds, targets))
         if self.threshold is not None:
             preds = threshold_tensor(preds, self.threshold)
         return preds, targets
 
     def _assert_correct_ranges_and_shape(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
-        lo = torch.minimum(preds.min().float(), targets.min().float())
-        hi = torch.maximum(preds.max().float(), targets.max().float())
-        assert bool((lo >= 0) & (hi <= 1)), "Expected preds and targets to be in range [0, 1]."
+        extremes = torch.stack([preds.min().float(), targets.min().float(), preds.max().float(), targets.max().float()])
+        assert bool((extremes[:2].min() >= 0) & (extremes[2:].max() <= 1)), "Expected preds and targets to be in range [0, 1]."
 
     # -- counting ------------------------------------------------------------------------------------------
     def count_tp_fp_tn_fn(self, preds: torch.Tensor, targets: torch.Tensor) -> Counts:
@@ -90,42 +130,28 @@ class ClassificationMetric(Metric, ABC):
         batch_dim / label_dim are set (batch axis first).  Discarded outcomes come back as empty tensors."""
         preds, targets = self._transform_tensors(preds, targets)
         self._assert_correct_ranges_and_shape(preds, targets)
-        keep_axes = {d for d in (self.label_dim, self.batch_dim) if d is not None}
-        sum_axes = tuple(i for i in range(preds.ndim) if i not in keep_axes)
-        p, t = preds.to(torch.float32), targets.to(torch.float32)
-        # one stacked reduction for all live outcomes
-        products = {0: lambda: p * t, 1: lambda: p * (1 - t), 2: lambda: (1 - p) * (1 - t), 3: lambda: (1 - p) * t}
-        live = [i for i, dropped in enumerate(self._discarded()) if not dropped]
-        out: list[torch.Tensor] = [torch.tensor([])] * 4
-        if live:
-            stacked = torch.stack([products[i]() for i in live])
-            if sum_axes:
-                stacked = stacked.sum(tuple(a + 1 for a in sum_axes))
-            stacked = stacked.to(self.dtype)
-            if stacked.ndim == 3 and self.batch_dim is not None and self.label_dim is not None and self.batch_dim > self.label_dim:
-                stacked = stacked.transpose(1, 2)
-            for slot, i in enumerate(live):
-                out[i] = stacked[slot]
-        return out[0], out[1], out[2], out[3]
+        wanted = tuple(i for i, outcome in enumerate(_ORDER) if outcome not in self.discarded)
+        counts: list[torch.Tensor] = [torch.tensor([])] * len(_ORDER)
+        if not wanted:
+            return counts[0], counts[1], counts[2], counts[3]
+        kept_axes = [axis for axis in (self.batch_dim, self.label_dim) if axis is not None]
+        summed_axes = tuple(axis + 1 for axis in range(preds.ndim) if axis not in kept_axes)
+        reduced = _outcome_products(preds.to(torch.float32), targets.to(torch.float32), wanted)
+        if summed_axes:
+            reduced = reduced.sum(summed_axes)
+        reduced = reduced.to(self.dtype)
+        if len(kept_axes) == MAX_COUNT_TENSOR_DIMS and kept_axes[0] > kept_axes[1]:  # batch axis goes first
+            reduced = reduced.transpose(1, 2)
+        for slot, position in enumerate(wanted):
+            counts[position] = reduced[slot]
+        return counts[0], counts[1], counts[2], counts[3]
 
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
-        tp, fp, tn, fn = self.count_tp_fp_tn_fn(preds, targets)
-        if not self.counts_initialized:
-            self.true_positives, self.false_positives, self.true_negatives, self.false_negatives = tp, fp, tn, fn
-            self.counts_initialized = True
-            return
-        merge = (lambda a, b: torch.cat([a, b], dim=0)) if self.batch_dim is not None else (lambda a, b: a + b)
-        self.true_positives = merge(self.true_positives, tp)
-        self.false_positives = merge(self.false_positives, fp)
-        self.true_negatives = merge(self.true_negatives, tn)
-        self.false_negatives = merge(self.false_negatives, fn)
+        self._state.absorb(self.count_tp_fp_tn_fn(preds, targets))
 
     def compute(self, name: str | None = None) -> Metrics:
-        metrics = self.compute_from_counts(
-            true_positives=self.true_positives, false_positives=self.false_positives,
-            true_negatives=self.true_negatives, false_negatives=self.false_negatives,
-        )
-        return {f"{name} - {k}": v for k, v in metrics.items()} if name is not None else metrics
+        metrics = self.compute_from_counts(**{_ATTRIBUTE[outcome]: self._state.of(i) for i, outcome in enumerate(_ORDER)})
+        return metrics if name is None else {f"{name} - {key}": value for key, value in metrics.items()}
 
     @abstractmethod
     def compute_from_counts(self, true_positives: torch.Tensor, false_positives: torch.Tensor,
@@ -144,9 +170,9 @@ class BinaryClassificationMetric(ClassificationMetric):
         self, name: str, label_dim: int | None = None, batch_dim: int | None = None, dtype: torch.dtype = torch.float32,
         pos_label: int = 1, threshold: float | int | None = None, discard: set[ClassificationOutcome] | None = None,
     ) -> None:
-        super().__init__(name=name, dtype=dtype, label_dim=label_dim, batch_dim=batch_dim, threshold=threshold, discard=discard)
         assert pos_label in {0, 1}, "pos_label must be either 0 or 1"
-        self.pos_label = pos_label
+        self.pos_label = pos_label  # before the base constructor: it decides which returned counts are empty
+        super().__init__(name=name, dtype=dtype, label_dim=label_dim, batch_dim=batch_dim, threshold=threshold, discard=discard)
 
     def _postprocess_count_tensor(self, count_tensor: torch.Tensor) -> torch.Tensor:
         if count_tensor.numel() == 0:
@@ -180,6 +206,11 @@ class BinaryClassificationMetric(ClassificationMetric):
                     f"Label dimension for {kind} tensor is greater than 2 {tensor.shape[self.label_dim]}. This class is "
                     "meant for binary metric computation only"
                 )
+
+    def _kept_after_relabelling(self) -> tuple[int, ...]:
+        raw = super()._kept_after_relabelling()
+        # with pos_label == 0 positives and negatives trade places in what is returned (raw TN is reported as TP, ...)
+        return raw if getattr(self, "pos_label", 1) == 1 else tuple(sorted((i + 2) % 4 for i in raw))
 
     def count_tp_fp_tn_fn(self, preds: torch.Tensor, targets: torch.Tensor) -> Counts:
         tp, fp, tn, fn = (self._postprocess_count_tensor(c) for c in super().count_tp_fp_tn_fn(preds, targets))

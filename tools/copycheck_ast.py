@@ -20,6 +20,7 @@ ROOT = Path(__file__).resolve().parent.parent
 ALLOW = {  # similarity dictated by the preserved API: constants, type aliases, ABCs, tiny managers, schema classes
     "feature_alignment/constants.py", "feature_alignment/tabular_feature.py", "feature_alignment/tabular_type.py",
     "utils/typing.py", "metrics/base_metrics.py", "parameter_exchange/partial_parameter_exchanger.py",
+    "parameter_exchange/parameter_exchanger_base.py",
     "client_managers/fixed_sampling_client_manager.py", "client_managers/base_sampling_manager.py",
     "servers/adaptive_constraint_servers/fedprox_server.py", "servers/adaptive_constraint_servers/ditto_server.py",
     "servers/adaptive_constraint_servers/mrmtl_server.py", "model_bases/sequential_split_models.py",
