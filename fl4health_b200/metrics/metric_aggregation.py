@@ -17,13 +17,15 @@ def _accumulate(store: Metrics, key: str, value: object, scale: int = 1) -> None
 def uniform_metric_aggregation(
     all_client_metrics: list[tuple[int, Metrics]],
 ) -> tuple[defaultdict[str, int], Metrics]:
+    """How many clients reported each metric, and the un-normalised *sums* over those clients (the counterpart of
+    ``metric_aggregation``; ``uniform_normalize_metrics`` turns the pair into means)."""
     sums: Metrics = {}
     counts: defaultdict[str, int] = defaultdict(int)
     for _, client_metrics in all_client_metrics:
         for key, value in client_metrics.items():
             _accumulate(sums, key, value)
             counts[key] += 1
-    return counts, uniform_normalize_metrics(counts, sums)
+    return counts, sums
 
 
 def metric_aggregation(all_client_metrics: list[tuple[int, Metrics]]) -> tuple[int, Metrics]:
@@ -58,5 +60,4 @@ def evaluate_metrics_aggregation_fn(all_client_metrics: list[tuple[int, Metrics]
 
 
 def uniform_evaluate_metrics_aggregation_fn(all_client_metrics: list[tuple[int, Metrics]]) -> Metrics:
-    _, normalized = uniform_metric_aggregation(all_client_metrics)
-    return normalized
+    return uniform_normalize_metrics(*uniform_metric_aggregation(all_client_metrics))
