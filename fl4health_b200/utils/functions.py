@@ -43,9 +43,9 @@ def pseudo_sort_scoring_function(client_result: tuple[Any, NDArrays, int]) -> fl
     _, client_arrays, sample_count = client_result
     total = 0.0
     for arr in client_arrays:
-        if isinstance(arr, np.ndarray) and arr.dtype.kind in ("U", "S", "O"):
-            continue
-        total += select_zeroeth_element(arr)
+        floating = arr.dtype.kind == "f" if isinstance(arr, np.ndarray) else getattr(arr, "is_floating_point", lambda: True)()
+        if floating:  # layer names, integer counters and index arrays do not take part
+            total += select_zeroeth_element(arr)
     return total + sample_count
 
 
