@@ -389,7 +389,7 @@ class BasicClient:
 
     def _run_train_unit(self, input: TorchInputType, target: TorchTargetType) -> tuple[TrainingLosses, TorchPredType]:
         outcome = self._executor.run_train(self._train_unit, self._graph_variant(), self._sync_optimizer_hyperparams, input, target)
-        self.train_loss_meter.mark_step()
+        self.train_loss_meter.mark_step(losses=outcome[0])
         return outcome
 
     def _run_val_unit(
@@ -402,7 +402,7 @@ class BasicClient:
             return losses, preds
 
         outcome = self._executor.run_eval(unit, (id(loss_meter), self._graph_variant()), input, target)
-        loss_meter.mark_step()
+        loss_meter.mark_step(losses=outcome[0])
         return outcome
 
     # captured-graph bookkeeping, exposed for tests / profiling scripts

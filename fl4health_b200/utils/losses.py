@@ -125,11 +125,12 @@ class LossMeter(Generic[LossesType]):
         self.loss_meter_type = loss_meter_type
         self.losses_type = losses_type
         self._sums: dict[str, torch.Tensor] = {}
+        self._seen: dict[str, int] = {}  # per key: in how many steps of this window it was reported
         self.count = 0
 
     def update(self, losses: LossesType) -> None:
         self.accumulate(losses)
-        self.count += 1
+        self.mark_step(losses=losses)
 
     def accumulate(self, losses: LossesType) -> None:
         """Device-side part of ``update`` (safe inside CUDA-graph capture once every key has been seen)."""
@@ -141,25 +142,32 @@ class LossMeter(Generic[LossesType]):
             else:
                 acc.add_(value.reshape(()))
 
-    def mark_step(self, n: int = 1) -> None:
-        """Count steps whose accumulation was replayed by a captured graph."""
+    def mark_step(self, n: int = 1, losses: LossesType | None = None) -> None:
+        """Host-side part of ``update``: count ``n`` steps (the accumulation itself may have been replayed by a captured
+        graph).  ``losses`` names the keys those steps reported -- a key that comes and goes (an optional penalty, an
+        ensemble member) is averaged over the steps that had it, like the reference's list of per-step dictionaries;
+        without it every known key counts."""
         self.count += n
+        for key in (losses._flat_items() if losses is not None else self._sums):
+            self._seen[key] = self._seen.get(key, 0) + n
 
     def clear(self) -> None:
         # zero in place: accumulators referenced by captured graphs must keep their addresses.
         for acc in self._sums.values():
             acc.zero_()
+        self._seen = {}
         self.count = 0
 
     def reset(self) -> None:
-        self._sums = {}
+        self._sums, self._seen = {}, {}
         self.count = 0
 
     def _reduced(self) -> dict[str, torch.Tensor]:
         assert self.count > 0, "Cannot compute the aggregate of an empty loss meter"
+        reported = {key: total for key, total in self._sums.items() if self._seen.get(key, 0) > 0}
         if self.loss_meter_type == LossMeterType.AVERAGE:
-            return {k: v / self.count for k, v in self._sums.items()}
-        return {k: v.clone() for k, v in self._sums.items()}
+            return {key: total / self._seen[key] for key, total in reported.items()}
+        return {key: total.clone() for key, total in reported.items()}
 
     def compute(self) -> LossesType:
         return self.losses_type.aggregate(self)  # type: ignore[return-value]
@@ -169,11 +177,13 @@ class LossMeter(Generic[LossesType]):
         loss_list: list[dict[str, torch.Tensor]], loss_meter_type: LossMeterType
     ) -> dict[str, torch.Tensor]:
         totals: dict[str, torch.Tensor] = {}
+        present: dict[str, int] = {}
         for loss_dict in loss_list:
             for key, loss in loss_dict.items():
                 totals[key] = totals[key] + loss if key in totals else loss.clone()
-        if loss_meter_type == LossMeterType.AVERAGE:
-            return {key: total / len(loss_list) for key, total in totals.items()}
+                present[key] = present.get(key, 0) + 1
+        if loss_meter_type == LossMeterType.AVERAGE:  # over the dictionaries that carry the key
+            return {key: total / present[key] for key, total in totals.items()}
         return totals
 
     # --- state (pickled by the client state checkpointer) -------------------------------------------------
@@ -181,3 +191,8 @@ class LossMeter(Generic[LossesType]):
         state = self.__dict__.copy()
         state["_sums"] = {k: v.detach().cpu() for k, v in self._sums.items()}
         return state
+
+    def __setstate__(self, state: dict) -> None:
+        self.__dict__.update(state)
+        if "_seen" not in state:  # snapshots written before per-key step counts existed: every key was seen every step
+            self._seen = dict.fromkeys(self._sums, self.count)

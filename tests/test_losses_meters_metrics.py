@@ -93,3 +93,29 @@ def test_binary_soft_dice_and_metric_manager_keys() -> None:
         manager.update({"prediction": logits[0], "aux": logits[0]}, {"prediction": targets[0], "other": targets[0]})
     manager.reset()
     assert manager.metrics_per_prediction_type == {}
+
+
+def test_loss_meter_averages_a_key_over_the_steps_that_reported_it() -> None:
+    """An optional term (a penalty that is only active in some steps) is averaged over the steps that had it, as with the
+    reference's list of per-step dictionaries; after ``clear`` a key that is not reported again does not linger."""
+    import torch
+
+    from fl4health_b200.utils.losses import LossMeter, LossMeterType, TrainingLosses
+
+    meter = LossMeter(LossMeterType.AVERAGE, TrainingLosses)
+    meter.update(TrainingLosses(torch.tensor(1.0), {"penalty": torch.tensor(4.0)}))
+    meter.update(TrainingLosses(torch.tensor(3.0)))
+    meter.update(TrainingLosses(torch.tensor(5.0), {"penalty": torch.tensor(2.0)}))
+    assert meter.compute().as_dict() == {"penalty": 3.0, "backward": 3.0}
+    meter.clear()
+    meter.update(TrainingLosses(torch.tensor(2.0)))
+    assert meter.compute().as_dict() == {"backward": 2.0}
+    # the split form used around captured graphs: accumulate on the device, count on the host
+    meter.clear()
+    step = TrainingLosses(torch.tensor(1.0), {"penalty": torch.tensor(1.0)})
+    for _ in range(4):
+        meter.accumulate(step)
+        meter.mark_step(losses=step)
+    assert meter.compute().as_dict() == {"penalty": 1.0, "backward": 1.0} and meter.count == 4
+    summed = LossMeter.aggregate_losses_dict([{"a": torch.tensor(1.0)}, {"a": torch.tensor(3.0), "b": torch.tensor(5.0)}], LossMeterType.AVERAGE)
+    assert float(summed["a"]) == 2.0 and float(summed["b"]) == 5.0
