@@ -100,6 +100,7 @@ class BasicClient:
             setattr(self, f"{split}_metric_manager", MetricManager(metrics=self.metrics, metric_manager_name=split))
 
         self.initialized = False
+        self._answering_fit = False
         self.initial_weights: NDArrays | None = None
         self.total_steps = self.total_epochs = 0
         self.num_test_samples: int | None = None
@@ -239,7 +240,7 @@ class BasicClient:
         ``on_init_parameters_config_fn``) reaching a client that has already been set up — a properties poll (nnU-Net plan
         negotiation, tabular feature alignment) may have initialised it.  Clients that pack side information into their
         regular payload must answer this request with the plain model state, exactly like an uninitialised client."""
-        return self.initialized and config.get("current_server_round") == 0
+        return self.initialized and config.get("current_server_round") == 0 and not self._answering_fit
 
     def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
         """The very first fit installs *all* weights (full exchange) whatever the exchanger; afterwards the client's
@@ -315,7 +316,11 @@ class BasicClient:
         if state_io:
             self._save_client_state()
         with tracing.phase("push_parameters"):
-            return self.get_parameters(config), self.num_train_samples, metrics
+            self._answering_fit = True  # round 0 can be a FIT too (SCAFFOLD's warm start): its answer is the regular payload
+            try:
+                return self.get_parameters(config), self.num_train_samples, metrics
+            finally:
+                self._answering_fit = False
 
     def evaluate(self, parameters: NDArrays, config: Config) -> tuple[float, int, dict[str, Scalar]]:
         if not self.initialized:

@@ -25,6 +25,7 @@ from fl4health_b200.engine.options import EngineOptions
 from fl4health_b200.metrics.base_metrics import Metric
 from fl4health_b200.ops import flat as flat_ops
 from fl4health_b200.parallel.arena import TrainableRegionLayout, arena_of
+from fl4health_b200.parameter_exchange.full_exchanger import FullParameterExchanger
 from fl4health_b200.parameter_exchange.packing_exchanger import FullParameterExchangerWithPacking
 from fl4health_b200.parameter_exchange.parameter_exchanger_base import ParameterExchanger
 from fl4health_b200.parameter_exchange.parameter_packer import ParameterPackerWithControlVariates

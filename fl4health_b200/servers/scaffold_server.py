@@ -14,6 +14,7 @@ from fl4health_b200.common.typing import Config, Scalar, ndarrays_to_parameters,
 from fl4health_b200.reporting.base_reporter import BaseReporter
 from fl4health_b200.servers.base_server import FlServer
 from fl4health_b200.servers.client_manager import ClientManager
+from fl4health_b200.utils.functions import decode_and_pseudo_sort_results
 from fl4health_b200.strategies.scaffold import Scaffold
 
 
@@ -62,14 +63,18 @@ class ScaffoldServer(FlServer):
         log(DEBUG, f"Warm start: strategy sampled {len(client_instructions)} clients")
         results, failures = self.transport.fit_clients(client_instructions, self.max_workers, timeout, group_id=0)
         log(DEBUG, f"Warm Start: Received {len(results)} results and {len(failures)} failures")
-        aggregated, _ = self.strategy.aggregate_fit(0, results, failures)
-        assert aggregated is not None
-        _, variates = self.strategy.parameter_packer.unpack_parameters(parameters_to_ndarrays(aggregated))
-        # keep the ORIGINAL weights; adopt only the warmed-up control variates
-        original_weights, _ = self.strategy.parameter_packer.unpack_parameters(parameters_to_ndarrays(initial_parameters))
-        self.strategy.server_model_weights = original_weights
-        self.strategy.server_control_variates = variates
-        return ndarrays_to_parameters(self.strategy.parameter_packer.pack_parameters(original_weights, variates))
+        if not results:
+            log(ERROR, "Warm Start initialization failed: no client returned a result")
+            return initial_parameters
+        packer = self.strategy.parameter_packer
+        decoded = [arrays for _, arrays, _ in decode_and_pseudo_sort_results(results, materialize=False)]
+        _, variate_updates = packer.unpack_parameters(self.strategy.aggregate(decoded))
+        # The clients start round 1 from the ORIGINAL weights and the warmed-up variates c0 + (|S|/N) mean(delta c_i).  As
+        # in the reference (scaffold_server.py:96-143, where the value is computed but never stored) the strategy's own
+        # running variates are NOT advanced by the warm start: round 1's server update starts from the initial ones.
+        warmed = self.strategy.compute_updated_parameters(self.strategy.fraction_fit, self.strategy.server_control_variates, variate_updates)
+        original_weights, _ = packer.unpack_parameters(parameters_to_ndarrays(initial_parameters))
+        return ndarrays_to_parameters(packer.pack_parameters(original_weights, warmed))
 
     def fit(self, num_rounds: int, timeout: float | None = None) -> tuple[History, float]:
         assert isinstance(self.strategy, Scaffold)

@@ -1,0 +1,252 @@
+"""Whole federations vs the reference: the same clients (model, data, optimizer, seeds) and the same server set-up, run
+(1) by the UNMODIFIED reference -- its ``FlServer`` / strategy / client classes over the stand-alone Flower transport on
+localhost -- and (2) by this framework's in-process simulation.  The per-round histories (aggregated validation loss,
+aggregated fit and evaluation metrics) must coincide."""
+import importlib
+import socket
+import sys
+import threading
+from pathlib import Path
+
+import torch
+from torch import nn
+from torch.utils.data import DataLoader
+
+ROUNDS, CLIENTS, LOCAL_STEPS, BATCH = 3, 3, 4, 16
+agreed = 0
+# the reference's clients run as threads of this process and share the global generator: seeding + construction is atomic
+_MODEL_LOCK = threading.Lock()
+
+
+def cohort(index: int) -> tuple[torch.Tensor, torch.Tensor]:
+    generator = torch.Generator().manual_seed(100 + index)
+    features = torch.randn(96, 10, generator=generator) + 0.4 * index
+    labels = (features[:, :3].sum(dim=1) + 0.3 * torch.randn(96, generator=generator) > 0.4 * index * 3).long()
+    return features, labels
+
+
+class Net(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.body = nn.Sequential(nn.Linear(10, 16), nn.ReLU())
+        self.head = nn.Linear(16, 2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.head(self.body(x))
+
+
+def user_hooks(side, index: int, model_factory=Net, lr: float = 0.05) -> dict:
+    """The four user hooks, identical on both sides (``side`` resolves the package the dataset class comes from)."""
+    dataset_module = side("utils.dataset")
+
+    def get_model(self, config):
+        with _MODEL_LOCK:
+            torch.manual_seed(7)  # every client starts from the same initialisation, as if broadcast
+            return model_factory().to(self.device)
+
+    def get_data_loaders(self, config):
+        features, labels = cohort(index)
+        train = dataset_module.TensorDataset(features[:64], labels[:64])
+        val = dataset_module.TensorDataset(features[64:], labels[64:])
+        return DataLoader(train, batch_size=BATCH, shuffle=False), DataLoader(val, batch_size=BATCH, shuffle=False)
+
+    def get_optimizer(self, config):
+        return torch.optim.SGD(self.model.parameters(), lr=lr, momentum=0.9)
+
+    def get_criterion(self, config):
+        return nn.CrossEntropyLoss()
+
+    return {"get_model": get_model, "get_data_loaders": get_data_loaders, "get_optimizer": get_optimizer, "get_criterion": get_criterion}
+
+
+def resolver(prefix: str):
+    return lambda dotted: importlib.import_module(f"{prefix}.{dotted}")
+
+
+def round_config(extra: dict):
+    def config_fn(server_round: int) -> dict:
+        config = {"current_server_round": server_round, "local_steps": LOCAL_STEPS, "batch_size": BATCH, "n_server_rounds": ROUNDS, **extra}
+        if "local_epochs" in extra:
+            del config["local_steps"]  # the two are mutually exclusive
+        return config
+
+    return config_fn
+
+
+def build(side, scenario: dict, ours: bool):
+    """Server and clients of one scenario from the package ``side`` resolves."""
+    client_cls = getattr(side(scenario["client"][0]), scenario["client"][1])
+    accuracy = side("metrics").Accuracy if hasattr(side("metrics"), "Accuracy") else side("metrics.metrics").Accuracy
+    clients = []
+    for index in range(CLIENTS):
+        hooks = user_hooks(side, index, **scenario.get("hook_args", {}))
+        hooks.update(scenario.get("extra_hooks", lambda side, index: {})(side, index))
+        cls = type(f"Client{index}", (client_cls,), hooks)
+        clients.append(cls(data_path=Path("."), metrics=[accuracy()], device=torch.device("cpu"), client_name=f"client_{index}",
+                           **scenario.get("client_args", lambda side: {})(side)))
+    aggregation = side("metrics.metric_aggregation")
+    config_fn = round_config(scenario.get("config", {}))
+    strategy_cls = getattr(side(scenario["strategy"][0]), scenario["strategy"][1])
+    strategy_args = dict(on_fit_config_fn=config_fn, on_evaluate_config_fn=config_fn,
+                         fit_metrics_aggregation_fn=aggregation.fit_metrics_aggregation_fn,
+                         evaluate_metrics_aggregation_fn=aggregation.evaluate_metrics_aggregation_fn, min_available_clients=CLIENTS)
+    if scenario.get("min_fit", True):
+        strategy_args.update(min_fit_clients=CLIENTS, min_evaluate_clients=CLIENTS)
+    strategy_args.update(scenario.get("strategy_args", lambda side, ours: {})(side, ours))
+    strategy = strategy_cls(**strategy_args)
+    server_cls = getattr(side(scenario["server"][0]), scenario["server"][1])
+    manager = scenario.get("manager", lambda side, ours: (side("servers.client_manager") if ours else importlib.import_module("flwr.server.client_manager")).SimpleClientManager())(side, ours)
+    server = server_cls(client_manager=manager, fl_config={"n_server_rounds": ROUNDS}, strategy=strategy,
+                        on_init_parameters_config_fn=config_fn, accept_failures=False, **scenario.get("server_args", lambda side: {})(side))
+    return server, clients
+
+
+def run_reference(scenario: dict):
+    import flwr
+
+    server, clients = build(resolver("fl4health"), scenario, ours=False)
+    with socket.socket() as probe:
+        probe.bind(("127.0.0.1", 0))
+        port = probe.getsockname()[1]
+    address = f"127.0.0.1:{port}"
+    threads = [threading.Thread(target=flwr.client.start_client, kwargs=dict(server_address=address, client=client.to_client(), cid=client.client_name), daemon=True)
+               for client in clients]
+    for thread in threads:
+        thread.start()
+    history = flwr.server.start_server(server=server, server_address=address, config=flwr.server.ServerConfig(num_rounds=ROUNDS))
+    for thread in threads:
+        thread.join(60)
+    return history
+
+
+def run_ours(scenario: dict):
+    from fl4health_b200.simulation import run_simulation
+
+    server, clients = build(resolver("fl4health_b200"), scenario, ours=True)
+    return run_simulation(server, clients, num_rounds=ROUNDS)
+
+
+def compare(name: str, theirs, ours, tol: float) -> None:
+    global agreed
+    assert [r for r, _ in theirs.losses_distributed] == [r for r, _ in ours.losses_distributed], name
+    for (server_round, a), (_, b) in zip(theirs.losses_distributed, ours.losses_distributed):
+        assert abs(a - b) <= tol * max(1.0, abs(a)), (name, "loss", server_round, a, b)
+    for label, left, right in (("fit", theirs.metrics_distributed_fit, ours.metrics_distributed_fit), ("eval", theirs.metrics_distributed, ours.metrics_distributed)):
+        assert set(left) == set(right), (name, label, sorted(left), sorted(right))
+        for key in left:
+            for (server_round, a), (_, b) in zip(left[key], right[key]):
+                assert abs(float(a) - float(b)) <= tol * max(1.0, abs(float(a))), (name, label, key, server_round, a, b)
+    print(f"  {name}: {len(theirs.losses_distributed)} rounds, {len(theirs.metrics_distributed_fit)} fit / {len(theirs.metrics_distributed)} eval metric series agree", file=sys.stderr)
+    agreed += 1
+
+
+def seeded(factory):
+    with _MODEL_LOCK:
+        torch.manual_seed(7)
+        return factory()
+
+
+def initial_parameters(factory=Net):
+    """The server-side initial model: the same seeded initialisation the clients build."""
+    return lambda side, ours: {"initial_parameters": side("utils.parameter_extraction").get_all_model_parameters(seeded(factory))}
+
+
+def adaptive_constraint(factory=Net, **kwargs):
+    settings = dict(initial_loss_weight=0.1, adapt_loss_weight=True, loss_weight_delta=0.05, loss_weight_patience=1)
+    settings.update(kwargs)
+    return lambda side, ours: {**initial_parameters(factory)(side, ours), **settings}
+
+
+def two_optimizers(first: str, second: str, first_of, second_of):
+    def hooks(side, index):
+        def get_optimizer(self, config):
+            return {first: torch.optim.SGD(first_of(self).parameters(), lr=0.05, momentum=0.9),
+                    second: torch.optim.SGD(second_of(self).parameters(), lr=0.05, momentum=0.9)}
+
+        return {"get_optimizer": get_optimizer}
+
+    return hooks
+
+
+def model_hook(build_model):
+    """Replace ``get_model`` by a seeded factory that needs classes from the side's own package."""
+    def hooks(side, index):
+        def get_model(self, config):
+            with _MODEL_LOCK:
+                torch.manual_seed(7)
+                return build_model(side).to(self.device)
+
+        return {"get_model": get_model}
+
+    return hooks
+
+
+def merged(*hook_makers):
+    def hooks(side, index):
+        out = {}
+        for make in hook_makers:
+            out.update(make(side, index))
+        return out
+
+    return hooks
+
+
+class Body(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.layers = nn.Sequential(nn.Linear(10, 16), nn.ReLU())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.layers(x)
+
+
+def parallel_head(side):
+    module = side("model_bases.parallel_split_models")
+
+    class Head(module.ParallelSplitHeadModule):
+        def __init__(self) -> None:
+            super().__init__(module.ParallelFeatureJoinMode.CONCATENATE)
+            self.classifier = nn.Linear(32, 2)
+
+        def parallel_output_join(self, local_tensor, global_tensor):
+            return torch.cat([local_tensor, global_tensor], dim=1)
+
+        def head_forward(self, input_tensor):
+            return self.classifier(input_tensor)
+
+    return Head()
+
+
+FEDAVG = dict(strategy=("strategies.basic_fedavg", "BasicFedAvg"), server=("servers.base_server", "FlServer"))
+SCENARIOS = {
+    "fedavg": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG),
+    "fedavg_epochs": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, config={"local_epochs": 2}),
+    "fedprox": dict(client=("clients.fed_prox_client", "FedProxClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                    server=("servers.adaptive_constraint_servers.fedprox_server", "FedProxServer"), strategy_args=adaptive_constraint()),
+    "ditto": dict(client=("clients.ditto_client", "DittoClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                  server=("servers.adaptive_constraint_servers.ditto_server", "DittoServer"), strategy_args=adaptive_constraint(initial_loss_weight=0.5),
+                  extra_hooks=two_optimizers("global", "local", lambda c: c.global_model, lambda c: c.model)),
+    "mr_mtl": dict(client=("clients.mr_mtl_client", "MrMtlClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                   server=("servers.adaptive_constraint_servers.mrmtl_server", "MrMtlServer"), strategy_args=adaptive_constraint(adapt_loss_weight=False)),
+    "scaffold": dict(client=("clients.scaffold_client", "ScaffoldClient"), strategy=("strategies.scaffold", "Scaffold"), server=("servers.scaffold_server", "ScaffoldServer"),
+                     min_fit=False, hook_args={"lr": 0.05}, server_args=lambda side: {"warm_start": True},
+                     manager=lambda side, ours: side("client_managers.fixed_without_replacement_manager").FixedSamplingByFractionClientManager(),
+                     strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "model": seeded(Net), "learning_rate": 1.0}),
+    "apfl": dict(client=("clients.apfl_client", "ApflClient"), **FEDAVG,
+                 extra_hooks=merged(model_hook(lambda side: side("model_bases.apfl_base").ApflModule(Net(), alpha_lr=0.05)),
+                                    two_optimizers("local", "global", lambda c: c.model.local_model, lambda c: c.model.global_model))),
+    "moon": dict(client=("clients.moon_client", "MoonClient"), **FEDAVG, client_args=lambda side: {"contrastive_weight": 2.0},
+                 extra_hooks=model_hook(lambda side: side("model_bases.moon_base").MoonModel(Body(), nn.Linear(8, 2), nn.Linear(16, 8)))),
+    "fedper": dict(client=("clients.fedper_client", "FedPerClient"), **FEDAVG,
+                   extra_hooks=model_hook(lambda side: side("model_bases.sequential_split_models").SequentiallySplitExchangeBaseModel(Body(), nn.Linear(16, 2)))),
+    "fenda": dict(client=("clients.fenda_client", "FendaClient"), **FEDAVG,
+                  extra_hooks=model_hook(lambda side: side("model_bases.fenda_base").FendaModel(Body(), Body(), parallel_head(side)))),
+    "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
+                  strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
+}
+
+if __name__ == "__main__":
+    wanted = sys.argv[1:] or list(SCENARIOS)
+    for name in wanted:
+        compare(name, run_reference(SCENARIOS[name]), run_ours(SCENARIOS[name]), tol=2e-4)
+    print("configs agree:", agreed)

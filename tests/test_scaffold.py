@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from fl4health_b200.clients.scaffold_client import ScaffoldClient
-from fl4health_b200.common.typing import NDArrays, ndarrays_to_parameters
+from fl4health_b200.common.typing import NDArrays, ndarrays_to_parameters, parameters_to_ndarrays
 from fl4health_b200.engine.fused_optim import FlatSGD
 from fl4health_b200.metrics.metric_aggregation import evaluate_metrics_aggregation_fn, fit_metrics_aggregation_fn
 from fl4health_b200.servers.client_manager import SimpleClientManager
@@ -150,3 +150,29 @@ def test_server_flat_step_matches_per_tensor_update() -> None:
             assert got.dtype == want.dtype and torch.allclose(got.double(), want.double(), atol=1e-6)
         flat_strategy.server_model_weights, flat_strategy.server_control_variates = new_x, new_c
         list_strategy.server_model_weights, list_strategy.server_control_variates = ref_x, ref_c
+
+
+def test_warm_start_hands_variates_to_clients_without_advancing_the_strategy() -> None:
+    """Round 0 is a FIT whose answer is the regular packed payload (it used to be mistaken for the initial-parameters
+    request); afterwards the clients hold warmed-up variates and the original weights, while the strategy's own running
+    variates are still the initial ones -- the reference's behaviour, pinned by tests/differential/check_federations.py."""
+    from fl4health_b200.client_managers.fixed_without_replacement_manager import FixedSamplingByFractionClientManager
+    from fl4health_b200.simulation import register_clients
+
+    set_all_random_seeds(11)
+    clients = make_mixed_clients(ScaffoldClient, 2, model_fn=staticmethod(TinyNet), momentum=0.0, lr=0.05)
+    template = TinyNet()
+    initial = [v.clone() for v in template.state_dict().values()]
+    strategy = Scaffold(
+        initial_parameters=ndarrays_to_parameters([v.clone() for v in initial]), model=template, min_available_clients=2,
+        on_fit_config_fn=fit_config_fn(), on_evaluate_config_fn=fit_config_fn(),
+        fit_metrics_aggregation_fn=fit_metrics_aggregation_fn, evaluate_metrics_aggregation_fn=evaluate_metrics_aggregation_fn,
+    )
+    server = ScaffoldServer(FixedSamplingByFractionClientManager(), {"n_server_rounds": 1}, strategy, warm_start=True)
+    register_clients(server, clients)
+    packed = parameters_to_ndarrays(server._get_initial_parameters(server_round=0, timeout=None))
+    weights, variates = strategy.parameter_packer.unpack_parameters(packed)
+    assert all(torch.equal(torch.as_tensor(_np(w)), torch.as_tensor(_np(v))) for w, v in zip(weights, initial))
+    assert any(float(torch.as_tensor(_np(v)).abs().sum()) > 0 for v in variates)  # warmed up
+    assert all(float(torch.as_tensor(_np(v)).abs().sum()) == 0 for v in strategy.server_control_variates)  # not advanced
+    assert all(client.client_control_variates is not None for client in clients)
