@@ -14,8 +14,17 @@ from torch.utils.data import DataLoader
 
 ROUNDS, CLIENTS, LOCAL_STEPS, BATCH = 3, 3, 4, 16
 agreed = 0
-# the reference's clients run as threads of this process and share the global generator: seeding + construction is atomic
-_MODEL_LOCK = threading.Lock()
+# The reference's clients run as threads of this process and share the global generator with everything else (every
+# DataLoader iterator draws a base seed from it), so models are NOT initialised from it: after construction every
+# randomly initialised layer is refilled from a private generator.
+def pin_initialisation(module: nn.Module, seed: int = 7) -> nn.Module:
+    generator = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for layer in module.modules():
+            if isinstance(layer, (nn.Linear, nn.Embedding, nn.Conv1d, nn.Conv2d)):
+                for parameter in layer.parameters(recurse=False):
+                    parameter.copy_(torch.randn(parameter.shape, generator=generator) * (0.25 if parameter.dim() > 1 else 0.05))
+    return module
 
 
 def cohort(index: int) -> tuple[torch.Tensor, torch.Tensor]:
@@ -40,9 +49,7 @@ def user_hooks(side, index: int, model_factory=Net, lr: float = 0.05) -> dict:
     dataset_module = side("utils.dataset")
 
     def get_model(self, config):
-        with _MODEL_LOCK:
-            torch.manual_seed(7)  # every client starts from the same initialisation, as if broadcast
-            return model_factory().to(self.device)
+        return pin_initialisation(model_factory()).to(self.device)  # every client starts from the same initialisation
 
     def get_data_loaders(self, config):
         features, labels = cohort(index)
@@ -66,8 +73,8 @@ def resolver(prefix: str):
 def round_config(extra: dict):
     def config_fn(server_round: int) -> dict:
         config = {"current_server_round": server_round, "local_steps": LOCAL_STEPS, "batch_size": BATCH, "n_server_rounds": ROUNDS, **extra}
-        if "local_epochs" in extra:
-            del config["local_steps"]  # the two are mutually exclusive
+        if "local_epochs" in extra or "local_head_steps" in extra:
+            del config["local_steps"]  # mutually exclusive ways of saying how long to train
         return config
 
     return config_fn
@@ -141,9 +148,7 @@ def compare(name: str, theirs, ours, tol: float) -> None:
 
 
 def seeded(factory):
-    with _MODEL_LOCK:
-        torch.manual_seed(7)
-        return factory()
+    return pin_initialisation(factory())
 
 
 def initial_parameters(factory=Net):
@@ -172,9 +177,7 @@ def model_hook(build_model):
     """Replace ``get_model`` by a seeded factory that needs classes from the side's own package."""
     def hooks(side, index):
         def get_model(self, config):
-            with _MODEL_LOCK:
-                torch.manual_seed(7)
-                return build_model(side).to(self.device)
+            return pin_initialisation(build_model(side)).to(self.device)
 
         return {"get_model": get_model}
 
@@ -189,6 +192,15 @@ def merged(*hook_makers):
         return out
 
     return hooks
+
+
+class NormNet(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.first, self.norm, self.head = nn.Linear(10, 16), nn.BatchNorm1d(16), nn.Linear(16, 2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.head(torch.relu(self.norm(self.first(x))))
 
 
 class Body(nn.Module):
@@ -241,6 +253,52 @@ SCENARIOS = {
                    extra_hooks=model_hook(lambda side: side("model_bases.sequential_split_models").SequentiallySplitExchangeBaseModel(Body(), nn.Linear(16, 2)))),
     "fenda": dict(client=("clients.fenda_client", "FendaClient"), **FEDAVG,
                   extra_hooks=model_hook(lambda side: side("model_bases.fenda_base").FendaModel(Body(), Body(), parallel_head(side)))),
+    "fedrep": dict(client=("clients.fedrep_client", "FedRepClient"), **FEDAVG, config={"local_head_steps": 2, "local_rep_steps": 3},
+                   extra_hooks=merged(model_hook(lambda side: side("model_bases.fedrep_base").FedRepModel(Body(), nn.Linear(16, 2))),
+                                      two_optimizers("representation", "head", lambda c: c.model.base_module, lambda c: c.model.head_module))),
+    "fedbn": dict(client=("clients.fedbn_client", "FedBnClient"), **FEDAVG, hook_args={"model_factory": lambda: NormNet()},
+                  extra_hooks=lambda side, index: {"get_parameter_exchanger": lambda self, config: side("parameter_exchange.layer_exchanger").LayerExchangerWithExclusions(self.model, {nn.BatchNorm1d})}),
+    "perfcl": dict(client=("clients.perfcl_client", "PerFclClient"), **FEDAVG,
+                   client_args=lambda side: {"global_feature_contrastive_loss_weight": 0.5, "local_feature_contrastive_loss_weight": 2.0},
+                   extra_hooks=model_hook(lambda side: side("model_bases.perfcl_base").PerFclModel(Body(), Body(), parallel_head(side)))),
+    "gpfl": dict(client=("clients.gpfl_client", "GpflClient"), **FEDAVG, client_args=lambda side: {"lam": 0.05, "mu": 0.02},
+                 extra_hooks=merged(model_hook(lambda side: side("model_bases.gpfl_base").GpflModel(Body(), nn.Linear(16, 2), feature_dim=16, num_classes=2)),
+                                    lambda side, index: {"get_optimizer": lambda self, config: {
+                                        "model": torch.optim.SGD(self.model.gpfl_main_module.parameters(), lr=0.05),
+                                        "gce": torch.optim.SGD(self.model.gce.embedding.parameters(), lr=0.05, weight_decay=0.02),
+                                        "cov": torch.optim.SGD(self.model.cov.parameters(), lr=0.05, weight_decay=0.02)}})),
+    "ensemble": dict(client=("clients.ensemble_client", "EnsembleClient"), **FEDAVG,
+                     extra_hooks=merged(model_hook(lambda side: side("model_bases.ensemble_base").EnsembleModel({"model_0": Net(), "model_1": Net()})),
+                                        lambda side, index: {"get_optimizer": lambda self, config: {
+                                            name: torch.optim.SGD(member.parameters(), lr=0.05, momentum=0.9) for name, member in self.model.ensemble_models.items()}})),
+    "dynamic_layers": dict(client=("clients.partial_weight_exchange_client", "PartialWeightExchangeClient"), strategy=("strategies.fedavg_dynamic_layer", "FedAvgDynamicLayer"),
+                           server=("servers.base_server", "FlServer"), strategy_args=initial_parameters(), client_args=lambda side: {"store_initial_model": True},
+                           extra_hooks=lambda side, index: {"get_parameter_exchanger": lambda self, config: side("parameter_exchange.layer_exchanger").DynamicLayerExchanger(
+                               side("parameter_exchange.parameter_selection_criteria").LayerSelectionFunctionConstructor(0.01, 0.5, True, True).select_by_percentage())}),
+    "sparse_coo": dict(client=("clients.partial_weight_exchange_client", "PartialWeightExchangeClient"), strategy=("strategies.fedavg_sparse_coo_tensor", "FedAvgSparseCooTensor"),
+                       server=("servers.base_server", "FlServer"), strategy_args=initial_parameters(), client_args=lambda side: {"store_initial_model": True},
+                       extra_hooks=lambda side, index: {"get_parameter_exchanger": lambda self, config: side("parameter_exchange.sparse_coo_parameter_exchanger").SparseCooParameterExchanger(
+                           0.3, side("parameter_exchange.parameter_selection_criteria").largest_final_magnitude_scores)}),
+    "feddg_ga": dict(client=("clients.basic_client", "BasicClient"), strategy=("strategies.feddg_ga", "FedDgGa"), server=("servers.base_server", "FlServer"),
+                     strategy_args=initial_parameters(), config={"evaluate_after_fit": True, "pack_losses_with_val_metrics": True},
+                     manager=lambda side, ours: side("client_managers.fixed_sampling_client_manager").FixedSamplingClientManager()),
+    "fenda_ditto": dict(client=("clients.fenda_ditto_client", "FendaDittoClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                        server=("servers.base_server", "FlServer"),
+                        strategy_args=lambda side, ours: {**adaptive_constraint(initial_loss_weight=0.5)(side, ours), "initial_parameters": side("utils.parameter_extraction").get_all_model_parameters(
+                            seeded(lambda: side("model_bases.sequential_split_models").SequentiallySplitExchangeBaseModel(Body(), nn.Linear(16, 2))))},
+                        extra_hooks=merged(model_hook(lambda side: side("model_bases.fenda_base").FendaModel(Body(), Body(), parallel_head(side))),
+                                           lambda side, index: {"get_global_model": lambda self, config: seeded(
+                                               lambda: side("model_bases.sequential_split_models").SequentiallySplitModel(Body(), nn.Linear(16, 2))).to(self.device)},
+                                           two_optimizers("global", "local", lambda c: c.global_model, lambda c: c.model))),
+    "constrained_fenda": dict(client=("clients.constrained_fenda_client", "ConstrainedFendaClient"), **FEDAVG,
+                              client_args=lambda side: {"loss_container": side("losses.fenda_loss_config").ConstrainedFendaLossContainer(
+                                  None, side("losses.fenda_loss_config").CosineSimilarityLossContainer(torch.device("cpu"), 0.5),
+                                  side("losses.fenda_loss_config").MoonContrastiveLossContainer(torch.device("cpu"), 1.5))},
+                              extra_hooks=model_hook(lambda side: side("model_bases.fenda_base").FendaModelWithFeatureState(Body(), Body(), parallel_head(side), flatten_features=True))),
+    "constrained_fenda_perfcl": dict(client=("clients.constrained_fenda_client", "ConstrainedFendaClient"), **FEDAVG,
+                                     client_args=lambda side: {"loss_container": side("losses.fenda_loss_config").ConstrainedFendaLossContainer(
+                                         side("losses.fenda_loss_config").PerFclLossContainer(torch.device("cpu"), 0.7, 1.3), None, None)},
+                                     extra_hooks=model_hook(lambda side: side("model_bases.fenda_base").FendaModelWithFeatureState(Body(), Body(), parallel_head(side), flatten_features=True))),
     "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
                   strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
 }

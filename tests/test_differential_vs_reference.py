@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not (REFERENCE / "fl4health").is_dir(), reason="
 def test_agrees_with_the_reference(script: Path) -> None:
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(ROOT / "baseline" / "stubs"), str(REFERENCE), str(ROOT)]),
                CUDA_VISIBLE_DEVICES="")
-    run = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600, cwd="/tmp")
+    run = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=1200, cwd="/tmp")
     assert run.returncode == 0, (run.stdout[-1500:], run.stderr[-3000:])
     last = [line for line in run.stdout.splitlines() if line.startswith("configs agree:")]
     assert last and int(last[-1].split(":")[1]) > 0, run.stdout[-1500:]
