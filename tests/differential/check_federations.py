@@ -89,6 +89,9 @@ def build(side, scenario: dict, ours: bool):
         hooks = user_hooks(side, index, **scenario.get("hook_args", {}))
         hooks.update(scenario.get("extra_hooks", lambda side, index: {})(side, index))
         cls = type(f"Client{index}", (client_cls,), hooks)
+        if scenario.get("personalize"):  # dynamically personalised flexible clients
+            personalized = side("mixins.personalized")
+            cls = personalized.make_it_personal(cls, getattr(personalized.PersonalizedMode, scenario["personalize"]))
         clients.append(cls(data_path=Path("."), metrics=[accuracy()], device=torch.device("cpu"), client_name=f"client_{index}",
                            **scenario.get("client_args", lambda side: {})(side)))
     aggregation = side("metrics.metric_aggregation")
@@ -145,6 +148,24 @@ def compare(name: str, theirs, ours, tol: float) -> None:
                 assert abs(float(a) - float(b)) <= tol * max(1.0, abs(float(a))), (name, label, key, server_round, a, b)
     print(f"  {name}: {len(theirs.losses_distributed)} rounds, {len(theirs.metrics_distributed_fit)} fit / {len(theirs.metrics_distributed)} eval metric series agree", file=sys.stderr)
     agreed += 1
+
+
+def optional_hooks(side, index):
+    """A test loader, a step-wise learning-rate schedule and a bounded validation pass."""
+    dataset_module = side("utils.dataset")
+
+    def get_test_data_loader(self, config):
+        features, labels = cohort(index + 10)
+        return DataLoader(dataset_module.TensorDataset(features[:40], labels[:40]), batch_size=BATCH, shuffle=False)
+
+    def get_lr_scheduler(self, optimizer_key, config):
+        return torch.optim.lr_scheduler.StepLR(self.optimizers[optimizer_key], step_size=3, gamma=0.5)
+
+    return {"get_test_data_loader": get_test_data_loader, "get_lr_scheduler": get_lr_scheduler}
+
+
+# (Early stopping is not compared: in this reference version ``EarlyStopper.should_stop`` calls the client's validation
+# with a logging mode its own assertion rejects -- ``basic_client.py:844`` -- so the reference arm cannot run it.)
 
 
 def seeded(factory):
@@ -299,6 +320,13 @@ SCENARIOS = {
                                      client_args=lambda side: {"loss_container": side("losses.fenda_loss_config").ConstrainedFendaLossContainer(
                                          side("losses.fenda_loss_config").PerFclLossContainer(torch.device("cpu"), 0.7, 1.3), None, None)},
                                      extra_hooks=model_hook(lambda side: side("model_bases.fenda_base").FendaModelWithFeatureState(Body(), Body(), parallel_head(side), flatten_features=True))),
+    "flexible": dict(client=("clients.flexible.base", "FlexibleClient"), **FEDAVG),
+    "flexible_ditto": dict(client=("clients.flexible.base", "FlexibleClient"), personalize="DITTO", strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                           server=("servers.adaptive_constraint_servers.ditto_server", "DittoServer"), strategy_args=adaptive_constraint(initial_loss_weight=0.5),
+                           extra_hooks=lambda side, index: {"get_optimizer": lambda self, config: {"local": torch.optim.SGD(self.model.parameters(), lr=0.05, momentum=0.9)}}),
+    "flexible_mr_mtl": dict(client=("clients.flexible.base", "FlexibleClient"), personalize="MR_MTL", strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                            server=("servers.adaptive_constraint_servers.mrmtl_server", "MrMtlServer"), strategy_args=adaptive_constraint(adapt_loss_weight=False)),
+    "options": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, extra_hooks=optional_hooks, config={"num_validation_steps": 1}),
     "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
                   strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
 }
