@@ -28,7 +28,8 @@ def fold_loss_dict_into_metrics(
 
 
 def set_pack_losses_with_val_metrics(config: Config) -> bool:
-    pack = bool(config.get("pack_losses_with_val_metrics", False))
+    pack = config.get("pack_losses_with_val_metrics", False)
+    pack = pack if isinstance(pack, bool) else False  # anything but a real boolean counts as "not requested"
     if pack:
         log(INFO, "As specified in the config, all validation losses will be packed into validation metrics")
     return pack
