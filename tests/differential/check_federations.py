@@ -55,7 +55,9 @@ def user_hooks(side, index: int, model_factory=Net, lr: float = 0.05) -> dict:
         features, labels = cohort(index)
         train = dataset_module.TensorDataset(features[:64], labels[:64])
         val = dataset_module.TensorDataset(features[64:], labels[64:])
-        return DataLoader(train, batch_size=BATCH, shuffle=False), DataLoader(val, batch_size=BATCH, shuffle=False)
+        # private generators: a DataLoader iterator draws its base seed from the generator it is given, else the global one
+        return (DataLoader(train, batch_size=BATCH, shuffle=False, generator=torch.Generator().manual_seed(1)),
+                DataLoader(val, batch_size=BATCH, shuffle=False, generator=torch.Generator().manual_seed(2)))
 
     def get_optimizer(self, config):
         return torch.optim.SGD(self.model.parameters(), lr=lr, momentum=0.9)

@@ -1,0 +1,105 @@
+"""Clients whose local step draws random numbers, driven directly (no server) with the global generator seeded identically
+before every call on both sides: FedPM (Bernoulli masks sampled from learnt scores in every forward; binary masks on the
+wire) and a plain model converted to a masked one on the fly."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch import nn
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from check_federations import resolver, user_hooks  # noqa: E402
+
+import flwr.common as fc
+import fl4health_b200.common.typing as mt
+
+agreed = 0
+
+
+def pin_everything(module: nn.Module, seed: int = 7) -> nn.Module:
+    generator = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, parameter in sorted(module.named_parameters()):
+            parameter.copy_(torch.randn(parameter.shape, generator=generator) * 0.3)
+    return module
+
+
+def to_numpy(arrays) -> list[np.ndarray]:
+    """Copies: what a client returns may alias its live parameters."""
+    return [(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)).copy() for a in arrays]
+
+
+def same_payload(a, b, what) -> None:
+    a, b = to_numpy(a), to_numpy(b)
+    assert len(a) == len(b), (what, len(a), len(b))
+    for x, y in zip(a, b):
+        assert x.shape == y.shape, (what, x.shape, y.shape)
+        if x.dtype.kind in "US":
+            assert (x == y).all(), what
+        else:
+            assert np.allclose(x.astype(np.float64), y.astype(np.float64), atol=1e-5), (what, np.abs(x.astype(np.float64) - y.astype(np.float64)).max())
+
+
+def fedpm_clients(already_masked: bool):
+    built = []
+    for prefix in ("fl4health", "fl4health_b200"):
+        side = resolver(prefix)
+        masked = side("model_bases.masked_layers.masked_linear").MaskedLinear
+
+        def model_factory(masked=masked):
+            if already_masked:
+                return nn.Sequential(masked(10, 16), nn.ReLU(), masked(16, 2))
+            return nn.Sequential(nn.Linear(10, 16), nn.ReLU(), nn.Linear(16, 2))
+
+        hooks = user_hooks(side, 0, lr=0.1)
+        hooks["get_model"] = lambda self, config, factory=model_factory: pin_everything(factory()).to(self.device)
+        if not already_masked:  # conversion re-initialises the scores: pin them right after set-up
+            base_setup = side("clients.fedpm_client").FedPmClient.setup_client
+
+            def setup_client(self, config, base_setup=base_setup):
+                base_setup(self, config)
+                pin_everything(self.model)
+
+            hooks["setup_client"] = setup_client
+        cls = type("PmClient", (side("clients.fedpm_client").FedPmClient,), hooks)
+        accuracy = side("metrics").Accuracy
+        built.append(cls(data_path=Path("."), metrics=[accuracy()], device=torch.device("cpu"), client_name="client_0"))
+    return built
+
+
+# (only models that are masked from the start: when the reference converts a plain model inside ``setup_client`` its
+# optimizer already holds the unconverted model's parameters, so the new scores are never trained there)
+for already_masked in (True,):
+    theirs, ours = fedpm_clients(already_masked)
+    config = {"current_server_round": 1, "local_steps": 4, "batch_size": 16, "is_masked_model": already_masked}
+    torch.manual_seed(100); initial_ref = theirs.get_parameters(dict(config, current_server_round=0))
+    torch.manual_seed(100); initial_mine = ours.get_parameters(dict(config, current_server_round=0))
+    same_payload(initial_ref, initial_mine, "initial parameters")
+    payload = to_numpy(initial_ref)
+    for server_round in (1, 2, 3):
+        config["current_server_round"] = server_round
+        torch.manual_seed(200 + server_round); out_ref, n_ref, metrics_ref = theirs.fit([p.copy() for p in payload], dict(config))
+        torch.manual_seed(200 + server_round); out_mine, n_mine, metrics_mine = ours.fit([p.copy() for p in payload], dict(config))
+        # the scores learnt in this round (every forward sampled the same masks on both sides)
+        for (name, a), (_, b) in zip(theirs.model.state_dict().items(), ours.model.state_dict().items()):
+            assert torch.allclose(a, b, atol=1e-6), (server_round, name, (a - b).abs().max())
+        # what travels: binary masks + the names of the score tensors.  The masks themselves are independent draws (the
+        # reference samples them with scipy / NumPy, we sample on the device), so structure and rates are compared
+        ref_arrays, my_arrays = to_numpy(out_ref), to_numpy(out_mine)
+        assert len(ref_arrays) == len(my_arrays) and [a.shape for a in ref_arrays] == [a.shape for a in my_arrays]
+        assert (ref_arrays[-1] == my_arrays[-1]).all()  # layer names
+        for mask_ref, mask_mine in zip(ref_arrays[:-1], my_arrays[:-1]):
+            assert set(np.unique(mask_ref)) <= {0, 1} and set(np.unique(mask_mine)) <= {0, 1}
+        rate_ref = np.concatenate([m.reshape(-1) for m in ref_arrays[:-1]]).mean()
+        rate_mine = np.concatenate([m.reshape(-1).astype(np.float64) for m in my_arrays[:-1]]).mean()
+        assert abs(rate_ref - rate_mine) < 0.15, (rate_ref, rate_mine)
+        assert n_ref == n_mine and metrics_ref.keys() == metrics_mine.keys()
+        assert all(abs(float(metrics_ref[k]) - float(metrics_mine[k])) < 1e-5 for k in metrics_ref), (metrics_ref, metrics_mine)
+        # the server would answer with per-parameter probabilities: feed both the same "aggregate" (the masks themselves)
+        torch.manual_seed(300 + server_round); loss_ref, _, eval_ref = theirs.evaluate(to_numpy(out_ref), dict(config))
+        torch.manual_seed(300 + server_round); loss_mine, _, eval_mine = ours.evaluate(to_numpy(out_ref), dict(config))
+        assert abs(loss_ref - loss_mine) < 1e-5 and all(abs(float(eval_ref[k]) - float(eval_mine[k])) < 1e-5 for k in eval_ref)
+        payload = to_numpy(out_ref)
+    agreed += 1
+print("configs agree:", agreed)
