@@ -30,7 +30,7 @@ def to_numpy(arrays) -> list[np.ndarray]:
     return [(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)).copy() for a in arrays]
 
 
-def same_payload(a, b, what) -> None:
+def same_payload(a, b, what, tol: float = 1e-5) -> None:
     a, b = to_numpy(a), to_numpy(b)
     assert len(a) == len(b), (what, len(a), len(b))
     for x, y in zip(a, b):
@@ -38,7 +38,7 @@ def same_payload(a, b, what) -> None:
         if x.dtype.kind in "US":
             assert (x == y).all(), what
         else:
-            assert np.allclose(x.astype(np.float64), y.astype(np.float64), atol=1e-5), (what, np.abs(x.astype(np.float64) - y.astype(np.float64)).max())
+            assert np.allclose(x.astype(np.float64), y.astype(np.float64), atol=tol), (what, np.abs(x.astype(np.float64) - y.astype(np.float64)).max())
 
 
 def fedpm_clients(already_masked: bool):
@@ -101,5 +101,48 @@ for already_masked in (True,):
         torch.manual_seed(300 + server_round); loss_mine, _, eval_mine = ours.evaluate(to_numpy(out_ref), dict(config))
         assert abs(loss_ref - loss_mine) < 1e-5 and all(abs(float(eval_ref[k]) - float(eval_mine[k])) < 1e-5 for k in eval_ref)
         payload = to_numpy(out_ref)
+    agreed += 1
+
+
+# -- Ditto / MR-MTL with a Deep-MMD feature-alignment term: the deep kernel is trained every few steps on shuffled samples ------
+def mmd_clients(module_path: str, class_name: str, optimizers: bool):
+    built = []
+    for prefix in ("fl4health", "fl4health_b200"):
+        side = resolver(prefix)
+        hooks = user_hooks(side, 1)
+        if optimizers:
+            hooks["get_optimizer"] = lambda self, config: {"global": torch.optim.SGD(self.global_model.parameters(), lr=0.05, momentum=0.9),
+                                                           "local": torch.optim.SGD(self.model.parameters(), lr=0.05, momentum=0.9)}
+        cls = type("MmdClient", (getattr(side(module_path), class_name),), hooks)
+        torch.manual_seed(55); np.random.seed(55)
+        client = cls(data_path=Path("."), metrics=[side("metrics").Accuracy()], device=torch.device("cpu"), client_name="client_0",
+                     deep_mmd_loss_weight=2.0, feature_extraction_layers_with_size={"body": 16}, mmd_kernel_train_interval=2, num_accumulating_batches=2)
+        built.append(client)
+    theirs, ours = built
+    for layer, loss in theirs.deep_mmd_losses.items():  # same deep kernel on both sides
+        ours.deep_mmd_losses[layer].featurizer.load_state_dict(loss.featurizer.state_dict())
+        for name in ("epsilon_opt", "sigma_q_opt", "sigma_phi_opt"):
+            getattr(ours.deep_mmd_losses[layer], name).data.copy_(getattr(loss, name).data)
+    return theirs, ours
+
+
+for module_path, class_name, two_optimizers, packs_weight in (
+    ("clients.deep_mmd_clients.ditto_deep_mmd_client", "DittoDeepMmdClient", True, True),
+    ("clients.deep_mmd_clients.mr_mtl_deep_mmd_client", "MrMtlDeepMmdClient", False, True),
+):
+    theirs, ours = mmd_clients(module_path, class_name, two_optimizers)
+    config = {"current_server_round": 1, "local_steps": 6, "batch_size": 16}
+    torch.manual_seed(100); initial_ref = to_numpy(theirs.get_parameters(dict(config, current_server_round=0)))
+    torch.manual_seed(100); initial_mine = to_numpy(ours.get_parameters(dict(config, current_server_round=0)))
+    same_payload(initial_ref, initial_mine, "initial parameters")
+    payload = initial_ref + [np.array(0.5)]  # the server appends the drift-penalty weight
+    for server_round in (1, 2):
+        config["current_server_round"] = server_round
+        torch.manual_seed(400 + server_round); np.random.seed(server_round); out_ref, _, metrics_ref = theirs.fit([p.copy() for p in payload], dict(config))
+        torch.manual_seed(400 + server_round); np.random.seed(server_round); out_mine, _, metrics_mine = ours.fit([p.copy() for p in payload], dict(config))
+        same_payload(to_numpy(out_ref)[:-1], to_numpy(out_mine)[:-1], f"{class_name} round {server_round} weights", tol=2e-4)  # the deep kernel trains in fp64 there, fp32 here
+        assert abs(float(to_numpy(out_ref)[-1]) - float(to_numpy(out_mine)[-1])) < 1e-4  # the packed training loss
+        assert metrics_ref.keys() == metrics_mine.keys() and all(abs(float(metrics_ref[k]) - float(metrics_mine[k])) < 1e-4 for k in metrics_ref), (metrics_ref, metrics_mine)
+        payload = to_numpy(out_ref)[:-1] + [np.array(0.5)]
     agreed += 1
 print("configs agree:", agreed)
