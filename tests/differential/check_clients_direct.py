@@ -1,6 +1,7 @@
-"""Clients whose local step draws random numbers, driven directly (no server) with the global generator seeded identically
-before every call on both sides: FedPM (Bernoulli masks sampled from learnt scores in every forward; binary masks on the
-wire) and a plain model converted to a masked one on the fly."""
+"""Clients driven directly (no server), with the global generator seeded identically before every call on both sides where
+the local step draws random numbers: FedPM (Bernoulli masks sampled from learnt scores in every forward; binary masks on
+the wire), Ditto / MR-MTL with a Deep-MMD term (deep kernel trained on shuffled samples), the client-level-DP clipping
+client (clipped update + clipping bit), the FedPCA client (local components, evaluation of merged components)."""
 import sys
 from pathlib import Path
 
@@ -144,5 +145,77 @@ for module_path, class_name, two_optimizers, packs_weight in (
         assert abs(float(to_numpy(out_ref)[-1]) - float(to_numpy(out_mine)[-1])) < 1e-4  # the packed training loss
         assert metrics_ref.keys() == metrics_mine.keys() and all(abs(float(metrics_ref[k]) - float(metrics_mine[k])) < 1e-4 for k in metrics_ref), (metrics_ref, metrics_mine)
         payload = to_numpy(out_ref)[:-1] + [np.array(0.5)]
+    agreed += 1
+
+
+# -- client-level DP: the clipping client (update = new - old weights, clipped to the bound the server sent; clipping bit) ---
+for adaptive, bound in ((True, 0.05), (True, 50.0), (False, 0.05)):
+    built = []
+    for prefix in ("fl4health", "fl4health_b200"):
+        side = resolver(prefix)
+        cls = type("ClipClient", (side("clients.clipping_client").NumpyClippingClient,), user_hooks(side, 2))
+        built.append(cls(data_path=Path("."), metrics=[side("metrics").Accuracy()], device=torch.device("cpu"), client_name="client_0"))
+    theirs, ours = built
+    config = {"current_server_round": 1, "local_steps": 4, "batch_size": 16, "adaptive_clipping": adaptive}
+    initial = to_numpy(theirs.get_parameters(dict(config, current_server_round=0)))
+    same_payload(initial, to_numpy(ours.get_parameters(dict(config, current_server_round=0))), "initial parameters")
+    payload = initial + [np.array(bound)]
+    for server_round in (1, 2, 3):
+        config["current_server_round"] = server_round
+        out_ref, n_ref, _ = theirs.fit([p.copy() for p in payload], dict(config))
+        out_mine, n_mine, _ = ours.fit([p.copy() for p in payload], dict(config))
+        ref_arrays, my_arrays = to_numpy(out_ref), to_numpy(out_mine)
+        if server_round == 1:
+            # On a CPU device the reference's round-1 "initial weights" are NumPy views of the live parameters
+            # (``push_parameters`` -> ``.cpu().numpy()`` shares storage), so its first update is identically zero; on a GPU
+            # the same line copies.  Ours is the true update; the comparison starts with round 2.
+            assert all(not a.any() for a in ref_arrays[:-1]) and any(a.any() for a in my_arrays[:-1])
+            payload = [w + u for w, u in zip(payload[:-1], my_arrays[:-1])] + [np.array(bound)]
+            continue
+        same_payload(ref_arrays[:-1], my_arrays[:-1], f"clipped update (bound {bound})", tol=1e-6)
+        assert float(np.asarray(ref_arrays[-1]).reshape(-1)[0]) == float(np.asarray(my_arrays[-1]).reshape(-1)[0]) and n_ref == n_mine, (ref_arrays[-1], my_arrays[-1])  # the clipping bit
+        norm = np.sqrt(sum(float((a.astype(np.float64) ** 2).sum()) for a in my_arrays[:-1]))
+        assert norm <= bound * (1 + 1e-5)
+        loss_ref, _, eval_ref = theirs.evaluate([p.copy() for p in payload], dict(config))
+        loss_mine, _, eval_mine = ours.evaluate([p.copy() for p in payload], dict(config))
+        assert abs(loss_ref - loss_mine) < 1e-5 and all(abs(float(eval_ref[k]) - float(eval_mine[k])) < 1e-6 for k in eval_ref)
+        payload = [w + u for w, u in zip(payload[:-1], ref_arrays[:-1])] + [np.array(bound)]  # the server applies the update
+    agreed += 1
+
+# -- FedPCA client: local principal components, then evaluation of merged components ---------------------------------------------
+import tempfile  # noqa: E402
+
+from torch.utils.data import DataLoader  # noqa: E402
+
+for low_rank, full_svd in ((False, True), (True, False)):
+    built = []
+    for prefix in ("fl4health", "fl4health_b200"):
+        side = resolver(prefix)
+        dataset_module = side("utils.dataset")
+
+        def get_data_loaders(self, config, dataset_module=dataset_module):
+            generator = torch.Generator().manual_seed(77)
+            data = torch.randn(90, 12, generator=generator) @ torch.randn(12, 12, generator=generator)
+            labels = torch.zeros(90).long()
+            return (DataLoader(dataset_module.TensorDataset(data[:60], labels[:60]), batch_size=20), DataLoader(dataset_module.TensorDataset(data[60:], labels[60:]), batch_size=20))
+
+        def get_data_tensor(self, data_loader):
+            return torch.cat([batch for batch, _ in data_loader], dim=0)
+
+        cls = type("PcaClient", (side("clients.fed_pca_client").FedPCAClient,), {"get_data_loaders": get_data_loaders, "get_data_tensor": get_data_tensor})
+        built.append(cls(Path("."), torch.device("cpu"), Path(tempfile.mkdtemp()), client_name="client_0"))
+    theirs, ours = built
+    config = {"current_server_round": 1, "low_rank": low_rank, "full_svd": full_svd, "rank_estimation": 6, "center_data": True, "num_components_eval": 4}
+    torch.manual_seed(5); out_ref, n_ref, metrics_ref = theirs.fit([], dict(config))
+    torch.manual_seed(5); out_mine, n_mine, metrics_mine = ours.fit([], dict(config))
+    (pc_ref, sv_ref), (pc_mine, sv_mine) = to_numpy(out_ref), to_numpy(out_mine)
+    k = 4
+    assert n_ref == n_mine and pc_ref.shape == pc_mine.shape and np.allclose(sv_ref[:k], sv_mine[:k], rtol=1e-3, atol=1e-3), (sv_ref, sv_mine)
+    assert np.allclose(np.abs((pc_ref[:, :k] * pc_mine[:, :k]).sum(axis=0)), 1.0, atol=1e-3)  # same directions up to sign
+    assert metrics_ref.keys() == metrics_mine.keys() and all(abs(float(metrics_ref[m]) - float(metrics_mine[m])) < 1e-3 for m in metrics_ref), (metrics_ref, metrics_mine)
+    loss_ref, _, eval_ref = theirs.evaluate([pc_ref.copy(), sv_ref.copy()], dict(config))
+    loss_mine, _, eval_mine = ours.evaluate([pc_ref.copy(), sv_ref.copy()], dict(config))
+    assert abs(loss_ref - loss_mine) < 1e-3 * max(1.0, abs(loss_ref)), (loss_ref, loss_mine)
+    assert all(abs(float(eval_ref[m]) - float(eval_mine[m])) < 1e-3 * max(1.0, abs(float(eval_ref[m]))) for m in eval_ref), (eval_ref, eval_mine)
     agreed += 1
 print("configs agree:", agreed)
