@@ -75,7 +75,7 @@ def resolver(prefix: str):
 def round_config(extra: dict):
     def config_fn(server_round: int) -> dict:
         config = {"current_server_round": server_round, "local_steps": LOCAL_STEPS, "batch_size": BATCH, "n_server_rounds": ROUNDS, **extra}
-        if "local_epochs" in extra or "local_head_steps" in extra:
+        if "local_epochs" in extra or "local_head_steps" in extra or "local_head_epochs" in extra:
             del config["local_steps"]  # mutually exclusive ways of saying how long to train
         return config
 
@@ -329,6 +329,25 @@ SCENARIOS = {
     "flexible_mr_mtl": dict(client=("clients.flexible.base", "FlexibleClient"), personalize="MR_MTL", strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
                             server=("servers.adaptive_constraint_servers.mrmtl_server", "MrMtlServer"), strategy_args=adaptive_constraint(adapt_loss_weight=False)),
     "options": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, extra_hooks=optional_hooks, config={"num_validation_steps": 1}),
+    # the same algorithms under other round configurations
+    "fedavg_unweighted_eval_after_fit": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, config={"evaluate_after_fit": True, "pack_losses_with_val_metrics": True},
+                                             strategy_args=lambda side, ours: {"weighted_aggregation": False, "weighted_eval_losses": False}),
+    "fedprox_epochs_unweighted": dict(client=("clients.fed_prox_client", "FedProxClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                                      server=("servers.adaptive_constraint_servers.fedprox_server", "FedProxServer"), config={"local_epochs": 1},
+                                      strategy_args=adaptive_constraint(weighted_aggregation=False, weighted_train_losses=False, loss_weight_patience=2)),
+    "ditto_epochs": dict(client=("clients.ditto_client", "DittoClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                         server=("servers.adaptive_constraint_servers.ditto_server", "DittoServer"), strategy_args=adaptive_constraint(initial_loss_weight=1.0, adapt_loss_weight=False),
+                         config={"local_epochs": 2}, extra_hooks=two_optimizers("global", "local", lambda c: c.global_model, lambda c: c.model)),
+    "apfl_epochs": dict(client=("clients.apfl_client", "ApflClient"), **FEDAVG, config={"local_epochs": 1},
+                        extra_hooks=merged(model_hook(lambda side: side("model_bases.apfl_base").ApflModule(Net(), adaptive_alpha=False, alpha=0.25)),
+                                           two_optimizers("local", "global", lambda c: c.model.local_model, lambda c: c.model.global_model))),
+    "scaffold_cold_start_epochs": dict(client=("clients.scaffold_client", "ScaffoldClient"), strategy=("strategies.scaffold", "Scaffold"), server=("servers.scaffold_server", "ScaffoldServer"),
+                                       min_fit=False, hook_args={"lr": 0.05}, config={"local_epochs": 1},
+                                       manager=lambda side, ours: side("client_managers.fixed_without_replacement_manager").FixedSamplingByFractionClientManager(),
+                                       strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "model": seeded(Net), "learning_rate": 0.5}),
+    "fedrep_epochs": dict(client=("clients.fedrep_client", "FedRepClient"), **FEDAVG, config={"local_head_epochs": 1, "local_rep_epochs": 1},
+                          extra_hooks=merged(model_hook(lambda side: side("model_bases.fedrep_base").FedRepModel(Body(), nn.Linear(16, 2))),
+                                             two_optimizers("representation", "head", lambda c: c.model.base_module, lambda c: c.model.head_module))),
     "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
                   strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
 }
