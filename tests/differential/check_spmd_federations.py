@@ -23,10 +23,17 @@ SPMD_SCENARIOS = ["fedavg", "fedprox", "scaffold", "fedper", "feddg_ga", "flash"
 
 def worker(name: str, out_path: str) -> None:
     from fl4health_b200.parallel.spmd import SpmdContext, build_spmd_federation
+    from fl4health_b200.parallel.spmd_multi import build_spmd_federation_multi
 
     ctx = SpmdContext()
     server, clients = build(resolver("fl4health_b200"), SCENARIOS[name], ours=True)
-    build_spmd_federation(ctx, server, clients[ctx.rank], fused=False)
+    if ctx.world_size == CLIENTS:
+        build_spmd_federation(ctx, server, clients[ctx.rank], fused=False)
+    else:  # fewer ranks than clients: uneven hosting (rank 0 takes the remainder), two-level reduction
+        per_rank = CLIENTS // ctx.world_size
+        first = ctx.rank * per_rank + (CLIENTS % ctx.world_size if ctx.rank else 0)
+        count = per_rank + (CLIENTS % ctx.world_size if ctx.rank == 0 else 0)
+        build_spmd_federation_multi(ctx, server, clients[first:first + count])
     history, _ = server.fit(num_rounds=ROUNDS)
     if ctx.rank == 0:
         Path(out_path).write_text(json.dumps({
@@ -36,13 +43,13 @@ def worker(name: str, out_path: str) -> None:
     ctx.shutdown()
 
 
-def run_spmd(name: str) -> SimpleNamespace:
+def run_spmd(name: str, ranks: int = CLIENTS) -> SimpleNamespace:
     with socket.socket() as probe:
         probe.bind(("127.0.0.1", 0))
         port = probe.getsockname()[1]
     out = Path(tempfile.mkdtemp(prefix="spmd_")) / f"{name}.json"
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", FL4H_LOG_LEVEL="ERROR")
-    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={CLIENTS}", "--master-addr", "127.0.0.1",
+    command = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), str(Path(__file__).resolve()), "--worker", name, str(out)]
     done = subprocess.run(command, env=env, capture_output=True, text=True, timeout=600)
     assert done.returncode == 0, (name, done.stdout[-2000:], done.stderr[-3000:])
@@ -60,4 +67,7 @@ if __name__ == "__main__":
         wanted = ALL_SPMD_SCENARIOS if sys.argv[1:] == ["all"] else (sys.argv[1:] or SPMD_SCENARIOS)
         for name in wanted:
             compare(f"spmd:{name}", run_reference(SCENARIOS[name]), run_spmd(name), tol=2e-4)
+        if not sys.argv[1:] or sys.argv[1:] == ["all"]:
+            for name in ("fedavg", "scaffold"):  # three clients hosted by two processes ([2, 1])
+                compare(f"spmd, 2 ranks host 3 clients:{name}", run_reference(SCENARIOS[name]), run_spmd(name, ranks=2), tol=2e-4)
         print("configs agree:", check_federations.agreed)
