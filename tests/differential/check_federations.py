@@ -128,6 +128,7 @@ def run_reference(scenario: dict):
     history = flwr.server.start_server(server=server, server_address=address, config=flwr.server.ServerConfig(num_rounds=ROUNDS))
     for thread in threads:
         thread.join(60)
+    server.shutdown()  # flushes the reporters, as the reference's example servers do after ``start_server`` returns
     return history
 
 
