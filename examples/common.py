@@ -28,11 +28,36 @@ DEFAULTS: dict[str, Any] = {
 SHAPES = {"mnist": ((1, 28, 28), 10), "cifar": ((3, 32, 32), 10)}
 
 
+# The reference's example configs name the same knobs differently per example; a YAML written for it can be passed to
+# ``--config`` as is.  Left: the reference's key; right: the key the scenarios read.
+REFERENCE_KEY_ALIASES = {
+    "initial_proximal_weight": "initial_loss_weight", "adapt_proximal_weight": "adapt_loss_weight",
+    "adaptive_proximal_weight": "adapt_loss_weight", "proximal_weight_delta": "loss_weight_delta",
+    "proximal_weight_patience": "loss_weight_patience", "beta": "heterogeneity_beta",
+    "server_noise_multiplier": "weight_noise_multiplier", "clipping_bit_noise_multiplier": "clipping_noise_multiplier",
+    "clipping_bound": "initial_clipping_bound", "server_momentum": "server_beta", "weighted_averaging": "weighted_aggregation",
+    "ckpt_path": "checkpoint_path",
+}
+
+
+def translate_reference_keys(raw: dict[str, Any]) -> dict[str, Any]:
+    """Reference-style keys renamed to the scenarios' names (a key given under both names keeps the native one); a
+    null ``local_epochs`` / ``local_steps`` -- the reference writes the unused one as null -- is dropped."""
+    out = {key: value for key, value in raw.items() if key not in REFERENCE_KEY_ALIASES}
+    for key, value in raw.items():
+        if key in REFERENCE_KEY_ALIASES:
+            out.setdefault(REFERENCE_KEY_ALIASES[key], value)
+    for duration in ("local_epochs", "local_steps"):
+        if duration in out and out[duration] is None:
+            del out[duration]
+    return out  # (when ``local_epochs`` is given it takes precedence over the default step count: make_config_fn)
+
+
 def load_example_config(scenario: str, path: str | None = None, overrides: dict[str, Any] | None = None) -> dict[str, Any]:
     config = dict(DEFAULTS)
     file = Path(path) if path else CONFIG_DIR / f"{scenario}.yaml"
     if file.exists():
-        config.update(yaml.safe_load(file.read_text()) or {})
+        config.update(translate_reference_keys(yaml.safe_load(file.read_text()) or {}))
     config.update({k: v for k, v in (overrides or {}).items() if v is not None})
     return config
 

@@ -134,7 +134,8 @@ def _adaptive_strategy(config: dict[str, Any]) -> Any:
 
     return FedAvgWithAdaptiveConstraint(
         initial_parameters=None, initial_loss_weight=config.get("initial_loss_weight", 0.1),
-        adapt_loss_weight=config.get("adapt_loss_weight", True), loss_weight_delta=0.05, loss_weight_patience=2, **strategy_kwargs(config))
+        adapt_loss_weight=config.get("adapt_loss_weight", True), loss_weight_delta=config.get("loss_weight_delta", 0.05),
+        loss_weight_patience=config.get("loss_weight_patience", 2), **strategy_kwargs(config))
 
 
 @scenario("fedprox_example")
