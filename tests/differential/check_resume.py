@@ -24,7 +24,10 @@ def build(prefix: str, state_dir: Path | None):
     for index in range(CLIENTS):
         module = None
         if state_dir is not None:
+            checkpointing = side("checkpointing.checkpointer")
             module = side("checkpointing.client_module").ClientCheckpointAndStateModule(
+                pre_aggregation=[checkpointing.LatestTorchModuleCheckpointer(str(state_dir), f"client_{index}_pre_latest.pkl")],
+                post_aggregation=[checkpointing.BestLossTorchModuleCheckpointer(str(state_dir), f"client_{index}_post_best.pkl")],
                 state_checkpointer=side("checkpointing.state_checkpointer").ClientStateCheckpointer(state_dir))
         cls = type(f"Client{index}", (client_cls,), user_hooks(side, index))
         clients.append(cls(data_path=Path("."), metrics=[accuracy()], device=torch.device("cpu"), client_name=f"client_{index}",
@@ -70,7 +73,7 @@ def run(prefix: str, state_dir: Path | None, rounds: int):
 
 
 if __name__ == "__main__":
-    outcomes, files = {}, {}
+    outcomes, files, models = {}, {}, {}
     for prefix in ("fl4health", "fl4health_b200"):
         state_dir = Path(tempfile.mkdtemp(prefix=f"state_{prefix}_"))
         first = run(prefix, state_dir, rounds=2)
@@ -79,8 +82,15 @@ if __name__ == "__main__":
         resumed = run(prefix, state_dir, rounds=4)  # new objects, same directory
         assert [r for r, _ in resumed.losses_distributed] == [1, 2, 3, 4], (prefix, resumed.losses_distributed)
         outcomes[prefix] = resumed
+        models[prefix] = {p.name: torch.load(p, weights_only=False).state_dict() for p in sorted(state_dir.glob("*.pkl")) if "model" in p.name or "client_" in p.name}
     assert files["fl4health"] == files["fl4health_b200"], files  # same artefacts under the same names
     compare("resume after 2 of 4 rounds", outcomes["fl4health"], outcomes["fl4health_b200"], tol=2e-4)
-    uninterrupted = run("fl4health_b200", None, rounds=4)
+    # the model checkpoints both sides left behind (server: best / latest; clients: latest before, best after aggregation)
+    assert models["fl4health"].keys() == models["fl4health_b200"].keys() and len(models["fl4health"]) == 2 + 2 * CLIENTS, sorted(models["fl4health"])
+    for name, state in models["fl4health"].items():
+        for (key, a), (_, b) in zip(state.items(), models["fl4health_b200"][name].items()):
+            assert torch.allclose(a, b, atol=2e-4), (name, key, (a - b).abs().max())
+    check_federations.agreed += 1
+    uninterrupted = run("fl4health_b200", Path(tempfile.mkdtemp(prefix="state_uninterrupted_")), rounds=4)  # same modules, no stop
     compare("resumed == uninterrupted (ours)", uninterrupted, outcomes["fl4health_b200"], tol=1e-6)
     print("configs agree:", check_federations.agreed)
