@@ -1,5 +1,9 @@
-"""sklearn transformers that apply a text vectoriser column-wise to DataFrames (parity:
-``fl4health/feature_alignment/string_columns_transformer.py:9-88``)."""
+"""sklearn transformers that hand text columns of a DataFrame to a text vectoriser (parity:
+``fl4health/feature_alignment/string_columns_transformer.py:9-88``).
+
+Both public classes are the same adapter -- turn the frame into ONE series of strings, then ``fit`` / ``transform`` the
+wrapped vectoriser on it -- and differ only in how the series is formed: all columns joined per row, or the single
+column a ``ColumnTransformer`` passes for one feature."""
 
 from __future__ import annotations
 
@@ -9,35 +13,32 @@ import pandas as pd
 from sklearn.base import BaseEstimator, TransformerMixin
 
 
-class TextMulticolumnTransformer(BaseEstimator, TransformerMixin):
-    """Joins all string columns of a frame into one text per row, then vectorises."""
-
+class _TextFrameAdapter(BaseEstimator, TransformerMixin):
     def __init__(self, transformer: Any) -> None:
         self.transformer = transformer
 
-    @staticmethod
-    def _joined(x: pd.DataFrame) -> pd.Series:
-        return x.astype(str).agg(" ".join, axis=1)
+    def _as_text(self, frame: pd.DataFrame) -> pd.Series:
+        raise NotImplementedError
 
-    def fit(self, x: pd.DataFrame, y: pd.DataFrame | None = None) -> TextMulticolumnTransformer:  # noqa: ARG002
-        self.transformer.fit(self._joined(x))
+    def fit(self, x: pd.DataFrame, y: pd.DataFrame | None = None) -> Any:  # noqa: ARG002
+        self.transformer.fit(self._as_text(x))
         return self
 
-    def transform(self, x: pd.DataFrame) -> pd.DataFrame:
-        return self.transformer.transform(self._joined(x))
+    def transform(self, x: pd.DataFrame) -> Any:
+        """The vectoriser's output (a sparse matrix for the usual count / tf-idf vectorisers)."""
+        return self.transformer.transform(self._as_text(x))
 
 
-class TextColumnTransformer(BaseEstimator, TransformerMixin):
-    """Vectorises a single-column frame (what ``ColumnTransformer`` hands over for one feature)."""
+class TextMulticolumnTransformer(_TextFrameAdapter):
+    """Every row's string columns joined with spaces into one document."""
 
-    def __init__(self, transformer: Any) -> None:
-        self.transformer = transformer
+    def _as_text(self, frame: pd.DataFrame) -> pd.Series:
+        return frame.astype(str).agg(" ".join, axis=1)
 
-    def fit(self, x: pd.DataFrame, y: pd.DataFrame | None = None) -> TextColumnTransformer:  # noqa: ARG002
-        assert isinstance(x, pd.DataFrame) and x.shape[1] == 1
-        self.transformer.fit(x.iloc[:, 0].astype(str))
-        return self
 
-    def transform(self, x: pd.DataFrame) -> pd.DataFrame:
-        assert isinstance(x, pd.DataFrame) and x.shape[1] == 1
-        return self.transformer.transform(x.iloc[:, 0].astype(str))
+class TextColumnTransformer(_TextFrameAdapter):
+    """A single-column frame: that column's strings are the documents."""
+
+    def _as_text(self, frame: pd.DataFrame) -> pd.Series:
+        assert isinstance(frame, pd.DataFrame) and frame.shape[1] == 1, "expects exactly one text column"
+        return frame.iloc[:, 0].astype(str)
