@@ -240,7 +240,7 @@ class BasicClient:
         ``on_init_parameters_config_fn``) reaching a client that has already been set up — a properties poll (nnU-Net plan
         negotiation, tabular feature alignment) may have initialised it.  Clients that pack side information into their
         regular payload must answer this request with the plain model state, exactly like an uninitialised client."""
-        return self.initialized and config.get("current_server_round") == 0 and not self._answering_fit
+        return self.initialized and config.get("current_server_round") == 0 and not getattr(self, "_answering_fit", False)
 
     def set_parameters(self, parameters: NDArrays, config: Config, fitting_round: bool) -> None:
         """The very first fit installs *all* weights (full exchange) whatever the exchanger; afterwards the client's
