@@ -349,6 +349,21 @@ SCENARIOS = {
     "fedrep_epochs": dict(client=("clients.fedrep_client", "FedRepClient"), **FEDAVG, config={"local_head_epochs": 1, "local_rep_epochs": 1},
                           extra_hooks=merged(model_hook(lambda side: side("model_bases.fedrep_base").FedRepModel(Body(), nn.Linear(16, 2))),
                                              two_optimizers("representation", "head", lambda c: c.model.base_module, lambda c: c.model.head_module))),
+    # constructor options of the personalised clients
+    "moon_two_old_models": dict(client=("clients.moon_client", "MoonClient"), **FEDAVG, client_args=lambda side: {"contrastive_weight": 1.0, "temperature": 0.2, "len_old_models_buffer": 2},
+                                extra_hooks=model_hook(lambda side: side("model_bases.moon_base").MoonModel(Body(), nn.Linear(16, 2)))),
+    "fenda_ditto_frozen_extractor": dict(client=("clients.fenda_ditto_client", "FendaDittoClient"), strategy=("strategies.fedavg_with_adaptive_constraint", "FedAvgWithAdaptiveConstraint"),
+                                         server=("servers.base_server", "FlServer"), client_args=lambda side: {"freeze_global_feature_extractor": True},
+                                         strategy_args=lambda side, ours: {**adaptive_constraint(initial_loss_weight=0.5)(side, ours), "initial_parameters": side("utils.parameter_extraction").get_all_model_parameters(
+                                             seeded(lambda: side("model_bases.sequential_split_models").SequentiallySplitExchangeBaseModel(Body(), nn.Linear(16, 2))))},
+                                         extra_hooks=merged(model_hook(lambda side: side("model_bases.fenda_base").FendaModel(Body(), Body(), parallel_head(side))),
+                                                            lambda side, index: {"get_global_model": lambda self, config: seeded(
+                                                                lambda: side("model_bases.sequential_split_models").SequentiallySplitModel(Body(), nn.Linear(16, 2))).to(self.device)},
+                                                            two_optimizers("global", "local", lambda c: c.global_model, lambda c: c.model))),
+    "perfcl_temperatures": dict(client=("clients.perfcl_client", "PerFclClient"), **FEDAVG,
+                                client_args=lambda side: {"global_feature_loss_temperature": 0.1, "local_feature_loss_temperature": 1.5,
+                                                          "global_feature_contrastive_loss_weight": 1.0, "local_feature_contrastive_loss_weight": 0.25},
+                                extra_hooks=model_hook(lambda side: side("model_bases.perfcl_base").PerFclModel(Body(), Body(), parallel_head(side)))),
     "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
                   strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
 }
