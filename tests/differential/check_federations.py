@@ -109,7 +109,8 @@ def build(side, scenario: dict, ours: bool):
     server_cls = getattr(side(scenario["server"][0]), scenario["server"][1])
     manager = scenario.get("manager", lambda side, ours: (side("servers.client_manager") if ours else importlib.import_module("flwr.server.client_manager")).SimpleClientManager())(side, ours)
     server = server_cls(client_manager=manager, fl_config={"n_server_rounds": ROUNDS}, strategy=strategy,
-                        on_init_parameters_config_fn=config_fn, accept_failures=False, **scenario.get("server_args", lambda side: {})(side))
+                        on_init_parameters_config_fn=config_fn, accept_failures=scenario.get("accept_failures", False),
+                        **scenario.get("server_args", lambda side: {})(side))
     return server, clients
 
 
@@ -144,7 +145,12 @@ def compare(name: str, theirs, ours, tol: float) -> None:
     assert [r for r, _ in theirs.losses_distributed] == [r for r, _ in ours.losses_distributed], name
     for (server_round, a), (_, b) in zip(theirs.losses_distributed, ours.losses_distributed):
         assert abs(a - b) <= tol * max(1.0, abs(a)), (name, "loss", server_round, a, b)
-    for label, left, right in (("fit", theirs.metrics_distributed_fit, ours.metrics_distributed_fit), ("eval", theirs.metrics_distributed, ours.metrics_distributed)):
+    central_theirs, central_ours = getattr(theirs, "losses_centralized", []), getattr(ours, "losses_centralized", [])
+    assert len(central_theirs) == len(central_ours), (name, central_theirs, central_ours)
+    for (round_a, a), (round_b, b) in zip(central_theirs, central_ours):
+        assert round_a == round_b and abs(a - b) <= tol * max(1.0, abs(a)), (name, "central loss", central_theirs, central_ours)
+    for label, left, right in (("fit", theirs.metrics_distributed_fit, ours.metrics_distributed_fit), ("eval", theirs.metrics_distributed, ours.metrics_distributed),
+                               ("central", getattr(theirs, "metrics_centralized", {}), getattr(ours, "metrics_centralized", {}))):
         assert set(left) == set(right), (name, label, sorted(left), sorted(right))
         for key in left:
             for (server_round, a), (_, b) in zip(left[key], right[key]):
@@ -169,6 +175,33 @@ def optional_hooks(side, index):
 
 # (Early stopping is not compared: in this reference version ``EarlyStopper.should_stop`` calls the client's validation
 # with a logging mode its own assertion rejects -- ``basic_client.py:844`` -- so the reference arm cannot run it.)
+
+
+def failing_client_hooks(side, index):
+    """Client 2 raises during its round-2 fit; the others carry on."""
+    base = side("clients.basic_client").BasicClient
+
+    def fit(self, parameters, config):
+        if index == 2 and config["current_server_round"] == 2:
+            raise RuntimeError("simulated client failure")
+        return base.fit(self, parameters, config)
+
+    return {"fit": fit}
+
+
+def central_evaluation(side, ours):
+    """Server-side evaluation of the aggregate on held-out data after every round (and of the initial model)."""
+    features, labels = cohort(9)
+
+    def evaluate_fn(server_round, arrays, config):
+        model = Net()
+        tensors = [torch.as_tensor(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a) for a in arrays]
+        model.load_state_dict(dict(zip(model.state_dict(), tensors)))
+        with torch.no_grad():
+            logits = model(features)
+        return float(nn.functional.cross_entropy(logits, labels)), {"central - accuracy": float((logits.argmax(1) == labels).float().mean())}
+
+    return {**initial_parameters()(side, ours), "evaluate_fn": evaluate_fn}
 
 
 def seeded(factory):
@@ -364,6 +397,10 @@ SCENARIOS = {
                                 client_args=lambda side: {"global_feature_loss_temperature": 0.1, "local_feature_loss_temperature": 1.5,
                                                           "global_feature_contrastive_loss_weight": 1.0, "local_feature_contrastive_loss_weight": 0.25},
                                 extra_hooks=model_hook(lambda side: side("model_bases.perfcl_base").PerFclModel(Body(), Body(), parallel_head(side)))),
+    # server behaviour: a client that fails mid-run (tolerated), centralised evaluation next to the federated one
+    "client_failure_tolerated": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, extra_hooks=failing_client_hooks, accept_failures=True,
+                                     strategy_args=lambda side, ours: {"min_fit_clients": 2, "min_evaluate_clients": 2, "min_available_clients": 2, "accept_failures": True}),
+    "central_evaluation": dict(client=("clients.basic_client", "BasicClient"), **FEDAVG, strategy_args=central_evaluation),
     "flash": dict(client=("clients.flash_client", "FlashClient"), strategy=("strategies.flash", "Flash"), server=("servers.base_server", "FlServer"),
                   strategy_args=lambda side, ours: {**initial_parameters()(side, ours), "eta": 0.1, "eta_l": 0.05}, config={"local_epochs": 1, "gamma": 0.5}),
 }
