@@ -15,6 +15,19 @@ ROOT = Path(__file__).resolve().parent.parent
 REFERENCE = ROOT / "baseline" / "_ref"
 SCRIPTS = sorted((Path(__file__).parent / "differential").glob("check_*.py"))
 
+
+
+def _ensure_reference_copy() -> None:
+    """Same outcome as ``baseline/install_reference.sh`` / ``reference_arm.reference_available``: an unmodified copy of
+    the pure-Python reference package (``baseline/_ref`` is git-ignored, so a fresh checkout does not have it)."""
+    source = Path(os.environ.get("FL4H_REFERENCE_SRC", "/root/reference")) / "fl4health"
+    if not (REFERENCE / "fl4health" / "__init__.py").exists() and (source / "__init__.py").exists():
+        import shutil
+
+        shutil.copytree(source, REFERENCE / "fl4health", ignore=shutil.ignore_patterns("__pycache__"), dirs_exist_ok=True)
+
+
+_ensure_reference_copy()
 pytestmark = pytest.mark.skipif(not (REFERENCE / "fl4health").is_dir(), reason="reference arm not installed (baseline/install_reference.sh)")
 
 
