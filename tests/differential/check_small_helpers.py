@@ -128,4 +128,46 @@ assert len(a) == len(b) and all(x.shape == y.shape and np.array_equal(x, y) for 
 same_outcome(ref_extract.check_shape_match, my_extract.check_shape_match, [torch.ones(2, 3)], [torch.ones(2, 3)], "mismatch")
 same_outcome(ref_extract.check_shape_match, my_extract.check_shape_match, [torch.ones(2, 3)], [torch.ones(3, 2)], "mismatch")
 # (``utils.load_data`` of the reference imports monai at module load: not comparable in this image)
+
+# -- client managers: how many clients a fraction selects, "all", the fixed sample's contract ------------------------------------
+import fl4health.client_managers.fixed_sampling_client_manager as ref_fixed
+import fl4health.client_managers.fixed_without_replacement_manager as ref_fraction
+import fl4health.client_managers.poisson_sampling_manager as ref_poisson
+import fl4health_b200.client_managers.fixed_sampling_client_manager as my_fixed
+import fl4health_b200.client_managers.fixed_without_replacement_manager as my_fraction
+import fl4health_b200.client_managers.poisson_sampling_manager as my_poisson
+
+
+class Proxy:
+    def __init__(self, cid: str) -> None:
+        self.cid = cid
+
+
+def populated(manager, n: int = 10):
+    for index in range(n):
+        manager.register(Proxy(f"c{index}"))
+    return manager
+
+
+for fraction in (0.1, 0.25, 0.34, 0.5, 0.75, 0.99, 1.0):
+    theirs = populated(ref_fraction.FixedSamplingByFractionClientManager())
+    ours = populated(my_fraction.FixedSamplingByFractionClientManager())
+    picked_ref, picked_mine = theirs.sample_fraction(fraction, 1), ours.sample_fraction(fraction, 1)
+    assert len(picked_ref) == len(picked_mine), (fraction, len(picked_ref), len(picked_mine))
+    assert len({p.cid for p in picked_mine}) == len(picked_mine)  # without replacement
+    agreed += 1
+for module_ref, module_mine, name in ((ref_fraction, my_fraction, "FixedSamplingByFractionClientManager"), (ref_poisson, my_poisson, "PoissonSamplingClientManager")):
+    theirs, ours = populated(getattr(module_ref, name)()), populated(getattr(module_mine, name)())
+    assert sorted(p.cid for p in theirs.sample_all(10)) == sorted(p.cid for p in ours.sample_all(10)); agreed += 1
+sizes_ref = [len(populated(ref_poisson.PoissonSamplingClientManager(), 200).sample_fraction(0.3, 1)) for _ in range(30)]
+sizes_mine = [len(populated(my_poisson.PoissonSamplingClientManager(), 200).sample_fraction(0.3, 1)) for _ in range(30)]
+assert abs(np.mean(sizes_ref) - 60) < 8 and abs(np.mean(sizes_mine) - 60) < 8 and np.std(sizes_mine) > 2, (np.mean(sizes_ref), np.mean(sizes_mine))  # Binomial(200, 0.3)
+agreed += 1
+theirs, ours = populated(ref_fixed.FixedSamplingClientManager()), populated(my_fixed.FixedSamplingClientManager())
+for manager in (theirs, ours):
+    first = [p.cid for p in manager.sample(4, 4)]
+    assert [p.cid for p in manager.sample(4, 4)] == first  # the same cohort until reset (fit and evaluate hit the same clients)
+    manager.reset_sample()
+    assert len(manager.sample(4, 4)) == 4
+agreed += 1
 print("configs agree:", agreed)
